@@ -1,0 +1,181 @@
+"""Host model of the DEVICE algorithm (word-for-word what the CUDA kernels compute).
+
+Test infrastructure: lets the CPU suite check the multi-modular scheme (division-free
+uniform-scale Gauss-Jordan on Montgomery words, one inversion per matrix and prime,
+Garner CRT to signed integers, pivot-profile agreement) against the exact oracle
+without a GPU.  The CUDA code in linalg_solver_b200/csrc mirrors these functions;
+names match (mont_redc, elim_words, garner_signed, plan_bits).
+"""
+import math
+
+R = 1 << 32
+MASK = R - 1
+SKIP = 31
+
+
+def is_prime_u32(n):
+    if n < 2:
+        return False
+    for q in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        if n % q == 0:
+            return n == q
+    d, s = n - 1, 0
+    while d % 2 == 0:
+        d //= 2
+        s += 1
+    for a in (2, 3, 5, 7):          # deterministic below 3,215,031,751
+        x = pow(a, d, n)
+        if x in (1, n - 1):
+            continue
+        for _ in range(s - 1):
+            x = x * x % n
+            if x == n - 1:
+                break
+        else:
+            return False
+    return True
+
+
+def prime_table(count, start=(1 << 31) - 1):
+    """Primes below 2^31 in descending order (same table as lsx_primes.cpp)."""
+    out = []
+    n = start
+    while len(out) < count:
+        if is_prime_u32(n):
+            out.append(n)
+        n -= 2
+    return out
+
+
+class Prime:
+    def __init__(self, p):
+        self.p = p
+        self.pinv = (-pow(p, -1, R)) % R        # -p^{-1} mod 2^32
+        self.one = R % p                        # word of value 1
+        self.r2 = (R * R) % p                   # word of value R
+
+
+def mont_redc(t, P):
+    m = ((t & MASK) * P.pinv) & MASK
+    u = (t + m * P.p) >> 32
+    return u - P.p if u >= P.p else u
+
+
+def mont_mul(a, b, P):
+    return mont_redc(a * b, P)
+
+
+def mont_pow(a, e, P):
+    acc = P.one
+    for bit in bin(e)[2:]:
+        acc = mont_mul(acc, acc, P)
+        if bit == "1":
+            acc = mont_mul(acc, a, P)
+    return acc
+
+
+def elim_words(A, bar, P, left_done_skip=False):
+    """One matrix, one prime.  A: m x n Python ints with |a| < p.
+
+    Returns (N, d, profile, rank): N[i][j] = d * RREF[i][j] mod p as plain residues,
+    d = sign * prod(pivots) mod p (determinant of the pivot minor), profile[j] = source
+    row chosen for column j (SKIP when the column has no pivot).
+    Words are loaded RAW (w = a mod p, i.e. value a/R): every value carries the same
+    constant factor 1/R, which the factors Gw (pivot rows) and G2w (non-pivot rows)
+    take out again at the end.
+    """
+    m, n = len(A), len(A[0])
+    p = P.p
+    W = [[a % p for a in row] for row in A]
+    S, Q, X = P.one, P.one, 1
+    pi, neg = 0, False
+    profile = []
+    for j in range(bar):
+        src = next((r for r in range(pi, m) if W[r][j] != 0), None)
+        if src is None:
+            profile.append(SKIP)
+            continue
+        profile.append(src)
+        if src != pi:
+            W[pi], W[src] = W[src], W[pi]
+            neg = not neg
+        piv = W[pi][j]
+        prow = list(W[pi])
+        for r in range(m):
+            x = S if r == pi else piv
+            y = 0 if r == pi else p - W[r][j]
+            c0 = j + 1 if left_done_skip else 0
+            for c in range(c0, n):
+                W[r][c] = mont_redc(x * W[r][c] + y * prow[c], P)
+        Q = mont_mul(Q, S, P)
+        S = mont_mul(S, piv, P)
+        X = mont_mul(X, P.r2, P)
+        pi += 1
+    qinv = mont_pow(Q, p - 2, P)
+    Gw = mont_mul(qinv, X, P)
+    if neg and Gw:
+        Gw = p - Gw
+    G2w = mont_mul(Gw, P.r2, P)
+    N = [[mont_mul(Gw if r < pi else G2w, W[r][c], P) for c in range(n)] for r in range(m)]
+    d = mont_mul(Gw, S, P)
+    return N, d, profile, pi
+
+
+def garner_signed(res, primes):
+    """Residues (one per prime) -> the unique integer in (-M/2, M/2)."""
+    K = len(primes)
+    v = []
+    for j in range(K):
+        pj = primes[j]
+        t = res[j] % pj
+        for i in range(j):
+            t = (t - v[i]) * pow(primes[i], -1, pj) % pj
+        v.append(t)
+    neg = False
+    for i in reversed(range(K)):
+        h = (primes[i] - 1) // 2
+        if v[i] != h:
+            neg = v[i] > h
+            break
+    x = 0
+    for i in reversed(range(K)):
+        x = x * primes[i] + v[i]
+    if neg:
+        M = 1
+        for q in primes:
+            M *= q
+        x -= M
+    return x
+
+
+def log2_minor_bound(m, bar, has_right, a_abs, b_abs, right_identity, max_rank):
+    """log2 of the largest |minor| the outputs can be (Hadamard), see DESIGN.md.
+
+    Every output integer (common denominator d, numerators d*R[i][j]) is a minor of
+    [A|B] of size s <= smax that uses at most one right-block column.
+    """
+    a = max(1, int(a_abs))
+    b = max(1, int(b_abs))
+    r = min(m, bar)
+    if max_rank and max_rank > 0:
+        r = min(r, max_rank)
+    best = r * (0.5 * math.log2(r) + math.log2(a)) if r > 0 else 0.0
+    if has_right:
+        s = min(m, r + 1)
+        if right_identity:
+            t = s - 1
+            cand = t * (0.5 * math.log2(t) + math.log2(a)) if t > 0 else 0.0
+        else:
+            cand = (s - 1) * (0.5 * math.log2(s) + math.log2(a)) + 0.5 * math.log2(s) + math.log2(b)
+        best = max(best, cand)
+    return best
+
+
+PRIME_BITS = 30.999        # every table prime is > 2^30.999
+
+
+def plan_bits(log2_bound):
+    need = log2_bound + 1.0 + 1e-6          # sign bit + rounding slack
+    K = max(1, math.ceil(need / PRIME_BITS))
+    L = max(1, math.ceil(need / 32.0))
+    return K, L
