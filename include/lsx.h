@@ -1,0 +1,196 @@
+/*
+ * lsx.h -- C-ABI of the B200 exact elimination engine (liblsx.so).
+ *
+ * Drop-in boundary for ONE hot path of koskja/linalg-solver: Gauss-Jordan
+ * `Matrix.row_reduce` (reference linalg_solver/linalg.py:534-630) and the calls whose
+ * results are functions of it: `determinant` (linalg.py:183-262), `inverse` (682-743),
+ * `rank` (745-747), `kernel` (749-756), `find_preimage_of` (632-680, 870-999).
+ *
+ * The reference has no FFI for this path (its only native module, linalg-helper, is a
+ * sparsity-pattern planner: linalg-helper/src/lib.rs:122-143).  The functions below are
+ * what a binding for the path would call: from Python through ctypes
+ * (linalg_solver_b200/_lib.py) or from the Rust crate through an `extern "C"` block
+ * (INTEGRATION.md shows both stubs).
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; no C++/torch types.  Every function returns an int:
+ *    LSX_OK or a negative LSX_ERR_* code, never throws, never aborts.
+ *    lsx_last_error(ctx) gives a human-readable message for the last failure on ctx.
+ *  - Inputs are batches of row-major int32 matrices, `batch` of them back to back.
+ *  - Outputs are exact.  Every rational result is given as an integer numerator over ONE
+ *    common denominator per matrix (the determinant of the pivot minor), each integer as
+ *    `limbs` 32-bit little-endian words in two's complement (limbs == 1 is an int32,
+ *    limbs == 2 an int64).  `limbs` and the number of 31-bit primes used come from the
+ *    lsx_plan_* query (Hadamard bound of the declared entry magnitudes); the caller
+ *    allocates all buffers.
+ *  - `mem` says where ALL data pointers of the call live: LSX_MEM_DEVICE (device
+ *    pointers on ctx's GPU; the call only enqueues work on ctx's stream) or LSX_MEM_HOST
+ *    (host pointers; the call copies in, computes, copies out and returns when done).
+ *  - Mathematical failure is a per-matrix status bit, not an error code
+ *    (reference: `Matrix.NoSolution()`, linalg.py:524-532).  Shape errors return
+ *    LSX_ERR_BAD_SHAPE (reference: ValueError, linalg.py:643, 693).
+ *  - A ctx is bound to one GPU and one stream and must not be used from two threads at
+ *    once; different ctxs are independent.
+ */
+#ifndef LSX_H
+#define LSX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSX_ABI_VERSION 1
+
+/* return codes */
+#define LSX_OK                 0
+#define LSX_ERR_BAD_SHAPE     -1   /* dimensions/bar_col/limits invalid for the call          */
+#define LSX_ERR_CUDA          -2   /* CUDA runtime failure, see lsx_last_error                */
+#define LSX_ERR_BOUND         -3   /* declared magnitudes need more primes than supported     */
+#define LSX_ERR_NULL          -4   /* required pointer is NULL                                */
+#define LSX_ERR_UNSUPPORTED   -5   /* shape outside what the kernels cover                    */
+#define LSX_ERR_NO_DEVICE     -6   /* no usable CUDA device                                   */
+
+/* memory space of the data pointers of a call */
+#define LSX_MEM_HOST   0
+#define LSX_MEM_DEVICE 1
+
+/* per-matrix status bits */
+#define LSX_ST_SINGULAR      1   /* inverse: rank < n  -> reference returns NoSolution()      */
+#define LSX_ST_INCONSISTENT  2   /* solve: zero left row with non-zero rhs -> NoSolution()    */
+#define LSX_ST_BOUND         4   /* an entry exceeded the declared magnitude or the rank      */
+                                 /* exceeded max_rank: outputs for this matrix are not valid  */
+#define LSX_ST_NO_GOOD_PRIME 8   /* could not collect enough agreeing primes (never expected) */
+#define LSX_ST_GEN_TRUNC    16   /* solve: more free variables than gen_cap columns           */
+#define LSX_ST_RETRIED      32   /* informational: a bad prime was detected and replaced      */
+
+/* operations a plan describes */
+#define LSX_OP_RREF    1
+#define LSX_OP_INVERSE 2
+#define LSX_OP_DET     3
+#define LSX_OP_RANK    4
+#define LSX_OP_SOLVE   5
+
+typedef struct lsx_ctx lsx_ctx;
+
+typedef struct lsx_plan {
+    int32_t op;            /* LSX_OP_*                                                        */
+    int32_t m, n;          /* rows / columns of the matrix the elimination runs on ([A|B])    */
+    int32_t bar_col;       /* pivots are searched in columns [0, bar_col); 1 <= bar_col <= n  */
+    int32_t max_rank;      /* declared upper bound on the rank (<= min(m, bar_col))           */
+    int32_t n_primes;      /* 31-bit primes used per matrix                                   */
+    int32_t limbs;         /* 32-bit words per output integer                                 */
+    int32_t pivot_slots;   /* = min(m, bar_col): entries of pivot_col per matrix              */
+    int32_t gen_cap;       /* solve: generator columns stored per matrix                      */
+    int32_t reserved;
+    int64_t a_abs_max;     /* declared max |entry| of the left block                          */
+    int64_t b_abs_max;     /* declared max |entry| of the right block                         */
+    double  log2_bound;    /* log2 of the Hadamard bound every output integer satisfies       */
+} lsx_plan;
+
+/* ---- context ------------------------------------------------------------------------ */
+int  lsx_abi_version(void);
+int  lsx_create(int device_id, lsx_ctx** out);
+void lsx_destroy(lsx_ctx* ctx);
+const char* lsx_last_error(const lsx_ctx* ctx);
+/* Run on the caller's CUDA stream (a cudaStream_t passed as void*; NULL = the ctx's own). */
+int  lsx_set_stream(lsx_ctx* ctx, void* cuda_stream);
+/* Block until everything enqueued on the ctx's stream has finished. */
+int  lsx_synchronize(lsx_ctx* ctx);
+/* Number of kernels this ctx has launched so far (for launch accounting in benchmarks). */
+int64_t lsx_launch_count(const lsx_ctx* ctx);
+/* Test hook: replace the first `count` primes of the table (odd primes < 2^31, distinct),
+ * e.g. tiny primes to force the bad-prime path.  count == 0 restores the default table. */
+int  lsx_debug_set_primes(lsx_ctx* ctx, const uint32_t* primes, int count);
+/* Copy the first `count` primes of the table to out (host). */
+int  lsx_get_primes(const lsx_ctx* ctx, uint32_t* out, int count);
+
+/* ---- plans: how many primes / limbs a call needs -------------------------------------- */
+/* row_reduce of an m x n matrix whose columns >= bar_col only receive the row operations
+ * (linalg.py:534-630; the `bar_col or n-1` default of linalg.py:543 is applied by the
+ * caller).  max_rank <= 0 means unknown. */
+int lsx_plan_rref(int m, int n, int bar_col, int64_t a_abs_max, int64_t b_abs_max,
+                  int max_rank, lsx_plan* out);
+/* inverse of n x n through [A|I], bar_col = n (linalg.py:704-743) */
+int lsx_plan_inverse(int n, int64_t a_abs_max, lsx_plan* out);
+/* determinant of n x n: sign * product of the forward-sweep pivots (linalg.py:547-609) */
+int lsx_plan_det(int n, int64_t a_abs_max, lsx_plan* out);
+/* rank of m x n (linalg.py:745-747) */
+int lsx_plan_rank(int m, int n, int64_t a_abs_max, lsx_plan* out);
+/* find_preimage_of: A (m x n) x = b through [A|b], bar_col = n (linalg.py:648-680,
+ * 913-999); gen_cap = generator columns stored per matrix (<= n). */
+int lsx_plan_solve(int m, int n, int64_t a_abs_max, int64_t b_abs_max, int max_rank,
+                   int gen_cap, lsx_plan* out);
+
+/* ---- batched operations ---------------------------------------------------------------- */
+/*
+ * row_reduce.  A: [batch][m][n] int32.
+ *   num       [batch][m*n][limbs]        numerators: d * RREF entry
+ *   den       [batch][limbs]             d = determinant of the pivot minor (never 0)
+ *   pivot_col [batch][pivot_slots] int32 column of pivot k (row k), -1 padded
+ *   rank      [batch] int32
+ *   status    [batch] int32              LSX_ST_* bits
+ * Row choice follows the reference exactly (entry at the pivot position if non-zero,
+ * else the first lower non-zero row, linalg.py:548-567), so the right block of a
+ * rank-deficient input matches the reference too.
+ */
+int lsx_rref_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, int64_t batch,
+                   int mem, uint32_t* num, uint32_t* den, int32_t* pivot_col,
+                   int32_t* rank, int32_t* status);
+
+/*
+ * inverse + determinant.  A: [batch][n][n] int32.
+ *   adj    [batch][n*n][limbs]   A^-1 = adj / det   (zeros when singular)
+ *   det    [batch][limbs]        determinant (0 when singular)
+ *   status [batch]               LSX_ST_SINGULAR where the reference returns NoSolution()
+ */
+int lsx_inverse_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, int64_t batch,
+                      int mem, uint32_t* adj, uint32_t* det, int32_t* status);
+
+/* determinant (and rank, may be NULL).  A: [batch][n][n].  det: [batch][limbs]. */
+int lsx_det_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, int64_t batch,
+                  int mem, uint32_t* det, int32_t* rank, int32_t* status);
+
+/* rank.  A: [batch][m][n].  rank: [batch]. */
+int lsx_rank_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, int64_t batch,
+                   int mem, int32_t* rank, int32_t* status);
+
+/*
+ * find_preimage_of.  A: [batch][m][n], b: [batch][m].
+ *   den        [batch][limbs]                common denominator d
+ *   particular [batch][n][limbs]             numerators; free variables are 0
+ *   generators [batch][n][gen_cap][limbs]    numerators, column t belongs to the t-th free
+ *                                            column in ascending order: entry d at the free
+ *                                            column, -d*R[i][f] at pivot columns
+ *                                            (linalg.py:973-983); unused columns are 0
+ *   pivot_col  [batch][pivot_slots], rank [batch], status [batch]
+ *   status has LSX_ST_INCONSISTENT where the reference returns NoSolution().
+ */
+int lsx_solve_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, const int32_t* b,
+                    int64_t batch, int mem, uint32_t* den, uint32_t* particular,
+                    uint32_t* generators, int32_t* pivot_col, int32_t* rank,
+                    int32_t* status);
+
+/* ---- one large determinant, shardable by prime ------------------------------------------ */
+/* Number of primes the determinant of an n x n matrix with |entries| <= a_abs_max needs. */
+int lsx_det_large_prime_count(int n, int64_t a_abs_max, int* n_primes, double* log2_bound);
+/*
+ * det(A) mod p for the primes [prime_begin, prime_begin + prime_count) of the table.
+ * A: [n][n] int32.  residues: [prime_count] uint32 (plain residues), primes_out (may be
+ * NULL): the primes used.  Ranks shard the prime range and all-gather `residues`.
+ */
+int lsx_det_large_residues(lsx_ctx* ctx, const int32_t* A, int n, int prime_begin,
+                           int prime_count, int mem, uint32_t* residues,
+                           uint32_t* primes_out);
+/*
+ * CRT of `count` residues (for table primes [0, count)) to a signed integer of `limbs`
+ * words (two's complement, little endian).  residues/out follow `mem`.
+ */
+int lsx_crt_signed(lsx_ctx* ctx, const uint32_t* residues, int count, int limbs, int mem,
+                   uint32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSX_H */

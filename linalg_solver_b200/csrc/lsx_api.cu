@@ -1,0 +1,460 @@
+// C-ABI entry points of liblsx (declared in include/lsx.h): context, plans and the batched
+// operations.  Each operation validates shapes, stages host buffers when asked to, picks a kernel
+// family (fused register-resident kernels for small shapes, the shared-memory tile path otherwise)
+// and enqueues everything on the ctx stream.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "lsx_internal.h"
+
+int lsx_fail(lsx_ctx* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+// Grow-only device workspace.  Growing synchronises the stream first (nothing in flight may
+// still use the old block).
+int lsx_ws_reserve(lsx_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->ws_bytes) return LSX_OK;
+    LSX_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_ws) LSX_CUDA_TRY(ctx, cudaFree(ctx->d_ws));
+    ctx->d_ws = nullptr;
+    ctx->ws_bytes = 0;
+    size_t want = bytes + bytes / 8 + (1u << 20);
+    cudaError_t e = cudaMalloc(&ctx->d_ws, want);
+    if (e != cudaSuccess) {
+        want = bytes;
+        e = cudaMalloc(&ctx->d_ws, want);
+    }
+    if (e != cudaSuccess)
+        return lsx_fail(ctx, LSX_ERR_CUDA, "cudaMalloc of %zu workspace bytes failed: %s", want,
+                        cudaGetErrorString(e));
+    ctx->ws_bytes = want;
+    return LSX_OK;
+}
+
+static int io_reserve(lsx_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->io_bytes) return LSX_OK;
+    LSX_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_io) LSX_CUDA_TRY(ctx, cudaFree(ctx->d_io));
+    ctx->d_io = nullptr;
+    ctx->io_bytes = 0;
+    cudaError_t e = cudaMalloc(&ctx->d_io, bytes);
+    if (e != cudaSuccess)
+        return lsx_fail(ctx, LSX_ERR_CUDA, "cudaMalloc of %zu staging bytes failed: %s", bytes,
+                        cudaGetErrorString(e));
+    ctx->io_bytes = bytes;
+    return LSX_OK;
+}
+
+// ---- prime table upload -------------------------------------------------------------------------
+static int upload_tables(lsx_ctx* ctx) {
+    std::vector<PrimeRec> recs(LSX_TABLE_PRIMES);
+    for (int i = 0; i < LSX_TABLE_PRIMES; ++i) recs[i] = lsx_make_prime_rec(ctx->primes[i]);
+    std::vector<uint32_t> garner((size_t)LSX_GARNER_DIM * LSX_GARNER_DIM, 0u);
+    for (int i = 0; i < LSX_GARNER_DIM; ++i) {
+        for (int j = 0; j < LSX_GARNER_DIM; ++j) {
+            if (i == j) continue;
+            const uint32_t pi = ctx->primes[i], pj = ctx->primes[j];
+            if (pi % pj == 0) continue;
+            const uint32_t inv = lsx_inv_mod(pi % pj, pj);                  // p_i^{-1} mod p_j
+            garner[(size_t)i * LSX_GARNER_DIM + j] = (uint32_t)(((uint64_t)inv << 32) % pj);   // * R
+        }
+    }
+    LSX_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    LSX_CUDA_TRY(ctx, cudaMemcpy(ctx->d_primes, recs.data(), recs.size() * sizeof(PrimeRec), cudaMemcpyHostToDevice));
+    LSX_CUDA_TRY(ctx, cudaMemcpy(ctx->d_garner, garner.data(), garner.size() * 4, cudaMemcpyHostToDevice));
+    return LSX_OK;
+}
+
+extern "C" {
+
+int lsx_abi_version(void) { return LSX_ABI_VERSION; }
+
+int lsx_create(int device_id, lsx_ctx** out) {
+    if (!out) return LSX_ERR_NULL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return LSX_ERR_NO_DEVICE;
+    if (device_id < 0 || device_id >= ndev) return LSX_ERR_NO_DEVICE;
+    lsx_ctx* ctx = new (std::nothrow) lsx_ctx();
+    if (!ctx) return LSX_ERR_CUDA;
+    ctx->device = device_id;
+    if (cudaSetDevice(device_id) != cudaSuccess) {
+        delete ctx;
+        return LSX_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 2; ++i)
+        ok = cudaStreamCreateWithFlags(&ctx->copy_streams[i], cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 8; ++i)
+        ok = cudaEventCreateWithFlags(&ctx->events[i], cudaEventDisableTiming) == cudaSuccess;
+    ctx->stream = ctx->own_stream;
+    ok = ok && cudaMalloc(&ctx->d_primes, LSX_TABLE_PRIMES * sizeof(PrimeRec)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_garner, (size_t)LSX_GARNER_DIM * LSX_GARNER_DIM * 4) == cudaSuccess;
+    if (ok) {
+        lsx_fill_prime_table(ctx->primes, LSX_TABLE_PRIMES);
+        ok = upload_tables(ctx) == LSX_OK;
+    }
+    if (!ok) {
+        lsx_destroy(ctx);
+        return LSX_ERR_CUDA;
+    }
+    *out = ctx;
+    return LSX_OK;
+}
+
+void lsx_destroy(lsx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    if (ctx->d_ws) cudaFree(ctx->d_ws);
+    if (ctx->d_io) cudaFree(ctx->d_io);
+    if (ctx->d_primes) cudaFree(ctx->d_primes);
+    if (ctx->d_garner) cudaFree(ctx->d_garner);
+    for (auto& e : ctx->events)
+        if (e) cudaEventDestroy(e);
+    for (auto& s : ctx->copy_streams)
+        if (s) cudaStreamDestroy(s);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* lsx_last_error(const lsx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int lsx_set_stream(lsx_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return LSX_ERR_NULL;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return LSX_OK;
+}
+
+int lsx_synchronize(lsx_ctx* ctx) {
+    if (!ctx) return LSX_ERR_NULL;
+    LSX_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    LSX_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LSX_OK;
+}
+
+int64_t lsx_launch_count(const lsx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int lsx_debug_set_primes(lsx_ctx* ctx, const uint32_t* primes, int count) {
+    if (!ctx) return LSX_ERR_NULL;
+    if (count < 0 || count > LSX_TABLE_PRIMES) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "bad prime count %d", count);
+    LSX_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    lsx_fill_prime_table(ctx->primes, LSX_TABLE_PRIMES);
+    if (count > 0) {
+        if (!primes) return LSX_ERR_NULL;
+        // the replaced primes must be odd primes < 2^31, distinct from each other; table primes
+        // that collide with them are dropped from the tail
+        std::vector<uint32_t> t;
+        for (int i = 0; i < count; ++i) {
+            uint32_t p = primes[i];
+            if (p < 3 || p >= 0x80000000u || !lsx_is_prime_u32(p) || std::find(t.begin(), t.end(), p) != t.end())
+                return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "prime %u is not usable", p);
+            t.push_back(p);
+        }
+        std::vector<uint32_t> full;
+        lsx_fill_prime_table(full, LSX_TABLE_PRIMES + count);
+        for (uint32_t p : full) {
+            if ((int)t.size() >= LSX_TABLE_PRIMES) break;
+            if (std::find(t.begin(), t.begin() + count, p) == t.begin() + count) t.push_back(p);
+        }
+        ctx->primes = t;
+    }
+    return upload_tables(ctx);
+}
+
+int lsx_get_primes(const lsx_ctx* ctx, uint32_t* out, int count) {
+    if (!ctx || !out) return LSX_ERR_NULL;
+    if (count < 0 || count > LSX_TABLE_PRIMES) return LSX_ERR_BAD_SHAPE;
+    memcpy(out, ctx->primes.data(), (size_t)count * 4);
+    return LSX_OK;
+}
+
+// ---- plans ----------------------------------------------------------------------------------------
+static int fill_plan(lsx_plan* out, int op, int m, int n, int bar, int max_rank, int gen_cap, int64_t a, int64_t b,
+                     bool has_right, bool right_identity) {
+    if (!out) return LSX_ERR_NULL;
+    memset(out, 0, sizeof *out);
+    if (m < 1 || n < 1 || bar < 1 || bar > n || a < 0 || b < 0 || a > 0x7fffffffLL || b > 0x7fffffffLL)
+        return LSX_ERR_BAD_SHAPE;
+    if (m > 254) return LSX_ERR_UNSUPPORTED;
+    const int slots = m < bar ? m : bar;
+    if (max_rank <= 0 || max_rank > slots) max_rank = slots;
+    out->op = op;
+    out->m = m;
+    out->n = n;
+    out->bar_col = bar;
+    out->max_rank = max_rank;
+    out->pivot_slots = slots;
+    out->gen_cap = gen_cap;
+    out->a_abs_max = a;
+    out->b_abs_max = b;
+    out->log2_bound = lsx_log2_minor_bound(m, bar, has_right, a, b, right_identity, max_rank);
+    lsx_bits_to_plan(out->log2_bound, &out->n_primes, &out->limbs);
+    if (out->n_primes > LSX_MAX_BATCH_PRIMES) return LSX_ERR_BOUND;
+    return LSX_OK;
+}
+
+int lsx_plan_rref(int m, int n, int bar_col, int64_t a_abs_max, int64_t b_abs_max, int max_rank, lsx_plan* out) {
+    return fill_plan(out, LSX_OP_RREF, m, n, bar_col, max_rank, 0, a_abs_max, b_abs_max, bar_col < n, false);
+}
+int lsx_plan_inverse(int n, int64_t a_abs_max, lsx_plan* out) {
+    if (n < 1) return LSX_ERR_BAD_SHAPE;
+    return fill_plan(out, LSX_OP_INVERSE, n, 2 * n, n, n, 0, a_abs_max, 1, true, true);
+}
+int lsx_plan_det(int n, int64_t a_abs_max, lsx_plan* out) {
+    if (n < 1) return LSX_ERR_BAD_SHAPE;
+    return fill_plan(out, LSX_OP_DET, n, n, n, n, 0, a_abs_max, 0, false, false);
+}
+int lsx_plan_rank(int m, int n, int64_t a_abs_max, lsx_plan* out) {
+    return fill_plan(out, LSX_OP_RANK, m, n, n, 0, 0, a_abs_max, 0, false, false);
+}
+int lsx_plan_solve(int m, int n, int64_t a_abs_max, int64_t b_abs_max, int max_rank, int gen_cap, lsx_plan* out) {
+    if (n < 1 || gen_cap < 0 || gen_cap > n) return LSX_ERR_BAD_SHAPE;
+    return fill_plan(out, LSX_OP_SOLVE, m, n + 1, n, max_rank, gen_cap, a_abs_max, b_abs_max, true, false);
+}
+
+}  // extern "C"
+
+// ---- running a job: staging, chunking, kernel-family choice --------------------------------------
+namespace {
+
+struct Buf {          // one caller buffer: where it lives on the host side and its size per matrix
+    const void* src;  // input: caller pointer (host or device)
+    void* dst;        // output: caller pointer
+    size_t per;       // bytes per matrix
+    void** slot;      // the ElimJob field that receives the device pointer
+    bool input;
+};
+
+size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+
+int run_chunks(lsx_ctx* ctx, ElimJob job) {
+    // The tile path keeps K residue planes per matrix in scratch; bound the scratch by chunking.
+    static const size_t budget = []() {
+        const char* e = getenv("LSX_WS_MB");
+        size_t mb = e ? (size_t)strtoull(e, nullptr, 10) : 2048;
+        return (mb < 16 ? 16 : mb) << 20;
+    }();
+    int handled = 0;
+    int rc = lsx_run_small(ctx, job, &handled);
+    if (rc != LSX_OK) return rc;
+    if (handled) return LSX_OK;
+
+    const size_t per1 = lsx_generic_ws_bytes(job, 1), per2 = lsx_generic_ws_bytes(job, 2);
+    const size_t slope = per2 > per1 ? per2 - per1 : 1;
+    int64_t chunk = (int64_t)((budget > per1 ? budget - per1 : 0) / slope) + 1;
+    if (chunk > job.batch) chunk = job.batch;
+    if (chunk < 1) chunk = 1;
+    rc = lsx_ws_reserve(ctx, lsx_generic_ws_bytes(job, chunk) + 4096);
+    if (rc != LSX_OK) return rc;
+    const int m = job.m, n_in = job.n_in, L = job.L;
+    const int slots = m < job.bar ? m : job.bar;
+    const int nvars = job.n - 1;
+    for (int64_t b0 = 0; b0 < job.batch; b0 += chunk) {
+        ElimJob c = job;
+        c.batch = std::min(chunk, job.batch - b0);
+        c.A = job.A + b0 * m * n_in;
+        if (job.bvec) c.bvec = job.bvec + b0 * m;
+        if (job.num) {
+            const int64_t per = job.op == LSX_OP_INVERSE ? (int64_t)m * m : (int64_t)m * job.n;
+            c.num = job.num + b0 * per * L;
+        }
+        if (job.den) c.den = job.den + b0 * L;
+        if (job.particular) c.particular = job.particular + b0 * nvars * L;
+        if (job.generators) c.generators = job.generators + b0 * nvars * job.gen_cap * L;
+        if (job.pivot_col) c.pivot_col = job.pivot_col + b0 * slots;
+        if (job.rank) c.rank = job.rank + b0;
+        c.status = job.status + b0;
+        rc = lsx_run_generic(ctx, c, nullptr, nullptr, 0, 0);
+        if (rc != LSX_OK) return rc;
+    }
+    return LSX_OK;
+}
+
+// Stage (mem == HOST) or pass through (mem == DEVICE) the buffers, clear status, run, copy back.
+int run_job(lsx_ctx* ctx, ElimJob job, int mem, Buf* bufs, int nbufs, int32_t* status_user) {
+    LSX_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (mem != LSX_MEM_HOST && mem != LSX_MEM_DEVICE) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "bad mem flag %d", mem);
+    if (job.batch < 0) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "negative batch");
+    if (job.batch == 0) return LSX_OK;
+    if (job.batch > 0x7fffffffLL) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "batch above 2^31-1");
+    const size_t st_bytes = (size_t)job.batch * 4;
+    if (mem == LSX_MEM_DEVICE) {
+        for (int i = 0; i < nbufs; ++i)
+            if (bufs[i].slot) *bufs[i].slot = bufs[i].input ? const_cast<void*>(bufs[i].src) : bufs[i].dst;
+        job.status = status_user;
+        LSX_CUDA_TRY(ctx, cudaMemsetAsync(job.status, 0, st_bytes, ctx->stream));
+        return run_chunks(ctx, job);
+    }
+    size_t total = up256(st_bytes);
+    for (int i = 0; i < nbufs; ++i)
+        if (bufs[i].slot && (bufs[i].input ? bufs[i].src != nullptr : bufs[i].dst != nullptr))
+            total += up256(bufs[i].per * (size_t)job.batch);
+    int rc = io_reserve(ctx, total);
+    if (rc != LSX_OK) return rc;
+    char* base = (char*)ctx->d_io;
+    size_t off = 0;
+    job.status = (int32_t*)base;
+    off += up256(st_bytes);
+    std::vector<void*> dev(nbufs, nullptr);
+    for (int i = 0; i < nbufs; ++i) {
+        const bool present = bufs[i].slot && (bufs[i].input ? bufs[i].src != nullptr : bufs[i].dst != nullptr);
+        if (!present) continue;
+        dev[i] = base + off;
+        off += up256(bufs[i].per * (size_t)job.batch);
+        *bufs[i].slot = dev[i];
+        if (bufs[i].input)
+            LSX_CUDA_TRY(ctx, cudaMemcpyAsync(dev[i], bufs[i].src, bufs[i].per * (size_t)job.batch,
+                                              cudaMemcpyHostToDevice, ctx->stream));
+    }
+    LSX_CUDA_TRY(ctx, cudaMemsetAsync(job.status, 0, st_bytes, ctx->stream));
+    rc = run_chunks(ctx, job);
+    if (rc != LSX_OK) return rc;
+    for (int i = 0; i < nbufs; ++i)
+        if (dev[i] && !bufs[i].input)
+            LSX_CUDA_TRY(ctx, cudaMemcpyAsync(bufs[i].dst, dev[i], bufs[i].per * (size_t)job.batch,
+                                              cudaMemcpyDeviceToHost, ctx->stream));
+    LSX_CUDA_TRY(ctx, cudaMemcpyAsync(status_user, job.status, st_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    LSX_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LSX_OK;
+}
+
+int check_plan(lsx_ctx* ctx, const lsx_plan* plan, int op) {
+    if (!ctx) return LSX_ERR_NULL;
+    if (!plan) return lsx_fail(ctx, LSX_ERR_NULL, "plan is NULL");
+    if (plan->op != op) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "plan is for operation %d, call needs %d", plan->op, op);
+    if (plan->m < 1 || plan->n < 1 || plan->bar_col < 1 || plan->bar_col > plan->n || plan->m > 254)
+        return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "bad plan shape %dx%d bar %d", plan->m, plan->n, plan->bar_col);
+    if (plan->n_primes < 1 || plan->n_primes > LSX_MAX_BATCH_PRIMES || plan->limbs < 1 ||
+        plan->limbs > LSX_MAX_BATCH_PRIMES)
+        return lsx_fail(ctx, LSX_ERR_BOUND, "plan needs %d primes / %d limbs", plan->n_primes, plan->limbs);
+    return LSX_OK;
+}
+
+ElimJob job_from_plan(const lsx_plan* plan, int64_t batch) {
+    ElimJob j;
+    j.batch = batch;
+    j.m = plan->m;
+    j.n = plan->n;
+    j.n_in = plan->n;
+    j.bar = plan->bar_col;
+    j.a_abs_max = plan->a_abs_max;
+    j.b_abs_max = plan->b_abs_max;
+    j.max_rank = plan->max_rank;
+    j.op = plan->op;
+    j.K = plan->n_primes;
+    j.L = plan->limbs;
+    j.gen_cap = plan->gen_cap;
+    return j;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lsx_rref_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, int64_t batch, int mem, uint32_t* num,
+                   uint32_t* den, int32_t* pivot_col, int32_t* rank, int32_t* status) {
+    int rc = check_plan(ctx, plan, LSX_OP_RREF);
+    if (rc != LSX_OK) return rc;
+    if (batch > 0 && (!A || !num || !den || !status)) return lsx_fail(ctx, LSX_ERR_NULL, "rref: NULL buffer");
+    ElimJob j = job_from_plan(plan, batch);
+    const size_t L4 = (size_t)j.L * 4;
+    Buf bufs[] = {
+        {A, nullptr, (size_t)j.m * j.n * 4, (void**)&j.A, true},
+        {nullptr, num, (size_t)j.m * j.n * L4, (void**)&j.num, false},
+        {nullptr, den, L4, (void**)&j.den, false},
+        {nullptr, pivot_col, (size_t)plan->pivot_slots * 4, (void**)&j.pivot_col, false},
+        {nullptr, rank, 4, (void**)&j.rank, false},
+    };
+    return run_job(ctx, j, mem, bufs, 5, status);
+}
+
+int lsx_inverse_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, int64_t batch, int mem, uint32_t* adj,
+                      uint32_t* det, int32_t* status) {
+    int rc = check_plan(ctx, plan, LSX_OP_INVERSE);
+    if (rc != LSX_OK) return rc;
+    if (plan->n != 2 * plan->m || plan->bar_col != plan->m)
+        return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "inverse plan must be n x 2n with bar n");
+    if (batch > 0 && (!A || !adj || !det || !status)) return lsx_fail(ctx, LSX_ERR_NULL, "inverse: NULL buffer");
+    ElimJob j = job_from_plan(plan, batch);
+    j.n_in = j.m;
+    j.right_identity = 1;
+    const size_t L4 = (size_t)j.L * 4;
+    Buf bufs[] = {
+        {A, nullptr, (size_t)j.m * j.m * 4, (void**)&j.A, true},
+        {nullptr, adj, (size_t)j.m * j.m * L4, (void**)&j.num, false},
+        {nullptr, det, L4, (void**)&j.den, false},
+    };
+    return run_job(ctx, j, mem, bufs, 3, status);
+}
+
+int lsx_det_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, int64_t batch, int mem, uint32_t* det,
+                  int32_t* rank, int32_t* status) {
+    int rc = check_plan(ctx, plan, LSX_OP_DET);
+    if (rc != LSX_OK) return rc;
+    if (plan->n != plan->m) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "determinant needs a square matrix");
+    if (batch > 0 && (!A || !det || !status)) return lsx_fail(ctx, LSX_ERR_NULL, "det: NULL buffer");
+    ElimJob j = job_from_plan(plan, batch);
+    const size_t L4 = (size_t)j.L * 4;
+    Buf bufs[] = {
+        {A, nullptr, (size_t)j.m * j.n * 4, (void**)&j.A, true},
+        {nullptr, det, L4, (void**)&j.den, false},
+        {nullptr, rank, 4, (void**)&j.rank, false},
+    };
+    return run_job(ctx, j, mem, bufs, 3, status);
+}
+
+int lsx_rank_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, int64_t batch, int mem, int32_t* rank,
+                   int32_t* status) {
+    int rc = check_plan(ctx, plan, LSX_OP_RANK);
+    if (rc != LSX_OK) return rc;
+    if (batch > 0 && (!A || !rank || !status)) return lsx_fail(ctx, LSX_ERR_NULL, "rank: NULL buffer");
+    ElimJob j = job_from_plan(plan, batch);
+    Buf bufs[] = {
+        {A, nullptr, (size_t)j.m * j.n * 4, (void**)&j.A, true},
+        {nullptr, rank, 4, (void**)&j.rank, false},
+    };
+    return run_job(ctx, j, mem, bufs, 2, status);
+}
+
+int lsx_solve_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, const int32_t* b, int64_t batch, int mem,
+                    uint32_t* den, uint32_t* particular, uint32_t* generators, int32_t* pivot_col, int32_t* rank,
+                    int32_t* status) {
+    int rc = check_plan(ctx, plan, LSX_OP_SOLVE);
+    if (rc != LSX_OK) return rc;
+    if (plan->bar_col != plan->n - 1) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "solve plan must have bar = n - 1");
+    if (batch > 0 && (!A || !b || !den || !particular || !status || (plan->gen_cap > 0 && !generators)))
+        return lsx_fail(ctx, LSX_ERR_NULL, "solve: NULL buffer");
+    ElimJob j = job_from_plan(plan, batch);
+    j.n_in = j.n - 1;
+    const int nvars = j.n - 1;
+    const size_t L4 = (size_t)j.L * 4;
+    Buf bufs[] = {
+        {A, nullptr, (size_t)j.m * nvars * 4, (void**)&j.A, true},
+        {b, nullptr, (size_t)j.m * 4, (void**)&j.bvec, true},
+        {nullptr, den, L4, (void**)&j.den, false},
+        {nullptr, particular, (size_t)nvars * L4, (void**)&j.particular, false},
+        {nullptr, generators, (size_t)nvars * j.gen_cap * L4, (void**)&j.generators, false},
+        {nullptr, pivot_col, (size_t)plan->pivot_slots * 4, (void**)&j.pivot_col, false},
+        {nullptr, rank, 4, (void**)&j.rank, false},
+    };
+    return run_job(ctx, j, mem, bufs, 7, status);
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+// Internal declarations shared by the liblsx translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/lsx.h"
+
+// One table prime with its Montgomery constants (R = 2^32).
+struct PrimeRec {
+    uint32_t p;     // odd prime < 2^31
+    uint32_t pinv;  // -p^{-1} mod 2^32
+    uint32_t one;   // R mod p      (word whose value is 1)
+    uint32_t r2;    // R^2 mod p    (word whose value is R)
+};
+
+constexpr int LSX_TABLE_PRIMES = 2048;   // primes generated per ctx (descending from 2^31-1)
+constexpr int LSX_GARNER_DIM = 40;       // Garner inverse table covers the first 40 primes
+constexpr int LSX_MAX_BATCH_PRIMES = 32; // K limit of the batched operations
+constexpr int LSX_RETRY_EXTRA = 4;       // replacement primes tried for a flagged matrix
+constexpr int LSX_RETRY_CAP = 4096;      // flagged matrices handled per chunk
+constexpr int LSX_PROF_SKIP = 255;       // profile byte: column has no pivot
+constexpr int LSX_ST_INTERNAL_RETRY = 1 << 30;  // internal status bit, cleared before return
+
+struct lsx_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;       // stream work is enqueued on
+    cudaStream_t own_stream = nullptr;   // created by lsx_create
+    cudaStream_t copy_streams[2] = {nullptr, nullptr};
+    cudaEvent_t events[8] = {};
+    std::string err;
+    int64_t launches = 0;
+    std::vector<uint32_t> primes;        // host copy of the table
+    PrimeRec* d_primes = nullptr;        // [LSX_TABLE_PRIMES]
+    uint32_t* d_garner = nullptr;        // [GARNER_DIM][GARNER_DIM]: (p_i^{-1} * R) mod p_j
+    void* d_ws = nullptr;                // grow-only device workspace
+    size_t ws_bytes = 0;
+    void* d_io = nullptr;                // grow-only staging for LSX_MEM_HOST calls
+    size_t io_bytes = 0;
+};
+
+// ---- Montgomery arithmetic on 31-bit primes ------------------------------------------------
+#ifdef __CUDACC__
+#define LSX_HD __host__ __device__ __forceinline__
+#else
+#define LSX_HD inline
+#endif
+
+// REDC of t < 2 p^2 (fits 63 bits): returns t / R mod p in [0, p).
+LSX_HD uint32_t mont_redc(uint64_t t, uint32_t p, uint32_t pinv) {
+    uint32_t m = (uint32_t)t * pinv;
+    uint64_t u = t + (uint64_t)m * p;
+    uint32_t r = (uint32_t)(u >> 32);
+    uint32_t s = r - p;
+    return r < s ? r : s;               // r in [0, 2p): subtract p once if needed
+}
+LSX_HD uint32_t mont_mul(uint32_t a, uint32_t b, uint32_t p, uint32_t pinv) {
+    return mont_redc((uint64_t)a * b, p, pinv);
+}
+// x*a + y*b (one reduction for two products)
+LSX_HD uint32_t mont_fma2(uint32_t x, uint32_t a, uint32_t y, uint32_t b, uint32_t p, uint32_t pinv) {
+    return mont_redc((uint64_t)x * a + (uint64_t)y * b, p, pinv);
+}
+LSX_HD uint32_t mont_pow(uint32_t a, uint32_t e, uint32_t one, uint32_t p, uint32_t pinv) {
+    uint32_t acc = one;
+    for (int bit = 31; bit >= 0; --bit) {
+        acc = mont_mul(acc, acc, p, pinv);
+        if ((e >> bit) & 1u) acc = mont_mul(acc, a, p, pinv);
+    }
+    return acc;
+}
+// raw word of a signed input with |a| < p
+LSX_HD uint32_t word_of_int(int32_t a, uint32_t p) { return a < 0 ? (uint32_t)a + p : (uint32_t)a; }
+// raw word of any int32 (entries at or above p, tiny test primes)
+LSX_HD uint32_t word_of_int_any(int32_t a, uint32_t p) {
+    int64_t r = (int64_t)a % (int64_t)p;
+    return (uint32_t)(r < 0 ? r + (int64_t)p : r);
+}
+
+// ---- host helpers (lsx_primes.cpp) -----------------------------------------------------------
+bool lsx_is_prime_u32(uint32_t n);
+void lsx_fill_prime_table(std::vector<uint32_t>& out, int count);
+PrimeRec lsx_make_prime_rec(uint32_t p);
+uint32_t lsx_inv_mod(uint32_t a, uint32_t p);   // a^{-1} mod p (plain)
+// log2 of the Hadamard bound for the outputs of an elimination
+double lsx_log2_minor_bound(int m, int bar, bool has_right, int64_t a_abs, int64_t b_abs,
+                            bool right_identity, int max_rank);
+void lsx_bits_to_plan(double log2_bound, int* n_primes, int* limbs);
+
+// ---- kernels' host launchers -----------------------------------------------------------------
+struct ElimJob {
+    // input
+    const int32_t* A = nullptr;     // [batch][m][n_in]
+    const int32_t* bvec = nullptr;  // [batch][m] appended as last column (solve) or NULL
+    int64_t batch = 0;
+    int m = 0, n_in = 0, n = 0, bar = 0;
+    int right_identity = 0;         // columns n_in..n-1 are the identity
+    int64_t a_abs_max = 0, b_abs_max = 0;
+    int max_rank = 0;
+    int op = 0;
+    int K = 0, L = 0, gen_cap = 0;
+    // outputs (device pointers; which ones are used depends on op)
+    uint32_t* num = nullptr;        // rref: [batch][m*n][L]; inverse: [batch][m*m][L]
+    uint32_t* den = nullptr;        // [batch][L]
+    uint32_t* particular = nullptr; // solve
+    uint32_t* generators = nullptr; // solve
+    int32_t* pivot_col = nullptr;   // [batch][pivot_slots] or NULL
+    int32_t* rank = nullptr;        // [batch] or NULL
+    int32_t* status = nullptr;      // [batch]
+};
+
+// Generic path: one CTA per (matrix, prime), residues to scratch, then verify + CRT/assemble.
+// list == NULL: all matrices of the job.  Otherwise only the matrices in list[0..*list_count).
+int lsx_run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const int32_t* list_count,
+                    int list_cap, size_t ws_offset);
+size_t lsx_generic_ws_bytes(const ElimJob& job, int64_t batch);
+// Fused register-resident kernels for small shapes; *handled = 1 if the job was covered.
+int lsx_run_small(lsx_ctx* ctx, const ElimJob& job, int* handled);
+// det(A) mod p for table primes [prime_begin, prime_begin + count) through the tile kernel
+bool lsx_tile_fits(int m, int n);
+int lsx_tile_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_begin, int count, uint32_t* d_res);
+
+// blocked modular LU in global memory for n beyond the shared-memory tile
+int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_begin, int count, uint32_t* d_res);
+
+int lsx_ws_reserve(lsx_ctx* ctx, size_t bytes);
+int lsx_fail(lsx_ctx* ctx, int code, const char* fmt, ...);
+#define LSX_CUDA_TRY(ctx, expr)                                                              \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return lsx_fail((ctx), LSX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,             \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                    \
+    } while (0)

@@ -1,0 +1,206 @@
+// One large determinant, sharded by prime (config 5 of BASELINE.json): residues det(A) mod p for a
+// range of table primes, and the CRT of all residues to a signed multi-limb integer.
+//
+// The reference has no feasible route for this size (its determinant is a plan search over
+// sparsity patterns, determinant.rs:575-665, or an n! sum, linalg.py:264-345); the value is the
+// signed product of the forward-sweep pivots of linalg.py:547-609, computed here modulo each prime.
+#include <cmath>
+
+#include "lsx_internal.h"
+
+namespace {
+
+// ---- Garner CRT for up to LSX_TABLE_PRIMES residues, one CTA ----------------------------------------
+// Step j fixes the mixed-radix digit v_j = t_j and updates every later residue
+// t_k <- (t_k - v_j) * p_j^{-1} mod p_k.  The inverses come from a table built by k_inv_table.
+__global__ void k_inv_table(const PrimeRec* primes, int K, uint32_t* tab) {
+    // tab[j * K + k] = (p_j^{-1} mod p_k) * R mod p_k  for j < k  (Montgomery word of the inverse)
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)K * K) return;
+    const int j = (int)(t / K), k = (int)(t % K);
+    if (j >= k) return;
+    const PrimeRec P = primes[k];
+    uint32_t pj = primes[j].p % P.p;
+    const uint32_t w = mont_mul(pj, P.r2, P.p, P.pinv);                 // word of p_j
+    tab[t] = mont_pow(w, P.p - 2u, P.one, P.p, P.pinv);                 // word of p_j^{-1}
+}
+
+__global__ void __launch_bounds__(1024) k_garner_big(const PrimeRec* primes, const uint32_t* tab, const uint32_t* res,
+                                                      int K, int L, uint32_t* out, uint64_t* limb_ws) {
+    extern __shared__ uint32_t sm[];
+    uint32_t* t = sm;          // [K] running residues -> mixed-radix digits
+    __shared__ int s_neg;
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int k = tid; k < K; k += T) t[k] = res[k] % primes[k].p;
+    __syncthreads();
+    for (int j = 0; j < K; ++j) {
+        const uint32_t vj = t[j];
+        for (int k = j + 1 + tid; k < K; k += T) {
+            const PrimeRec P = primes[k];
+            uint32_t v = vj % P.p;
+            uint32_t x = t[k];
+            x = x >= v ? x - v : x + P.p - v;
+            t[k] = mont_mul(x, tab[(int64_t)j * K + k], P.p, P.pinv);
+        }
+        __syncthreads();
+    }
+    // sign: X > (M-1)/2 <=> digits compare above ((p_i - 1)/2)_i from the top
+    if (tid == 0) {
+        int neg = 0;
+        for (int i = K - 1; i >= 0; --i) {
+            const uint32_t h = (primes[i].p - 1u) >> 1;
+            if (t[i] != h) {
+                neg = t[i] > h;
+                break;
+            }
+        }
+        s_neg = neg;
+    }
+    __syncthreads();
+    const bool neg = s_neg != 0;
+    // negative: X - M = -(Y + 1) with Y = sum (p_i - 1 - v_i) P_i, so the result is ~Y
+    if (neg)
+        for (int k = tid; k < K; k += T) t[k] = primes[k].p - 1u - t[k];
+    __syncthreads();
+    // Horner from the top digit in a redundant limb form: limb l is a 64-bit word below 3 * 2^32
+    // (low 32 bits + a small overflow part).  acc <- acc * p_i + v_i with limb l handled by thread l;
+    // the two buffers live in global scratch (L can reach a few thousand limbs).
+    uint64_t* cur = limb_ws;
+    uint64_t* nxt = limb_ws + L;
+    for (int l = tid; l < L; l += T) cur[l] = 0;
+    __syncthreads();
+    for (int i = K - 1; i >= 0; --i) {
+        const uint64_t p = primes[i].p;
+        const uint32_t v = t[i];
+        for (int l = tid; l < L; l += T) {
+            const uint64_t c = cur[l];
+            uint64_t y = ((c & 0xffffffffull) * p) & 0xffffffffull;      // low word of lo * p
+            if (l) {
+                const uint64_t b = cur[l - 1];
+                y += ((b & 0xffffffffull) * p) >> 32;                    // high word of the limb below
+                y += (b >> 32) * p;                                      // its overflow part (< 3) times p
+            } else {
+                y += v;
+            }
+            nxt[l] = y;                                                  // < 2^32 + 2^32 + 2^32
+        }
+        __syncthreads();
+        uint64_t* tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+    }
+    if (tid == 0) {
+        uint64_t carry = 0;
+        for (int l = 0; l < L; ++l) {
+            const uint64_t y = cur[l] + carry;
+            const uint32_t w = (uint32_t)y;
+            out[l] = neg ? ~w : w;
+            carry = y >> 32;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int lsx_det_large_prime_count(int n, int64_t a_abs_max, int* n_primes, double* log2_bound) {
+    if (n < 1 || a_abs_max < 0 || !n_primes) return LSX_ERR_BAD_SHAPE;
+    const double a = (double)(a_abs_max < 1 ? 1 : a_abs_max);
+    const double bits = n * (0.5 * std::log2((double)n) + std::log2(a));
+    int K, L;
+    lsx_bits_to_plan(bits, &K, &L);
+    if (K > LSX_TABLE_PRIMES) return LSX_ERR_BOUND;
+    *n_primes = K;
+    if (log2_bound) *log2_bound = bits;
+    return LSX_OK;
+}
+
+int lsx_det_large_residues(lsx_ctx* ctx, const int32_t* A, int n, int prime_begin, int prime_count, int mem,
+                           uint32_t* residues, uint32_t* primes_out) {
+    if (!ctx) return LSX_ERR_NULL;
+    if (!A || !residues) return lsx_fail(ctx, LSX_ERR_NULL, "det_large: NULL buffer");
+    if (n < 1 || prime_begin < 0 || prime_count < 0 || prime_begin + prime_count > LSX_TABLE_PRIMES)
+        return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "det_large: bad n or prime range");
+    LSX_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (primes_out) {
+        if (mem == LSX_MEM_HOST)
+            memcpy(primes_out, ctx->primes.data() + prime_begin, (size_t)prime_count * 4);
+        else
+            LSX_CUDA_TRY(ctx, cudaMemcpyAsync(primes_out, ctx->primes.data() + prime_begin, (size_t)prime_count * 4,
+                                              cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (prime_count == 0) return LSX_OK;
+    const int32_t* dA = A;
+    uint32_t* dres = residues;
+    void* stage = nullptr;
+    if (mem == LSX_MEM_HOST) {
+        const size_t abytes = (size_t)n * n * 4, rbytes = (size_t)prime_count * 4;
+        LSX_CUDA_TRY(ctx, cudaMalloc(&stage, abytes + rbytes + 256));
+        dA = (const int32_t*)stage;
+        dres = (uint32_t*)((char*)stage + (abytes + 255) / 256 * 256);
+        cudaError_t e = cudaMemcpyAsync(stage, A, abytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+            cudaFree(stage);
+            return lsx_fail(ctx, LSX_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+        }
+    }
+    int rc;
+    if (lsx_tile_fits(n, n))
+        rc = lsx_tile_det_residues(ctx, dA, n, prime_begin, prime_count, dres);
+    else
+        rc = lsx_blocked_det_residues(ctx, dA, n, prime_begin, prime_count, dres);
+    if (rc == LSX_OK && mem == LSX_MEM_HOST) {
+        cudaError_t e = cudaMemcpyAsync(residues, dres, (size_t)prime_count * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = lsx_fail(ctx, LSX_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+    }
+    if (stage) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(stage);
+    }
+    return rc;
+}
+
+int lsx_crt_signed(lsx_ctx* ctx, const uint32_t* residues, int count, int limbs, int mem, uint32_t* out) {
+    if (!ctx) return LSX_ERR_NULL;
+    if (!residues || !out) return lsx_fail(ctx, LSX_ERR_NULL, "crt: NULL buffer");
+    if (count < 1 || count > LSX_TABLE_PRIMES || limbs < 1 || limbs > 4 * LSX_TABLE_PRIMES)
+        return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "crt: bad count or limbs");
+    // the Horner accumulator needs room for the full product of the primes
+    const int Lfull = count + 1;
+    const int L = limbs > Lfull ? limbs : Lfull;
+    LSX_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = (off + bytes + 255) / 256 * 256;
+        return o;
+    };
+    const size_t o_tab = take((size_t)count * count * 4), o_res = take((size_t)count * 4),
+                 o_out = take((size_t)L * 4), o_limb = take((size_t)2 * L * 8);
+    int rc = lsx_ws_reserve(ctx, off);
+    if (rc != LSX_OK) return rc;
+    char* base = (char*)ctx->d_ws;
+    uint32_t* d_res = (uint32_t*)(base + o_res);
+    LSX_CUDA_TRY(ctx, cudaMemcpyAsync(d_res, residues, (size_t)count * 4,
+                                      mem == LSX_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+    const int64_t nt = (int64_t)count * count;
+    k_inv_table<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_primes, count, (uint32_t*)(base + o_tab));
+    ctx->launches++;
+    k_garner_big<<<1, 1024, (size_t)count * 4, ctx->stream>>>(ctx->d_primes, (const uint32_t*)(base + o_tab), d_res, count,
+                                                             L, (uint32_t*)(base + o_out), (uint64_t*)(base + o_limb));
+    ctx->launches++;
+    LSX_CUDA_TRY(ctx, cudaGetLastError());
+    // out gets `limbs` words: the low limbs of the (sign-extended) L-limb value
+    if (limbs <= L) {
+        LSX_CUDA_TRY(ctx, cudaMemcpyAsync(out, base + o_out, (size_t)limbs * 4,
+                                          mem == LSX_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                                          ctx->stream));
+    }
+    if (mem == LSX_MEM_HOST) LSX_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return LSX_OK;
+}
+
+}  // extern "C"

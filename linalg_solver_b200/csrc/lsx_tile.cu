@@ -1,0 +1,742 @@
+// Generic path of the exact elimination engine: one CTA per (matrix, prime) with the residue
+// tile resident in shared memory, then profile verification and a Garner-CRT assemble kernel.
+//
+// This path covers every shape that fits shared memory (e.g. 64x128 [A|I]) and is also the
+// correctness backstop of the fused small-matrix kernels: matrices whose primes disagree on the
+// pivot profile (a "bad prime" divided an intermediate pivot candidate) are recomputed here with
+// replacement primes.
+//
+// Algorithm per (matrix, prime) -- mirrors tests/device_model.py::elim_words:
+//   uniform-scale division-free Gauss-Jordan on Montgomery words.  At a pivot step with pivot
+//   value piv (row pi, column j) and current common scale S every row r != pi becomes
+//   piv*row_r - W[r][j]*row_pi and the pivot row becomes S*row_pi, so ALL rows carry the scale
+//   S' = S*piv.  No modular inverse is needed inside the loop; one Fermat inversion at the end
+//   turns the tile into N = d * RREF with d = sign * prod(true pivots) (the determinant of the
+//   pivot minor).  The pivot rule is the reference's (linalg.py:548-567): the entry at the pivot
+//   position if non-zero, else the first lower row with a non-zero entry, else skip the column.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "lsx_internal.h"
+
+namespace {
+
+struct TileArgs {
+    const int32_t* A;
+    const int32_t* bvec;
+    const int32_t* list;        // NULL: slot == matrix index
+    const int32_t* list_count;  // device pointer (list mode)
+    int64_t batch;              // number of slots when list == NULL
+    int64_t cap;                // slot stride of the scratch arrays
+    int m, n_in, n, bar, right_identity;
+    int c0, c1;                 // columns [c0, c1) are stored to res
+    int64_t a_abs_max, b_abs_max;
+    const PrimeRec* primes;
+    uint32_t* res;              // [Ktot][cap][m*(c1-c0)]
+    uint32_t* dres;             // [Ktot][cap]
+    int32_t* rankk;             // [Ktot][cap]
+    uint8_t* prof;              // [Ktot][cap][bar]
+    int32_t* status;            // [batch] (indexed by matrix)
+};
+
+template <int T>
+__global__ void __launch_bounds__(T) k_tile_elim(const TileArgs a) {
+    extern __shared__ uint32_t smem[];
+    const int m = a.m, n = a.n, bar = a.bar;
+    uint32_t* W = smem;
+    uint32_t* prow = W + m * n;
+    uint32_t* ycol = prow + n;
+    int* sh = (int*)(ycol + m);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = T / 32;
+    const int kslot = blockIdx.y;
+    const PrimeRec P = a.primes[kslot];
+    const uint32_t p = P.p, pinv = P.pinv;
+    const int64_t nslots = a.list ? min((int64_t)*a.list_count, a.cap) : a.batch;
+    const int ncs = a.c1 - a.c0;
+
+    for (int64_t slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+        const int64_t mat = a.list ? (int64_t)a.list[slot] : slot;
+        // ---- load the tile as raw words (value = a / R, see device_model.elim_words) ----
+        bool bad = false;
+        for (int r = warp; r < m; r += NW) {
+            for (int c = lane; c < n; c += 32) {
+                int32_t v;
+                int64_t lim;
+                if (c < a.n_in) {
+                    v = a.A[(mat * m + r) * a.n_in + c];
+                    lim = c < bar ? a.a_abs_max : a.b_abs_max;
+                } else if (a.right_identity) {
+                    v = (c - a.n_in == r) ? 1 : 0;
+                    lim = 1;
+                } else {
+                    v = a.bvec[mat * m + r];
+                    lim = a.b_abs_max;
+                }
+                int64_t av = v < 0 ? -(int64_t)v : (int64_t)v;
+                bad |= av > lim;
+                W[r * n + c] = word_of_int_any(v, p);
+            }
+        }
+        if (bad) atomicOr(&a.status[mat], LSX_ST_BOUND);
+        __syncthreads();
+
+        uint32_t S = P.one, Q = P.one, X = 1u;
+        int pi = 0;
+        bool neg = false;
+        uint8_t* prof = a.prof + ((int64_t)kslot * a.cap + slot) * bar;
+        for (int j = 0; j < bar; ++j) {
+            if (pi >= m) {
+                if (tid == 0) prof[j] = LSX_PROF_SKIP;
+                continue;
+            }
+            // pivot search: first row >= pi with a non-zero entry in column j
+            if (warp == 0) {
+                int src = -1;
+                for (int base = pi; base < m; base += 32) {
+                    int r = base + lane;
+                    bool nz = r < m && W[r * n + j] != 0u;
+                    unsigned bal = __ballot_sync(0xffffffffu, nz);
+                    if (bal) {
+                        src = base + __ffs(bal) - 1;
+                        break;
+                    }
+                }
+                if (lane == 0) sh[0] = src;
+            }
+            __syncthreads();
+            const int src = sh[0];
+            if (src < 0) {
+                if (tid == 0) prof[j] = LSX_PROF_SKIP;
+                __syncthreads();   // sh[0] is rewritten in the next iteration
+                continue;
+            }
+            if (tid == 0) prof[j] = (uint8_t)src;
+            if (src != pi) {
+                for (int c = tid; c < n; c += T) {
+                    uint32_t t0 = W[pi * n + c];
+                    W[pi * n + c] = W[src * n + c];
+                    W[src * n + c] = t0;
+                }
+                neg = !neg;
+                __syncthreads();
+            }
+            const uint32_t piv = W[pi * n + j];
+            for (int c = tid; c < n; c += T) prow[c] = W[pi * n + c];
+            for (int r = tid; r < m; r += T) ycol[r] = (r == pi) ? 0u : p - W[r * n + j];
+            __syncthreads();
+            for (int r = warp; r < m; r += NW) {
+                const uint32_t x = (r == pi) ? S : piv;
+                const uint32_t y = ycol[r];
+                for (int c = lane; c < n; c += 32)
+                    W[r * n + c] = mont_fma2(x, W[r * n + c], y, prow[c], p, pinv);
+            }
+            __syncthreads();
+            Q = mont_mul(Q, S, p, pinv);
+            S = mont_mul(S, piv, p, pinv);
+            X = mont_mul(X, P.r2, p, pinv);
+            ++pi;
+        }
+        // ---- one inversion, then scale the tile to N = d * RREF (plain residues) ----
+        const uint32_t qinv = mont_pow(Q, p - 2u, P.one, p, pinv);
+        uint32_t Gw = mont_mul(qinv, X, p, pinv);
+        if (neg && Gw) Gw = p - Gw;
+        const uint32_t G2w = mont_mul(Gw, P.r2, p, pinv);
+        if (ncs > 0) {
+            uint32_t* out = a.res + ((int64_t)kslot * a.cap + slot) * ((int64_t)m * ncs);
+            for (int r = warp; r < m; r += NW) {
+                const uint32_t g = r < pi ? Gw : G2w;
+                for (int c = a.c0 + lane; c < a.c1; c += 32)
+                    out[r * ncs + (c - a.c0)] = mont_mul(g, W[r * n + c], p, pinv);
+            }
+        }
+        if (tid == 0) {
+            a.dres[(int64_t)kslot * a.cap + slot] = mont_mul(Gw, S, p, pinv);
+            a.rankk[(int64_t)kslot * a.cap + slot] = pi;
+        }
+        __syncthreads();   // tile is reloaded by the next slot
+    }
+}
+
+// ---- verification: pick the primes that agree with the lexicographically smallest profile ----
+struct VerifyArgs {
+    const int32_t* list;
+    const int32_t* list_count;
+    int64_t batch, cap;
+    int bar, K, Ktot, max_rank, pivot_slots, allow_retry;
+    const uint8_t* prof;
+    const int32_t* rankk;
+    uint8_t* sel;        // [cap][LSX_MAX_BATCH_PRIMES]
+    int32_t* rank_ws;    // [cap]
+    int32_t* piv_ws;     // [cap][pivot_slots]
+    int32_t* status;     // by matrix
+    int32_t* rank_out;   // by matrix or NULL
+    int32_t* piv_out;    // by matrix or NULL
+    int32_t* retry_list;
+    int32_t* retry_count;
+    int retry_cap;
+};
+
+__global__ void k_verify(const VerifyArgs a) {
+    const int64_t nslots = a.list ? min((int64_t)*a.list_count, a.cap) : a.batch;
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nslots) return;
+    const int64_t mat = a.list ? (int64_t)a.list[slot] : slot;
+    const int bar = a.bar;
+    // A prime whose profile deviates from the rational one picks a LATER row or skips a column
+    // at the first deviation (a non-zero candidate looked like zero), so the rational profile is
+    // the lexicographic minimum as soon as one prime is good; if the primes agreeing with the
+    // minimum have a product above the Hadamard bound the minimum is provably the rational
+    // profile.
+    int best = 0;
+    for (int k = 1; k < a.Ktot; ++k) {
+        const uint8_t* pk = a.prof + ((int64_t)k * a.cap + slot) * bar;
+        const uint8_t* pb = a.prof + ((int64_t)best * a.cap + slot) * bar;
+        for (int j = 0; j < bar; ++j) {
+            if (pk[j] != pb[j]) {
+                if (pk[j] < pb[j]) best = k;
+                break;
+            }
+        }
+    }
+    const uint8_t* pb = a.prof + ((int64_t)best * a.cap + slot) * bar;
+    int cnt = 0;
+    uint8_t* sel = a.sel + slot * LSX_MAX_BATCH_PRIMES;
+    for (int k = 0; k < a.Ktot && cnt < a.K; ++k) {
+        const uint8_t* pk = a.prof + ((int64_t)k * a.cap + slot) * bar;
+        bool same = true;
+        for (int j = 0; j < bar; ++j) same &= pk[j] == pb[j];
+        if (same) sel[cnt++] = (uint8_t)k;
+    }
+    int st = 0;
+    if (cnt < a.K) {
+        if (a.allow_retry) {
+            int pos = atomicAdd(a.retry_count, 1);
+            if (pos < a.retry_cap) {
+                a.retry_list[pos] = (int32_t)mat;
+                st = LSX_ST_INTERNAL_RETRY;
+            } else {
+                st = LSX_ST_NO_GOOD_PRIME;
+            }
+        } else {
+            st = LSX_ST_NO_GOOD_PRIME;
+        }
+    } else if (!a.allow_retry) {
+        st = LSX_ST_RETRIED;
+    }
+    const int rk = a.rankk[(int64_t)best * a.cap + slot];
+    if (a.max_rank > 0 && rk > a.max_rank) st |= LSX_ST_BOUND;
+    a.rank_ws[slot] = rk;
+    int c = 0;
+    for (int j = 0; j < bar; ++j) {
+        if (pb[j] != LSX_PROF_SKIP) {
+            a.piv_ws[slot * a.pivot_slots + c] = j;
+            if (a.piv_out) a.piv_out[mat * a.pivot_slots + c] = j;
+            ++c;
+        }
+    }
+    for (; c < a.pivot_slots; ++c) {
+        a.piv_ws[slot * a.pivot_slots + c] = -1;
+        if (a.piv_out) a.piv_out[mat * a.pivot_slots + c] = -1;
+    }
+    if (a.rank_out) a.rank_out[mat] = rk;
+    if (!a.allow_retry) atomicAnd(&a.status[mat], ~LSX_ST_INTERNAL_RETRY);
+    if (st) atomicOr(&a.status[mat], st);
+}
+
+// ---- assemble: Garner CRT of every needed integer, written in the layout of the operation ----
+struct AsmArgs {
+    const int32_t* list;
+    const int32_t* list_count;
+    int64_t batch, cap;
+    int op, m, n, n_in, bar, K, L, ncs, c0, pivot_slots, gen_cap;
+    const PrimeRec* primes;
+    const uint32_t* garner;   // [GD][GD]
+    const uint32_t* res;
+    const uint32_t* dres;
+    const uint8_t* sel;
+    const int32_t* rank_ws;
+    const int32_t* piv_ws;
+    int32_t* status;
+    uint32_t* num;
+    uint32_t* den;
+    uint32_t* particular;
+    uint32_t* generators;
+};
+
+template <int KT>
+__device__ __forceinline__ void crt_limbs(const uint32_t (&r)[KT], const uint8_t* sel, int K,
+                                          const PrimeRec* primes, const uint32_t* garner,
+                                          uint32_t (&acc)[KT], bool* is_zero) {
+    uint32_t v[KT];
+    uint32_t pp[KT];
+    bool zero = true;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+        v[j] = 0;
+        pp[j] = 0;
+        if (j < K) {
+            const int sj = sel[j];
+            const PrimeRec P = primes[sj];
+            pp[j] = P.p;
+            uint32_t t = r[j];
+            zero &= t == 0u;
+#pragma unroll
+            for (int i = 0; i < j; ++i) {
+                uint32_t vi = v[i];
+                if (vi >= P.p) vi -= P.p;
+                t = t >= vi ? t - vi : t + P.p - vi;
+                t = mont_mul(t, garner[(int)sel[i] * LSX_GARNER_DIM + sj], P.p, P.pinv);
+            }
+            v[j] = t;
+        }
+    }
+    *is_zero = zero;
+    // sign: X > (M-1)/2  <=>  mixed-radix digits compare above ((p_i - 1)/2)_i from the top
+    bool negv = false, decided = false;
+#pragma unroll
+    for (int i = KT - 1; i >= 0; --i) {
+        if (i < K && !decided) {
+            uint32_t h = (pp[i] - 1u) >> 1;
+            if (v[i] != h) {
+                negv = v[i] > h;
+                decided = true;
+            }
+        }
+    }
+    // negative: X - M = -(Y + 1) with Y = sum (p_i - 1 - v_i) P_i, so the result is ~Y
+    if (negv) {
+#pragma unroll
+        for (int i = 0; i < KT; ++i)
+            if (i < K) v[i] = pp[i] - 1u - v[i];
+    }
+#pragma unroll
+    for (int l = 0; l < KT; ++l) acc[l] = 0u;
+#pragma unroll
+    for (int i = KT - 1; i >= 0; --i) {
+        if (i < K) {
+            uint64_t carry = v[i];
+#pragma unroll
+            for (int l = 0; l < KT; ++l) {
+                uint64_t t = (uint64_t)acc[l] * pp[i] + carry;
+                acc[l] = (uint32_t)t;
+                carry = t >> 32;
+            }
+        }
+    }
+    if (negv) {
+#pragma unroll
+        for (int l = 0; l < KT; ++l) acc[l] = ~acc[l];
+    }
+}
+
+template <int KT>
+__device__ __forceinline__ void store_limbs(uint32_t* dst, const uint32_t (&acc)[KT], int L, bool negate,
+                                            bool zero_out) {
+    if (zero_out) {
+        for (int l = 0; l < L; ++l) dst[l] = 0u;
+        return;
+    }
+    if (!negate) {
+#pragma unroll
+        for (int l = 0; l < KT; ++l)
+            if (l < L) dst[l] = acc[l];
+    } else {
+        uint32_t carry = 1u;
+#pragma unroll
+        for (int l = 0; l < KT; ++l) {
+            if (l < L) {
+                uint32_t x = ~acc[l];
+                uint32_t y = x + carry;
+                carry = (y < x) ? 1u : 0u;
+                dst[l] = y;
+            }
+        }
+    }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(128) k_assemble(const AsmArgs a) {
+    const int64_t nslots = a.list ? min((int64_t)*a.list_count, a.cap) : a.batch;
+    const int64_t E = (int64_t)a.m * a.ncs;       // stored entries per matrix
+    const int64_t per = E + 1;                    // + the denominator
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nslots * per) return;
+    const int64_t slot = t / per;
+    const int64_t e = t - slot * per;
+    const int64_t mat = a.list ? (int64_t)a.list[slot] : slot;
+    const int st = a.status[mat];
+    if (st & (LSX_ST_INTERNAL_RETRY | LSX_ST_NO_GOOD_PRIME | LSX_ST_BOUND)) return;
+    const uint8_t* sel = a.sel + slot * LSX_MAX_BATCH_PRIMES;
+    const int K = a.K, L = a.L;
+    const int rank = a.rank_ws[slot];
+
+    uint32_t r[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        r[k] = 0;
+        if (k < K) {
+            const int64_t base = (int64_t)sel[k] * a.cap + slot;
+            r[k] = (e < E) ? a.res[base * E + e] : a.dres[base];
+        }
+    }
+    uint32_t acc[KT];
+    bool is_zero;
+    crt_limbs<KT>(r, sel, K, a.primes, a.garner, acc, &is_zero);
+
+    const int m = a.m;
+    if (e == E) {   // denominator / determinant
+        switch (a.op) {
+            case LSX_OP_RREF:
+            case LSX_OP_SOLVE:
+                store_limbs<KT>(a.den + mat * L, acc, L, false, false);
+                break;
+            case LSX_OP_INVERSE:
+                store_limbs<KT>(a.den + mat * L, acc, L, false, rank < m);
+                if (rank < m) atomicOr(&a.status[mat], LSX_ST_SINGULAR);
+                break;
+            case LSX_OP_DET:
+                store_limbs<KT>(a.den + mat * L, acc, L, false, rank < m);
+                break;
+            default:
+                break;
+        }
+        if (a.op == LSX_OP_SOLVE) {
+            // generator entries equal to d at the free columns (gen[f] = 1, linalg.py:976)
+            const int nvars = a.n - 1;
+            const int32_t* piv = a.piv_ws + slot * a.pivot_slots;
+            int k = 0, tfree = 0;
+            for (int c = 0; c < nvars; ++c) {
+                if (k < rank && piv[k] == c) {
+                    ++k;
+                    continue;
+                }
+                if (tfree < a.gen_cap)
+                    store_limbs<KT>(a.generators + ((mat * nvars + c) * a.gen_cap + tfree) * L, acc, L, false,
+                                    false);
+                ++tfree;
+            }
+            if (tfree > a.gen_cap) atomicOr(&a.status[mat], LSX_ST_GEN_TRUNC);
+        }
+        return;
+    }
+    const int i = (int)(e / a.ncs);
+    const int j = a.c0 + (int)(e - (int64_t)i * a.ncs);
+    switch (a.op) {
+        case LSX_OP_RREF:
+            store_limbs<KT>(a.num + (mat * E + e) * L, acc, L, false, false);
+            break;
+        case LSX_OP_INVERSE:
+            store_limbs<KT>(a.num + (mat * E + e) * L, acc, L, false, rank < m);
+            break;
+        case LSX_OP_SOLVE: {
+            const int nvars = a.n - 1;
+            const int32_t* piv = a.piv_ws + slot * a.pivot_slots;
+            if (i >= rank) {
+                // zero left row: inconsistent iff the rhs is non-zero (linalg.py:913-934)
+                if (j == nvars && !is_zero) atomicOr(&a.status[mat], LSX_ST_INCONSISTENT);
+                break;
+            }
+            const int ci = piv[i];
+            if (j == nvars) {
+                store_limbs<KT>(a.particular + (mat * nvars + ci) * L, acc, L, false, false);
+            } else {
+                // free column? its index among the free columns
+                int k = 0, tfree = 0;
+                bool is_pivot = false;
+                for (int c = 0; c <= j; ++c) {
+                    if (k < rank && piv[k] == c) {
+                        ++k;
+                        is_pivot = (c == j);
+                    } else if (c < j) {
+                        ++tfree;
+                    }
+                }
+                if (!is_pivot && tfree < a.gen_cap)
+                    store_limbs<KT>(a.generators + ((mat * nvars + ci) * a.gen_cap + tfree) * L, acc, L, true,
+                                    false);
+            }
+            break;
+        }
+        default:
+            break;
+    }
+}
+
+template <int T>
+int launch_tile(lsx_ctx* ctx, const TileArgs& ta, int Ktot, int64_t grid_x, size_t smem) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_tile_elim<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return lsx_fail(ctx, LSX_ERR_CUDA, "smem attribute: %s", cudaGetErrorString(e));
+    }
+    dim3 grid((unsigned)grid_x, (unsigned)Ktot);
+    k_tile_elim<T><<<grid, T, smem, ctx->stream>>>(ta);
+    ctx->launches++;
+    return LSX_OK;
+}
+
+}  // namespace
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+namespace {
+// Scratch layout of one generic pass (Ktot primes, `cap` slots).
+struct GenericWs {
+    size_t o_res, o_dres, o_rankk, o_prof, o_sel, o_rank, o_piv, o_rlist, o_rcount, total;
+};
+GenericWs generic_ws(int Ktot, int64_t cap, int m, int ncs, int bar, int pivot_slots) {
+    GenericWs w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    w.o_res = take((size_t)Ktot * cap * m * ncs * 4);
+    w.o_dres = take((size_t)Ktot * cap * 4);
+    w.o_rankk = take((size_t)Ktot * cap * 4);
+    w.o_prof = take((size_t)Ktot * cap * bar);
+    w.o_sel = take((size_t)cap * LSX_MAX_BATCH_PRIMES);
+    w.o_rank = take((size_t)cap * 4);
+    w.o_piv = take((size_t)cap * pivot_slots * 4);
+    w.o_rlist = take((size_t)LSX_RETRY_CAP * 4);
+    w.o_rcount = take(256);
+    w.total = off;
+    return w;
+}
+}  // namespace
+
+// Bytes of device workspace lsx_run_generic needs for `batch` matrices of this job (parent pass
+// plus the retry pass behind it).
+size_t lsx_generic_ws_bytes(const ElimJob& job, int64_t batch) {
+    int c0 = 0, c1 = job.n;
+    if (job.op == LSX_OP_INVERSE) c0 = job.n_in;
+    if (job.op == LSX_OP_DET || job.op == LSX_OP_RANK) c0 = c1 = 0;
+    const int pivot_slots = job.m < job.bar ? job.m : job.bar;
+    GenericWs a = generic_ws(job.K, batch, job.m, c1 - c0, job.bar, pivot_slots);
+    GenericWs b = generic_ws(job.K + LSX_RETRY_EXTRA, LSX_RETRY_CAP, job.m, c1 - c0, job.bar, pivot_slots);
+    return a.total + b.total;
+}
+
+// Runs the generic path for the matrices of `job` (all, or those in `list`).  When list == NULL
+// the K plan primes are used and matrices whose primes disagree are appended to an internal
+// retry list and recomputed with K + LSX_RETRY_EXTRA primes.  Scratch is taken from the ctx
+// workspace starting at byte ws_offset (the caller has reserved lsx_generic_ws_bytes).
+int lsx_run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const int32_t* list_count,
+                    int list_cap, size_t ws_offset) {
+    const bool list_mode = list != nullptr;
+    const int K = job.K;
+    const int Ktot = list_mode ? K + LSX_RETRY_EXTRA : K;
+    if (Ktot > LSX_GARNER_DIM || K > LSX_MAX_BATCH_PRIMES)
+        return lsx_fail(ctx, LSX_ERR_BOUND, "needs %d primes, limit is %d", K, LSX_MAX_BATCH_PRIMES);
+    const int m = job.m, n = job.n, bar = job.bar;
+    int c0 = 0, c1 = n;
+    if (job.op == LSX_OP_INVERSE) c0 = job.n_in;
+    if (job.op == LSX_OP_DET || job.op == LSX_OP_RANK) c0 = c1 = 0;
+    const int ncs = c1 - c0;
+    const int pivot_slots = m < bar ? m : bar;
+    const int64_t cap = list_mode ? list_cap : job.batch;
+    if (cap <= 0) return LSX_OK;
+
+    const size_t smem = ((size_t)m * n + n + m + 4) * sizeof(uint32_t);
+    if (smem > 200 * 1024)
+        return lsx_fail(ctx, LSX_ERR_UNSUPPORTED, "matrix %dx%d does not fit the shared-memory tile", m, n);
+
+    const GenericWs w = generic_ws(Ktot, cap, m, ncs, bar, pivot_slots);
+    if (ws_offset + w.total > ctx->ws_bytes)
+        return lsx_fail(ctx, LSX_ERR_CUDA, "internal: workspace too small (%zu + %zu > %zu)", ws_offset, w.total,
+                        ctx->ws_bytes);
+    char* base = (char*)ctx->d_ws + ws_offset;
+    const size_t o_res = w.o_res, o_dres = w.o_dres, o_rankk = w.o_rankk, o_prof = w.o_prof, o_sel = w.o_sel,
+                 o_rank = w.o_rank, o_piv = w.o_piv, o_rlist = w.o_rlist, o_rcount = w.o_rcount;
+    uint32_t* res = (uint32_t*)(base + o_res);
+    uint32_t* dres = (uint32_t*)(base + o_dres);
+    int32_t* rankk = (int32_t*)(base + o_rankk);
+    uint8_t* prof = (uint8_t*)(base + o_prof);
+    uint8_t* sel = (uint8_t*)(base + o_sel);
+    int32_t* rank_ws = (int32_t*)(base + o_rank);
+    int32_t* piv_ws = (int32_t*)(base + o_piv);
+    int32_t* rlist = (int32_t*)(base + o_rlist);
+    int32_t* rcount = (int32_t*)(base + o_rcount);
+
+    if (!list_mode) LSX_CUDA_TRY(ctx, cudaMemsetAsync(rcount, 0, 4, ctx->stream));
+
+    TileArgs ta{};
+    ta.A = job.A;
+    ta.bvec = job.bvec;
+    ta.list = list;
+    ta.list_count = list_count;
+    ta.batch = job.batch;
+    ta.cap = cap;
+    ta.m = m;
+    ta.n_in = job.n_in;
+    ta.n = n;
+    ta.bar = bar;
+    ta.right_identity = job.right_identity;
+    ta.c0 = c0;
+    ta.c1 = c1;
+    ta.a_abs_max = job.a_abs_max;
+    ta.b_abs_max = job.b_abs_max;
+    ta.primes = ctx->d_primes;
+    ta.res = res;
+    ta.dres = dres;
+    ta.rankk = rankk;
+    ta.prof = prof;
+    ta.status = job.status;
+
+    int64_t gx = list_mode ? 256 : job.batch;
+    const int64_t max_gx = (int64_t)ctx->sm_count * 64;
+    if (gx > max_gx) gx = max_gx;
+    const int cells = m * n;
+    int rc;
+    if (cells <= 128)
+        rc = launch_tile<32>(ctx, ta, Ktot, gx, smem);
+    else if (cells <= 1024)
+        rc = launch_tile<64>(ctx, ta, Ktot, gx, smem);
+    else if (cells <= 4096)
+        rc = launch_tile<128>(ctx, ta, Ktot, gx, smem);
+    else
+        rc = launch_tile<256>(ctx, ta, Ktot, gx, smem);
+    if (rc != LSX_OK) return rc;
+
+    VerifyArgs va{};
+    va.list = list;
+    va.list_count = list_count;
+    va.batch = job.batch;
+    va.cap = cap;
+    va.bar = bar;
+    va.K = K;
+    va.Ktot = Ktot;
+    va.max_rank = job.max_rank;
+    va.pivot_slots = pivot_slots;
+    va.allow_retry = list_mode ? 0 : 1;
+    va.prof = prof;
+    va.rankk = rankk;
+    va.sel = sel;
+    va.rank_ws = rank_ws;
+    va.piv_ws = piv_ws;
+    va.status = job.status;
+    va.rank_out = job.rank;
+    va.piv_out = job.pivot_col;
+    va.retry_list = rlist;
+    va.retry_count = rcount;
+    va.retry_cap = LSX_RETRY_CAP;
+    {
+        const int64_t nthreads = cap;
+        const int bs = 128;
+        k_verify<<<(unsigned)((nthreads + bs - 1) / bs), bs, 0, ctx->stream>>>(va);
+        ctx->launches++;
+    }
+
+    if (job.op != LSX_OP_RANK) {
+        if (job.op == LSX_OP_SOLVE) {
+            // unused generator/particular slots are zero
+            const int nvars = n - 1;
+            if (!list_mode) {
+                LSX_CUDA_TRY(ctx, cudaMemsetAsync(job.particular, 0, (size_t)job.batch * nvars * job.L * 4, ctx->stream));
+                if (job.generators && job.gen_cap > 0)
+                    LSX_CUDA_TRY(ctx, cudaMemsetAsync(job.generators, 0,
+                                                      (size_t)job.batch * nvars * job.gen_cap * job.L * 4, ctx->stream));
+            }
+        }
+        AsmArgs aa{};
+        aa.list = list;
+        aa.list_count = list_count;
+        aa.batch = job.batch;
+        aa.cap = cap;
+        aa.op = job.op;
+        aa.m = m;
+        aa.n = n;
+        aa.n_in = job.n_in;
+        aa.bar = bar;
+        aa.K = K;
+        aa.L = job.L;
+        aa.ncs = ncs;
+        aa.c0 = c0;
+        aa.pivot_slots = pivot_slots;
+        aa.gen_cap = job.gen_cap;
+        aa.primes = ctx->d_primes;
+        aa.garner = ctx->d_garner;
+        aa.res = res;
+        aa.dres = dres;
+        aa.sel = sel;
+        aa.rank_ws = rank_ws;
+        aa.piv_ws = piv_ws;
+        aa.status = job.status;
+        aa.num = job.num;
+        aa.den = job.den;
+        aa.particular = job.particular;
+        aa.generators = job.generators;
+        const int64_t nthreads = cap * ((int64_t)m * ncs + 1);
+        const int bs = 128;
+        const unsigned gridn = (unsigned)((nthreads + bs - 1) / bs);
+        if (K <= 4)
+            k_assemble<4><<<gridn, bs, 0, ctx->stream>>>(aa);
+        else if (K <= 8)
+            k_assemble<8><<<gridn, bs, 0, ctx->stream>>>(aa);
+        else if (K <= 16)
+            k_assemble<16><<<gridn, bs, 0, ctx->stream>>>(aa);
+        else
+            k_assemble<32><<<gridn, bs, 0, ctx->stream>>>(aa);
+        ctx->launches++;
+    }
+    LSX_CUDA_TRY(ctx, cudaGetLastError());
+
+    if (!list_mode) {
+        // recompute flagged matrices with replacement primes (a no-op grid when none was flagged)
+        rc = lsx_run_generic(ctx, job, rlist, rcount, LSX_RETRY_CAP, ws_offset + w.total);
+        if (rc != LSX_OK) return rc;
+    }
+    return LSX_OK;
+}
+
+// ---- det(A) mod p for a range of table primes through the tile kernel (n x n fits shared memory) ----
+namespace {
+__global__ void k_det_fix(const uint32_t* dres, const int32_t* rankk, int n, int count, uint32_t* residues) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) residues[k] = rankk[k] < n ? 0u : dres[k];
+}
+}  // namespace
+
+bool lsx_tile_fits(int m, int n) { return ((size_t)m * n + n + m + 4) * sizeof(uint32_t) <= 200 * 1024 && m <= 254; }
+
+int lsx_tile_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_begin, int count, uint32_t* d_res) {
+    const size_t smem = ((size_t)n * n + 2 * n + 4) * sizeof(uint32_t);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    const size_t o_dres = take((size_t)count * 4), o_rank = take((size_t)count * 4), o_prof = take((size_t)count * n),
+                 o_st = take(256);
+    int rc = lsx_ws_reserve(ctx, off);
+    if (rc != LSX_OK) return rc;
+    char* base = (char*)ctx->d_ws;
+    LSX_CUDA_TRY(ctx, cudaMemsetAsync(base + o_st, 0, 4, ctx->stream));
+    TileArgs ta{};
+    ta.A = dA;
+    ta.batch = 1;
+    ta.cap = 1;
+    ta.m = ta.n = ta.n_in = ta.bar = n;
+    ta.a_abs_max = 0x7fffffffLL;
+    ta.b_abs_max = 0;
+    ta.primes = ctx->d_primes + prime_begin;
+    ta.dres = (uint32_t*)(base + o_dres);
+    ta.rankk = (int32_t*)(base + o_rank);
+    ta.prof = (uint8_t*)(base + o_prof);
+    ta.status = (int32_t*)(base + o_st);
+    const int cells = n * n;
+    if (cells <= 1024)
+        rc = launch_tile<64>(ctx, ta, count, 1, smem);
+    else if (cells <= 4096)
+        rc = launch_tile<128>(ctx, ta, count, 1, smem);
+    else
+        rc = launch_tile<256>(ctx, ta, count, 1, smem);
+    if (rc != LSX_OK) return rc;
+    k_det_fix<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ta.dres, ta.rankk, n, count, d_res);
+    ctx->launches++;
+    LSX_CUDA_TRY(ctx, cudaGetLastError());
+    return LSX_OK;
+}

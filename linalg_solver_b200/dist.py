@@ -1,0 +1,65 @@
+"""Multi-GPU layout of the elimination path: one process per GPU, no data-path collective for
+batches (independent matrices), one all-gather of residues for a single large determinant.
+
+SURVEY.md section 8e: batches are sharded BY MATRIX in contiguous slices, every rank runs all
+primes and the CRT for its slice and the results stay sharded; a single large matrix is sharded
+BY PRIME (each rank holds its own int32 copy of A), the per-prime residues are all-gathered
+(NCCL over NVLink on GPUs, gloo in the CPU tests) and the CRT runs on every rank.
+"""
+from typing import List, Tuple
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [begin, end) of `total` units owned by `rank` (sizes differ by at most 1)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world %d/%d" % (rank, world))
+    base, extra = divmod(total, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(total: int, world: int) -> List[int]:
+    return [shard_range(total, r, world)[1] - shard_range(total, r, world)[0] for r in range(world)]
+
+
+def all_gather_residues(local, total: int, group=None):
+    """All-gather the per-prime residues of a by-prime sharded determinant.
+
+    `local` is this rank's 1-D tensor for primes shard_range(total, rank, world) (int32 storage of
+    uint32 residues, on the GPU under NCCL, on the CPU under gloo).  Returns the full tensor of
+    `total` residues in prime order on every rank.  Uneven shards are padded to the largest shard
+    so that one fixed-size all_gather suffices (about 4 B x 1100 primes for config 5).
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(total, world)
+    width = max(sizes) if sizes else 0
+    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
+    padded[: local.numel()] = local
+    out = torch.empty(world * width, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    parts = [out[r * width: r * width + sizes[r]] for r in range(world)]
+    return torch.cat(parts) if parts else out
+
+
+def det_large_sharded(engine, A, a_abs_max: int, group=None):
+    """Determinant of one large integer matrix, primes sharded over the ranks of `group`.
+
+    Returns (det_words, n_primes): `det_words` is the signed determinant as little-endian 32-bit
+    words (two's complement) on every rank.
+    """
+    import torch.distributed as dist
+
+    n = A.shape[0]
+    K, bits = engine.det_large_prime_count(n, a_abs_max)
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    b, e = shard_range(K, rank, world)
+    local = engine.det_large_residues(A, b, e - b)
+    full = all_gather_residues(local, K, group) if world > 1 else local
+    limbs = int(bits + 2) // 32 + 1
+    return engine.crt_signed(full, limbs), K

@@ -1,0 +1,337 @@
+"""Batched exact elimination on one GPU: thin Python face of the C-ABI (include/lsx.h).
+
+The reference has no batch API; these entry points are what its
+``Matrix`` methods are served from (linalg_solver_b200/matrix.py) and what the benchmark
+drives directly.  Inputs are ``int32[batch, m, n]`` arrays: numpy arrays (host memory, the call
+copies in and out) or torch CUDA tensors (device memory, the call only enqueues kernels on
+torch's current stream).  Outputs come back in the same kind of container.
+
+Every rational result is an integer numerator over ONE common denominator per matrix (the
+determinant of the pivot minor), each integer as ``limbs`` little-endian 32-bit words in two's
+complement; ``linalg_solver_b200.convert`` turns them into Python ints / Fractions.
+"""
+import ctypes
+import os
+from dataclasses import dataclass
+from typing import Any, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import Plan, lib
+
+
+class LsxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("liblsx error %s (%d): %s" % (_lib.ERR_NAMES.get(code, "?"), code, msg))
+        self.code = code
+
+
+def _is_torch(x):
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda")
+
+
+@dataclass
+class RrefResult:
+    num: Any          # [batch, m, n, limbs] uint32   numerators d * RREF
+    den: Any          # [batch, limbs] uint32         d
+    pivot_col: Any    # [batch, pivot_slots] int32    (-1 padded)
+    rank: Any         # [batch] int32
+    status: Any       # [batch] int32
+    plan: Plan
+
+
+@dataclass
+class InverseResult:
+    adj: Any          # [batch, n, n, limbs]   A^-1 = adj / det
+    det: Any          # [batch, limbs]
+    status: Any
+    plan: Plan
+
+
+@dataclass
+class DetResult:
+    det: Any          # [batch, limbs]
+    rank: Any
+    status: Any
+    plan: Plan
+
+
+@dataclass
+class RankResult:
+    rank: Any
+    status: Any
+    plan: Plan
+
+
+@dataclass
+class SolveResult:
+    den: Any          # [batch, limbs]
+    particular: Any   # [batch, n, limbs]
+    generators: Any   # [batch, n, gen_cap, limbs]
+    pivot_col: Any
+    rank: Any
+    status: Any
+    plan: Plan
+
+
+class Engine:
+    """One lsx context = one GPU + one stream.  Not thread-safe (one thread per Engine)."""
+
+    def __init__(self, device: Optional[int] = None):
+        if device is None:
+            device = int(os.environ.get("LSX_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        self.device = device
+        self._ctx = ctypes.c_void_p()
+        rc = lib.lsx_create(device, ctypes.byref(self._ctx))
+        if rc != _lib.OK:
+            self._ctx = None
+            raise LsxError(rc, "lsx_create(device=%d) failed: a CUDA device is required, there is no CPU fallback"
+                           % device)
+
+    # ---- plumbing -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            lib.lsx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != _lib.OK:
+            raise LsxError(rc, lib.lsx_last_error(self._ctx).decode(errors="replace"))
+
+    def synchronize(self):
+        self._check(lib.lsx_synchronize(self._ctx))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib.lsx_launch_count(self._ctx))
+
+    def primes(self, count: int):
+        out = np.empty(count, dtype=np.uint32)
+        self._check(lib.lsx_get_primes(self._ctx, out.ctypes.data, count))
+        return out
+
+    def debug_set_primes(self, primes):
+        arr = np.ascontiguousarray(np.asarray(primes, dtype=np.uint32))
+        self._check(lib.lsx_debug_set_primes(self._ctx, arr.ctypes.data if arr.size else None, int(arr.size)))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(lib.lsx_set_stream(self._ctx, cuda_stream_ptr))
+
+    def _prep_in(self, x, ndim, name):
+        """-> (array, pointer, mem, like) for an int32 input."""
+        if _is_torch(x):
+            import torch
+            if x.dtype != torch.int32:
+                raise TypeError("%s must be int32, got %s" % (name, x.dtype))
+            if x.dim() != ndim:
+                raise ValueError("%s must have %d dimensions" % (name, ndim))
+            x = x.contiguous()
+            if x.is_cuda:
+                if x.device.index != self.device:
+                    raise ValueError("%s lives on cuda:%s, this engine is bound to cuda:%d"
+                                     % (name, x.device.index, self.device))
+                self.set_stream(torch.cuda.current_stream(x.device).cuda_stream)
+                return x, x.data_ptr(), _lib.MEM_DEVICE, x
+            self.set_stream(None)
+            return x, x.data_ptr(), _lib.MEM_HOST, x
+        a = np.ascontiguousarray(x)
+        if a.dtype != np.int32:
+            if not np.issubdtype(a.dtype, np.integer):
+                raise TypeError("%s must be an integer array" % name)
+            if a.size and (a.max() > 2**31 - 1 or a.min() < -(2**31) + 1):
+                raise OverflowError("%s has entries outside int32" % name)
+            a = a.astype(np.int32)
+        if a.ndim != ndim:
+            raise ValueError("%s must have %d dimensions" % (name, ndim))
+        self.set_stream(None)
+        return a, a.ctypes.data, _lib.MEM_HOST, None
+
+    @staticmethod
+    def _alloc(like, shape, dtype):
+        if like is not None:
+            import torch
+            tdt = {np.uint32: torch.int32, np.int32: torch.int32}[dtype]   # uint32 words held in int32 storage
+            return torch.empty(shape, dtype=tdt, device=like.device, pin_memory=False)
+        return np.empty(shape, dtype=dtype)
+
+    @staticmethod
+    def _ptr(x):
+        if x is None:
+            return None
+        return x.data_ptr() if _is_torch(x) else x.ctypes.data
+
+    @staticmethod
+    def _absmax(x):
+        if _is_torch(x):
+            return int(x.abs().max().item()) if x.numel() else 0
+        return int(np.abs(x.astype(np.int64)).max()) if x.size else 0
+
+    # ---- plans ----------------------------------------------------------------------------
+    def plan_rref(self, m, n, bar_col, a_abs_max, b_abs_max=None, max_rank=0) -> Plan:
+        p = Plan()
+        self._check(lib.lsx_plan_rref(m, n, bar_col, a_abs_max, a_abs_max if b_abs_max is None else b_abs_max,
+                                      max_rank, ctypes.byref(p)))
+        return p
+
+    def plan_inverse(self, n, a_abs_max) -> Plan:
+        p = Plan()
+        self._check(lib.lsx_plan_inverse(n, a_abs_max, ctypes.byref(p)))
+        return p
+
+    def plan_det(self, n, a_abs_max) -> Plan:
+        p = Plan()
+        self._check(lib.lsx_plan_det(n, a_abs_max, ctypes.byref(p)))
+        return p
+
+    def plan_rank(self, m, n, a_abs_max) -> Plan:
+        p = Plan()
+        self._check(lib.lsx_plan_rank(m, n, a_abs_max, ctypes.byref(p)))
+        return p
+
+    def plan_solve(self, m, n, a_abs_max, b_abs_max, max_rank=0, gen_cap=None) -> Plan:
+        p = Plan()
+        self._check(lib.lsx_plan_solve(m, n, a_abs_max, b_abs_max, max_rank, n if gen_cap is None else gen_cap,
+                                       ctypes.byref(p)))
+        return p
+
+    # ---- batched operations ---------------------------------------------------------------
+    def rref_batch(self, A, bar_col, a_abs_max=None, b_abs_max=None, max_rank=0, plan=None) -> RrefResult:
+        """Gauss-Jordan of every ``A[i]`` with pivots in columns < bar_col (reference
+        linalg.py:534-630; the caller applies the ``bar_col or n-1`` default of line 543)."""
+        A, pA, mem, like = self._prep_in(A, 3, "A")
+        B, m, n = A.shape
+        if plan is None:
+            if a_abs_max is None:
+                a_abs_max = self._absmax(A)
+            plan = self.plan_rref(m, n, bar_col, a_abs_max, b_abs_max, max_rank)
+        L = plan.limbs
+        num = self._alloc(like, (B, m, n, L), np.uint32)
+        den = self._alloc(like, (B, L), np.uint32)
+        piv = self._alloc(like, (B, plan.pivot_slots), np.int32)
+        rank = self._alloc(like, (B,), np.int32)
+        status = self._alloc(like, (B,), np.int32)
+        self._check(lib.lsx_rref_batch(self._ctx, ctypes.byref(plan), pA, B, mem, self._ptr(num), self._ptr(den),
+                                       self._ptr(piv), self._ptr(rank), self._ptr(status)))
+        return RrefResult(num, den, piv, rank, status, plan)
+
+    def inverse_batch(self, A, a_abs_max=None, plan=None, out=None) -> InverseResult:
+        """A^-1 = adj / det through [A|I] (reference linalg.py:704-743); singular matrices get
+        status ST_SINGULAR (the reference returns ``NoSolution()``)."""
+        A, pA, mem, like = self._prep_in(A, 3, "A")
+        B, n, n2 = A.shape
+        if n != n2:
+            raise ValueError("Matrix must be square to invert.")
+        if plan is None:
+            plan = self.plan_inverse(n, self._absmax(A) if a_abs_max is None else a_abs_max)
+        L = plan.limbs
+        if out is None:
+            adj = self._alloc(like, (B, n, n, L), np.uint32)
+            det = self._alloc(like, (B, L), np.uint32)
+            status = self._alloc(like, (B,), np.int32)
+        else:
+            adj, det, status = out.adj, out.det, out.status
+        self._check(lib.lsx_inverse_batch(self._ctx, ctypes.byref(plan), pA, B, mem, self._ptr(adj), self._ptr(det),
+                                          self._ptr(status)))
+        return InverseResult(adj, det, status, plan)
+
+    def det_batch(self, A, a_abs_max=None, plan=None) -> DetResult:
+        """Determinants (sign * product of the forward-sweep pivots, linalg.py:547-609) and ranks."""
+        A, pA, mem, like = self._prep_in(A, 3, "A")
+        B, n, n2 = A.shape
+        if n != n2:
+            raise ValueError("Determinant requires a square matrix")
+        if plan is None:
+            plan = self.plan_det(n, self._absmax(A) if a_abs_max is None else a_abs_max)
+        det = self._alloc(like, (B, plan.limbs), np.uint32)
+        rank = self._alloc(like, (B,), np.int32)
+        status = self._alloc(like, (B,), np.int32)
+        self._check(lib.lsx_det_batch(self._ctx, ctypes.byref(plan), pA, B, mem, self._ptr(det), self._ptr(rank),
+                                      self._ptr(status)))
+        return DetResult(det, rank, status, plan)
+
+    def rank_batch(self, A, a_abs_max=None, plan=None) -> RankResult:
+        """Ranks (reference linalg.py:745-747)."""
+        A, pA, mem, like = self._prep_in(A, 3, "A")
+        B, m, n = A.shape
+        if plan is None:
+            plan = self.plan_rank(m, n, self._absmax(A) if a_abs_max is None else a_abs_max)
+        rank = self._alloc(like, (B,), np.int32)
+        status = self._alloc(like, (B,), np.int32)
+        self._check(lib.lsx_rank_batch(self._ctx, ctypes.byref(plan), pA, B, mem, self._ptr(rank), self._ptr(status)))
+        return RankResult(rank, status, plan)
+
+    def solve_batch(self, A, b, a_abs_max=None, b_abs_max=None, max_rank=0, gen_cap=None, plan=None) -> SolveResult:
+        """Solution sets of A x = b (reference linalg.py:632-680, 913-999): status ST_INCONSISTENT where
+        the reference returns ``NoSolution()``, else particular solution (free variables 0) and one
+        generator per free column in ascending order."""
+        A, pA, mem, like = self._prep_in(A, 3, "A")
+        b, pb, mem_b, _ = self._prep_in(b, 2, "b")
+        if mem != mem_b:
+            raise ValueError("A and b must live in the same memory space")
+        B, m, n = A.shape
+        if b.shape[0] != B or b.shape[1] != m:
+            raise ValueError("Matrix dimensions must match")
+        if plan is None:
+            plan = self.plan_solve(m, n, self._absmax(A) if a_abs_max is None else a_abs_max,
+                                   self._absmax(b) if b_abs_max is None else b_abs_max, max_rank, gen_cap)
+        L, G = plan.limbs, plan.gen_cap
+        den = self._alloc(like, (B, L), np.uint32)
+        part = self._alloc(like, (B, n, L), np.uint32)
+        gens = self._alloc(like, (B, n, G, L), np.uint32) if G > 0 else None
+        piv = self._alloc(like, (B, plan.pivot_slots), np.int32)
+        rank = self._alloc(like, (B,), np.int32)
+        status = self._alloc(like, (B,), np.int32)
+        self._check(lib.lsx_solve_batch(self._ctx, ctypes.byref(plan), pA, pb, B, mem, self._ptr(den), self._ptr(part),
+                                        self._ptr(gens), self._ptr(piv), self._ptr(rank), self._ptr(status)))
+        return SolveResult(den, part, gens, piv, rank, status, plan)
+
+    # ---- one large determinant, by prime ----------------------------------------------------
+    @staticmethod
+    def det_large_prime_count(n, a_abs_max):
+        k = ctypes.c_int()
+        bits = ctypes.c_double()
+        rc = lib.lsx_det_large_prime_count(n, a_abs_max, ctypes.byref(k), ctypes.byref(bits))
+        if rc != _lib.OK:
+            raise LsxError(rc, "det_large_prime_count")
+        return k.value, bits.value
+
+    def det_large_residues(self, A, prime_begin, prime_count):
+        """det(A) mod p for table primes [prime_begin, prime_begin + prime_count)."""
+        A, pA, mem, like = self._prep_in(A, 2, "A")
+        n, n2 = A.shape
+        if n != n2:
+            raise ValueError("Determinant requires a square matrix")
+        res = self._alloc(like, (prime_count,), np.uint32)
+        self._check(lib.lsx_det_large_residues(self._ctx, pA, n, prime_begin, prime_count, mem, self._ptr(res), None))
+        return res
+
+    def crt_signed(self, residues, limbs):
+        """Residues for table primes [0, len) -> signed integer as `limbs` 32-bit words."""
+        if _is_torch(residues):
+            like, mem = residues, (_lib.MEM_DEVICE if residues.is_cuda else _lib.MEM_HOST)
+            residues = residues.contiguous()
+            count = residues.numel()
+        else:
+            residues = np.ascontiguousarray(residues, dtype=np.uint32)
+            like, mem, count = None, _lib.MEM_HOST, residues.size
+        out = self._alloc(like, (limbs,), np.uint32)
+        self._check(lib.lsx_crt_signed(self._ctx, self._ptr(residues), count, limbs, mem, self._ptr(out)))
+        return out
+
+
+_default = None
+
+
+def default_engine() -> Engine:
+    """Process-wide engine on LSX_DEVICE / LOCAL_RANK / device 0 (created on first use)."""
+    global _default
+    if _default is None:
+        _default = Engine()
+    return _default

@@ -1,0 +1,319 @@
+"""``Matrix`` / ``Matrix.AffineSubspace`` / ``Matrix.NoSolution`` with the reference's method
+surface for the elimination path, served by the GPU engine.
+
+Mirrors reference linalg_solver/linalg.py: container and validation (11-58), ``zero/identity/
+diagonal/new_vector/transpose`` (409-422, 482-489), ``AffineSubspace`` (491-522), ``NoSolution``
+(524-532), ``row_reduce`` (534-630), ``find_preimage_of`` (632-680, 870-999), ``inverse`` (682-743),
+``rank`` (745-747), ``kernel`` (749-756) and the entry of ``determinant`` (183-207).  Same names,
+argument meaning, return shapes and error texts; the arithmetic runs in liblsx (there is no CPU
+fallback) and the reference's LaTeX ``Logger`` output is bypassed: ``row_reduce`` returns empty
+lists for its two log results, which the reference's own callers accept (linalg.py:1009-1010).
+
+Entries may be Python ints, ``fractions.Fraction`` or ``sympy`` rationals.  The device works on
+machine integers, so a matrix with fractional entries is multiplied by the common denominator
+first and the results are scaled back (exactly).  Plain ``int`` input is treated as exact
+rationals: the reference itself degrades to floats there (true division, linalg.py:574), which is
+why its own driver rationalises inputs first (main.py:20-31).
+"""
+from fractions import Fraction
+from math import gcd
+from typing import Any, Callable, Iterator, List, Tuple
+
+import numpy as np
+
+from . import _lib
+from .convert import limbs_to_ints, reduce_pq
+from .engine import default_engine
+
+_INT32_MAX = 2**31 - 1
+
+
+def _pq_of(x):
+    """(numerator, denominator) of an exact entry, or raise TypeError."""
+    if isinstance(x, bool):
+        return int(x), 1
+    if isinstance(x, int):
+        return x, 1
+    if isinstance(x, Fraction):
+        return x.numerator, x.denominator
+    p, q = getattr(x, "p", None), getattr(x, "q", None)        # sympy Rational / Integer
+    if p is not None and q is not None:
+        return int(p), int(q)
+    if isinstance(x, np.integer):
+        return int(x), 1
+    raise TypeError("the GPU elimination path takes exact integer/rational entries, got %r" % type(x))
+
+
+def _kind_of(items):
+    kind = "int"
+    for row in items:
+        for x in row:
+            if isinstance(x, (int, np.integer)):
+                continue
+            if isinstance(x, Fraction):
+                if kind == "int":
+                    kind = "fraction"
+            else:
+                kind = "sympy"
+    return kind
+
+
+def _wrap(kind, p, q=1):
+    if kind == "sympy":
+        import sympy
+        return sympy.Rational(p, q)
+    if kind == "fraction":
+        return Fraction(p, q)
+    return Fraction(p, q) if q != 1 else p
+
+
+def _to_int_grid(rows):
+    """Exact entries -> (int32 array, common denominator D) with array == D * rows."""
+    pq = [[_pq_of(x) for x in row] for row in rows]
+    D = 1
+    for row in pq:
+        for _, q in row:
+            if q != 1:
+                D = D * q // gcd(D, q)
+    grid = [[p * (D // q) for p, q in row] for row in pq]
+    for row in grid:
+        for v in row:
+            if abs(v) > _INT32_MAX:
+                raise OverflowError("entry %d does not fit the device's int32 input after clearing denominators" % v)
+    return np.array(grid, dtype=np.int32).reshape(len(rows), len(rows[0]) if rows else 0), D
+
+
+class Matrix:
+    items: List[List[Any]]
+
+    def __init__(self, items: List[List[Any]]):
+        # validation as reference linalg.py:14-32
+        if not items:
+            raise ValueError("Matrix cannot be empty")
+        if not all(isinstance(row, list) for row in items):
+            raise ValueError("Matrix items must be a list of lists")
+        if not items[0]:
+            if any(row for row in items):
+                raise ValueError("Matrix rows cannot be empty if columns exist")
+            row_len = 0
+        else:
+            row_len = len(items[0])
+            if not all(len(row) == row_len for row in items):
+                raise ValueError("All matrix rows must have the same length")
+        self._cols = row_len
+        self.items = items
+
+    def __str__(self) -> str:
+        return "\n".join([" ".join([str(item) for item in row]) for row in self.items])
+
+    def __repr__(self) -> str:
+        return "Matrix(%r)" % (self.items,)
+
+    def __eq__(self, other):
+        return isinstance(other, Matrix) and self.items == other.items
+
+    @property
+    def rows(self) -> int:
+        return len(self.items)
+
+    @property
+    def cols(self) -> int:
+        if self.rows == 0:
+            return self._cols
+        return len(self.items[0])
+
+    def self_map(self, f: Callable[[Any], Any]) -> "Matrix":
+        return Matrix([[f(item) for item in row] for row in self.items])
+
+    def get_row(self, i: int) -> List[Any]:
+        return self.items[i]
+
+    def get_col(self, j: int) -> List[Any]:
+        return [row[j] for row in self.items]
+
+    def inorder_slot_iter(self) -> Iterator[Tuple[int, int]]:
+        for i in range(self.rows):
+            for j in range(self.cols):
+                yield (i, j)
+
+    @classmethod
+    def zero(cls, rows: int, cols: int) -> "Matrix":
+        return cls([[0] * cols for _ in range(rows)])
+
+    @classmethod
+    def identity(cls, size: int) -> "Matrix":
+        return cls([[1 if i == j else 0 for j in range(size)] for i in range(size)])
+
+    @classmethod
+    def diagonal(cls, items: List[Any]) -> "Matrix":
+        res = cls.zero(len(items), len(items))
+        for i, item in enumerate(items):
+            res.items[i][i] = item
+        return res
+
+    @classmethod
+    def new_vector(cls, items: List[Any]) -> "Matrix":
+        return cls([[i] for i in items])
+
+    def transpose(self) -> "Matrix":
+        return Matrix([[self.items[j][i] for j in range(self.rows)] for i in range(self.cols)])
+
+    class AffineSubspace:
+        """Reference linalg.py:491-522 (LaTeX ``cformat`` omitted: logging is bypassed)."""
+
+        def __init__(self, vec: List[Any], mat: "Matrix"):
+            self.vec = vec
+            self.generators = mat
+
+        def get_one(self) -> List[Any]:
+            return self.vec
+
+        def dim(self) -> int:
+            return self.generators.cols
+
+        def basis(self) -> List[List[Any]]:
+            return self.generators.transpose().items
+
+        def __repr__(self):
+            return "AffineSubspace(vec=%r, generators=%r)" % (self.vec, self.generators)
+
+    class NoSolution:
+        """Reference linalg.py:524-532."""
+
+        def __init__(self):
+            pass
+
+        def __repr__(self):
+            return "NoSolution()"
+
+    # ---- the elimination path -----------------------------------------------------------------
+    def row_reduce(self, bar_col: int = None):
+        """Reduced row echelon form on the columns left of ``bar_col`` (reference linalg.py:534-630).
+
+        Returns ``(A, pivots, intermediate_matrices, intermediate_steps)``; the two log lists are
+        empty on the device path.  ``bar_col`` falsy means ``cols - 1`` exactly as linalg.py:543.
+        """
+        m, n = self.rows, self.cols
+        bar = bar_col or n - 1
+        kind = _kind_of(self.items)
+        if n == 0 or bar <= 0:
+            # nothing to pivot on: the loop of linalg.py:547 never runs
+            return [list(r) for r in self.items], [], [], []
+        if bar > n:
+            bar = n
+        grid, D = _to_int_grid(self.items)
+        eng = default_engine()
+        amax = int(np.abs(grid.astype(np.int64)).max()) if grid.size else 0
+        res = eng.rref_batch(grid[None], bar, a_abs_max=amax, b_abs_max=amax)
+        _raise_on_status(int(res.status[0]))
+        num = limbs_to_ints(res.num[0])
+        den = limbs_to_ints(res.den[0])
+        rank = int(res.rank[0])
+        pivots = [(k, int(res.pivot_col[0][k])) for k in range(rank)]
+        out = []
+        for i in range(m):
+            # rows that never became a pivot row keep the scale D of the cleared denominators
+            d_i = den if i < rank else den * D
+            out.append([_wrap(kind, *reduce_pq(x, d_i)) for x in num[i]])
+        return out, pivots, [], []
+
+    def rank(self) -> int:
+        """Reference linalg.py:745-747."""
+        if self.cols == 0:
+            return 0
+        grid, _ = _to_int_grid(self.items)
+        res = default_engine().rank_batch(grid[None])
+        _raise_on_status(int(res.status[0]))
+        return int(res.rank[0])
+
+    def determinant(self, log_permutation_details: bool = False, use_optimal: bool = True) -> Any:
+        """Reference linalg.py:183-262.  n = 0 -> 1, n = 1 -> the entry, non-square -> ValueError
+        (determinant.py:772-773); otherwise sign * product of elimination pivots, from the device."""
+        n = self.rows
+        if n == 0:
+            return 1
+        if n == 1 and self.cols == 1:
+            return self.items[0][0]
+        if self.rows != self.cols:
+            raise ValueError("Determinant requires a square matrix")
+        kind = _kind_of(self.items)
+        grid, D = _to_int_grid(self.items)
+        res = default_engine().det_batch(grid[None])
+        _raise_on_status(int(res.status[0]))
+        d = limbs_to_ints(res.det[0])
+        return _wrap(kind, *reduce_pq(d, D ** n))
+
+    def inverse(self, log_matrices: bool = False, log_steps: bool = False, log_result: bool = False):
+        """Reference linalg.py:682-743: the inverse as a ``Matrix`` or ``Matrix.NoSolution()``.
+
+        Without log flags the reference answers through sympy and returns sympy numbers
+        (linalg.py:696-701); with a log flag it returns numbers of the input type (739-743).
+        The flags only select that type here; nothing is logged."""
+        if self.rows != self.cols:
+            raise ValueError("Matrix must be square to invert.")
+        n = self.rows
+        kind = "sympy" if not (log_matrices or log_steps or log_result) else _kind_of(self.items)
+        try:
+            grid, D = _to_int_grid(self.items)
+        except TypeError:
+            if kind == "sympy":
+                return Matrix.NoSolution()          # the reference swallows every exception here (700-701)
+            raise
+        res = default_engine().inverse_batch(grid[None])
+        st = int(res.status[0])
+        if st & _lib.ST_SINGULAR:
+            return Matrix.NoSolution()
+        _raise_on_status(st)
+        adj = limbs_to_ints(res.adj[0])
+        det = limbs_to_ints(res.det[0])
+        # (D A)^-1 = adj / det  =>  A^-1 = D adj / det
+        return Matrix([[_wrap(kind, *reduce_pq(D * adj[i][j], det)) for j in range(n)] for i in range(n)])
+
+    def find_preimage_of(self, vec: List[Any], log_matrices: bool = False, log_steps: bool = False,
+                         log_result: bool = False):
+        """Solution set of ``self * x = vec`` (reference linalg.py:632-680).
+
+        Default route (no log flag) mirrors ``_q_find_preimage_of`` (870-910): sympy numbers, generator
+        columns ordered like ``sorted(params, key=str)`` (895), ``Matrix.zero(n, 0)`` generators for a
+        unique solution (888).  With a log flag it mirrors ``_extract_affine_subspace`` (937-999):
+        input-typed numbers, ascending free-column order, ``None`` generators for a unique solution."""
+        if self.rows != len(vec):
+            raise ValueError("Matrix dimensions must match")
+        logged = log_matrices or log_steps or log_result
+        m, n = self.rows, self.cols
+        aug = [list(self.items[i]) + [vec[i]] for i in range(m)]
+        kind = _kind_of(aug) if logged else "sympy"
+        grid, _ = _to_int_grid(aug)
+        A = np.ascontiguousarray(grid[:, :n])
+        b = np.ascontiguousarray(grid[:, n])
+        res = default_engine().solve_batch(A[None], b[None], gen_cap=n)
+        st = int(res.status[0])
+        if st & _lib.ST_INCONSISTENT:
+            return Matrix.NoSolution()
+        _raise_on_status(st)
+        den = limbs_to_ints(res.den[0])
+        part = limbs_to_ints(res.particular[0])
+        rank = int(res.rank[0])
+        k = n - rank
+        particular = [_wrap(kind, *reduce_pq(x, den)) for x in part]
+        if not logged:
+            particular = [_wrap("sympy", *reduce_pq(x, den)) for x in part]
+        if k == 0:
+            return Matrix.AffineSubspace(particular, None if logged else Matrix.zero(n, 0))
+        gens = limbs_to_ints(res.generators[0])          # [n][gen_cap]
+        order = list(range(k)) if logged else sorted(range(k), key=lambda i: "tau%d" % i)
+        gen_items = [[_wrap(kind, *reduce_pq(gens[r][c], den)) for c in order] for r in range(n)]
+        return Matrix.AffineSubspace(particular, Matrix(gen_items))
+
+    def kernel(self):
+        """Reference linalg.py:749-756."""
+        return self.find_preimage_of([0] * self.rows)
+
+
+def _raise_on_status(st):
+    if st & _lib.ST_BOUND:
+        raise OverflowError("liblsx: an entry exceeded the declared magnitude bound")
+    if st & _lib.ST_NO_GOOD_PRIME:
+        raise RuntimeError("liblsx: could not collect enough agreeing primes")
+    if st & _lib.ST_GEN_TRUNC:
+        raise RuntimeError("liblsx: generator buffer too small")

