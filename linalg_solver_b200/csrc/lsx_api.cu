@@ -288,7 +288,7 @@ int run_chunks(lsx_ctx* ctx, ElimJob job) {
 }
 
 // Stage (mem == HOST) or pass through (mem == DEVICE) the buffers, clear status, run, copy back.
-int run_job(lsx_ctx* ctx, ElimJob job, int mem, Buf* bufs, int nbufs, int32_t* status_user) {
+int run_job(lsx_ctx* ctx, ElimJob& job, int mem, Buf* bufs, int nbufs, int32_t* status_user) {
     LSX_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (mem != LSX_MEM_HOST && mem != LSX_MEM_DEVICE) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "bad mem flag %d", mem);
     if (job.batch < 0) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "negative batch");
