@@ -100,6 +100,12 @@ int  lsx_set_stream(lsx_ctx* ctx, void* cuda_stream);
 int  lsx_synchronize(lsx_ctx* ctx);
 /* Number of kernels this ctx has launched so far (for launch accounting in benchmarks). */
 int64_t lsx_launch_count(const lsx_ctx* ctx);
+/* Device timing of the DOMINANT kernel of each following call (the elimination kernel): enable
+ * records a CUDA event pair around it on the ctx stream; lsx_timing_read waits for the recorded
+ * pairs, writes up to `cap` durations in milliseconds (oldest first), returns how many were
+ * recorded in *count and clears the list.  Used by bench.py for the roofline figure. */
+int  lsx_timing_enable(lsx_ctx* ctx, int enable);
+int  lsx_timing_read(lsx_ctx* ctx, float* ms_out, int cap, int* count);
 /* Test hook: replace the first `count` primes of the table (odd primes < 2^31, distinct),
  * e.g. tiny primes to force the bad-prime path.  count == 0 restores the default table. */
 int  lsx_debug_set_primes(lsx_ctx* ctx, const uint32_t* primes, int count);

@@ -53,6 +53,8 @@ SIGNATURES = {
     "lsx_set_stream": (_i, [_vp, _vp]),
     "lsx_synchronize": (_i, [_vp]),
     "lsx_launch_count": (_i64, [_vp]),
+    "lsx_timing_enable": (_i, [_vp, _i]),
+    "lsx_timing_read": (_i, [_vp, _vp, _i, ctypes.POINTER(_i)]),
     "lsx_debug_set_primes": (_i, [_vp, _vp, _i]),
     "lsx_get_primes": (_i, [_vp, _vp, _i]),
     "lsx_plan_rref": (_i, [_i, _i, _i, _i64, _i64, _i, _pp]),

@@ -59,6 +59,24 @@ static int io_reserve(lsx_ctx* ctx, size_t bytes) {
     return LSX_OK;
 }
 
+void lsx_timing_begin(lsx_ctx* ctx) {
+    if (!ctx->timing) return;
+    while ((int)ctx->tev.size() < 2 * (ctx->tev_used + 1)) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) {
+            ctx->timing = false;
+            return;
+        }
+        ctx->tev.push_back(e);
+    }
+    cudaEventRecord(ctx->tev[2 * ctx->tev_used], ctx->stream);
+}
+void lsx_timing_end(lsx_ctx* ctx) {
+    if (!ctx->timing) return;
+    cudaEventRecord(ctx->tev[2 * ctx->tev_used + 1], ctx->stream);
+    ctx->tev_used++;
+}
+
 // ---- prime table upload -------------------------------------------------------------------------
 static int upload_tables(lsx_ctx* ctx) {
     std::vector<PrimeRec> recs(LSX_TABLE_PRIMES);
@@ -128,6 +146,10 @@ void lsx_destroy(lsx_ctx* ctx) {
     if (ctx->d_garner) cudaFree(ctx->d_garner);
     for (auto& e : ctx->events)
         if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->tev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->pev)
+        if (e) cudaEventDestroy(e);
     for (auto& s : ctx->copy_streams)
         if (s) cudaStreamDestroy(s);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -150,6 +172,28 @@ int lsx_synchronize(lsx_ctx* ctx) {
 }
 
 int64_t lsx_launch_count(const lsx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int lsx_timing_enable(lsx_ctx* ctx, int enable) {
+    if (!ctx) return LSX_ERR_NULL;
+    ctx->timing = enable != 0;
+    ctx->tev_used = 0;
+    return LSX_OK;
+}
+
+int lsx_timing_read(lsx_ctx* ctx, float* ms_out, int cap, int* count) {
+    if (!ctx || !count) return LSX_ERR_NULL;
+    LSX_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int n = ctx->tev_used < cap ? ctx->tev_used : cap;
+    for (int i = 0; i < n; ++i) {
+        LSX_CUDA_TRY(ctx, cudaEventSynchronize(ctx->tev[2 * i + 1]));
+        float ms = 0.f;
+        LSX_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->tev[2 * i], ctx->tev[2 * i + 1]));
+        if (ms_out) ms_out[i] = ms;
+    }
+    *count = ctx->tev_used;
+    ctx->tev_used = 0;
+    return LSX_OK;
+}
 
 int lsx_debug_set_primes(lsx_ctx* ctx, const uint32_t* primes, int count) {
     if (!ctx) return LSX_ERR_NULL;
@@ -244,7 +288,29 @@ struct Buf {          // one caller buffer: where it lives on the host side and 
 
 size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 
-int run_chunks(lsx_ctx* ctx, ElimJob job) {
+// Sub-job for matrices [b0, b0 + cnt) of `job` (all pointers are device pointers).
+ElimJob slice_job(const ElimJob& job, int64_t b0, int64_t cnt) {
+    const int m = job.m, L = job.L;
+    const int slots = m < job.bar ? m : job.bar;
+    const int nvars = job.n - 1;
+    ElimJob c = job;
+    c.batch = cnt;
+    c.A = job.A + b0 * m * job.n_in;
+    if (job.bvec) c.bvec = job.bvec + b0 * m;
+    if (job.num) {
+        const int64_t per = job.op == LSX_OP_INVERSE ? (int64_t)m * m : (int64_t)m * job.n;
+        c.num = job.num + b0 * per * L;
+    }
+    if (job.den) c.den = job.den + b0 * L;
+    if (job.particular) c.particular = job.particular + b0 * nvars * L;
+    if (job.generators) c.generators = job.generators + b0 * nvars * job.gen_cap * L;
+    if (job.pivot_col) c.pivot_col = job.pivot_col + b0 * slots;
+    if (job.rank) c.rank = job.rank + b0;
+    c.status = job.status + b0;
+    return c;
+}
+
+int run_chunks(lsx_ctx* ctx, const ElimJob& job) {
     // The tile path keeps K residue planes per matrix in scratch; bound the scratch by chunking.
     static const size_t budget = []() {
         const char* e = getenv("LSX_WS_MB");
@@ -263,31 +329,26 @@ int run_chunks(lsx_ctx* ctx, ElimJob job) {
     if (chunk < 1) chunk = 1;
     rc = lsx_ws_reserve(ctx, lsx_generic_ws_bytes(job, chunk) + 4096);
     if (rc != LSX_OK) return rc;
-    const int m = job.m, n_in = job.n_in, L = job.L;
-    const int slots = m < job.bar ? m : job.bar;
-    const int nvars = job.n - 1;
     for (int64_t b0 = 0; b0 < job.batch; b0 += chunk) {
-        ElimJob c = job;
-        c.batch = std::min(chunk, job.batch - b0);
-        c.A = job.A + b0 * m * n_in;
-        if (job.bvec) c.bvec = job.bvec + b0 * m;
-        if (job.num) {
-            const int64_t per = job.op == LSX_OP_INVERSE ? (int64_t)m * m : (int64_t)m * job.n;
-            c.num = job.num + b0 * per * L;
-        }
-        if (job.den) c.den = job.den + b0 * L;
-        if (job.particular) c.particular = job.particular + b0 * nvars * L;
-        if (job.generators) c.generators = job.generators + b0 * nvars * job.gen_cap * L;
-        if (job.pivot_col) c.pivot_col = job.pivot_col + b0 * slots;
-        if (job.rank) c.rank = job.rank + b0;
-        c.status = job.status + b0;
-        rc = lsx_run_generic(ctx, c, nullptr, nullptr, 0, 0);
+        rc = lsx_run_generic(ctx, slice_job(job, b0, std::min(chunk, job.batch - b0)), nullptr, nullptr, 0, 0);
         if (rc != LSX_OK) return rc;
     }
     return LSX_OK;
 }
 
+cudaEvent_t pipe_event(lsx_ctx* ctx, size_t i) {
+    while (ctx->pev.size() <= i) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        ctx->pev.push_back(e);
+    }
+    return ctx->pev[i];
+}
+
 // Stage (mem == HOST) or pass through (mem == DEVICE) the buffers, clear status, run, copy back.
+// Host calls are pipelined in slices: copy-in, kernels and copy-out of different slices overlap on
+// three streams (the two copy directions use separate DMA engines), so a call with pinned host
+// buffers runs at the speed of the slower PCIe direction rather than the sum of all three phases.
 int run_job(lsx_ctx* ctx, ElimJob& job, int mem, Buf* bufs, int nbufs, int32_t* status_user) {
     LSX_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (mem != LSX_MEM_HOST && mem != LSX_MEM_DEVICE) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "bad mem flag %d", mem);
@@ -302,10 +363,12 @@ int run_job(lsx_ctx* ctx, ElimJob& job, int mem, Buf* bufs, int nbufs, int32_t* 
         LSX_CUDA_TRY(ctx, cudaMemsetAsync(job.status, 0, st_bytes, ctx->stream));
         return run_chunks(ctx, job);
     }
-    size_t total = up256(st_bytes);
+    size_t total = up256(st_bytes), per_matrix = 4;
     for (int i = 0; i < nbufs; ++i)
-        if (bufs[i].slot && (bufs[i].input ? bufs[i].src != nullptr : bufs[i].dst != nullptr))
+        if (bufs[i].slot && (bufs[i].input ? bufs[i].src != nullptr : bufs[i].dst != nullptr)) {
             total += up256(bufs[i].per * (size_t)job.batch);
+            per_matrix += bufs[i].per;
+        }
     int rc = io_reserve(ctx, total);
     if (rc != LSX_OK) return rc;
     char* base = (char*)ctx->d_io;
@@ -319,19 +382,47 @@ int run_job(lsx_ctx* ctx, ElimJob& job, int mem, Buf* bufs, int nbufs, int32_t* 
         dev[i] = base + off;
         off += up256(bufs[i].per * (size_t)job.batch);
         *bufs[i].slot = dev[i];
-        if (bufs[i].input)
-            LSX_CUDA_TRY(ctx, cudaMemcpyAsync(dev[i], bufs[i].src, bufs[i].per * (size_t)job.batch,
-                                              cudaMemcpyHostToDevice, ctx->stream));
     }
-    LSX_CUDA_TRY(ctx, cudaMemsetAsync(job.status, 0, st_bytes, ctx->stream));
-    rc = run_chunks(ctx, job);
-    if (rc != LSX_OK) return rc;
-    for (int i = 0; i < nbufs; ++i)
-        if (dev[i] && !bufs[i].input)
-            LSX_CUDA_TRY(ctx, cudaMemcpyAsync(bufs[i].dst, dev[i], bufs[i].per * (size_t)job.batch,
-                                              cudaMemcpyDeviceToHost, ctx->stream));
-    LSX_CUDA_TRY(ctx, cudaMemcpyAsync(status_user, job.status, st_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    LSX_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // slices of about 32 MiB of traffic, at most 64 of them
+    int64_t slice = (int64_t)((32u << 20) / per_matrix);
+    if (slice < 1) slice = 1;
+    if ((job.batch + slice - 1) / slice > 64) slice = (job.batch + 63) / 64;
+    cudaStream_t s_in = ctx->copy_streams[0], s_out = ctx->copy_streams[1], s_run = ctx->stream;
+    // the staging block may still be read by an earlier call's copies on this ctx: they were synchronised
+    // before that call returned, so only ordering against s_run matters here
+    size_t ev = 0;
+    for (int64_t b0 = 0; b0 < job.batch; b0 += slice) {
+        const int64_t cnt = std::min(slice, job.batch - b0);
+        for (int i = 0; i < nbufs; ++i)
+            if (dev[i] && bufs[i].input)
+                LSX_CUDA_TRY(ctx, cudaMemcpyAsync((char*)dev[i] + bufs[i].per * (size_t)b0,
+                                                  (const char*)bufs[i].src + bufs[i].per * (size_t)b0,
+                                                  bufs[i].per * (size_t)cnt, cudaMemcpyHostToDevice, s_in));
+        cudaEvent_t e_in = pipe_event(ctx, ev++), e_done = pipe_event(ctx, ev++);
+        if (!e_in || !e_done) return lsx_fail(ctx, LSX_ERR_CUDA, "cudaEventCreate failed");
+        LSX_CUDA_TRY(ctx, cudaEventRecord(e_in, s_in));
+        LSX_CUDA_TRY(ctx, cudaStreamWaitEvent(s_run, e_in, 0));
+        LSX_CUDA_TRY(ctx, cudaMemsetAsync(job.status + b0, 0, (size_t)cnt * 4, s_run));
+        rc = run_chunks(ctx, slice_job(job, b0, cnt));
+        if (rc != LSX_OK) {
+            cudaStreamSynchronize(s_in);
+            cudaStreamSynchronize(s_run);
+            cudaStreamSynchronize(s_out);
+            return rc;
+        }
+        LSX_CUDA_TRY(ctx, cudaEventRecord(e_done, s_run));
+        LSX_CUDA_TRY(ctx, cudaStreamWaitEvent(s_out, e_done, 0));
+        for (int i = 0; i < nbufs; ++i)
+            if (dev[i] && !bufs[i].input)
+                LSX_CUDA_TRY(ctx, cudaMemcpyAsync((char*)bufs[i].dst + bufs[i].per * (size_t)b0,
+                                                  (const char*)dev[i] + bufs[i].per * (size_t)b0,
+                                                  bufs[i].per * (size_t)cnt, cudaMemcpyDeviceToHost, s_out));
+        LSX_CUDA_TRY(ctx, cudaMemcpyAsync(status_user + b0, job.status + b0, (size_t)cnt * 4, cudaMemcpyDeviceToHost,
+                                          s_out));
+    }
+    LSX_CUDA_TRY(ctx, cudaStreamSynchronize(s_in));
+    LSX_CUDA_TRY(ctx, cudaStreamSynchronize(s_run));
+    LSX_CUDA_TRY(ctx, cudaStreamSynchronize(s_out));
     return LSX_OK;
 }
 

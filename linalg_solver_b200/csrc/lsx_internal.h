@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -40,7 +42,15 @@ struct lsx_ctx {
     size_t ws_bytes = 0;
     void* d_io = nullptr;                // grow-only staging for LSX_MEM_HOST calls
     size_t io_bytes = 0;
+    // optional device timing of the dominant kernel of each call (lsx_timing_enable)
+    bool timing = false;
+    int tev_used = 0;
+    std::vector<cudaEvent_t> tev;        // pairs: [2*i] before, [2*i+1] after
+    std::vector<cudaEvent_t> pev;        // events of the host-call pipeline
 };
+// Record CUDA events around the dominant kernel of an operation when timing is enabled.
+void lsx_timing_begin(lsx_ctx* ctx);
+void lsx_timing_end(lsx_ctx* ctx);
 
 // ---- Montgomery arithmetic on 31-bit primes ------------------------------------------------
 #ifdef __CUDACC__

@@ -471,7 +471,9 @@ int launch_tile(lsx_ctx* ctx, const TileArgs& ta, int Ktot, int64_t grid_x, size
         if (e != cudaSuccess) return lsx_fail(ctx, LSX_ERR_CUDA, "smem attribute: %s", cudaGetErrorString(e));
     }
     dim3 grid((unsigned)grid_x, (unsigned)Ktot);
+    lsx_timing_begin(ctx);
     k_tile_elim<T><<<grid, T, smem, ctx->stream>>>(ta);
+    lsx_timing_end(ctx);
     ctx->launches++;
     return LSX_OK;
 }

@@ -112,6 +112,17 @@ class Engine:
     def launch_count(self) -> int:
         return int(lib.lsx_launch_count(self._ctx))
 
+    def timing_enable(self, on: bool = True):
+        """Record CUDA events around the dominant kernel of each following call."""
+        self._check(lib.lsx_timing_enable(self._ctx, 1 if on else 0))
+
+    def timing_read(self, cap: int = 4096):
+        """Durations (ms) of the dominant kernels recorded since the last read (waits for them)."""
+        buf = np.zeros(cap, dtype=np.float32)
+        cnt = ctypes.c_int()
+        self._check(lib.lsx_timing_read(self._ctx, buf.ctypes.data, cap, ctypes.byref(cnt)))
+        return buf[: min(cnt.value, cap)].tolist()
+
     def primes(self, count: int):
         out = np.empty(count, dtype=np.uint32)
         self._check(lib.lsx_get_primes(self._ctx, out.ctypes.data, count))

@@ -179,3 +179,56 @@ def plan_bits(log2_bound):
     K = max(1, math.ceil(need / PRIME_BITS))
     L = max(1, math.ceil(need / 32.0))
     return K, L
+
+
+def inverse_inplace_words(A, P):
+    """Mirror of the fused small-matrix kernel (lsx_small.cu, k_inv_tpm): in-place uniform-scale
+    Gauss-Jordan inversion of one n x n matrix modulo ONE prime larger than every minor of A.
+
+    Returns (adj, det) as exact integers, or None when A is singular.  The column produced at step j
+    is stored in the pivot column's slot; `unit[r]` tracks which column of the (virtual) right block
+    still holds row r's unit entry, which gives the column permutation undone at the end.
+    """
+    n = len(A)
+    p = P.p
+    W = [[a % p for a in row] for row in A]
+    S, Q, X, D = P.one, P.one, 1, 1          # D: word of the right block's diagonal for unpivoted rows
+    neg = False
+    unit = list(range(n))
+    outcol = [0] * n
+    for j in range(n):
+        src = next((r for r in range(j, n) if W[r][j] != 0), None)
+        if src is None:
+            return None
+        if src != j:
+            W[j], W[src] = W[src], W[j]
+            unit[j], unit[src] = unit[src], unit[j]
+            neg = not neg
+        outcol[j] = unit[j]
+        piv = W[j][j]
+        prow = list(W[j])
+        for r in range(n):
+            if r == j:
+                for c in range(n):
+                    W[r][c] = mont_mul(S, D, P) if c == j else mont_mul(S, prow[c], P)
+            else:
+                f = W[r][j]
+                y = p - f if f else 0
+                for c in range(n):
+                    W[r][c] = mont_mul(y, D, P) if c == j else mont_redc(piv * W[r][c] + y * prow[c], P)
+        Q = mont_mul(Q, S, P)
+        S = mont_mul(S, piv, P)
+        D = mont_mul(D, piv, P)
+        X = mont_mul(X, P.r2, P)
+    qinv = mont_pow(Q, p - 2, P)
+    Gw = mont_mul(qinv, X, P)
+    if neg and Gw:
+        Gw = p - Gw
+    half = p >> 1
+    adj = [[0] * n for _ in range(n)]
+    for r in range(n):
+        for j in range(n):
+            v = mont_mul(Gw, W[r][j], P)
+            adj[r][outcol[j]] = v - p if v > half else v
+    det = sum(A[0][c] * adj[c][0] for c in range(n))
+    return adj, det

@@ -93,3 +93,33 @@ def test_bad_prime_profile_is_lexicographically_larger():
     good = dm.elim_words([[PRIMES[0], 1], [1, 1]], 2, PRECS[1])[2]
     assert good == [0, 1]
     assert bad > good
+
+
+def test_inplace_single_prime_inverse_matches_oracle():
+    rnd = random.Random(3)
+    P = PRECS[0]
+    n_sing = 0
+    for n in (1, 2, 3, 4, 5, 8):
+        for t in range(40):
+            A = [[rnd.randint(-5, 5) for _ in range(n)] for _ in range(n)]
+            if t % 5 == 0 and n > 1:
+                A[rnd.randrange(n)][0] = 0        # exercise row swaps
+            if t % 9 == 0 and n > 1:
+                A[-1] = list(A[0])                # singular
+            got = dm.inverse_inplace_words(A, P)
+            want = ref_port.inverse(A)
+            if want is None:
+                assert got is None
+                n_sing += 1
+                continue
+            adj, det = got
+            assert det == ref_port.bareiss_det(A)
+            assert [[Fraction(x, det) for x in row] for row in adj] == want
+    assert n_sing > 0
+    g = golden_io.load("c2_8x8")
+    for c in g["cases"][:64] + g["cases"][-8:]:
+        got = dm.inverse_inplace_words(c["A"], P)
+        want = ref_port.inverse(c["A"])
+        assert (got is None) == (want is None)
+        if got:
+            assert [[Fraction(x, got[1]) for x in row] for row in got[0]] == want

@@ -328,3 +328,35 @@ def test_device_memory_path_matches_host_path(eng):
     assert np.array_equal(host.adj.view(np.int32), dev.adj.cpu().numpy().reshape(host.adj.shape))
     assert np.array_equal(host.det.view(np.int32), dev.det.cpu().numpy().reshape(host.det.shape))
     assert np.array_equal(host.status, dev.status.cpu().numpy())
+
+
+def test_fused_small_inverse_equals_tile_path(eng, monkeypatch):
+    """The single-prime register-resident kernel and the multi-prime shared-memory path must agree
+    word for word, for every n <= 8, including singular inputs, row swaps and ragged batch sizes."""
+    rng = np.random.Generator(np.random.PCG64(99))
+    for n in range(1, 9):
+        for B in (1, 127, 128, 129, 1000):
+            A = rng.integers(-5, 6, size=(B, n, n), dtype=np.int32)
+            A[::7, :, 0] = 0 if n == 1 else A[::7, :, 0] * (rng.integers(0, 2, size=(len(A[::7]), n)))   # zeros in column 0
+            if n > 1:
+                A[::11, n - 1] = A[::11, 0]                    # singular
+            fused = eng.inverse_batch(A, a_abs_max=5)
+            monkeypatch.setenv("LSX_DISABLE_SMALL", "1")
+            tile = eng.inverse_batch(A, a_abs_max=5)
+            monkeypatch.delenv("LSX_DISABLE_SMALL")
+            assert np.array_equal(fused.status, tile.status & ~32)
+            assert np.array_equal(fused.det, tile.det)
+            assert np.array_equal(fused.adj, tile.adj)
+    # entries above the declared bound are flagged, not mis-computed
+    A = rng.integers(-5, 6, size=(300, 8, 8), dtype=np.int32)
+    A[5, 3, 3] = 77
+    r = eng.inverse_batch(A, a_abs_max=5)
+    assert int(r.status[5]) & 4 and not np.any(np.delete(r.status, 5) & 4)
+    # magnitudes the single-prime argument does not cover fall back to the multi-prime path and stay exact
+    A = rng.integers(-1000, 1001, size=(64, 8, 8), dtype=np.int32)
+    r = eng.inverse_batch(A)
+    assert r.plan.limbs > 1
+    adj, det = limbs_to_ints(r.adj), limbs_to_ints(r.det)
+    for i in range(0, 64, 9):
+        inv = ref_port.inverse(A[i].tolist())
+        assert [[Fraction(x, det[i]) for x in row] for row in adj[i]] == inv
