@@ -72,7 +72,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     desc, n, batch, _ = WORKLOADS[args.workload]
-    per_core = {8: 512, 64: 1}[n]
+    per_core = {8: 2048, 64: 1}[n]
     times = []
     cb = None
     for i in range(args.warmup + args.steps):
@@ -152,7 +152,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu:
-        cpu, _ = cpu_baseline(n, {8: 512, 64: 1}[n], SEED)      # before CUDA is initialised (fork pool)
+        cpu, _ = cpu_baseline(n, {8: 16384, 64: 2}[n], SEED)      # before CUDA is initialised (fork pool)
 
     import torch
     import torch.distributed as dist

@@ -148,7 +148,7 @@ k_inv_tpm(const int32_t* __restrict__ A, int64_t batch, PrimeRec P, int a_abs_ma
         uint32_t* mine = sm + tid * ST;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-            const int cj = (outcol >> (4 * j)) & 15u;
+            const int cj = zero_out ? j : (int)((outcol >> (4 * j)) & 15u);   // zeros go to every slot
 #pragma unroll
             for (int r = 0; r < N; ++r) {
                 const uint32_t v = mont_mul(Gw, W[r][j], p, pinv);

@@ -148,7 +148,9 @@ class Engine:
                 if x.device.index != self.device:
                     raise ValueError("%s lives on cuda:%s, this engine is bound to cuda:%d"
                                      % (name, x.device.index, self.device))
-                self.set_stream(torch.cuda.current_stream(x.device).cuda_stream)
+                # torch's default stream is the legacy NULL stream: pass the cudaStreamLegacy handle (0x1),
+                # because NULL means "the ctx's own stream" to lsx_set_stream
+                self.set_stream(torch.cuda.current_stream(x.device).cuda_stream or 1)
                 return x, x.data_ptr(), _lib.MEM_DEVICE, x
             self.set_stream(None)
             return x, x.data_ptr(), _lib.MEM_HOST, x
