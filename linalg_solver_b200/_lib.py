@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "liblsx.so")
+SO_PATH = os.environ.get("LSX_LIB_PATH") or os.path.join(_HERE, "liblsx.so")   # override: kernel experiments
 
 if not os.path.exists(SO_PATH):
     raise ImportError(

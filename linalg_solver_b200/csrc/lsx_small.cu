@@ -1,14 +1,18 @@
 // Fused register-resident kernels for batches of small matrices.
 //
-// k_inv_tpm<N>: inverse + determinant of n x n matrices (n <= 8), ONE launch per batch, one thread
-// per matrix.  Input is read once (coalesced, staged through shared memory), the adjugate, the
+// k_inv_tpm<N, HEAD>: inverse + determinant of n x n matrices (n <= 8), ONE launch per batch, one
+// thread per matrix.  Input is read once (coalesced, staged through shared memory), the adjugate, the
 // determinant and the status word are written once -- the algorithmic byte count of SURVEY.md
-// section 8d -- and everything in between lives in registers:
-//   * in-place uniform-scale Gauss-Jordan on Montgomery words modulo ONE 31-bit prime (mirror:
-//     tests/device_model.py::inverse_inplace_words).  The path is taken only when the Hadamard bound
-//     of every minor of A is below the prime, so zero tests modulo p are exact (no bad primes, the
-//     pivot row choice equals the reference's, linalg.py:548-567) and the adjugate entries are
-//     recovered exactly by the symmetric lift;
+// section 8d -- and everything in between lives in registers (mirror of the arithmetic:
+// tests/device_model.py::inverse_inplace_v2):
+//   * in-place division-free Gauss-Jordan modulo ONE 31-bit prime.  The path is taken only when the
+//     Hadamard bound of every minor of A is below the prime, so zero tests modulo p are exact (no bad
+//     primes; the pivot row choice equals the reference's, linalg.py:548-567) and the adjugate
+//     entries are recovered exactly by the symmetric lift;
+//   * the first HEAD pivot steps run on plain int32 (two IMADs per entry, no reduction) while the
+//     entries provably fit; the remaining steps use Montgomery words (one two-product REDC per entry);
+//   * pivot rows are left unscaled; the per-row factor, the sign and the single modular inversion are
+//     folded into the multipliers of the LAST pivot step, so there is no separate scaling pass;
 //   * the determinant, which may need one more bit than the prime offers, comes from the exact
 //     integer identity det = sum_c A[0][c] * adj[c][0];
 //   * singular matrices (no pivot in some column) get LSX_ST_SINGULAR and zeros, which is where the
@@ -17,7 +21,13 @@
 
 namespace {
 
-constexpr int TPM_THREADS = 128;
+#ifndef LSX_TPM_THREADS
+#define LSX_TPM_THREADS 128
+#endif
+#ifndef LSX_TPM_MINB
+#define LSX_TPM_MINB 4
+#endif
+constexpr int TPM_THREADS = LSX_TPM_THREADS;
 
 template <int N>
 struct TpmSmem {
@@ -25,8 +35,26 @@ struct TpmSmem {
     static constexpr int STRIDE = E | 1;     // odd stride: lane t reads word t*STRIDE + e without bank conflicts
 };
 
-template <int N>
-__global__ void __launch_bounds__(TPM_THREADS, 3)
+__device__ __forceinline__ uint32_t mont_sqn(uint32_t x, int k, uint32_t p, uint32_t pinv) {
+    for (int i = 0; i < k; ++i) x = mont_mul(x, x, p, pinv);
+    return x;
+}
+// a^(p-2): addition chain (30 squarings + 8 products) for p = 2^31 - 1, square-and-multiply otherwise
+__device__ __forceinline__ uint32_t mont_inverse(uint32_t a, const PrimeRec& P) {
+    const uint32_t p = P.p, pinv = P.pinv;
+    if (p != 0x7fffffffu) return mont_pow(a, p - 2u, P.one, p, pinv);
+    const uint32_t x2 = mont_mul(mont_sqn(a, 1, p, pinv), a, p, pinv);
+    const uint32_t x4 = mont_mul(mont_sqn(x2, 2, p, pinv), x2, p, pinv);
+    const uint32_t x8 = mont_mul(mont_sqn(x4, 4, p, pinv), x4, p, pinv);
+    const uint32_t x16 = mont_mul(mont_sqn(x8, 8, p, pinv), x8, p, pinv);
+    const uint32_t x24 = mont_mul(mont_sqn(x16, 8, p, pinv), x8, p, pinv);
+    const uint32_t x28 = mont_mul(mont_sqn(x24, 4, p, pinv), x4, p, pinv);
+    const uint32_t x29 = mont_mul(mont_sqn(x28, 1, p, pinv), a, p, pinv);
+    return mont_mul(mont_sqn(x29, 2, p, pinv), a, p, pinv);
+}
+
+template <int N, int HEAD>
+__global__ void __launch_bounds__(TPM_THREADS, LSX_TPM_MINB)
 k_inv_tpm(const int32_t* __restrict__ A, int64_t batch, PrimeRec P, int a_abs_max, int32_t* __restrict__ adj,
           int32_t* __restrict__ det, int32_t* __restrict__ status) {
     constexpr int E = TpmSmem<N>::E, ST = TpmSmem<N>::STRIDE;
@@ -60,7 +88,7 @@ k_inv_tpm(const int32_t* __restrict__ A, int64_t batch, PrimeRec P, int a_abs_ma
     __syncthreads();
 
     const bool active = tid < nmat;
-    uint32_t W[N][N];
+    uint32_t W[N][N];          // head: two's-complement integers; tail: Montgomery words
     int32_t a0[N];
     int amax = 0;
     {
@@ -71,22 +99,54 @@ k_inv_tpm(const int32_t* __restrict__ A, int64_t batch, PrimeRec P, int a_abs_ma
             for (int c = 0; c < N; ++c) {
                 const int32_t v = active ? (int32_t)mine[r * N + c] : (r == c ? 1 : 0);
                 if (r == 0) a0[c] = v;
-                amax = max(amax, v < 0 ? -v : v);     // INT_MIN stays negative and trips the check below
+                amax = max(amax, v < 0 ? -v : v);
                 if (v == INT32_MIN) amax = INT32_MAX;
-                W[r][c] = word_of_int(v, p);
+                W[r][c] = (uint32_t)v;
             }
     }
     const bool bound_bad = amax > a_abs_max;
+    if (bound_bad) {           // keep the integer head inside its proven range: compute on the identity instead
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int c = 0; c < N; ++c) W[r][c] = r == c ? 1u : 0u;
+    }
 
-    uint32_t S = P.one, Q = P.one, X = 1u, D = 1u;
     uint32_t unit = 0;                      // N fields of 4 bits: unit[r]
 #pragma unroll
     for (int r = 0; r < N; ++r) unit |= (uint32_t)r << (4 * r);
     uint32_t outcol = 0;                    // N fields of 4 bits: column of the result held in slot j
     bool neg = false, singular = false;
+    uint32_t cw[N];                         // per-row multiplier words (what pivot row k still lacks)
+    uint32_t sig = 1u;                      // head: product of the pivots so far (exact integer)
+    uint32_t S = 1u, Q = P.one;
 
 #pragma unroll
     for (int j = 0; j < N; ++j) {
+        constexpr bool kDummy = false;
+        (void)kDummy;
+        const bool head = j < HEAD;
+        const bool last = j == N - 1;
+        if (j == HEAD) {
+            // ---- switch to Montgomery words: raw load, S = sigma_h raw, Q = word(prod sigma_k) ----
+            uint32_t qh = 1u;               // plain product of the head sigmas modulo p
+            uint32_t sk = 1u;
+#pragma unroll
+            for (int k = 0; k < HEAD; ++k) {
+                // cw[k] was stored as the plain integer sigma_k (positive or negative, small)
+                const uint32_t sw = word_of_int((int32_t)cw[k], p);
+                qh = (uint32_t)(((uint64_t)qh * sw) % p);
+                cw[k] = mont_mul(sw, P.r2, p, pinv);
+                sk = sw;
+            }
+            (void)sk;
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < N; ++c) W[r][c] = word_of_int((int32_t)W[r][c], p);
+            S = word_of_int((int32_t)sig, p);
+            Q = mont_mul(qh, P.r2, p, pinv);
+        }
         if (!singular) {
             int src = -1;
 #pragma unroll
@@ -116,31 +176,58 @@ k_inv_tpm(const int32_t* __restrict__ A, int64_t batch, PrimeRec P, int a_abs_ma
                 uint32_t prow[N];
 #pragma unroll
                 for (int c = 0; c < N; ++c) prow[c] = W[j][c];
+                if (head) {
+                    // plain two's-complement integers: W[r][c] = piv * W[r][c] - f * prow[c]
 #pragma unroll
-                for (int r = 0; r < N; ++r) {
-                    if (r == j) {
-#pragma unroll
-                        for (int c = 0; c < N; ++c)
-                            W[r][c] = mont_mul(S, c == j ? D : prow[c], p, pinv);
-                    } else {
+                    for (int r = 0; r < N; ++r) {
+                        if (r == j) continue;
                         const uint32_t f = W[r][j];
-                        const uint32_t y = f ? p - f : 0u;
 #pragma unroll
                         for (int c = 0; c < N; ++c)
-                            W[r][c] = (c == j) ? mont_mul(y, D, p, pinv) : mont_fma2(piv, W[r][c], y, prow[c], p, pinv);
+                            W[r][c] = (c == j) ? (0u - f * sig) : (piv * W[r][c] - f * prow[c]);
                     }
+                    W[j][j] = sig;
+                    cw[j] = sig;
+                    sig *= piv;
+                } else {
+                    cw[j] = S;
+                    Q = mont_mul(Q, S, p, pinv);
+                    uint32_t qinv = 0u;
+                    if (last) {
+                        qinv = mont_inverse(Q, P);
+                        if (neg) qinv = p - qinv;           // Q is a unit, so qinv != 0
+                    }
+#pragma unroll
+                    for (int r = 0; r < N; ++r) {
+                        if (r == j) {
+                            if (last) {
+                                const uint32_t g = mont_mul(qinv, cw[r], p, pinv);
+#pragma unroll
+                                for (int c = 0; c < N; ++c) W[r][c] = mont_mul(g, c == j ? S : prow[c], p, pinv);
+                            } else {
+                                W[r][j] = S;
+                            }
+                        } else {
+                            const uint32_t f = W[r][j];
+                            uint32_t y = f ? p - f : 0u;
+                            uint32_t x = piv;
+                            if (last) {
+                                const uint32_t g = mont_mul(qinv, cw[r], p, pinv);
+                                x = mont_mul(g, x, p, pinv);
+                                y = mont_mul(g, y, p, pinv);
+                            }
+#pragma unroll
+                            for (int c = 0; c < N; ++c)
+                                W[r][c] = (c == j) ? mont_mul(y, S, p, pinv) : mont_fma2(x, W[r][c], y, prow[c], p, pinv);
+                        }
+                    }
+                    S = mont_mul(S, piv, p, pinv);
                 }
-                Q = mont_mul(Q, S, p, pinv);
-                S = mont_mul(S, piv, p, pinv);
-                D = mont_mul(D, piv, p, pinv);
-                X = mont_mul(X, P.r2, p, pinv);
             }
         }
     }
 
-    // ---- one inversion, scale to adj = det * A^-1, symmetric lift, undo the column permutation ----
-    uint32_t Gw = mont_mul(mont_pow(Q, p - 2u, P.one, p, pinv), X, p, pinv);
-    if (neg && Gw) Gw = p - Gw;
+    // ---- symmetric lift, undo the column permutation, determinant ----
     const uint32_t half = p >> 1;
     const bool zero_out = singular || bound_bad;
     __syncthreads();                       // everybody has read its input tile: reuse it for the output
@@ -151,7 +238,7 @@ k_inv_tpm(const int32_t* __restrict__ A, int64_t batch, PrimeRec P, int a_abs_ma
             const int cj = zero_out ? j : (int)((outcol >> (4 * j)) & 15u);   // zeros go to every slot
 #pragma unroll
             for (int r = 0; r < N; ++r) {
-                const uint32_t v = mont_mul(Gw, W[r][j], p, pinv);
+                const uint32_t v = W[r][j];
                 const int32_t s = v > half ? (int32_t)(v - p) : (int32_t)v;
                 mine[r * N + cj] = zero_out ? 0u : (uint32_t)s;
             }
@@ -189,20 +276,43 @@ k_inv_tpm(const int32_t* __restrict__ A, int64_t batch, PrimeRec P, int a_abs_ma
     }
 }
 
-template <int N>
-int launch_inv_tpm(lsx_ctx* ctx, const ElimJob& job) {
+// Leading pivot steps that provably stay inside int32: entries grow like B -> 2 B^2 per step.
+int head_steps_for(int n, int64_t a_abs_max) {
+    int h = 0;
+    double B = (double)(a_abs_max < 1 ? 1 : a_abs_max);
+    const int hmax = n - 1 < 3 ? n - 1 : 3;
+    while (h < hmax) {
+        B = 2.0 * B * B;
+        if (B >= 2147483648.0) break;
+        ++h;
+    }
+    return h;
+}
+
+template <int N, int HEAD>
+int launch_inv_tpm_h(lsx_ctx* ctx, const ElimJob& job) {
     const size_t smem = (size_t)TPM_THREADS * TpmSmem<N>::STRIDE * 4;
     if (smem > 48 * 1024)
-        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_inv_tpm<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_inv_tpm<N, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((job.batch + TPM_THREADS - 1) / TPM_THREADS);
     const PrimeRec P = lsx_make_prime_rec(ctx->primes[0]);
     lsx_timing_begin(ctx);
-    k_inv_tpm<N><<<grid, TPM_THREADS, smem, ctx->stream>>>(job.A, job.batch, P, (int)job.a_abs_max, (int32_t*)job.num,
-                                                           (int32_t*)job.den, job.status);
+    k_inv_tpm<N, HEAD><<<grid, TPM_THREADS, smem, ctx->stream>>>(job.A, job.batch, P, (int)job.a_abs_max,
+                                                                 (int32_t*)job.num, (int32_t*)job.den, job.status);
     lsx_timing_end(ctx);
     ctx->launches++;
     LSX_CUDA_TRY(ctx, cudaGetLastError());
     return LSX_OK;
+}
+
+// Two instantiations per size: the full integer head when the declared magnitudes allow it, none otherwise.
+template <int N>
+int launch_inv_tpm(lsx_ctx* ctx, const ElimJob& job) {
+    constexpr int HMAX = N - 1 < 3 ? N - 1 : 3;
+    const char* e = getenv("LSX_TPM_HEAD");
+    const int want = e ? atoi(e) : HMAX;
+    if (HMAX > 0 && want >= HMAX && head_steps_for(N, job.a_abs_max) >= HMAX) return launch_inv_tpm_h<N, HMAX>(ctx, job);
+    return launch_inv_tpm_h<N, 0>(ctx, job);
 }
 
 }  // namespace

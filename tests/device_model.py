@@ -232,3 +232,125 @@ def inverse_inplace_words(A, P):
             adj[r][outcol[j]] = v - p if v > half else v
     det = sum(A[0][c] * adj[c][0] for c in range(n))
     return adj, det
+
+
+def head_steps_for(n, a_abs_max):
+    """Number of leading pivot steps that can run on plain int32 (no reduction): entries grow like
+    B -> 2 B^2 per step (pivot rows are left unscaled, see inverse_inplace_v2)."""
+    h, B = 0, max(1, int(a_abs_max))
+    while h < min(3, n - 1):
+        B = 2 * B * B
+        if B >= 2 ** 31:
+            break
+        h += 1
+    return h
+
+
+def mont_inv_mersenne31(a, P):
+    """a^(p-2) for p = 2^31 - 1 by an addition chain: 30 squarings + 8 multiplications."""
+    def sqn(x, k):
+        for _ in range(k):
+            x = mont_mul(x, x, P)
+        return x
+    x2 = mont_mul(sqn(a, 1), a, P)            # a^(2^2 - 1)
+    x4 = mont_mul(sqn(x2, 2), x2, P)          # 2^4 - 1
+    x8 = mont_mul(sqn(x4, 4), x4, P)
+    x16 = mont_mul(sqn(x8, 8), x8, P)
+    x24 = mont_mul(sqn(x16, 8), x8, P)
+    x28 = mont_mul(sqn(x24, 4), x4, P)
+    x29 = mont_mul(sqn(x28, 1), a, P)         # 2^29 - 1
+    return mont_mul(sqn(x29, 2), a, P)        # 4 (2^29 - 1) + 1 = 2^31 - 3
+
+
+def inverse_inplace_v2(A, P, head):
+    """Mirror of k_inv_tpm (lsx_small.cu), second version.
+
+    In-place Gauss-Jordan inversion of one n x n matrix modulo one prime with
+      * `head` leading pivot steps on plain integers (int32 range guaranteed by head_steps_for),
+      * pivot rows left UNSCALED (row k then lacks the factor sigma_k = prod_{i<k} piv_i, which is
+        put back by the per-row multiplier at the end),
+      * the final scaling folded into the multipliers of the last pivot step, so the single modular
+        inversion happens before that step.
+    Returns (adj, det) or None (singular).
+    """
+    n = len(A)
+    p = P.p
+    W = [[int(a) for a in row] for row in A]
+    unit = list(range(n))
+    outcol = [0] * n
+    neg = False
+    sig = 1                       # sigma_j = product of the pivots so far (head: exact integer)
+    cw = [0] * n                  # per-row multiplier word (deficit of pivot row k)
+    qh = 1                        # head: product of sigma_k, k < head (exact integer, reduced mod p)
+
+    def pivot(j, zero):
+        nonlocal neg
+        src = next((r for r in range(j, n) if W[r][j] != zero), None)
+        if src is None:
+            return False
+        if src != j:
+            W[j], W[src] = W[src], W[j]
+            unit[j], unit[src] = unit[src], unit[j]
+            neg = not neg
+        outcol[j] = unit[j]
+        return True
+
+    for j in range(head):
+        if not pivot(j, 0):
+            return None
+        piv = W[j][j]
+        prow = list(W[j])
+        for r in range(n):
+            if r == j:
+                continue
+            f = W[r][j]
+            for c in range(n):
+                W[r][c] = -f * sig if c == j else piv * W[r][c] - f * prow[c]
+                assert abs(W[r][c]) < 2 ** 31
+        W[j][j] = sig
+        cw[j] = mont_mul(sig % p, P.r2, P)
+        qh = qh * sig % p
+        sig = sig * piv
+        assert abs(sig) < 2 ** 31
+    # ---- switch to Montgomery words: raw load, S = D = sigma_h raw ----
+    W = [[x % p for x in row] for row in W]
+    S = sig % p
+    Q = mont_mul(qh, P.r2, P)
+    for j in range(head, n):
+        last = j == n - 1
+        if not pivot(j, 0):
+            return None
+        piv = W[j][j]
+        prow = list(W[j])
+        cw[j] = S
+        Q = mont_mul(Q, S, P)
+        if last:
+            qinv = mont_inv_mersenne31(Q, P) if p == 2 ** 31 - 1 else mont_pow(Q, p - 2, P)
+            if neg:
+                qinv = p - qinv
+        for r in range(n):
+            if r == j:
+                if last:
+                    g = mont_mul(qinv, cw[r], P)
+                    for c in range(n):
+                        W[r][c] = mont_mul(g, S if c == j else prow[c], P)
+                else:
+                    W[r][j] = S
+                continue
+            f = W[r][j]
+            y = p - f if f else 0
+            x = piv
+            if last:
+                g = mont_mul(qinv, cw[r], P)
+                x, y = mont_mul(g, x, P), mont_mul(g, y, P)
+            for c in range(n):
+                W[r][c] = mont_mul(y, S, P) if c == j else mont_redc(x * W[r][c] + y * prow[c], P)
+        S = mont_mul(S, piv, P)
+    half = p >> 1
+    adj = [[0] * n for _ in range(n)]
+    for r in range(n):
+        for j in range(n):
+            v = W[r][j]
+            adj[r][outcol[j]] = v - p if v > half else v
+    det = sum(A[0][c] * adj[c][0] for c in range(n))
+    return adj, det

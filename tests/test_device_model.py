@@ -123,3 +123,37 @@ def test_inplace_single_prime_inverse_matches_oracle():
         assert (got is None) == (want is None)
         if got:
             assert [[Fraction(x, got[1]) for x in row] for row in got[0]] == want
+
+
+def test_inplace_v2_head_steps_and_folding():
+    assert dm.head_steps_for(8, 5) == 3 and dm.head_steps_for(8, 7) == 3 and dm.head_steps_for(8, 8) == 2
+    assert dm.head_steps_for(8, 127) == 2 and dm.head_steps_for(8, 128) == 1 and dm.head_steps_for(8, 40000) == 0
+    assert dm.head_steps_for(2, 5) == 1 and dm.head_steps_for(1, 5) == 0
+    P = PRECS[0]
+    x = 123456789
+    assert dm.mont_inv_mersenne31(x, P) == dm.mont_pow(x, P.p - 2, P)
+    rnd = random.Random(17)
+    n_sing = 0
+    for P in (PRECS[0], PRECS[1]):
+        for n in (1, 2, 3, 4, 5, 6, 7, 8):
+            for head in range(0, min(3, n - 1) + 1):
+                for t in range(12):
+                    A = [[rnd.randint(-5, 5) for _ in range(n)] for _ in range(n)]
+                    if t % 4 == 0 and n > 1:
+                        A[rnd.randrange(n)][0] = 0
+                        A[0][0] = 0
+                    if t % 5 == 0 and n > 1:
+                        A[-1] = list(A[0])
+                    if t % 6 == 1 and n > 2:
+                        A[n - 1][n - 1] = 0
+                        A[n - 2][n - 2] = 0
+                    got = dm.inverse_inplace_v2(A, P, head)
+                    want = ref_port.inverse(A)
+                    if want is None:
+                        assert got is None
+                        n_sing += 1
+                        continue
+                    adj, det = got
+                    assert det == ref_port.bareiss_det(A), (n, head, A)
+                    assert [[Fraction(x, det) for x in row] for row in adj] == want, (n, head, A)
+    assert n_sing > 10

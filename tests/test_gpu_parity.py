@@ -341,6 +341,11 @@ def test_fused_small_inverse_equals_tile_path(eng, monkeypatch):
             if n > 1:
                 A[::11, n - 1] = A[::11, 0]                    # singular
             fused = eng.inverse_batch(A, a_abs_max=5)
+            monkeypatch.setenv("LSX_TPM_HEAD", "0")             # same kernel without the plain-integer head steps
+            nohead = eng.inverse_batch(A, a_abs_max=5)
+            monkeypatch.delenv("LSX_TPM_HEAD")
+            assert np.array_equal(fused.adj, nohead.adj) and np.array_equal(fused.det, nohead.det)
+            assert np.array_equal(fused.status, nohead.status)
             monkeypatch.setenv("LSX_DISABLE_SMALL", "1")
             tile = eng.inverse_batch(A, a_abs_max=5)
             monkeypatch.delenv("LSX_DISABLE_SMALL")
