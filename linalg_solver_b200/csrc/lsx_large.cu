@@ -146,7 +146,7 @@ int lsx_det_large_residues(lsx_ctx* ctx, const int32_t* A, int n, int prime_begi
         }
     }
     int rc;
-    if (lsx_tile_fits(n, n))
+    if (lsx_tile_fits(n, n) && !getenv("LSX_FORCE_BLOCKED"))
         rc = lsx_tile_det_residues(ctx, dA, n, prime_begin, prime_count, dres);
     else
         rc = lsx_blocked_det_residues(ctx, dA, n, prime_begin, prime_count, dres);

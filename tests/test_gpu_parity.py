@@ -365,3 +365,39 @@ def test_fused_small_inverse_equals_tile_path(eng, monkeypatch):
     for i in range(0, 64, 9):
         inv = ref_port.inverse(A[i].tolist())
         assert [[Fraction(x, det[i]) for x in row] for row in adj[i]] == inv
+
+
+def test_blocked_lu_residues_match_tile_path(eng, monkeypatch):
+    """The global-memory blocked LU (used above n ~ 220) against the shared-memory tile kernel on
+    sizes both can do, including ragged n, zero pivots (row swaps) and singular matrices."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    for n in (1, 5, 63, 64, 65, 100, 130, 200):
+        A = rng.integers(-5, 6, size=(n, n), dtype=np.int32)
+        variants = [A]
+        if n > 2:
+            B = A.copy()
+            B[0, 0] = 0
+            B[1, 0] = 0
+            B[n // 2, n // 2:] = 0                       # forces later swaps too
+            variants.append(B)
+            C = A.copy()
+            C[n - 1] = C[0]                              # singular
+            variants.append(C)
+        for M in variants:
+            tile = eng.det_large_residues(M, 3, 9)
+            monkeypatch.setenv("LSX_FORCE_BLOCKED", "1")
+            blk = eng.det_large_residues(M, 3, 9)
+            monkeypatch.delenv("LSX_FORCE_BLOCKED")
+            assert np.array_equal(tile, blk), n
+    assert not np.any(eng.det_large_residues(C, 0, 4))
+
+
+def test_c5_standin_256_blocked_and_sharded_crt(eng):
+    from linalg_solver_b200 import dist as lsx_dist
+    g = golden_io.load("c5_standins")
+    c = [x for x in g["cases"] if x["n"] == 256][0]
+    rng = np.random.Generator(np.random.PCG64(c["seed"]))
+    A = rng.integers(-5, 6, size=(256, 256), dtype=np.int64).astype(np.int32)
+    words, K = lsx_dist.det_large_sharded(eng, A, 5)
+    assert limbs_to_ints(words) == int(c["det"])
+    assert K == eng.det_large_prime_count(256, 5)[0]
