@@ -321,6 +321,9 @@ int run_chunks(lsx_ctx* ctx, const ElimJob& job) {
     int rc = lsx_run_small(ctx, job, &handled);
     if (rc != LSX_OK) return rc;
     if (handled) return LSX_OK;
+    rc = lsx_run_subwarp(ctx, job, &handled);
+    if (rc != LSX_OK) return rc;
+    if (handled) return LSX_OK;
 
     const size_t per1 = lsx_generic_ws_bytes(job, 1), per2 = lsx_generic_ws_bytes(job, 2);
     const size_t slope = per2 > per1 ? per2 - per1 : 1;

@@ -129,6 +129,8 @@ int lsx_run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const
 size_t lsx_generic_ws_bytes(const ElimJob& job, int64_t batch);
 // Fused register-resident kernels for small shapes; *handled = 1 if the job was covered.
 int lsx_run_small(lsx_ctx* ctx, const ElimJob& job, int* handled);
+// Fused sub-warp kernel (row per lane, all primes + CRT in one launch) for m <= 32, n <= 33.
+int lsx_run_subwarp(lsx_ctx* ctx, const ElimJob& job, int* handled);
 // det(A) mod p for table primes [prime_begin, prime_begin + count) through the tile kernel
 bool lsx_tile_fits(int m, int n);
 int lsx_tile_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_begin, int count, uint32_t* d_res);

@@ -1,0 +1,514 @@
+// Fused sub-warp kernel for batches of small matrices (m <= 32 rows, n <= 33 columns): ONE launch does
+// every prime, the pivot-profile agreement check, the Garner CRT and the scatter into the layout of
+// the operation (RREF grid / adjugate / particular solution + generators / determinant / rank).
+//
+//   * G lanes hold one matrix (G = 4, 8, 16 or 32; one ROW per lane, the row's NC words in registers),
+//     32/G matrices per warp.  Because rows are lanes, the pivot ROW index may be data dependent
+//     (rank-deficient inputs skip columns) while every register index stays static.
+//   * pivot search = ballot over "non-zero at or below the pivot position" + ffs: the LOWEST such row,
+//     which is the reference's rule (linalg.py:548-567; not a max-magnitude search); row swaps are
+//     physical lane exchanges by shuffle, the pivot row is broadcast by shuffle.
+//   * per prime: uniform-scale division-free Gauss-Jordan on Montgomery words with one Fermat
+//     inversion (mirror: tests/device_model.py::elim_words); residues N = d * RREF go to shared
+//     memory; the profile (source row per column) of every prime is compared with the first prime's.
+//   * all K primes agree  =>  the profile is the rational one (their product exceeds the Hadamard
+//     bound of every minor) and the matrix is finished here; otherwise it is
+//     appended to a retry list and recomputed by the tile path with replacement primes.
+// Inputs are read once and outputs written once; residues never touch HBM.
+#include <utility>
+
+#include "lsx_crt.cuh"
+#include "lsx_internal.h"
+
+namespace {
+
+constexpr int SW_THREADS = 128;
+constexpr int SW_SKIP = 63;          // profile code of a column without pivot
+
+struct SwArgs {
+    const int32_t* A;
+    const int32_t* bvec;
+    int64_t batch;
+    int m, n_in, n, bar, right_identity, op;
+    int K, L, gen_cap, pivot_slots, max_rank;
+    int a_abs_max, b_abs_max;
+    const PrimeRec* primes;
+    const uint32_t* garner;
+    uint32_t* num;
+    uint32_t* den;
+    uint32_t* particular;
+    uint32_t* generators;
+    int32_t* pivot_col;
+    int32_t* rank;
+    int32_t* status;
+    int32_t* retry_list;
+    int32_t* retry_count;
+    int retry_cap;
+};
+
+// Garner CRT of the K residues of one entry (scaled on the fly by the per-prime factor) to a signed
+// L-limb integer, stored negated / zeroed on request.  Prime records and Garner inverses come from
+// shared memory (loaded once per CTA).  One copy per KT (not inlined: the kernel calls it in a loop).
+struct SwTables {
+    const PrimeRec* primes;      // [K]            (shared memory)
+    const uint32_t* garner;      // [K][K]: (p_i^-1 mod p_j) * R mod p_j
+};
+
+template <int KT>
+__device__ __noinline__ void crt_entry(const uint32_t* res, int res_stride, const uint32_t* scale, int scale_stride, int K,
+                                        int L, SwTables T, uint32_t* dst, bool negate, bool zero_out) {
+    uint32_t v[KT], pp[KT], acc[KT];
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+        v[j] = 0u;
+        pp[j] = 0u;
+        if (j < K) {
+            const PrimeRec P = T.primes[j];
+            pp[j] = P.p;
+            uint32_t t = res ? mont_mul(scale[j * scale_stride], res[j * res_stride], P.p, P.pinv) : scale[j * scale_stride];
+#pragma unroll
+            for (int i = 0; i < j; ++i) {
+                uint32_t vi = v[i];
+                if (vi >= P.p) vi -= P.p;
+                t = t >= vi ? t - vi : t + P.p - vi;
+                t = mont_mul(t, T.garner[i * K + j], P.p, P.pinv);
+            }
+            v[j] = t;
+        }
+    }
+    bool negv = false, decided = false;
+#pragma unroll
+    for (int i = KT - 1; i >= 0; --i) {
+        if (i < K && !decided) {
+            const uint32_t h = (pp[i] - 1u) >> 1;
+            if (v[i] != h) {
+                negv = v[i] > h;
+                decided = true;
+            }
+        }
+    }
+    if (negv) {
+#pragma unroll
+        for (int i = 0; i < KT; ++i)
+            if (i < K) v[i] = pp[i] - 1u - v[i];
+    }
+#pragma unroll
+    for (int l = 0; l < KT; ++l) acc[l] = 0u;
+#pragma unroll
+    for (int i = KT - 1; i >= 0; --i) {
+        if (i < K) {
+            uint64_t carry = v[i];
+#pragma unroll
+            for (int l = 0; l < KT; ++l) {
+                const uint64_t t = (uint64_t)acc[l] * pp[i] + carry;
+                acc[l] = (uint32_t)t;
+                carry = t >> 32;
+            }
+        }
+    }
+    if (negv) {
+#pragma unroll
+        for (int l = 0; l < KT; ++l) acc[l] = ~acc[l];
+    }
+    store_limbs<KT>(dst, acc, L, negate, zero_out);
+}
+
+__device__ __forceinline__ void crt_entry_any(const uint32_t* res, int res_stride, const uint32_t* scale, int scale_stride,
+                                              int K, int L, SwTables T, uint32_t* dst, bool negate, bool zero_out) {
+    if (K <= 1) crt_entry<1>(res, res_stride, scale, scale_stride, K, L, T, dst, negate, zero_out);
+    else if (K <= 4) crt_entry<4>(res, res_stride, scale, scale_stride, K, L, T, dst, negate, zero_out);
+    else crt_entry<8>(res, res_stride, scale, scale_stride, K, L, T, dst, negate, zero_out);
+}
+
+struct SwState {
+    uint32_t S, Q, X;
+    uint64_t prof;
+    int pi;
+    bool neg;
+};
+
+// One pivot column J (compile-time, so that every register index is static).
+template <int G, int NC, int J>
+__device__ __forceinline__ void sw_step(uint32_t (&row)[NC], SwState& st, const PrimeRec& P, int r, int gbase, unsigned gmask,
+                                        int m, int bar, bool live) {
+    constexpr unsigned FULL = 0xffffffffu;
+    if (J >= bar) return;                 // uniform over the grid
+    const uint32_t p = P.p, pinv = P.pinv;
+    const int pi = st.pi;
+    const bool nz = r >= pi && r < m && row[J] != 0u;
+    const unsigned bal = (__ballot_sync(FULL, nz) >> gbase) & gmask;
+    const bool has = bal != 0u && pi < m;
+    const int src = has ? __ffs(bal) - 1 : pi;
+    if (__any_sync(FULL, has && src != pi)) {
+        // physical swap of rows pi and src (lanes of groups without a swap read themselves)
+        const int partner = (has && src != pi) ? (r == pi ? src : (r == src ? pi : r)) : r;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) row[c] = __shfl_sync(FULL, row[c], gbase + partner);
+    }
+    st.neg ^= has && src != pi;
+    if (r == J % G) st.prof |= (uint64_t)(has ? src : SW_SKIP) << (6 * (J / G));
+    if (!__any_sync(FULL, has)) return;   // no group of this warp has a pivot in column J
+    const int pl = gbase + (has ? pi : 0);
+    const uint32_t piv = __shfl_sync(FULL, row[J], pl);
+    const uint32_t f = row[J];
+    const bool isp = r == pi;
+    const uint32_t x = has ? (isp ? st.S : piv) : P.one;
+    const uint32_t y = (has && !isp && f) ? p - f : 0u;
+    // While no column has been skipped (pi == J in every group of the warp) the columns left of J are
+    // finished pivot columns: they are not maintained any more (their final values are known: d on
+    // the pivot row, 0 elsewhere) and only columns > J are updated.
+    if (__all_sync(FULL, !live || (has && pi == J))) {
+#pragma unroll
+        for (int c = J + 1; c < NC; ++c) {
+            const uint32_t pc = __shfl_sync(FULL, row[c], pl);
+            row[c] = mont_fma2(x, row[c], y, pc, p, pinv);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const uint32_t pc = __shfl_sync(FULL, row[c], pl);
+            row[c] = mont_fma2(x, row[c], y, pc, p, pinv);
+        }
+    }
+    if (has) {
+        st.Q = mont_mul(st.Q, st.S, p, pinv);
+        st.S = mont_mul(st.S, piv, p, pinv);
+        st.X = mont_mul(st.X, P.r2, p, pinv);
+        ++st.pi;
+    }
+}
+
+template <int G, int NC, int... Js>
+__device__ __forceinline__ void sw_steps(uint32_t (&row)[NC], SwState& st, const PrimeRec& P, int r, int gbase, unsigned gmask,
+                                         int m, int bar, bool live, std::integer_sequence<int, Js...>) {
+    (sw_step<G, NC, Js>(row, st, P, r, gbase, gmask, m, bar, live), ...);
+}
+
+template <int G, int NC>
+__global__ void __launch_bounds__(SW_THREADS) k_subwarp(const SwArgs a) {
+    extern __shared__ uint32_t sm[];          // res[K][NC][SW_THREADS] then dres[K][SW_THREADS]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int r = lane % G;                   // my row
+    const int gbase = lane - r;               // first lane of my group
+    const unsigned gmask = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+    constexpr unsigned FULL = 0xffffffffu;
+    const int m = a.m, n = a.n, bar = a.bar, K = a.K, L = a.L;
+    const int64_t mat = ((int64_t)blockIdx.x * SW_THREADS + tid) / G;
+    const bool live = mat < a.batch;          // whole groups are live or not
+    const bool rowlive = live && r < m;
+    // shared memory: res[K][NC][T] raw words, then per prime Gw / G2w / d / meta [K][4][T] (slot of the
+    // group's first lane), then the prime records [K] and the Garner inverses [K][K]
+    uint32_t* scal = sm + (size_t)K * NC * SW_THREADS;
+    PrimeRec* s_primes = reinterpret_cast<PrimeRec*>(scal + (size_t)K * 4 * SW_THREADS);
+    uint32_t* s_garner = reinterpret_cast<uint32_t*>(s_primes + K);
+    for (int i = tid; i < K; i += SW_THREADS) s_primes[i] = a.primes[i];
+    for (int i = tid; i < K * K; i += SW_THREADS) s_garner[i] = a.garner[(i / K) * LSX_GARNER_DIM + (i % K)];
+    __syncthreads();
+
+    // ---- load my row (kept as integers for every prime) ----
+    int32_t in[NC];
+    bool bad = false;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        int32_t v = 0;
+        if (rowlive && c < n) {
+            int lim;
+            if (c < a.n_in) {
+                v = a.A[(mat * m + r) * a.n_in + c];
+                lim = c < bar ? a.a_abs_max : a.b_abs_max;
+            } else if (a.right_identity) {
+                v = (c - a.n_in == r) ? 1 : 0;
+                lim = 1;
+            } else {
+                v = a.bvec[mat * m + r];
+                lim = a.b_abs_max;
+            }
+            bad |= v > lim || v < -lim;
+        }
+        in[c] = v;
+    }
+    bad = (__ballot_sync(FULL, bad) >> gbase & gmask) != 0;
+
+    uint64_t prof0 = 0;                       // my share of the first prime's profile
+    int rank0 = 0;
+    bool mismatch = false;
+
+    for (int k = 0; k < K; ++k) {
+        const PrimeRec P = s_primes[k];
+        const uint32_t p = P.p;
+        uint32_t row[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) row[c] = word_of_int(in[c], p);
+        uint32_t S = P.one, Q = P.one, X = 1u;
+        int pi = 0;
+        bool neg = false;
+        uint64_t prof = 0;
+        SwState st{S, Q, X, prof, pi, neg};
+        sw_steps<G, NC>(row, st, P, r, gbase, gmask, m, bar, live, std::make_integer_sequence<int, NC>{});
+        S = st.S;
+        Q = st.Q;
+        X = st.X;
+        prof = st.prof;
+        pi = st.pi;
+        neg = st.neg;
+        // ---- raw words to shared memory; the scaling factors follow after the prime loop ----
+#pragma unroll
+        for (int c = 0; c < NC; ++c) sm[((size_t)k * NC + c) * SW_THREADS + tid] = row[c];
+        if (r == 0) {
+            uint32_t* sc = scal + (size_t)k * 4 * SW_THREADS + tid;
+            sc[0] = Q;
+            sc[SW_THREADS] = X;
+            sc[2 * SW_THREADS] = S;
+            sc[3 * SW_THREADS] = (uint32_t)pi | (neg ? 256u : 0u);
+        }
+        if (k == 0) {
+            prof0 = prof;
+            rank0 = pi;
+        } else {
+            mismatch |= prof != prof0 || pi != rank0;
+        }
+    }
+    mismatch = ((__ballot_sync(FULL, mismatch) >> gbase) & gmask) != 0u;
+    __syncwarp();
+
+    // ---- one Fermat inversion per (matrix, prime), spread over the lanes of the group ----
+    const int gt0 = tid - r;                  // slot of the group's first lane
+    for (int k = r; k < K; k += G) {
+        const PrimeRec P = s_primes[k];
+        const uint32_t p = P.p, pinv = P.pinv;
+        uint32_t* sc = scal + (size_t)k * 4 * SW_THREADS + gt0;
+        const uint32_t Q = sc[0], X = sc[SW_THREADS], S = sc[2 * SW_THREADS], meta = sc[3 * SW_THREADS];
+        uint32_t Gw = mont_mul(mont_pow(Q, p - 2u, P.one, p, pinv), X, p, pinv);
+        if ((meta & 256u) && Gw) Gw = p - Gw;
+        sc[0] = Gw;                                         // factor of pivot rows:      N = Gw * W
+        sc[SW_THREADS] = mont_mul(Gw, P.r2, p, pinv);       // factor of non-pivot rows
+        sc[2 * SW_THREADS] = mont_mul(Gw, S, p, pinv);      // d = det of the pivot minor (plain residue)
+    }
+    __syncwarp();
+
+    // ---- pivot columns from the first prime's profile ----
+    unsigned pivmask = 0;                     // bit j: column j holds a pivot (bar <= 32)
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        if (j < bar) {
+            const uint64_t share = __shfl_sync(FULL, prof0, gbase + j % G);
+            if ((int)((share >> (6 * (j / G))) & 63u) != SW_SKIP) pivmask |= 1u << j;
+        }
+    }
+    const int rank = rank0;
+    if (!live) return;
+    int st = 0;
+    if (bad) st |= LSX_ST_BOUND;
+    if (a.max_rank > 0 && rank > a.max_rank) st |= LSX_ST_BOUND;
+    if (mismatch && !bad) {
+        // a bad prime: hand the matrix to the tile path (replacement primes)
+        if (r == 0) {
+            const int pos = atomicAdd(a.retry_count, 1);
+            if (pos < a.retry_cap) {
+                a.retry_list[pos] = (int32_t)mat;
+                atomicOr(&a.status[mat], LSX_ST_INTERNAL_RETRY);
+            } else {
+                atomicOr(&a.status[mat], LSX_ST_NO_GOOD_PRIME);
+            }
+        }
+        return;
+    }
+    if (r == 0) {
+        if (a.rank) a.rank[mat] = rank;
+        if (a.pivot_col) {
+            int cnt = 0;
+            for (int j = 0; j < bar; ++j)
+                if (pivmask >> j & 1u) a.pivot_col[mat * a.pivot_slots + cnt++] = j;
+            for (; cnt < a.pivot_slots; ++cnt) a.pivot_col[mat * a.pivot_slots + cnt] = -1;
+        }
+    }
+    if (st) {
+        if (r == 0) atomicOr(&a.status[mat], st);
+        return;
+    }
+    if (a.op == LSX_OP_RANK) return;
+
+    // ---- CRT + scatter: the entries of a matrix are dealt round-robin to the lanes of its group ----
+    const SwTables T{s_primes, s_garner};
+    const uint32_t* sc_piv = scal + gt0;                      // [k * 4T]: Gw
+    const uint32_t* sc_non = scal + SW_THREADS + gt0;         // G2w
+    const uint32_t* sc_d = scal + 2 * SW_THREADS + gt0;       // d
+    const int sstr = 4 * SW_THREADS, rstr = NC * SW_THREADS;
+    auto res_of = [&](int i, int c) { return sm + (size_t)c * SW_THREADS + gt0 + i; };
+    const bool singular = rank < m;
+    if (r == 0) {
+        const bool zero_det = (a.op == LSX_OP_INVERSE || a.op == LSX_OP_DET) && singular;
+        crt_entry_any(nullptr, 0, sc_d, sstr, K, L, T, a.den + mat * L, false, zero_det);
+        if (a.op == LSX_OP_INVERSE && singular) atomicOr(&a.status[mat], LSX_ST_SINGULAR);
+    }
+    if (a.op == LSX_OP_DET) return;
+    if (a.op == LSX_OP_RREF) {
+        const int E = m * n;
+        for (int e = r; e < E; e += G) {
+            const int i = e / n, c = e - i * n;
+            uint32_t* dst = a.num + ((mat * m + i) * (int64_t)n + c) * L;
+            if (c < bar && (pivmask >> c & 1u)) {
+                // finished pivot column: d on its pivot row, 0 elsewhere
+                const bool mine = i < rank && c == (int)__fns(pivmask, 0, i + 1);
+                crt_entry_any(nullptr, 0, sc_d, sstr, K, L, T, dst, false, !mine);
+            } else {
+                crt_entry_any(res_of(i, c), rstr, i < rank ? sc_piv : sc_non, sstr, K, L, T, dst, false, false);
+            }
+        }
+    } else if (a.op == LSX_OP_INVERSE) {
+        const int nn = a.n_in, E = m * nn;
+        for (int e = r; e < E; e += G) {
+            const int i = e / nn, c = e - i * nn;
+            crt_entry_any(res_of(i, nn + c), rstr, i < rank ? sc_piv : sc_non, sstr, K, L, T,
+                          a.num + ((mat * m + i) * (int64_t)nn + c) * L, false, singular);
+        }
+    } else {   // LSX_OP_SOLVE
+        const int nvars = n - 1;
+        if (r >= rank && r < m) {
+            // zero left row: inconsistent iff the rhs is non-zero (linalg.py:913-934); the scale is a unit
+            bool zero = true;
+            for (int k = 0; k < K; ++k) zero &= sm[((size_t)k * NC + nvars) * SW_THREADS + tid] == 0u;
+            if (!zero) atomicOr(&a.status[mat], LSX_ST_INCONSISTENT);
+        }
+        const unsigned freemask = ~pivmask & (nvars >= 32 ? 0xffffffffu : ((1u << nvars) - 1u));
+        const int nfree = nvars - rank;
+        const int per = nfree + 1, E = rank * per + nfree;
+        for (int e = r; e < E; e += G) {
+            if (e < rank * per) {
+                const int i = e / per, q = e - i * per;
+                const int pcol = (int)__fns(pivmask, 0, i + 1);
+                if (q == nfree) {
+                    crt_entry_any(res_of(i, nvars), rstr, sc_piv, sstr, K, L, T, a.particular + (mat * nvars + pcol) * L,
+                                  false, false);
+                } else if (q < a.gen_cap) {
+                    const int fc = (int)__fns(freemask, 0, q + 1);
+                    crt_entry_any(res_of(i, fc), rstr, sc_piv, sstr, K, L, T,
+                                  a.generators + ((mat * nvars + pcol) * (int64_t)a.gen_cap + q) * L, true, false);
+                }
+            } else {
+                // generator entries equal to d at the free columns (gen[f] = 1, linalg.py:976)
+                const int q = e - rank * per;
+                if (q < a.gen_cap) {
+                    const int fc = (int)__fns(freemask, 0, q + 1);
+                    crt_entry_any(nullptr, 0, sc_d, sstr, K, L, T,
+                                  a.generators + ((mat * nvars + fc) * (int64_t)a.gen_cap + q) * L, false, false);
+                }
+            }
+        }
+        if (r == 0 && nfree > a.gen_cap) atomicOr(&a.status[mat], LSX_ST_GEN_TRUNC);
+    }
+}
+
+size_t sw_smem_bytes(int K, int NC) {
+    return ((size_t)K * NC + (size_t)K * 4) * SW_THREADS * 4 + (size_t)K * sizeof(PrimeRec) + (size_t)K * K * 4;
+}
+
+template <int G, int NC>
+int launch_sw(lsx_ctx* ctx, const SwArgs& a) {
+    const size_t smem = sw_smem_bytes(a.K, NC);
+    if (smem > 48 * 1024)
+        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_subwarp<G, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t threads = a.batch * G;
+    const unsigned grid = (unsigned)((threads + SW_THREADS - 1) / SW_THREADS);
+    lsx_timing_begin(ctx);
+    k_subwarp<G, NC><<<grid, SW_THREADS, smem, ctx->stream>>>(a);
+    lsx_timing_end(ctx);
+    ctx->launches++;
+    LSX_CUDA_TRY(ctx, cudaGetLastError());
+    return LSX_OK;
+}
+
+// Instantiated shapes: G lanes per matrix, NC register columns (n is padded up to NC with zero columns).
+struct SwShape { int G, NC; };
+constexpr SwShape kShapes[] = {{4, 4}, {4, 5}, {4, 8}, {4, 9}, {8, 9}, {8, 12}, {8, 17}, {16, 17}, {16, 24}, {16, 33}, {32, 33}};
+
+bool pick_shape(int m, int n, SwShape* out) {
+    for (const SwShape& s : kShapes)
+        if (m <= s.G && n <= s.NC) {
+            *out = s;
+            return true;
+        }
+    return false;
+}
+
+int launch_shape(lsx_ctx* ctx, const SwArgs& a, SwShape s) {
+    switch (s.G * 100 + s.NC) {
+        case 404: return launch_sw<4, 4>(ctx, a);
+        case 405: return launch_sw<4, 5>(ctx, a);
+        case 408: return launch_sw<4, 8>(ctx, a);
+        case 409: return launch_sw<4, 9>(ctx, a);
+        case 809: return launch_sw<8, 9>(ctx, a);
+        case 812: return launch_sw<8, 12>(ctx, a);
+        case 817: return launch_sw<8, 17>(ctx, a);
+        case 1617: return launch_sw<16, 17>(ctx, a);
+        case 1624: return launch_sw<16, 24>(ctx, a);
+        case 1633: return launch_sw<16, 33>(ctx, a);
+        default: return launch_sw<32, 33>(ctx, a);
+    }
+}
+
+}  // namespace
+
+// *handled = 1 when the shape/plan is covered; bad-prime matrices are then recomputed by the tile path.
+int lsx_run_subwarp(lsx_ctx* ctx, const ElimJob& job, int* handled) {
+    *handled = 0;
+    if (getenv("LSX_DISABLE_SUBWARP")) return LSX_OK;
+    if (job.m > 32 || job.n > 33 || job.bar > 32 || job.K > 8 || job.L > 8) return LSX_OK;
+    if (job.a_abs_max >= (1 << 30) || job.b_abs_max >= (1 << 30)) return LSX_OK;
+    SwShape shape;
+    if (!pick_shape(job.m, job.n, &shape)) return LSX_OK;
+    const int NC = shape.NC;
+    if (sw_smem_bytes(job.K, NC) > 160 * 1024) return LSX_OK;
+
+    // scratch: retry list + counter, then room for the tile path's retry pass
+    const size_t o_list = 0, o_count = (size_t)LSX_RETRY_CAP * 4, o_child = o_count + 256;
+    int rc = lsx_ws_reserve(ctx, o_child + lsx_generic_ws_bytes(job, 1) + 4096);
+    if (rc != LSX_OK) return rc;
+    char* base = (char*)ctx->d_ws;
+    int32_t* rlist = (int32_t*)(base + o_list);
+    int32_t* rcount = (int32_t*)(base + o_count);
+    LSX_CUDA_TRY(ctx, cudaMemsetAsync(rcount, 0, 4, ctx->stream));
+    if (job.op == LSX_OP_SOLVE) {
+        const int nvars = job.n - 1;
+        LSX_CUDA_TRY(ctx, cudaMemsetAsync(job.particular, 0, (size_t)job.batch * nvars * job.L * 4, ctx->stream));
+        if (job.generators && job.gen_cap > 0)
+            LSX_CUDA_TRY(ctx, cudaMemsetAsync(job.generators, 0, (size_t)job.batch * nvars * job.gen_cap * job.L * 4,
+                                              ctx->stream));
+    }
+    SwArgs a{};
+    a.A = job.A;
+    a.bvec = job.bvec;
+    a.batch = job.batch;
+    a.m = job.m;
+    a.n_in = job.n_in;
+    a.n = job.n;
+    a.bar = job.bar;
+    a.right_identity = job.right_identity;
+    a.op = job.op;
+    a.K = job.K;
+    a.L = job.L;
+    a.gen_cap = job.gen_cap;
+    a.pivot_slots = job.m < job.bar ? job.m : job.bar;
+    a.max_rank = job.max_rank;
+    a.a_abs_max = (int)job.a_abs_max;
+    a.b_abs_max = (int)job.b_abs_max;
+    a.primes = ctx->d_primes;
+    a.garner = ctx->d_garner;
+    a.num = job.num;
+    a.den = job.den;
+    a.particular = job.particular;
+    a.generators = job.generators;
+    a.pivot_col = job.pivot_col;
+    a.rank = job.rank;
+    a.status = job.status;
+    a.retry_list = rlist;
+    a.retry_count = rcount;
+    a.retry_cap = LSX_RETRY_CAP;
+    rc = launch_shape(ctx, a, shape);
+    if (rc != LSX_OK) return rc;
+    // bad-prime matrices (normally none): tile path in list mode, scratch behind the list
+    rc = lsx_run_generic(ctx, job, rlist, rcount, LSX_RETRY_CAP, o_child);
+    if (rc != LSX_OK) return rc;
+    *handled = 1;
+    return LSX_OK;
+}

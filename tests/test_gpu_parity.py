@@ -401,3 +401,51 @@ def test_c5_standin_256_blocked_and_sharded_crt(eng):
     words, K = lsx_dist.det_large_sharded(eng, A, 5)
     assert limbs_to_ints(words) == int(c["det"])
     assert K == eng.det_large_prime_count(256, 5)[0]
+
+
+def test_subwarp_kernel_equals_tile_path(eng, monkeypatch):
+    """Fused sub-warp kernel (row per lane, all primes + CRT in one launch) against the tile path, word
+    for word, over every lane-group size, ragged shapes, rank-deficient inputs and all operations."""
+    import random
+    rnd = random.Random(23)
+    rng = np.random.Generator(np.random.PCG64(23))
+    shapes = [(1, 1), (2, 3), (4, 4), (4, 5), (3, 9), (5, 5), (8, 9), (7, 12), (8, 16), (9, 9), (16, 17), (13, 20),
+              (16, 32), (17, 17), (32, 33), (20, 7)]
+    for m, n in shapes:
+        B = 67
+        rk = rng.integers(0, min(m, n) + 1, size=B)
+        mats = np.zeros((B, m, n), dtype=np.int32)
+        for i in range(B):
+            L_ = rng.integers(-3, 4, size=(m, rk[i]))
+            R_ = rng.integers(-3, 4, size=(rk[i], n))
+            mats[i] = L_ @ R_
+        mats[::5] = rng.integers(-9, 10, size=mats[::5].shape)
+        bar = rnd.randint(1, min(n, 32))
+        def both(f):
+            x = f()
+            monkeypatch.setenv("LSX_DISABLE_SUBWARP", "1")
+            y = f()
+            monkeypatch.delenv("LSX_DISABLE_SUBWARP")
+            return x, y
+        x, y = both(lambda: eng.rref_batch(mats, bar))
+        assert np.array_equal(x.status & ~32, y.status & ~32), (m, n, bar)
+        for f in ("num", "den", "pivot_col", "rank"):
+            assert np.array_equal(getattr(x, f), getattr(y, f)), (m, n, bar, f)
+        if n <= 32:
+            x, y = both(lambda: eng.rank_batch(mats))
+            assert np.array_equal(x.rank, y.rank)
+            b = rng.integers(-9, 10, size=(B, m), dtype=np.int32)
+            b[::2] = np.einsum("bij,bj->bi", mats[::2], rng.integers(-2, 3, size=(len(mats[::2]), n)))
+            x, y = both(lambda: eng.solve_batch(mats, b))
+            assert np.array_equal(x.status & ~32, y.status & ~32)
+            ok = (x.status & 2) == 0
+            for f in ("den", "particular", "generators", "pivot_col", "rank"):
+                assert np.array_equal(getattr(x, f)[ok], getattr(y, f)[ok]), (m, n, f)
+        if m == n:
+            x, y = both(lambda: eng.det_batch(mats))
+            assert np.array_equal(x.det, y.det) and np.array_equal(x.rank, y.rank)
+            if n <= 16:
+                big = mats * 1000 + 1                        # magnitudes beyond the single-prime kernel
+                x, y = both(lambda: eng.inverse_batch(big))
+                assert np.array_equal(x.status & ~32, y.status & ~32)
+                assert np.array_equal(x.adj, y.adj) and np.array_equal(x.det, y.det)
