@@ -160,6 +160,207 @@ __global__ void __launch_bounds__(T) k_tile_elim(const TileArgs a) {
     }
 }
 
+// ---- register-tiled variant: the residue tile lives in REGISTERS, shared memory only carries the
+// pivot column, the pivot row and the row order ------------------------------------------------------
+// 256 threads as a 16 x 16 grid; thread (ty, tx) owns the cells (ty + 16 a, tx + 16 b), a < RA, b < CB
+// (m <= 16 RA, n <= 16 CB).  Rows never move physically: the row order is a permutation in shared
+// memory (perm[logical position] = physical row), so the reference's "swap rows" (linalg.py:548-567)
+// costs two bytes.  Per pivot step every cell needs one two-product update from registers, CB pivot-row
+// words and RA pivot-column words from shared memory -- the smem traffic of k_tile_elim (3 accesses
+// per cell and step) is gone.  While no column has been skipped, 16-column blocks that lie completely
+// left of the pivot column are finished pivot columns and are not updated any more.
+template <int RA, int CB>
+__global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const TileArgs a) {
+    __shared__ uint32_t prow[16 * CB];
+    __shared__ uint32_t colbuf[16 * RA];
+    __shared__ uint8_t perm[16 * RA];
+    __shared__ uint8_t inv[16 * RA];
+    const int m = a.m, n = a.n, bar = a.bar;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
+    const int kslot = blockIdx.y;
+    const PrimeRec P = a.primes[kslot];
+    const uint32_t p = P.p, pinv = P.pinv;
+    const int64_t nslots = a.list ? min((int64_t)*a.list_count, a.cap) : a.batch;
+    const int ncs = a.c1 - a.c0;
+
+    for (int64_t slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+        const int64_t mat = a.list ? (int64_t)a.list[slot] : slot;
+        uint32_t W[RA][CB];
+        bool bad = false;
+#pragma unroll
+        for (int ia = 0; ia < RA; ++ia) {
+            const int r = ty + 16 * ia;
+#pragma unroll
+            for (int ib = 0; ib < CB; ++ib) {
+                const int c = tx + 16 * ib;
+                int32_t v = 0;
+                if (r < m && c < n) {
+                    int64_t lim;
+                    if (c < a.n_in) {
+                        v = a.A[(mat * m + r) * a.n_in + c];
+                        lim = c < bar ? a.a_abs_max : a.b_abs_max;
+                    } else if (a.right_identity) {
+                        v = (c - a.n_in == r) ? 1 : 0;
+                        lim = 1;
+                    } else {
+                        v = a.bvec[mat * m + r];
+                        lim = a.b_abs_max;
+                    }
+                    const int64_t av = v < 0 ? -(int64_t)v : (int64_t)v;
+                    bad |= av > lim;
+                }
+                W[ia][ib] = word_of_int_any(v, p);
+            }
+        }
+        if (bad) atomicOr(&a.status[mat], LSX_ST_BOUND);
+        if (tid < 16 * RA) perm[tid] = (uint8_t)tid;
+        __syncthreads();
+
+        uint32_t S = P.one, Q = P.one, X = 1u;
+        int pi = 0;
+        bool neg = false, tri = true;          // tri: no column skipped so far (pi == j)
+        uint8_t* prof = a.prof + ((int64_t)kslot * a.cap + slot) * bar;
+        for (int j = 0; j < bar; ++j) {
+            if (pi >= m) {
+                if (tid == 0) prof[j] = LSX_PROF_SKIP;
+                continue;
+            }
+            // 1. publish column j (indexed by physical row)
+            if (tx == (j & 15)) {
+                switch (j >> 4) {              // uniform: no select chain over the register tile
+#define LSX_PUB_COL(B)                                                        \
+    case B:                                                                    \
+        if (B < CB) {                                                          \
+            _Pragma("unroll") for (int ia = 0; ia < RA; ++ia) colbuf[ty + 16 * ia] = W[ia][B < CB ? B : 0]; \
+        }                                                                      \
+        break;
+                    LSX_PUB_COL(0) LSX_PUB_COL(1) LSX_PUB_COL(2) LSX_PUB_COL(3)
+                    LSX_PUB_COL(4) LSX_PUB_COL(5) LSX_PUB_COL(6) LSX_PUB_COL(7)
+#undef LSX_PUB_COL
+                    default: break;
+                }
+            }
+            __syncthreads();
+            // 2. pivot search over logical positions pi .. m-1: the first non-zero.  Every warp does it
+            //    for itself (a few instructions), which saves a barrier; thread 0 records the result.
+            int src = -1;
+            for (int base = pi; base < m; base += 32) {
+                const int q = base + lane;
+                const bool nz = q < m && colbuf[perm[q]] != 0u;
+                const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                if (bal) {
+                    src = base + __ffs(bal) - 1;
+                    break;
+                }
+            }
+            if (tid == 0) prof[j] = src >= 0 ? (uint8_t)src : (uint8_t)LSX_PROF_SKIP;
+            if (src < 0) {
+                tri = false;
+                __syncthreads();               // colbuf is rewritten by the next column
+                continue;
+            }
+            neg ^= src != pi;
+            const int prp = perm[src];         // physical row of the pivot (perm is swapped after the barrier)
+            // 3. publish the pivot row
+            if (ty == (prp & 15)) {
+                switch (prp >> 4) {
+#define LSX_PUB_ROW(Aidx)                                                     \
+    case Aidx:                                                                 \
+        if (Aidx < RA) {                                                       \
+            _Pragma("unroll") for (int ib = 0; ib < CB; ++ib) prow[tx + 16 * ib] = W[Aidx < RA ? Aidx : 0][ib]; \
+        }                                                                      \
+        break;
+                    LSX_PUB_ROW(0) LSX_PUB_ROW(1) LSX_PUB_ROW(2) LSX_PUB_ROW(3)
+                    LSX_PUB_ROW(4) LSX_PUB_ROW(5) LSX_PUB_ROW(6) LSX_PUB_ROW(7)
+#undef LSX_PUB_ROW
+                    default: break;
+                }
+            }
+            const uint32_t piv = colbuf[prp];
+            uint32_t xs[RA], ys[RA];
+#pragma unroll
+            for (int ia = 0; ia < RA; ++ia) {
+                const int r = ty + 16 * ia;
+                const uint32_t f = colbuf[r];
+                const bool isp = r == prp;
+                xs[ia] = isp ? S : piv;
+                ys[ia] = (isp || f == 0u) ? 0u : p - f;
+            }
+            __syncthreads();
+            // 4. update (register resident)
+            const int b0 = tri ? ((j + 1) >> 4) : 0;        // blocks left of the pivot column are finished
+#pragma unroll
+            for (int ib = 0; ib < CB; ++ib) {
+                if (ib >= b0) {
+                    const uint32_t pc = prow[tx + 16 * ib];
+#pragma unroll
+                    for (int ia = 0; ia < RA; ++ia) W[ia][ib] = mont_fma2(xs[ia], W[ia][ib], ys[ia], pc, p, pinv);
+                }
+            }
+            Q = mont_mul(Q, S, p, pinv);
+            S = mont_mul(S, piv, p, pinv);
+            X = mont_mul(X, P.r2, p, pinv);
+            if (tid == 0 && src != pi) {       // every warp has read perm[src] before the barrier above
+                const uint8_t t0 = perm[pi];
+                perm[pi] = perm[src];
+                perm[src] = t0;
+            }
+            ++pi;
+            __syncthreads();                   // prow / colbuf / perm are rewritten by the next column
+        }
+        // ---- one inversion, scale to N = d * RREF (plain residues), rows in logical order ----
+        if (tid < m) inv[perm[tid]] = (uint8_t)tid;
+        __syncthreads();
+        const uint32_t qinv = mont_pow(Q, p - 2u, P.one, p, pinv);
+        uint32_t Gw = mont_mul(qinv, X, p, pinv);
+        if (neg && Gw) Gw = p - Gw;
+        const uint32_t G2w = mont_mul(Gw, P.r2, p, pinv);
+        if (ncs > 0) {
+            uint32_t* out = a.res + ((int64_t)kslot * a.cap + slot) * ((int64_t)m * ncs);
+#pragma unroll
+            for (int ia = 0; ia < RA; ++ia) {
+                const int r = ty + 16 * ia;
+                if (r < m) {
+                    const int q = inv[r];
+                    const uint32_t g = q < pi ? Gw : G2w;
+#pragma unroll
+                    for (int ib = 0; ib < CB; ++ib) {
+                        const int c = tx + 16 * ib;
+                        if (c >= a.c0 && c < a.c1) out[q * ncs + (c - a.c0)] = mont_mul(g, W[ia][ib], p, pinv);
+                    }
+                }
+            }
+        }
+        if (tid == 0) {
+            a.dres[(int64_t)kslot * a.cap + slot] = mont_mul(Gw, S, p, pinv);
+            a.rankk[(int64_t)kslot * a.cap + slot] = pi;
+        }
+        __syncthreads();
+    }
+}
+
+template <int RA, int CB>
+int launch_tile_reg(lsx_ctx* ctx, const TileArgs& ta, int Ktot, int64_t grid_x) {
+    dim3 grid((unsigned)grid_x, (unsigned)Ktot);
+    lsx_timing_begin(ctx);
+    k_tile_reg<RA, CB><<<grid, 256, 0, ctx->stream>>>(ta);
+    lsx_timing_end(ctx);
+    ctx->launches++;
+    return LSX_OK;
+}
+
+// Picks a register-tiled instantiation for the shape, or returns false (fall back to k_tile_elim).
+bool launch_tile_reg_any(lsx_ctx* ctx, const TileArgs& ta, int Ktot, int64_t grid_x, int* rc) {
+    if (getenv("LSX_DISABLE_TILE_REG")) return false;
+    const int m = ta.m, n = ta.n;
+    if (m > 128 || n > 128 || m * n < 256) return false;
+    if (m <= 32 && n <= 48) *rc = launch_tile_reg<2, 3>(ctx, ta, Ktot, grid_x);
+    else if (m <= 64 && n <= 80) *rc = launch_tile_reg<4, 5>(ctx, ta, Ktot, grid_x);
+    else if (m <= 64 && n <= 128) *rc = launch_tile_reg<4, 8>(ctx, ta, Ktot, grid_x);
+    else *rc = launch_tile_reg<8, 8>(ctx, ta, Ktot, grid_x);
+    return true;
+}
+
 // ---- verification: pick the primes that agree with the lexicographically smallest profile ----
 struct VerifyArgs {
     const int32_t* list;
@@ -334,9 +535,28 @@ __global__ void __launch_bounds__(128) k_assemble(const AsmArgs a) {
     const int i = (int)(e / a.ncs);
     const int j = a.c0 + (int)(e - (int64_t)i * a.ncs);
     switch (a.op) {
-        case LSX_OP_RREF:
-            store_limbs<KT>(a.num + (mat * E + e) * L, acc, L, false, false);
+        case LSX_OP_RREF: {
+            // pivot columns are not maintained by every elimination kernel: their values are known
+            // (d on the pivot row, 0 elsewhere)
+            const int32_t* piv = a.piv_ws + slot * a.pivot_slots;
+            bool is_pivot_col = false, mine = false;
+            for (int k = 0; k < rank; ++k)
+                if (piv[k] == j) {
+                    is_pivot_col = true;
+                    mine = k == i;
+                }
+            if (is_pivot_col) {
+                uint32_t rd[KT], accd[KT];
+                bool zd;
+#pragma unroll
+                for (int k = 0; k < KT; ++k) rd[k] = k < K ? a.dres[(int64_t)sel[k] * a.cap + slot] : 0u;
+                crt_limbs<KT>(rd, sel, K, a.primes, a.garner, accd, &zd);
+                store_limbs<KT>(a.num + (mat * E + e) * L, accd, L, false, !mine);
+            } else {
+                store_limbs<KT>(a.num + (mat * E + e) * L, acc, L, false, false);
+            }
             break;
+        }
         case LSX_OP_INVERSE:
             store_limbs<KT>(a.num + (mat * E + e) * L, acc, L, false, rank < m);
             break;
@@ -502,7 +722,8 @@ int lsx_run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const
     if (gx > max_gx) gx = max_gx;
     const int cells = m * n;
     int rc;
-    if (cells <= 128)
+    if (launch_tile_reg_any(ctx, ta, Ktot, gx, &rc)) {
+    } else if (cells <= 128)
         rc = launch_tile<32>(ctx, ta, Ktot, gx, smem);
     else if (cells <= 1024)
         rc = launch_tile<64>(ctx, ta, Ktot, gx, smem);

@@ -449,3 +449,50 @@ def test_subwarp_kernel_equals_tile_path(eng, monkeypatch):
                 x, y = both(lambda: eng.inverse_batch(big))
                 assert np.array_equal(x.status & ~32, y.status & ~32)
                 assert np.array_equal(x.adj, y.adj) and np.array_equal(x.det, y.det)
+
+
+def test_register_tiled_kernel_equals_smem_kernel(eng, monkeypatch):
+    """k_tile_reg (tile in registers, logical row permutation, finished column blocks skipped) against
+    k_tile_elim, word for word, on mid-size shapes with rank-deficient inputs and forced row swaps."""
+    rng = np.random.Generator(np.random.PCG64(41))
+    def both(f):
+        x = f()
+        monkeypatch.setenv("LSX_DISABLE_TILE_REG", "1")
+        y = f()
+        monkeypatch.delenv("LSX_DISABLE_TILE_REG")
+        return x, y
+    for m, n, bar in [(34, 34, 34), (40, 41, 40), (33, 70, 33), (64, 64, 64), (64, 65, 64), (50, 100, 50),
+                      (64, 128, 64), (100, 90, 60), (80, 80, 80), (20, 40, 15)]:
+        B = 9
+        mats = np.zeros((B, m, n), dtype=np.int32)
+        for i in range(B):
+            rk = int(rng.integers(max(1, min(m, n) - 20), min(m, n) + 1))
+            mats[i] = rng.integers(-2, 3, size=(m, rk)) @ rng.integers(-2, 3, size=(rk, n))
+        mats[0] = rng.integers(-5, 6, size=(m, n))
+        mats[1] = rng.integers(-5, 6, size=(m, n))
+        mats[1, 0, 0] = 0
+        mats[1, 1, :2] = 0                                   # swaps in the first columns
+        x, y = both(lambda: eng.rref_batch(mats, bar))
+        assert np.array_equal(x.status, y.status), (m, n)
+        for f in ("num", "den", "pivot_col", "rank"):
+            assert np.array_equal(getattr(x, f), getattr(y, f)), (m, n, bar, f)
+        x, y = both(lambda: eng.rank_batch(mats))
+        assert np.array_equal(x.rank, y.rank)
+        if m == n:
+            x, y = both(lambda: eng.det_batch(mats))
+            assert np.array_equal(x.det, y.det)
+            if n <= 64:
+                x, y = both(lambda: eng.inverse_batch(mats))
+                assert np.array_equal(x.status, y.status)
+                assert np.array_equal(x.adj, y.adj) and np.array_equal(x.det, y.det)
+        if bar == n or True:
+            b = rng.integers(-5, 6, size=(B, m), dtype=np.int32)
+            b[::2] = np.einsum("bij,bj->bi", mats[::2], rng.integers(-2, 3, size=(len(mats[::2]), n)))
+            x, y = both(lambda: eng.solve_batch(mats, b))
+            assert np.array_equal(x.status, y.status)
+            ok = (x.status & 2) == 0
+            for f in ("den", "particular", "generators", "pivot_col", "rank"):
+                assert np.array_equal(getattr(x, f)[ok], getattr(y, f)[ok]), (m, n, f)
+    # an exact check against the oracle on one rank-deficient mid-size input
+    A = (rng.integers(-2, 3, size=(36, 30)) @ rng.integers(-2, 3, size=(30, 40))).astype(np.int32)
+    check_rref_against_oracle(eng, [A.tolist()], 38)
