@@ -30,32 +30,62 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # name: (description, n, batch per GPU, algorithmic bytes per matrix)
+    "c1": ("10k x 4x4 determinant + rank + row_reduce (default bar_col=3), entries uniform [-5,5]", 4, 10000, 152),
     "c2": ("2^20 x 8x8 det + inverse via [A|I] row_reduce(bar_col=8), entries uniform [-5,5]", 8, 1 << 20, 556),
-    "c4inv": ("2^12 x 64x64 inverse via [A|I] row_reduce(bar_col=64), entries uniform [-5,5]", 64, 1 << 12, 196912),
+    "c3": ("2^18 x find_preimage_of on 16x17 [A|b], A = B(16x10) C(10x16) rank 10, entries of B, C uniform [-5,5]",
+           16, 1 << 18, 2964),
+    "c4inv": ("2^12 (of 2^16) x 64x64 inverse via [A|I] row_reduce(bar_col=64), entries uniform [-5,5]", 64, 1 << 12,
+              196912),
 }
 SEED = 20260002
+METRIC = {"c1": "exact det+rank+RREF matrices/sec", "c2": "exact det+inverse matrices/sec",
+          "c3": "exact find_preimage_of systems/sec", "c4inv": "exact inverse matrices/sec"}
 
 
-def make_inputs(n, batch, seed):
+def make_inputs(n, batch, seed, workload="c2"):
+    """-> dict of int32 arrays for one rank's batch."""
     import numpy as np
     rng = np.random.Generator(np.random.PCG64(seed))
-    return rng.integers(-5, 6, size=(batch, n, n), dtype=np.int32)
+    if workload == "c3":
+        Bm = rng.integers(-5, 6, size=(batch, 16, 10), dtype=np.int64)
+        Cm = rng.integers(-5, 6, size=(batch, 10, 16), dtype=np.int64)
+        A = np.einsum("bik,bkj->bij", Bm, Cm)
+        x0 = rng.integers(-5, 6, size=(batch, 16), dtype=np.int64)
+        b = np.einsum("bij,bj->bi", A, x0)
+        b[1::2] = rng.integers(-5, 6, size=b[1::2].shape)          # odd systems: random rhs (inconsistent w.h.p.)
+        return {"A": A.astype(np.int32), "b": b.astype(np.int32)}
+    return {"A": rng.integers(-5, 6, size=(batch, n, n), dtype=np.int32)}
 
 
 # ------------------------------------------------------------------------------------- CPU arm
-def _cpu_one(a):
+def _cpu_one(item):
+    """One unit of the workload through the oracle port (same calls the reference would make)."""
     from oracle import ref_port
+    wl, a, b = item
+    if wl == "c1":
+        d = ref_port.determinant(a)
+        return d.numerator, ref_port.rank(a), ref_port.row_reduce(a)[1]
+    if wl == "c3":
+        res = ref_port.find_preimage_of(a, b)
+        return None if res is None else res[0][0].numerator
     inv = ref_port.inverse(a)
-    det = ref_port.determinant(a)
-    return det.numerator, (None if inv is None else inv[0][0].numerator)
+    det = ref_port.determinant(a) if wl == "c2" else None
+    return (det.numerator if det is not None else None), (None if inv is None else inv[0][0].numerator)
 
 
-def cpu_baseline(n, per_core, seed):
-    """The oracle port (oracle/ref_port.py: Fraction Gauss-Jordan of reference linalg.py:534-630 on
-    [A|I] + determinant) on a bounded sample of the workload, all host cores."""
+CPU_PER_CORE = {"c1": 4096, "c2": 2048, "c3": 64, "c4inv": 1}
+
+
+def cpu_baseline(workload, per_core, seed):
+    """The oracle port (oracle/ref_port.py: Fraction Gauss-Jordan of reference linalg.py:534-630 and the
+    calls on it) on a bounded sample of the workload, all host cores."""
     from multiprocessing import get_context
+    desc, n, _, _ = WORKLOADS[workload]
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    sample = make_inputs(n, cores * per_core, seed).tolist()
+    data = make_inputs(n, cores * per_core, seed, workload)
+    A = data["A"].tolist()
+    b = data["b"].tolist() if "b" in data else [None] * len(A)
+    sample = [(workload, A[i], b[i]) for i in range(len(A))]
     ctx = get_context("fork")
     with ctx.Pool(cores) as pool:
         pool.map(_cpu_one, sample[:cores], chunksize=1)          # start the workers
@@ -63,8 +93,8 @@ def cpu_baseline(n, per_core, seed):
         out = pool.map(_cpu_one, sample, chunksize=max(1, per_core // 8))
         dt = time.perf_counter() - t0
     return {"value": len(sample) / dt, "unit": "matrices/s", "cores": cores, "kind": "port",
-            "sample": "%d of the workload's %dx%d matrices (seed %d), det + inverse each, oracle/ref_port.py, "
-                      "multiprocessing over %d cores, %.1f s" % (len(sample), n, n, seed, cores, dt)}, out
+            "sample": "%d units of the workload (%s; seed %d) through oracle/ref_port.py, multiprocessing over "
+                      "%d cores, %.1f s" % (len(sample), workload, seed, cores, dt)}, out
 
 
 def run_reference_arm(args):
@@ -72,17 +102,17 @@ def run_reference_arm(args):
     if rank != 0:
         return
     desc, n, batch, _ = WORKLOADS[args.workload]
-    per_core = {8: 2048, 64: 1}[n]
+    per_core = CPU_PER_CORE[args.workload]
     times = []
     cb = None
     for i in range(args.warmup + args.steps):
-        cb, _ = cpu_baseline(n, per_core, SEED + i)
+        cb, _ = cpu_baseline(args.workload, per_core, SEED + i)
         if i >= args.warmup:
             times.append(cb["value"])
     val = statistics.mean(times)
     cb["value"] = val
     line = {
-        "impl": "reference", "metric": "exact det+inverse matrices/sec", "value": val, "unit": "matrices/s",
+        "impl": "reference", "metric": METRIC[args.workload], "value": val, "unit": "matrices/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * per_core * cb["cores"] / val, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "exact rationals (fractions.Fraction)", "data": "synthetic",
@@ -142,9 +172,103 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------- GPU arm
-def run_ours(args):
-    import numpy as np
+class Job:
+    """One workload bound to an engine: device-resident step, host-buffer (end-to-end) step, oracle check."""
 
+    def __init__(self, eng, workload, rank, dev):
+        import numpy as np
+        import torch
+        self.eng, self.wl, self.np, self.torch = eng, workload, np, torch
+        desc, n, batch, _ = WORKLOADS[workload]
+        self.n, self.batch = n, batch
+        # by-matrix sharding: every rank owns an independent batch (its own seed), no collective on the data path
+        data = make_inputs(n, batch, SEED + 1000 * rank, workload)
+        self.host = {k: torch.from_numpy(v).pin_memory() for k, v in data.items()}
+        self.dev = {k: v.to(dev) for k, v in self.host.items()}
+        if workload == "c1":
+            self.plans = (eng.plan_det(4, 5), eng.plan_rank(4, 4, 5), eng.plan_rref(4, 4, 3, 5, 5))
+        elif workload == "c3":
+            bmax = int(data["b"].max()), int(-data["b"].min())
+            self.plans = (eng.plan_solve(16, 16, 250, max(bmax), 10, 6),)
+        else:
+            self.plans = (eng.plan_inverse(n, 5),)
+        self.res = self.run(self.dev)                         # allocates the outputs; reused by every step
+        self.host_out = None
+
+    def run(self, src, out=None):
+        e, A = self.eng, src["A"]
+        if self.wl == "c1":
+            o = out or (None, None, None)
+            return (e.det_batch(A, plan=self.plans[0], out=o[0]), e.rank_batch(A, plan=self.plans[1], out=o[1]),
+                    e.rref_batch(A, 3, plan=self.plans[2], out=o[2]))
+        if self.wl == "c3":
+            return (e.solve_batch(A, src["b"], plan=self.plans[0], out=out[0] if out else None),)
+        return (e.inverse_batch(A, plan=self.plans[0], out=out[0] if out else None),)
+
+    def step_device(self):
+        self.run(self.dev, self.res)
+
+    def _fields(self, r):
+        return [(k, v) for k, v in vars(r).items() if k != "plan" and v is not None]
+
+    def make_host_outputs(self):
+        torch = self.torch
+        outs = []
+        for r in self.res:
+            kw = {k: torch.empty(tuple(v.shape), dtype=torch.int32).pin_memory().numpy() for k, v in self._fields(r)}
+            outs.append(type(r)(plan=r.plan, **{k: kw.get(k) for k in vars(r) if k != "plan"}))
+        self.host_out = tuple(outs)
+        self.host_np = {k: v.numpy() for k, v in self.host.items()}
+
+    def step_e2e(self):
+        self.run(self.host_np, self.host_out)                 # returns when the results are in host memory
+
+    def h2d_bytes(self):
+        return int(sum(v.numpy().nbytes for v in self.host.values()))
+
+    def d2h_bytes(self):
+        return int(sum(v.nbytes for r in self.host_out for _, v in self._fields(r)))
+
+    def check_e2e_equals_device(self):
+        np = self.np
+        for rh, rd in zip(self.host_out, self.res):
+            for (k, vh), (_, vd) in zip(self._fields(rh), self._fields(rd)):
+                assert np.array_equal(vh.reshape(-1)[:4096], vd.reshape(-1)[:4096].cpu().numpy()), k
+
+    def check_against_oracle(self):
+        """A few units of this very batch against the CPU oracle (untimed)."""
+        from fractions import Fraction
+        from linalg_solver_b200.convert import limbs_to_ints
+        from oracle import ref_port
+        k = 8 if self.n <= 16 else 1
+        A = self.host["A"][:k].tolist()
+        if self.wl == "c1":
+            d, rk, rr = self.res
+            dets, num, den = limbs_to_ints(d.det[:k]), limbs_to_ints(rr.num[:k]), limbs_to_ints(rr.den[:k])
+            for i in range(k):
+                R, piv = ref_port.row_reduce(A[i])
+                assert dets[i] == ref_port.bareiss_det(A[i]) and int(rk.rank[i]) == ref_port.rank(A[i])
+                assert [[Fraction(x, den[i]) for x in row] for row in num[i]] == R
+        elif self.wl == "c3":
+            (r,) = self.res
+            b = self.host["b"][:k].tolist()
+            den, part = limbs_to_ints(r.den[:k]), limbs_to_ints(r.particular[:k])
+            for i in range(k):
+                want = ref_port.find_preimage_of(A[i], b[i])
+                if want is None:
+                    assert int(r.status[i]) & 2
+                else:
+                    assert int(r.status[i]) == 0 and [Fraction(x, den[i]) for x in part[i]] == want[0]
+        else:
+            (r,) = self.res
+            adj, det = limbs_to_ints(r.adj[:k]), limbs_to_ints(r.det[:k])
+            for i in range(k):
+                want = ref_port.inverse(A[i])
+                got = None if det[i] == 0 else [[Fraction(x, det[i]) for x in row] for row in adj[i]]
+                assert got == want and det[i] == ref_port.bareiss_det(A[i]), "device result differs from the oracle"
+
+
+def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -152,7 +276,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu:
-        cpu, _ = cpu_baseline(n, {8: 16384, 64: 2}[n], SEED)      # before CUDA is initialised (fork pool)
+        cpu, _ = cpu_baseline(args.workload, 8 * CPU_PER_CORE[args.workload], SEED)   # before CUDA init (fork pool)
 
     import torch
     import torch.distributed as dist
@@ -169,32 +293,13 @@ def run_ours(args):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize(dev)
 
-    # by-matrix sharding: every rank owns an independent batch (its own seed), no collective on the data path
-    A_host = torch.from_numpy(make_inputs(n, batch, SEED + 1000 * rank)).pin_memory()
-    A_dev = A_host.to(dev, non_blocking=False)
-    plan = eng.plan_inverse(n, 5)
-    res = eng.inverse_batch(A_dev, plan=plan)                   # allocates outputs; reused by every step
+    job = Job(eng, args.workload, rank, dev)
     torch.cuda.synchronize(dev)
-
-    # ---- parity spot check of this very configuration against the oracle (untimed) ----
     if rank == 0:
-        from fractions import Fraction
-        from linalg_solver_b200.convert import limbs_to_ints
-        from oracle import ref_port
-        k = 8 if n <= 8 else 1
-        adj = limbs_to_ints(res.adj[:k])
-        det = limbs_to_ints(res.det[:k])
-        for i in range(k):
-            a = A_host[i].tolist()
-            want = ref_port.inverse(a)
-            got = None if det[i] == 0 else [[Fraction(x, det[i]) for x in row] for row in adj[i]]
-            assert got == want and det[i] == ref_port.bareiss_det(a), "device result differs from the oracle"
-
-    def step_device():
-        eng.inverse_batch(A_dev, plan=plan, out=res)
+        job.check_against_oracle()
 
     for _ in range(args.warmup):
-        step_device()
+        job.step_device()
     barrier()
     launches0 = eng.launch_count
     eng.timing_enable(True)
@@ -205,7 +310,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
-        step_device()
+        job.step_device()
     ev1.record()
     barrier()
     t1 = time.perf_counter()
@@ -216,27 +321,17 @@ def run_ours(args):
     clocks = sampler.stop(t0, t1)
 
     # ---- end to end through the C-ABI with host buffers (pinned): H2D + kernels + D2H per step ----
-    L = plan.limbs
-    adj_h = torch.empty((batch, n, n, L), dtype=torch.int32).pin_memory()
-    det_h = torch.empty((batch, L), dtype=torch.int32).pin_memory()
-    st_h = torch.empty((batch,), dtype=torch.int32).pin_memory()
-    from linalg_solver_b200.engine import InverseResult
-    out_h = InverseResult(adj_h.numpy(), det_h.numpy(), st_h.numpy(), plan)
-    A_np = A_host.numpy()
-
-    def step_e2e():
-        eng.inverse_batch(A_np, plan=plan, out=out_h)           # returns when the results are in host memory
-
+    job.make_host_outputs()
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
-        step_e2e()
+        job.step_e2e()
     barrier()
     e0 = time.perf_counter()
     for _ in range(e2e_steps):
-        step_e2e()
+        job.step_e2e()
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - e0) * 1e3 / e2e_steps
-    assert np.array_equal(out_h.adj.reshape(-1)[:4096], res.adj.reshape(-1)[:4096].cpu().numpy())
+    job.check_e2e_equals_device()
 
     # ---- reduce over ranks: the slowest rank defines the step ----
     stats = torch.tensor([ms_total, e2e_ms, float(launches)], dtype=torch.float64, device=dev)
@@ -253,32 +348,33 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        k_ms = statistics.mean(kernel_ms) if kernel_ms else ms_step
-        launches_per_step = max(1, len(kernel_ms) // args.steps) if kernel_ms else 1
-        achieved = alg_bytes * batch / launches_per_step / (k_ms * 1e-3) / 1e9
+        # dominant kernel = the elimination kernel(s) of a step (device-timed inside the library)
+        per_step = max(1, len(kernel_ms) // args.steps) if kernel_ms else 1
+        k_ms = sum(kernel_ms) / args.steps if kernel_ms else ms_step
+        achieved = alg_bytes * batch / (k_ms * 1e-3) / 1e9
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             traffic = tr.get(args.workload, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
+        plan = job.plans[-1]
         line = {
-            "metric": "exact det+inverse matrices/sec", "value": value, "unit": "matrices/s", "n_gpus": world,
+            "metric": METRIC[args.workload], "value": value, "unit": "matrices/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 (Montgomery words modulo 31-bit primes)",
             "data": "synthetic",
-            "config": {"workload": desc, "batch_per_gpu": batch, "primes": int(plan.n_primes), "limbs": int(L),
-                       "sharding": "by matrix, no collective", "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2"
-                       % ((alg_bytes * batch) / 1e6)},
+            "config": {"workload": desc, "batch_per_gpu": batch, "primes": int(plan.n_primes), "limbs": int(plan.limbs),
+                       "sharding": "by matrix, no collective",
+                       "l2": "inputs+outputs per step (%.0f MB) vs the 126 MB L2" % ((alg_bytes * batch) / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel_ms": k_ms, "kernel_launches_per_step": launches_per_step,
+                         "traffic": traffic, "kernel_ms": k_ms, "kernel_launches_per_step": per_step,
                          "algorithmic_bytes_per_matrix": alg_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"},
             "cpu_baseline": cpu,
             "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "matrices/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(A_np.nbytes),
-                    "d2h_bytes_per_step": int(out_h.adj.nbytes + out_h.det.nbytes + out_h.status.nbytes),
-                    "path": "lsx_inverse_batch(mem=LSX_MEM_HOST) via ctypes, pinned host buffers"},
+                    "h2d_bytes_per_step": job.h2d_bytes(), "d2h_bytes_per_step": job.d2h_bytes(),
+                    "path": "lsx_*_batch(mem=LSX_MEM_HOST) via ctypes, pinned host buffers"},
             "gpu_launches": int(stats[2]),
             "clocks": clocks,
         }

@@ -215,7 +215,7 @@ class Engine:
         return p
 
     # ---- batched operations ---------------------------------------------------------------
-    def rref_batch(self, A, bar_col, a_abs_max=None, b_abs_max=None, max_rank=0, plan=None) -> RrefResult:
+    def rref_batch(self, A, bar_col, a_abs_max=None, b_abs_max=None, max_rank=0, plan=None, out=None) -> RrefResult:
         """Gauss-Jordan of every ``A[i]`` with pivots in columns < bar_col (reference
         linalg.py:534-630; the caller applies the ``bar_col or n-1`` default of line 543)."""
         A, pA, mem, like = self._prep_in(A, 3, "A")
@@ -225,11 +225,14 @@ class Engine:
                 a_abs_max = self._absmax(A)
             plan = self.plan_rref(m, n, bar_col, a_abs_max, b_abs_max, max_rank)
         L = plan.limbs
-        num = self._alloc(like, (B, m, n, L), np.uint32)
-        den = self._alloc(like, (B, L), np.uint32)
-        piv = self._alloc(like, (B, plan.pivot_slots), np.int32)
-        rank = self._alloc(like, (B,), np.int32)
-        status = self._alloc(like, (B,), np.int32)
+        if out is not None:
+            num, den, piv, rank, status = out.num, out.den, out.pivot_col, out.rank, out.status
+        else:
+            num = self._alloc(like, (B, m, n, L), np.uint32)
+            den = self._alloc(like, (B, L), np.uint32)
+            piv = self._alloc(like, (B, plan.pivot_slots), np.int32)
+            rank = self._alloc(like, (B,), np.int32)
+            status = self._alloc(like, (B,), np.int32)
         self._check(lib.lsx_rref_batch(self._ctx, ctypes.byref(plan), pA, B, mem, self._ptr(num), self._ptr(den),
                                        self._ptr(piv), self._ptr(rank), self._ptr(status)))
         return RrefResult(num, den, piv, rank, status, plan)
@@ -254,7 +257,7 @@ class Engine:
                                           self._ptr(status)))
         return InverseResult(adj, det, status, plan)
 
-    def det_batch(self, A, a_abs_max=None, plan=None) -> DetResult:
+    def det_batch(self, A, a_abs_max=None, plan=None, out=None) -> DetResult:
         """Determinants (sign * product of the forward-sweep pivots, linalg.py:547-609) and ranks."""
         A, pA, mem, like = self._prep_in(A, 3, "A")
         B, n, n2 = A.shape
@@ -262,25 +265,32 @@ class Engine:
             raise ValueError("Determinant requires a square matrix")
         if plan is None:
             plan = self.plan_det(n, self._absmax(A) if a_abs_max is None else a_abs_max)
-        det = self._alloc(like, (B, plan.limbs), np.uint32)
-        rank = self._alloc(like, (B,), np.int32)
-        status = self._alloc(like, (B,), np.int32)
+        if out is not None:
+            det, rank, status = out.det, out.rank, out.status
+        else:
+            det = self._alloc(like, (B, plan.limbs), np.uint32)
+            rank = self._alloc(like, (B,), np.int32)
+            status = self._alloc(like, (B,), np.int32)
         self._check(lib.lsx_det_batch(self._ctx, ctypes.byref(plan), pA, B, mem, self._ptr(det), self._ptr(rank),
                                       self._ptr(status)))
         return DetResult(det, rank, status, plan)
 
-    def rank_batch(self, A, a_abs_max=None, plan=None) -> RankResult:
+    def rank_batch(self, A, a_abs_max=None, plan=None, out=None) -> RankResult:
         """Ranks (reference linalg.py:745-747)."""
         A, pA, mem, like = self._prep_in(A, 3, "A")
         B, m, n = A.shape
         if plan is None:
             plan = self.plan_rank(m, n, self._absmax(A) if a_abs_max is None else a_abs_max)
-        rank = self._alloc(like, (B,), np.int32)
-        status = self._alloc(like, (B,), np.int32)
+        if out is not None:
+            rank, status = out.rank, out.status
+        else:
+            rank = self._alloc(like, (B,), np.int32)
+            status = self._alloc(like, (B,), np.int32)
         self._check(lib.lsx_rank_batch(self._ctx, ctypes.byref(plan), pA, B, mem, self._ptr(rank), self._ptr(status)))
         return RankResult(rank, status, plan)
 
-    def solve_batch(self, A, b, a_abs_max=None, b_abs_max=None, max_rank=0, gen_cap=None, plan=None) -> SolveResult:
+    def solve_batch(self, A, b, a_abs_max=None, b_abs_max=None, max_rank=0, gen_cap=None, plan=None,
+                    out=None) -> SolveResult:
         """Solution sets of A x = b (reference linalg.py:632-680, 913-999): status ST_INCONSISTENT where
         the reference returns ``NoSolution()``, else particular solution (free variables 0) and one
         generator per free column in ascending order."""
@@ -295,12 +305,15 @@ class Engine:
             plan = self.plan_solve(m, n, self._absmax(A) if a_abs_max is None else a_abs_max,
                                    self._absmax(b) if b_abs_max is None else b_abs_max, max_rank, gen_cap)
         L, G = plan.limbs, plan.gen_cap
-        den = self._alloc(like, (B, L), np.uint32)
-        part = self._alloc(like, (B, n, L), np.uint32)
-        gens = self._alloc(like, (B, n, G, L), np.uint32) if G > 0 else None
-        piv = self._alloc(like, (B, plan.pivot_slots), np.int32)
-        rank = self._alloc(like, (B,), np.int32)
-        status = self._alloc(like, (B,), np.int32)
+        if out is not None:
+            den, part, gens, piv, rank, status = out.den, out.particular, out.generators, out.pivot_col, out.rank, out.status
+        else:
+            den = self._alloc(like, (B, L), np.uint32)
+            part = self._alloc(like, (B, n, L), np.uint32)
+            gens = self._alloc(like, (B, n, G, L), np.uint32) if G > 0 else None
+            piv = self._alloc(like, (B, plan.pivot_slots), np.int32)
+            rank = self._alloc(like, (B,), np.int32)
+            status = self._alloc(like, (B,), np.int32)
         self._check(lib.lsx_solve_batch(self._ctx, ctypes.byref(plan), pA, pb, B, mem, self._ptr(den), self._ptr(part),
                                         self._ptr(gens), self._ptr(piv), self._ptr(rank), self._ptr(status)))
         return SolveResult(den, part, gens, piv, rank, status, plan)
