@@ -9,9 +9,10 @@ from . import _lib                                   # noqa: F401  (fails loudly
 from .engine import (DetResult, Engine, InverseResult, LsxError, RankResult, RrefResult,   # noqa: F401
                      SolveResult, default_engine)
 from .matrix import Matrix                            # noqa: F401
+from .random_matrix import RandomMatrixBuilder        # noqa: F401
 from . import convert, dist                           # noqa: F401
 
 AffineSubspace = Matrix.AffineSubspace
 NoSolution = Matrix.NoSolution
 
-__all__ = ["Matrix", "AffineSubspace", "NoSolution", "Engine", "LsxError", "default_engine", "convert", "dist"]
+__all__ = ["Matrix", "AffineSubspace", "NoSolution", "RandomMatrixBuilder", "Engine", "LsxError", "default_engine", "convert", "dist"]

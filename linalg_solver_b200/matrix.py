@@ -158,6 +158,19 @@ class Matrix:
     def transpose(self) -> "Matrix":
         return Matrix([[self.items[j][i] for j in range(self.rows)] for i in range(self.cols)])
 
+    def scalar_mul(self, scalar: Any) -> "Matrix":
+        return Matrix([[scalar * item for item in row] for row in self.items])
+
+    def __mul__(self, other) -> "Matrix":
+        """Matrix product / scalar multiple (reference linalg.py:101-181 without its LaTeX log); host
+        arithmetic on the entry objects, used by the input builder (random_matrix.py:129)."""
+        if not isinstance(other, Matrix):
+            return self.scalar_mul(other)
+        if self.cols != other.rows:
+            raise ValueError("Matrix dimensions must match")
+        cols = list(zip(*other.items)) if other.items and other.items[0] else []
+        return Matrix([[sum((a * b for a, b in zip(row, col)), 0) for col in cols] for row in self.items])
+
     class AffineSubspace:
         """Reference linalg.py:491-522 (LaTeX ``cformat`` omitted: logging is bypassed)."""
 
@@ -308,6 +321,16 @@ class Matrix:
     def kernel(self):
         """Reference linalg.py:749-756."""
         return self.find_preimage_of([0] * self.rows)
+
+    def find_eigenspace(self, eigenvalue: Any):
+        """Reference linalg.py:758-770: nullspace of ``A - eigenvalue * I`` through ``kernel()`` (SURVEY.md
+        section 8f item 1; the eigenvalue must be an exact rational for the device path)."""
+        if self.rows != self.cols:
+            raise ValueError("Matrix must be square to find eigenspace.")
+        items = [list(row) for row in self.items]
+        for i in range(self.rows):
+            items[i][i] = items[i][i] - eigenvalue
+        return Matrix(items).kernel()
 
 
 def _raise_on_status(st):

@@ -117,3 +117,42 @@ def test_find_preimage_and_kernel_routes():
     assert [pq(x) for x in ker.vec] == [[0, 1], [0, 1]]
     assert [pq(x) for row in ker.generators.items for x in row] == [[-2, 1], [1, 1]]
     assert ker.basis() == ker.generators.transpose().items
+
+
+def test_random_matrix_builder_reproduces_reference_inputs():
+    """Same seed, same draw order, device rank() in the rejection loops (reference
+    random_matrix.py:103-129): the builder must yield the reference's own matrices (golden inputs)."""
+    import random
+    from linalg_solver_b200 import Matrix, RandomMatrixBuilder
+    g1 = golden_io.load("c1_4x4")
+    random.seed(20260001)
+    for c in g1["cases"][:200]:
+        assert RandomMatrixBuilder.new().with_size(4, 4).build().items == c["A"]
+    g3 = golden_io.load("c3_16x17")
+    for i in (0, 1, 2, 7, 500):
+        random.seed(202600030000 + i)
+        A = RandomMatrixBuilder.new().with_size(16, 16).with_rank(10).build()
+        assert A.items == g3["cases"][i]["A"]
+        assert A.rank() == 10
+    random.seed(5)
+    F = RandomMatrixBuilder.new(num_rows=6, num_cols=6, rank=6).build()
+    assert F.rank() == 6 and not isinstance(F.inverse(), Matrix.NoSolution)
+    big = RandomMatrixBuilder.new().with_size(64, 64).with_rank(48).build()     # infeasible in the reference
+    assert big.rank() == 48 and big.kernel().dim() == 16
+    with pytest.raises(AssertionError):
+        RandomMatrixBuilder.new().with_size(3, 3).with_rank(4).build()
+
+
+def test_find_eigenspace_and_mul():
+    import sympy
+    from linalg_solver_b200 import Matrix
+    A = Matrix([[2, 0, 0], [0, 3, 4], [0, 4, 9]])
+    es = A.find_eigenspace(11)
+    assert es.dim() == 1
+    v = [x[0] for x in es.generators.items]
+    assert [pq(x) for x in v] == [[0, 1], [1, 2], [1, 1]]
+    assert A.find_eigenspace(sympy.Rational(5)).dim() == 0
+    with pytest.raises(ValueError, match="Matrix must be square to find eigenspace."):
+        Matrix([[1, 2, 3]]).find_eigenspace(1)
+    P = Matrix([[1, 2], [3, 4]]) * Matrix([[0, 1], [1, 0]])
+    assert P.items == [[2, 1], [4, 3]] and (Matrix([[1, 2]]) * 3).items == [[3, 6]]
