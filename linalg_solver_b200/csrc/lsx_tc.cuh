@@ -1,0 +1,374 @@
+// Tensor-core trailing update of the blocked modular LU (config 5 of BASELINE.json), sm_100a only.
+//
+//   C[r][c] <- (C[r][c] * 2^32 + sum_k L[r][k] * U[k][c]) / 2^32  mod p      r in [r0,r1), c in [c0,c1), k in [k0,k0+K)
+//
+// with L = W[.][k0..k0+K) (the negated Montgomery multipliers left by the panel kernels) and
+// U = W[k0..k0+K)[.], for G primes side by side (W is [G][n][n] words).  This is the dense contraction of
+// the forward sweep of reference linalg.py:587-596 (row_i -= factor * pivot_row) for a whole block of
+// pivots at once, and the only genuinely GEMM-shaped piece of the path.
+//
+// 31-bit residues do not fit a tensor-core operand, so each word is split into four unsigned bytes
+// (k_tc_split_a / k_tc_split_b, written straight in the no-swizzle K-major core-matrix layout tcgen05
+// wants) and the 16 byte-plane products are issued as `tcgen05.mma.kind::i8` (u8 x u8 -> s32) into SEVEN
+// TMEM accumulators Q_t, t = a + b the byte weight: Q_t = sum_{a+b=t} La * Ub^T.  Every Q_t stays below
+// 4 * K * 255^2 < 2^26 for K <= 256, so the s32 accumulation is exact.  The epilogue reads the seven
+// accumulators with tcgen05.ld, forms  S = sum_t Q_t * (2^(8t) mod p)  < 2^60 in 64 bits and finishes with
+// one Montgomery reduction:  C + REDC(S) mod p  — bit-identical to the integer-pipe k_gemm.
+//
+// CTA = (prime g, 128-row tile, a contiguous group of 64-column tiles).  The A planes of the row tile stay
+// resident in shared memory for the whole CTA; B planes stream through a ring of 16 KB stages filled by
+// cp.async.bulk (TMA engine, SASS UBLKCP) and released by tcgen05.commit.  Warp 0 = TMEM allocator + copy
+// producer, warp 1 = MMA issuer (one lane), warps 2..9 = epilogue (two warps per TMEM lane quadrant).
+#pragma once
+#include "lsx_internal.h"
+
+namespace lsx_tc {
+
+constexpr int TM = 128;            // rows per CTA tile (= TMEM lanes)
+constexpr int TN = 64;             // columns per accumulator tile
+constexpr int KC = 64;             // contraction bytes per smem stage
+constexpr int A_CHUNK = 4 * TM * KC;   // 32768 B: four byte planes of a 128 x 64 slice
+constexpr int B_CHUNK = 4 * TN * KC;   // 16384 B
+constexpr int STAGES = 4;
+constexpr int THREADS = 320;
+constexpr int TMEM_COLS = 512;     // 7 accumulators x 64 columns = 448, rounded to a power of two
+constexpr int MAX_K = 256;
+
+struct Region {
+    int n;            // order of W (row stride in words)
+    int r0, r1;       // rows of C updated
+    int c0, c1;       // columns of C updated
+    int k0, K;        // contraction range; K is a multiple of 64, at most MAX_K
+    int row_tiles;    // ceil((r1 - r0) / 128)
+    int col_tiles;    // ceil((c1 - c0) / 64)
+    int tiles_per_cta;  // column tiles handled by one CTA
+};
+
+inline size_t a_plane_bytes(const Region& g) { return (size_t)g.row_tiles * g.K * 4 * TM; }   // per prime
+inline size_t b_plane_bytes(const Region& g) { return (size_t)g.col_tiles * g.K * 4 * TN; }   // per prime
+inline size_t smem_bytes(int K) { return (size_t)(K / KC) * A_CHUNK + (size_t)STAGES * B_CHUNK + 256; }
+
+#ifdef __CUDACC__
+
+// ---- byte-plane split ---------------------------------------------------------------------------------
+// A planes of prime g, row tile ti:  [K/64][plane a][k16 = 4][row = 128][16 B]
+__global__ void __launch_bounds__(256) k_tc_split_a(const uint32_t* __restrict__ W, uint8_t* __restrict__ AP, Region g) {
+    const int q_per = g.K / 16;                       // 16-byte k groups
+    const int64_t per_prime = (int64_t)g.row_tiles * TM * q_per;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per_prime) return;
+    const int prime = blockIdx.y;
+    const int r = (int)(t % TM);
+    const int q = (int)((t / TM) % q_per);
+    const int ti = (int)(t / ((int64_t)TM * q_per));
+    const int row = g.r0 + ti * TM + r;
+    uint32_t w[16];
+    if (row < g.r1) {
+        const uint32_t* src = W + ((int64_t)prime * g.n + row) * g.n + g.k0 + q * 16;
+        if ((g.n & 3) == 0 && (g.k0 & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint4 v = *reinterpret_cast<const uint4*>(src + 4 * i);
+                w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = src[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = 0u;
+    }
+    uint8_t* dst = AP + ((int64_t)prime * g.row_tiles + ti) * ((int64_t)g.K * 4 * TM) + (int64_t)(q / 4) * A_CHUNK +
+                   (q % 4) * (TM * 16) + r * 16;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            o[i] = ((w[4 * i] >> (8 * a)) & 255u) | (((w[4 * i + 1] >> (8 * a)) & 255u) << 8) |
+                   (((w[4 * i + 2] >> (8 * a)) & 255u) << 16) | (((w[4 * i + 3] >> (8 * a)) & 255u) << 24);
+        *reinterpret_cast<uint4*>(dst + a * (4 * TM * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// B planes of prime g, column tile tj:  [K/64][plane b][k16 = 4][col = 64][16 B]   (U transposed: K-major)
+__global__ void __launch_bounds__(256) k_tc_split_b(const uint32_t* __restrict__ W, uint8_t* __restrict__ BP, Region g) {
+    const int q_per = g.K / 16;
+    const int64_t per_prime = (int64_t)g.col_tiles * TN * q_per;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per_prime) return;
+    const int prime = blockIdx.y;
+    const int c = (int)(t % TN);
+    const int q = (int)((t / TN) % q_per);
+    const int tj = (int)(t / ((int64_t)TN * q_per));
+    const int col = g.c0 + tj * TN + c;
+    uint32_t w[16];
+    if (col < g.c1) {
+        const uint32_t* src = W + ((int64_t)prime * g.n + g.k0 + q * 16) * g.n + col;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = src[(int64_t)i * g.n];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = 0u;
+    }
+    uint8_t* dst = BP + ((int64_t)prime * g.col_tiles + tj) * ((int64_t)g.K * 4 * TN) + (int64_t)(q / 4) * B_CHUNK +
+                   (q % 4) * (TN * 16) + c * 16;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            o[i] = ((w[4 * i] >> (8 * b)) & 255u) | (((w[4 * i + 1] >> (8 * b)) & 255u) << 8) |
+                   (((w[4 * i + 2] >> (8 * b)) & 255u) << 16) | (((w[4 * i + 3] >> (8 * b)) & 255u) << 24);
+        *reinterpret_cast<uint4*>(dst + b * (4 * TN * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, u8 x u8 -> s32, M = 128, N = 64, K = 32 per instruction
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, no swizzle, K-major: element (row, k-byte) lives at
+// (row % 8) * 16 + (row / 8) * SBO + (k / 16) * LBO + (k % 16).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+struct GemmArgs {
+    uint32_t* W;                // [G][n][n]
+    const uint8_t* AP;          // byte planes of L, see k_tc_split_a
+    const uint8_t* BP;          // byte planes of U, see k_tc_split_b
+    const PrimeRec* primes;     // [G]
+    Region g;
+    int swap_lbo_sbo;           // test hook: exchange the two descriptor strides
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const Region& g = a.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ti = blockIdx.x, prime = blockIdx.z;
+    const int tj0 = blockIdx.y * g.tiles_per_cta;
+    const int tj1 = min(g.col_tiles, tj0 + g.tiles_per_cta);
+    const int ntiles = tj1 - tj0;
+    const int kchunks = g.K / KC;
+
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + (size_t)kchunks * A_CHUNK;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)STAGES * B_CHUNK);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    const uint32_t bar_a_full = smem_u32(bars + 0);
+    const uint32_t bar_acc_full = smem_u32(bars + 1);
+    const uint32_t bar_acc_empty = smem_u32(bars + 2);
+    const uint32_t bar_b_full = smem_u32(bars + 4);              // [STAGES]
+    const uint32_t bar_b_empty = smem_u32(bars + 4 + STAGES);    // [STAGES]
+
+    if (ntiles <= 0) return;                                     // uniform per CTA
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_init(bar_a_full, 1);
+            mbar_init(bar_acc_full, 1);
+            mbar_init(bar_acc_empty, 8);
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(bar_b_full + 8 * s, 1);
+                mbar_init(bar_b_empty + 8 * s, 1);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== copy producer =====
+        if (lane == 0) {
+            const uint8_t* srcA = a.AP + ((int64_t)prime * g.row_tiles + ti) * ((int64_t)g.K * 4 * TM);
+            mbar_expect_tx(bar_a_full, (uint32_t)(kchunks * A_CHUNK));
+            for (int kc = 0; kc < kchunks; ++kc)
+                bulk_g2s(smem_u32(smA + (size_t)kc * A_CHUNK), srcA + (size_t)kc * A_CHUNK, A_CHUNK, bar_a_full);
+            int stage = 0, phase = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                const uint8_t* srcB = a.BP + ((int64_t)prime * g.col_tiles + tj0 + t) * ((int64_t)g.K * 4 * TN);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(bar_b_full + 8 * stage, B_CHUNK);
+                    bulk_g2s(smem_u32(smB + (size_t)stage * B_CHUNK), srcB + (size_t)kc * B_CHUNK, B_CHUNK,
+                             bar_b_full + 8 * stage);
+                    if (++stage == STAGES) stage = 0, phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread =====
+        if (lane == 0) {
+            // instruction descriptor: D = s32 (2 << 4), A = B = u8 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (2u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            uint32_t a_lbo = TM * 16, b_lbo = TN * 16, a_sbo = 128, b_sbo = 128;
+            if (a.swap_lbo_sbo) {
+                uint32_t t0 = a_lbo; a_lbo = a_sbo; a_sbo = t0;
+                t0 = b_lbo; b_lbo = b_sbo; b_sbo = t0;
+            }
+            const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
+            mbar_wait(bar_a_full, 0);
+            tc_fence_after();
+            int stage = 0, phase = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                mbar_wait(bar_acc_empty, (uint32_t)((t & 1) ^ 1));
+                tc_fence_after();
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(bar_b_full + 8 * stage, phase);
+                    tc_fence_after();
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+#pragma unroll
+                        for (int pa = 0; pa < 4; ++pa) {
+                            const uint64_t ad =
+                                smem_desc(smA_u + kc * A_CHUNK + pa * (4 * TM * 16) + s * (2 * TM * 16), a_lbo, a_sbo);
+#pragma unroll
+                            for (int pb = 0; pb < 4; ++pb) {
+                                const uint64_t bd = smem_desc(
+                                    smB_u + stage * B_CHUNK + pb * (4 * TN * 16) + s * (2 * TN * 16), b_lbo, b_sbo);
+                                const uint32_t first = (kc == 0 && s == 0 && (pa == 0 || pb == 3)) ? 0u : 1u;
+                                tc_mma_i8(tmem_base + (uint32_t)((pa + pb) * TN), ad, bd, idesc, first);
+                            }
+                        }
+                    }
+                    tc_commit(bar_b_empty + 8 * stage);          // frees the stage when these MMAs have read it
+                    if (++stage == STAGES) stage = 0, phase ^= 1;
+                }
+                tc_commit(bar_acc_full);                         // accumulators of tile t complete
+            }
+        }
+    } else {
+        // ===== epilogue: 8 warps; warp w reads TMEM lanes 32 * (w % 4) .. + 31, half of the 64 columns =====
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const PrimeRec P = a.primes[prime];
+        const uint32_t p = P.p, pinv = P.pinv;
+        const uint64_t c4 = P.one;                               // 2^32 mod p
+        const uint64_t c5 = (c4 << 8) % p, c6 = (c5 << 8) % p;   // 2^40, 2^48 mod p
+        const int row = g.r0 + ti * TM + quad * 32 + lane;
+        uint32_t* Wg = a.W + (int64_t)prime * g.n * g.n;
+        const bool vec_ok = (g.n & 3) == 0 && (g.c0 & 3) == 0;
+        for (int t = 0; t < ntiles; ++t) {
+            mbar_wait(bar_acc_full, (uint32_t)(t & 1));
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+                const int cl = half * 32 + ch * 16;              // first column of the chunk inside the tile
+                uint32_t q[7][16];
+#pragma unroll
+                for (int s = 0; s < 7; ++s) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * TN + cl), q[s]);
+                tmem_wait_ld();
+                const int col = g.c0 + (tj0 + t) * TN + cl;
+                if (row < g.r1 && col < g.c1) {
+                    uint32_t* cp = Wg + (int64_t)row * g.n + col;
+                    uint32_t cv[16];
+                    const bool full = vec_ok && col + 16 <= g.c1;
+                    if (full) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(cp + 4 * i);
+                            cv[4 * i] = v.x, cv[4 * i + 1] = v.y, cv[4 * i + 2] = v.z, cv[4 * i + 3] = v.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) cv[i] = col + i < g.c1 ? cp[i] : 0u;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        uint64_t acc = (uint64_t)q[0][i] + ((uint64_t)q[1][i] << 8) + ((uint64_t)q[2][i] << 16) +
+                                       ((uint64_t)q[3][i] << 24) + (uint64_t)q[4][i] * c4 + (uint64_t)q[5][i] * c5 +
+                                       (uint64_t)q[6][i] * c6;
+                        const uint32_t r = mont_redc(acc, p, pinv);
+                        const uint32_t o = cv[i] + r;
+                        cv[i] = min(o, o - p);
+                    }
+                    if (full) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            *reinterpret_cast<uint4*>(cp + 4 * i) = make_uint4(cv[4 * i], cv[4 * i + 1], cv[4 * i + 2], cv[4 * i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (col + i < g.c1) cp[i] = cv[i];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace lsx_tc
