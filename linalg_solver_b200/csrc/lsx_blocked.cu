@@ -4,24 +4,36 @@
 // det(A) mod p = sign * product of the pivots of the forward sweep of reference linalg.py:547-609
 // (any non-zero pivot gives the same determinant; the first non-zero at or below the diagonal is
 // used, like the reference).  For a group of G primes the residue matrices W_g = A mod p_g live side
-// by side in HBM ([G][n][n] words) and every kernel below works on all of them in one launch:
+// by side in HBM ([G][n][n] words) and every kernel below works on all of them in one launch.
+//
+// Recursive blocking (host side, lu() / trsm() below):
+//   outer blocks of 256 columns; inside a block the panel is halved down to 8-column base panels
 //   k_load      A -> residues
-//   k_panel     one CTA per prime: unblocked elimination of the n x NB panel with row pivoting;
-//               multipliers are stored as (p - l) * R mod p ("negated Montgomery form") so that every
-//               later update is   redc((w << 32) + lneg * u) = w - l * u   with ONE reduction
-//   k_swap_trsm row swaps of the panel applied to the trailing columns + unit-lower triangular solve
-//   k_gemm      trailing update A22 -= L21 * U12: register-tiled, 64-bit accumulators with a lazy
-//               high-word reduction (one IMAD.WIDE + one VIADDMNMX per multiply-add), one REDC at the end
+//   k_lu8       base panel: one CTA per prime, the rows x 8 panel lives in REGISTERS (row per thread slot),
+//               pivot = first non-zero row at or below the diagonal (block-wide min), multipliers are stored
+//               as (p - l) * R mod p ("negated Montgomery form") so that every later update is
+//               redc((w << 32) + lneg * u) = w - l * u  with ONE reduction
+//   k_swap      row swaps of a pivot range applied to a column range (left L columns and right columns)
+//   k_trsm      unit-lower triangular solve with a <= 64-wide diagonal block held in shared memory
+//   gemm()      C -= L * U on a rectangular region: contraction depth 64 / 128 / 256 -> tcgen05 int8-split
+//               tensor-core kernel (lsx_tc.cuh: byte planes, 7 TMEM accumulators, cp.async.bulk staging);
+//               smaller depths (8 / 16 / 32, inside a 64-column panel) -> k_gemm_int on the integer pipe
+//               (64-bit accumulators, lazy high-word reduction, one REDC at the end)
 //   k_finish    sign, zero flag, Montgomery -> plain residue
 #include <algorithm>
 
 #include "lsx_internal.h"
+#include "lsx_tc.cuh"
 
 namespace {
 
-constexpr int NB = 64;            // panel width
-constexpr int PANEL_T = 1024;
-constexpr int GM = 128, GN = 64;  // trailing-update tile per CTA (256 threads, 8 x 4 outputs each)
+constexpr int NB_OUT = 256;       // outer block (tensor-core contraction depth of the trailing update)
+constexpr int NB_BASE = 8;        // register-resident base panel
+constexpr int LU8_T = 512;        // threads of the base-panel CTA
+constexpr int LU8_RPT = 8;        // rows per thread kept in registers -> 4096 rows
+constexpr int PANEL_T = 1024;     // threads of the global-memory fallback panel (more than 4096 rows)
+constexpr int GM = 128, GN = 64;  // k_gemm_int tile per CTA (256 threads, 8 x 4 outputs each)
+constexpr int KI = 64;            // largest contraction depth of k_gemm_int / k_trsm
 
 __device__ __forceinline__ uint64_t mac_lazy(uint64_t acc, uint32_t a, uint32_t b, uint32_t p) {
     acc += (uint64_t)a * b;                       // acc < p*2^32 before, product < 2^62: no overflow
@@ -52,8 +64,141 @@ __global__ void k_load(const int32_t* __restrict__ A, LargeArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(PANEL_T) k_panel(LargeArgs a, int k0, int nb) {
-    __shared__ uint32_t prow[NB];
+// c = piv^-1 * R^2 as a word, so that mont_mul(w, c) = (w / piv) * R; pivM = word of piv * R
+__device__ __forceinline__ uint32_t pivot_scale(uint32_t piv, const PrimeRec& P, uint32_t* pivM_out) {
+    const uint32_t pivM = mont_mul(piv, P.r2, P.p, P.pinv);
+    const uint32_t invM = mont_pow(pivM, P.p - 2u, P.one, P.p, P.pinv);
+    *pivM_out = pivM;
+    return mont_mul(invM, P.r2, P.p, P.pinv);
+}
+
+// ---- base panel in registers: rows [k0, n) x columns [k0, k0 + nb), nb <= 8, n - k0 <= LU8_T * LU8_RPT ----
+__global__ void __launch_bounds__(LU8_T) k_lu8(LargeArgs a, int k0, int nb) {
+    __shared__ uint32_t rowbuf[2][NB_BASE];      // [0]: old row j, [1]: pivot row (old row src)
+    __shared__ int red[LU8_T / 32];
+    const int n = a.n, g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const PrimeRec P = a.primes[g];
+    const uint32_t p = P.p, pinv = P.pinv;
+    uint32_t* Wg = a.W + (int64_t)g * n * n;
+    const bool vec = nb == NB_BASE && (n & 3) == 0 && (k0 & 3) == 0;
+    uint32_t v[LU8_RPT][NB_BASE];
+#pragma unroll
+    for (int i = 0; i < LU8_RPT; ++i) {
+        const int r = k0 + tid + i * LU8_T;
+        if (r < n) {
+            const uint32_t* src = Wg + (int64_t)r * n + k0;
+            if (vec) {
+                const uint4 x = *reinterpret_cast<const uint4*>(src), y = *reinterpret_cast<const uint4*>(src + 4);
+                v[i][0] = x.x, v[i][1] = x.y, v[i][2] = x.z, v[i][3] = x.w;
+                v[i][4] = y.x, v[i][5] = y.y, v[i][6] = y.z, v[i][7] = y.w;
+            } else {
+#pragma unroll
+                for (int c = 0; c < NB_BASE; ++c) v[i][c] = c < nb ? src[c] : 0u;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NB_BASE; ++c) v[i][c] = 0u;
+        }
+    }
+    uint32_t detM = a.detM[g];
+    int flags = a.flags[g];
+#pragma unroll
+    for (int jj = 0; jj < NB_BASE; ++jj) {
+        if (jj < nb) {                                            // uniform
+            const int j = k0 + jj;
+            // ---- pivot search: first row >= j with a non-zero entry in column jj ----
+            int best = INT32_MAX;
+#pragma unroll
+            for (int i = LU8_RPT - 1; i >= 0; --i) {
+                const int r = k0 + tid + i * LU8_T;
+                if (r >= j && r < n && v[i][jj] != 0u) best = r;
+            }
+            for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (lane == 0) red[warp] = best;
+            __syncthreads();
+            best = lane < LU8_T / 32 ? red[lane] : INT32_MAX;
+            for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+            int src = best;
+            const bool zero_col = src == INT32_MAX;
+            if (zero_col) src = j;                                // column is zero below the diagonal: det = 0
+            // ---- exchange rows j and src through shared memory; everyone then reads the pivot row ----
+#pragma unroll
+            for (int i = 0; i < LU8_RPT; ++i) {
+                const int r = k0 + tid + i * LU8_T;
+                if (r == j) {
+#pragma unroll
+                    for (int c = 0; c < NB_BASE; ++c) rowbuf[0][c] = v[i][c];
+                }
+                if (r == src) {
+#pragma unroll
+                    for (int c = 0; c < NB_BASE; ++c) rowbuf[1][c] = v[i][c];
+                }
+            }
+            __syncthreads();
+            if (src != j) {
+#pragma unroll
+                for (int i = 0; i < LU8_RPT; ++i) {
+                    const int r = k0 + tid + i * LU8_T;
+                    if (r == j) {
+#pragma unroll
+                        for (int c = 0; c < NB_BASE; ++c) v[i][c] = rowbuf[1][c];
+                    }
+                    if (r == src) {
+#pragma unroll
+                        for (int c = 0; c < NB_BASE; ++c) v[i][c] = rowbuf[0][c];
+                    }
+                }
+            }
+            uint32_t prow[NB_BASE];
+#pragma unroll
+            for (int c = 0; c < NB_BASE; ++c) prow[c] = rowbuf[1][c];
+            uint32_t pivM;
+            const uint32_t cscale = pivot_scale(prow[jj], P, &pivM);   // every thread, redundantly: no broadcast
+            if (tid == 0) {
+                a.piv_row[(int64_t)g * n + j] = src;
+                if (zero_col) flags |= 2;
+                else detM = mont_mul(detM, pivM, p, pinv);
+                if (src != j) flags ^= 1;
+            }
+#pragma unroll
+            for (int i = 0; i < LU8_RPT; ++i) {
+                const int r = k0 + tid + i * LU8_T;
+                if (r > j && r < n) {
+                    const uint32_t lm = mont_mul(v[i][jj], cscale, p, pinv);
+                    const uint32_t ln = lm ? p - lm : 0u;
+#pragma unroll
+                    for (int c = jj + 1; c < NB_BASE; ++c)
+                        v[i][c] = mont_redc(mac_lazy((uint64_t)v[i][c] << 32, ln, prow[c], p), p, pinv);
+                    v[i][jj] = ln;
+                }
+            }
+            __syncthreads();                                      // rowbuf / red are reused by the next column
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < LU8_RPT; ++i) {
+        const int r = k0 + tid + i * LU8_T;
+        if (r < n) {
+            uint32_t* dst = Wg + (int64_t)r * n + k0;
+            if (vec) {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(v[i][0], v[i][1], v[i][2], v[i][3]);
+                *reinterpret_cast<uint4*>(dst + 4) = make_uint4(v[i][4], v[i][5], v[i][6], v[i][7]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < NB_BASE; ++c)
+                    if (c < nb) dst[c] = v[i][c];
+            }
+        }
+    }
+    if (tid == 0) {
+        a.detM[g] = detM;
+        a.flags[g] = flags;
+    }
+}
+
+// ---- fallback base panel in global memory (more rows than the register panel holds) ----
+__global__ void __launch_bounds__(PANEL_T) k_panel_gmem(LargeArgs a, int k0, int nb) {
+    __shared__ uint32_t prow[NB_BASE];
     __shared__ int red[PANEL_T / 32];
     __shared__ uint32_t s_c;
     const int n = a.n, g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -65,7 +210,6 @@ __global__ void __launch_bounds__(PANEL_T) k_panel(LargeArgs a, int k0, int nb) 
     int flags = a.flags[g];
     for (int jj = 0; jj < nb; ++jj) {
         const int j = k0 + jj;
-        // ---- pivot search: first row >= j with a non-zero entry in column j ----
         int best = INT32_MAX;
         for (int r = j + tid; r < n; r += PANEL_T)
             if (Wg[(int64_t)r * n + j] != 0u) {
@@ -78,7 +222,7 @@ __global__ void __launch_bounds__(PANEL_T) k_panel(LargeArgs a, int k0, int nb) 
         best = red[lane];                                  // NW == 32
         for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
         int src = best;
-        if (src == INT32_MAX) {                            // column is zero below the diagonal: det = 0
+        if (src == INT32_MAX) {
             flags |= 2;
             src = j;
         }
@@ -94,11 +238,9 @@ __global__ void __launch_bounds__(PANEL_T) k_panel(LargeArgs a, int k0, int nb) 
         __syncthreads();
         if (tid < nb) prow[tid] = Wg[(int64_t)j * n + k0 + tid];
         if (warp == 0) {
-            // c = piv^-1 * R^2, so that mont_mul(w, c) = (w / piv) * R
-            const uint32_t piv = Wg[(int64_t)j * n + j];
-            const uint32_t pivM = mont_mul(piv, P.r2, p, pinv);
-            const uint32_t invM = mont_pow(pivM, p - 2u, P.one, p, pinv);
-            if (lane == 0) s_c = mont_mul(invM, P.r2, p, pinv);
+            uint32_t pivM;
+            const uint32_t c = pivot_scale(Wg[(int64_t)j * n + j], P, &pivM);
+            if (lane == 0) s_c = c;
             if (tid == 0 && !(flags & 2)) detM = mont_mul(detM, pivM, p, pinv);
         }
         __syncthreads();
@@ -121,77 +263,88 @@ __global__ void __launch_bounds__(PANEL_T) k_panel(LargeArgs a, int k0, int nb) 
     }
 }
 
-// Trailing columns c >= k0 + nb: apply the panel's row swaps, then solve the unit-lower system.
-__global__ void __launch_bounds__(128) k_swap_trsm(LargeArgs a, int k0, int nb) {
-    extern __shared__ __align__(16) uint32_t sm[];
-    uint32_t* Ln = sm;                    // [nb][NB] negated Montgomery multipliers of L11
-    uint32_t* us = Ln + NB * NB;          // [nb][128]
-    __shared__ int pr[NB];
+// Row swaps of pivots [ja, jb) applied, in order, to columns [ca, cb).
+__global__ void __launch_bounds__(128) k_swap(LargeArgs a, int ja, int jb, int ca, int cb) {
+    __shared__ int pr[NB_OUT];
     const int n = a.n, g = blockIdx.y, tid = threadIdx.x;
-    const PrimeRec P = a.primes[g];
-    const uint32_t p = P.p, pinv = P.pinv;
+    uint32_t* Wg = a.W + (int64_t)g * n * n;
+    const int c = ca + blockIdx.x * 128 + tid;
+    for (int jbase = ja; jbase < jb; jbase += NB_OUT) {
+        const int cnt = min(NB_OUT, jb - jbase);
+        __syncthreads();
+        for (int e = tid; e < cnt; e += 128) pr[e] = a.piv_row[(int64_t)g * n + jbase + e];
+        __syncthreads();
+        if (c < cb)
+            for (int e = 0; e < cnt; ++e) {
+                const int j = jbase + e, src = pr[e];
+                if (src != j) {
+                    const uint32_t t0 = Wg[(int64_t)j * n + c];
+                    Wg[(int64_t)j * n + c] = Wg[(int64_t)src * n + c];
+                    Wg[(int64_t)src * n + c] = t0;
+                }
+            }
+    }
+}
+
+// Columns [ca, cb): solve the unit-lower system of the diagonal block rows/cols [k0, k0 + nb), nb <= 64.
+__global__ void __launch_bounds__(128) k_trsm(LargeArgs a, int k0, int nb, int ca, int cb) {
+    extern __shared__ __align__(16) uint32_t sm[];
+    uint32_t* Ln = sm;                    // [nb][KI] negated Montgomery multipliers of L11
+    uint32_t* us = Ln + KI * KI;          // [nb][128]
+    const int n = a.n, g = blockIdx.y, tid = threadIdx.x;
+    const uint32_t p = a.primes[g].p, pinv = a.primes[g].pinv;
     uint32_t* Wg = a.W + (int64_t)g * n * n;
     for (int e = tid; e < nb * nb; e += 128) {
         const int i = e / nb, t = e % nb;
-        Ln[i * NB + t] = Wg[(int64_t)(k0 + i) * n + k0 + t];
+        Ln[i * KI + t] = Wg[(int64_t)(k0 + i) * n + k0 + t];
     }
-    if (tid < nb) pr[tid] = a.piv_row[(int64_t)g * n + k0 + tid];
     __syncthreads();
-    const int c = k0 + nb + blockIdx.x * 128 + tid;
-    if (c >= n) return;
-    for (int jj = 0; jj < nb; ++jj) {
-        const int j = k0 + jj, src = pr[jj];
-        if (src != j) {
-            const uint32_t t0 = Wg[(int64_t)j * n + c];
-            Wg[(int64_t)j * n + c] = Wg[(int64_t)src * n + c];
-            Wg[(int64_t)src * n + c] = t0;
-        }
-    }
+    const int c = ca + blockIdx.x * 128 + tid;
+    if (c >= cb) return;
     for (int i = 0; i < nb; ++i) {
         uint64_t acc = (uint64_t)Wg[(int64_t)(k0 + i) * n + c] << 32;
-        for (int t = 0; t < i; ++t) acc = mac_lazy(acc, Ln[i * NB + t], us[t * 128 + tid], p);
+        for (int t = 0; t < i; ++t) acc = mac_lazy(acc, Ln[i * KI + t], us[t * 128 + tid], p);
         const uint32_t u = mont_redc(acc, p, pinv);
         us[i * 128 + tid] = u;
         Wg[(int64_t)(k0 + i) * n + c] = u;
     }
 }
 
-// A22[i][j] = redc((A22[i][j] << 32) + sum_k Lneg[i][k] * U[k][j])   for i, j >= k0 + nb
-__global__ void __launch_bounds__(256) k_gemm(LargeArgs a, int k0, int nb) {
+// C[i][j] = redc((C[i][j] << 32) + sum_k Lneg[i][k] * U[k][j])  on rows [r0, r1) x cols [c0, c1),
+// Lneg = W[.][k0 .. k0 + K), U = W[k0 .. k0 + K)[.], K <= 64: integer pipe.
+__global__ void __launch_bounds__(256) k_gemm_int(LargeArgs a, int r0, int r1, int c0, int c1, int k0, int K) {
     extern __shared__ __align__(16) uint32_t sm[];
     constexpr int LDL = GM + 4;
-    uint32_t* Lt = sm;                    // [NB][LDL]  (k-major: Lt[k][i])
-    uint32_t* Us = Lt + NB * LDL;         // [NB][GN]
+    uint32_t* Lt = sm;                    // [K][LDL]  (k-major: Lt[k][i])
+    uint32_t* Us = Lt + KI * LDL;         // [K][GN]
     const int n = a.n, g = blockIdx.z, tid = threadIdx.x;
-    const PrimeRec P = a.primes[g];
-    const uint32_t p = P.p, pinv = P.pinv;
+    const uint32_t p = a.primes[g].p, pinv = a.primes[g].pinv;
     uint32_t* Wg = a.W + (int64_t)g * n * n;
-    const int r0 = k0 + nb + blockIdx.y * GM, c0 = k0 + nb + blockIdx.x * GN;
-    // ---- stage L21 tile (transposed) and U12 tile ----
-    for (int e = tid; e < GM * NB; e += 256) {
-        const int i = e / NB, k = e % NB;
-        const int r = r0 + i;
-        Lt[k * LDL + i] = (r < n && k < nb) ? Wg[(int64_t)r * n + k0 + k] : 0u;
+    const int rb = r0 + blockIdx.y * GM, cbase = c0 + blockIdx.x * GN;
+    for (int e = tid; e < GM * K; e += 256) {
+        const int i = e / K, k = e % K;
+        const int r = rb + i;
+        Lt[k * LDL + i] = r < r1 ? Wg[(int64_t)r * n + k0 + k] : 0u;
     }
-    for (int e = tid; e < NB * GN; e += 256) {
+    for (int e = tid; e < K * GN; e += 256) {
         const int k = e / GN, j = e % GN;
-        const int c = c0 + j;
-        Us[k * GN + j] = (c < n && k < nb) ? Wg[(int64_t)(k0 + k) * n + c] : 0u;
+        const int c = cbase + j;
+        Us[k * GN + j] = c < c1 ? Wg[(int64_t)(k0 + k) * n + c] : 0u;
     }
     __syncthreads();
     const int tx = tid & 15, ty = tid >> 4;           // 16 x 16 threads: 4 columns x 8 rows each
     uint64_t acc[8][4];
 #pragma unroll
     for (int x = 0; x < 8; ++x) {
-        const int r = r0 + ty * 8 + x;
+        const int r = rb + ty * 8 + x;
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
-            const int c = c0 + tx * 4 + y;
-            acc[x][y] = (r < n && c < n) ? (uint64_t)Wg[(int64_t)r * n + c] << 32 : 0ull;
+            const int c = cbase + tx * 4 + y;
+            acc[x][y] = (r < r1 && c < c1) ? (uint64_t)Wg[(int64_t)r * n + c] << 32 : 0ull;
         }
     }
 #pragma unroll 4
-    for (int k = 0; k < NB; ++k) {
+    for (int k = 0; k < K; ++k) {
         const uint4 l0 = *reinterpret_cast<const uint4*>(Lt + k * LDL + ty * 8);
         const uint4 l1 = *reinterpret_cast<const uint4*>(Lt + k * LDL + ty * 8 + 4);
         const uint4 u = *reinterpret_cast<const uint4*>(Us + k * GN + tx * 4);
@@ -204,11 +357,11 @@ __global__ void __launch_bounds__(256) k_gemm(LargeArgs a, int k0, int nb) {
     }
 #pragma unroll
     for (int x = 0; x < 8; ++x) {
-        const int r = r0 + ty * 8 + x;
+        const int r = rb + ty * 8 + x;
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
-            const int c = c0 + tx * 4 + y;
-            if (r < n && c < n) Wg[(int64_t)r * n + c] = mont_redc(acc[x][y], p, pinv);
+            const int c = cbase + tx * 4 + y;
+            if (r < r1 && c < c1) Wg[(int64_t)r * n + c] = mont_redc(acc[x][y], p, pinv);
         }
     }
 }
@@ -224,6 +377,102 @@ __global__ void k_finish(LargeArgs a, uint32_t* residues) {
     residues[g] = x;
 }
 
+// ---- host-side recursion over one group of primes -----------------------------------------------------
+struct Driver {
+    lsx_ctx* ctx;
+    LargeArgs a;
+    uint8_t* AP;          // byte planes for the tensor-core update (lsx_tc.cuh)
+    uint8_t* BP;
+    bool use_tc;
+    int n;
+
+    static int left_width(int w) {               // largest power of two below w (w > NB_BASE)
+        int h = NB_BASE;
+        while (h * 2 < w) h *= 2;
+        return h;
+    }
+    void gemm(int r0, int r1, int c0, int c1, int k0, int K) {
+        if (r1 <= r0 || c1 <= c0) return;
+        cudaStream_t st = ctx->stream;
+        if (use_tc && K % lsx_tc::KC == 0 && K <= lsx_tc::MAX_K) {
+            lsx_tc::Region g{};
+            g.n = n, g.r0 = r0, g.r1 = r1, g.c0 = c0, g.c1 = c1, g.k0 = k0, g.K = K;
+            g.row_tiles = (r1 - r0 + lsx_tc::TM - 1) / lsx_tc::TM;
+            g.col_tiles = (c1 - c0 + lsx_tc::TN - 1) / lsx_tc::TN;
+            const int units = g.row_tiles * a.G;
+            int groups = std::min(g.col_tiles, std::max(1, (2 * ctx->sm_count + units - 1) / units));
+            g.tiles_per_cta = (g.col_tiles + groups - 1) / groups;
+            groups = (g.col_tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
+            const int64_t ta = (int64_t)g.row_tiles * lsx_tc::TM * (K / 16), tb = (int64_t)g.col_tiles * lsx_tc::TN * (K / 16);
+            lsx_tc::k_tc_split_a<<<dim3((unsigned)((ta + 255) / 256), a.G), 256, 0, st>>>(a.W, AP, g);
+            lsx_tc::k_tc_split_b<<<dim3((unsigned)((tb + 255) / 256), a.G), 256, 0, st>>>(a.W, BP, g);
+            lsx_tc::GemmArgs ga{};
+            ga.W = a.W, ga.AP = AP, ga.BP = BP, ga.primes = a.primes, ga.g = g, ga.swap_lbo_sbo = 0;
+            const bool big = K == NB_OUT;
+            if (big) lsx_timing_begin(ctx);
+            lsx_tc::k_gemm_tc<<<dim3(g.row_tiles, groups, a.G), lsx_tc::THREADS, lsx_tc::smem_bytes(K), st>>>(ga);
+            if (big) lsx_timing_end(ctx);
+            ctx->launches += 3;
+            return;
+        }
+        for (int kk = 0; kk < K; kk += KI) {      // integer pipe, at most 64 deep per launch
+            const int kd = std::min(KI, K - kk);
+            const size_t smem = (size_t)(KI * (GM + 4) + KI * GN) * 4;
+            k_gemm_int<<<dim3((c1 - c0 + GN - 1) / GN, (r1 - r0 + GM - 1) / GM, a.G), 256, smem, st>>>(a, r0, r1, c0, c1,
+                                                                                                        k0 + kk, kd);
+            ctx->launches++;
+        }
+    }
+    void swap(int ja, int jb, int ca, int cb) {
+        if (jb <= ja || cb <= ca) return;
+        k_swap<<<dim3((cb - ca + 127) / 128, a.G), 128, 0, ctx->stream>>>(a, ja, jb, ca, cb);
+        ctx->launches++;
+    }
+    // columns [ca, cb): U = L11^-1 * A for the diagonal block [k0, k0 + w)
+    void trsm(int k0, int w, int ca, int cb) {
+        if (cb <= ca || w <= 0) return;
+        if (w <= KI) {
+            const size_t smem = (size_t)(KI * KI + KI * 128) * 4;
+            k_trsm<<<dim3((cb - ca + 127) / 128, a.G), 128, smem, ctx->stream>>>(a, k0, w, ca, cb);
+            ctx->launches++;
+            return;
+        }
+        const int w1 = left_width(w);
+        trsm(k0, w1, ca, cb);
+        gemm(k0 + w1, k0 + w, ca, cb, k0, w1);
+        trsm(k0 + w1, w - w1, ca, cb);
+    }
+    // LU of rows [k0, n) x columns [k0, k0 + w); row swaps are applied to columns [cl, k0 + w) only
+    // (cl = first column of the enclosing outer block: the L columns to its left are never read again).
+    void lu(int k0, int w, int cl) {
+        if (w <= NB_BASE) {
+            if (n - k0 <= LU8_T * LU8_RPT) k_lu8<<<a.G, LU8_T, 0, ctx->stream>>>(a, k0, w);
+            else k_panel_gmem<<<a.G, PANEL_T, 0, ctx->stream>>>(a, k0, w);
+            ctx->launches++;
+            swap(k0, k0 + w, cl, k0);                       // multipliers of earlier panels in the same block
+            return;
+        }
+        const int w1 = left_width(w);
+        lu(k0, w1, cl);
+        swap(k0, k0 + w1, k0 + w1, k0 + w);                 // right half of this panel
+        trsm(k0, w1, k0 + w1, k0 + w);
+        gemm(k0 + w1, n, k0 + w1, k0 + w, k0, w1);
+        lu(k0 + w1, w - w1, cl);
+    }
+    void run() {
+        for (int k0 = 0; k0 < n; k0 += NB_OUT) {
+            const int w = std::min(NB_OUT, n - k0);
+            lu(k0, w, k0);
+            const int ce = k0 + w;
+            if (ce < n) {
+                swap(k0, ce, ce, n);
+                trsm(k0, w, ce, n);
+                gemm(ce, n, ce, n, k0, w);
+            }
+        }
+    }
+};
+
 }  // namespace
 
 int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_begin, int count, uint32_t* d_res) {
@@ -232,8 +481,16 @@ int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_b
         size_t mb = e ? (size_t)strtoull(e, nullptr, 10) : 24576;
         return (mb < 64 ? 64 : mb) << 20;
     }();
-    const size_t per = (size_t)n * n * 4 + (size_t)n * 4 + 64;
+    const bool use_tc = !getenv("LSX_NO_TC");
+    const size_t rt = (size_t)(n + lsx_tc::TM - 1) / lsx_tc::TM, ct = (size_t)(n + lsx_tc::TN - 1) / lsx_tc::TN;
+    const size_t ap_per = rt * lsx_tc::TM * 4 * NB_OUT, bp_per = ct * lsx_tc::TN * 4 * NB_OUT;   // byte planes per prime
+    const size_t per = (size_t)n * n * 4 + (size_t)n * 4 + 64 + (use_tc ? ap_per + bp_per : 0);
+    // groups of about one prime per SM, evenly sized, within the workspace budget
     int G = (int)std::min<size_t>((size_t)count, std::max<size_t>(1, budget / per));
+    if (G > ctx->sm_count) {
+        const int ngroups = (count + ctx->sm_count - 1) / ctx->sm_count;
+        G = std::min(G, (count + ngroups - 1) / ngroups);
+    }
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -241,40 +498,36 @@ int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_b
         return o;
     };
     const size_t o_w = take((size_t)G * n * n * 4), o_piv = take((size_t)G * n * 4), o_det = take((size_t)G * 4),
-                 o_flag = take((size_t)G * 4);
+                 o_flag = take((size_t)G * 4), o_ap = take(use_tc ? G * ap_per : 0), o_bp = take(use_tc ? G * bp_per : 0);
     int rc = lsx_ws_reserve(ctx, off);
     if (rc != LSX_OK) return rc;
     char* base = (char*)ctx->d_ws;
-    const size_t smem_trsm = (size_t)(NB * NB + NB * 128) * 4;
-    const size_t smem_gemm = (size_t)(NB * (GM + 4) + NB * GN) * 4;
-    LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_swap_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_trsm));
-    LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm));
+    const size_t smem_trsm = (size_t)(KI * KI + KI * 128) * 4;
+    const size_t smem_gemm = (size_t)(KI * (GM + 4) + KI * GN) * 4;
+    LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_trsm));
+    LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_gemm_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm));
+    if (use_tc)
+        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(lsx_tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)lsx_tc::smem_bytes(lsx_tc::MAX_K)));
     for (int g0 = 0; g0 < count; g0 += G) {
         const int Gc = std::min(G, count - g0);
-        LargeArgs a{};
-        a.W = (uint32_t*)(base + o_w);
-        a.primes = ctx->d_primes + prime_begin + g0;
-        a.piv_row = (int32_t*)(base + o_piv);
-        a.detM = (uint32_t*)(base + o_det);
-        a.flags = (int32_t*)(base + o_flag);
-        a.n = n;
-        a.G = Gc;
-        k_load<<<dim3(ctx->sm_count * 2, Gc), 256, 0, ctx->stream>>>(dA, a);
+        Driver d{};
+        d.ctx = ctx;
+        d.a.W = (uint32_t*)(base + o_w);
+        d.a.primes = ctx->d_primes + prime_begin + g0;
+        d.a.piv_row = (int32_t*)(base + o_piv);
+        d.a.detM = (uint32_t*)(base + o_det);
+        d.a.flags = (int32_t*)(base + o_flag);
+        d.a.n = n;
+        d.a.G = Gc;
+        d.AP = (uint8_t*)(base + o_ap);
+        d.BP = (uint8_t*)(base + o_bp);
+        d.use_tc = use_tc;
+        d.n = n;
+        k_load<<<dim3(ctx->sm_count * 2, Gc), 256, 0, ctx->stream>>>(dA, d.a);
         ctx->launches++;
-        for (int k0 = 0; k0 < n; k0 += NB) {
-            const int nb = std::min(NB, n - k0);
-            k_panel<<<Gc, PANEL_T, 0, ctx->stream>>>(a, k0, nb);
-            ctx->launches++;
-            const int rest = n - k0 - nb;
-            if (rest > 0) {
-                k_swap_trsm<<<dim3((rest + 127) / 128, Gc), 128, smem_trsm, ctx->stream>>>(a, k0, nb);
-                lsx_timing_begin(ctx);
-                k_gemm<<<dim3((rest + GN - 1) / GN, (rest + GM - 1) / GM, Gc), 256, smem_gemm, ctx->stream>>>(a, k0, nb);
-                lsx_timing_end(ctx);
-                ctx->launches += 2;
-            }
-        }
-        k_finish<<<(Gc + 127) / 128, 128, 0, ctx->stream>>>(a, d_res + g0);
+        d.run();
+        k_finish<<<(Gc + 127) / 128, 128, 0, ctx->stream>>>(d.a, d_res + g0);
         ctx->launches++;
         LSX_CUDA_TRY(ctx, cudaGetLastError());
     }

@@ -392,6 +392,32 @@ def test_blocked_lu_residues_match_tile_path(eng, monkeypatch):
     assert not np.any(eng.det_large_residues(C, 0, 4))
 
 
+def test_blocked_lu_tensor_core_path_vs_numpy_oracle(eng, monkeypatch):
+    """Recursive blocked LU with the tcgen05 int8-split trailing update (depths 64/128/256) against
+    oracle/det_mod_p.py and against the same LU with the integer-pipe GEMM (LSX_NO_TC), on sizes that
+    exercise full and ragged outer blocks, row swaps and singular inputs."""
+    from oracle.det_mod_p import det_mod_p
+    rng = np.random.Generator(np.random.PCG64(505))
+    for n in (257, 320, 520, 1000):
+        A = rng.integers(-5, 6, size=(n, n), dtype=np.int32)
+        B = A.copy()
+        B[0, 0] = 0
+        B[1, 0] = 0
+        B[n // 2, : n // 2 + 3] = 0                          # zero pivot deep inside: swap across blocks
+        C = A.copy()
+        C[n - 2] = C[3]                                      # singular
+        for M in (A, B, C):
+            tc = eng.det_large_residues(M, 5, 3)
+            monkeypatch.setenv("LSX_NO_TC", "1")
+            ip = eng.det_large_residues(M, 5, 3)
+            monkeypatch.delenv("LSX_NO_TC")
+            assert np.array_equal(tc, ip), n
+            if n <= 520:
+                primes = eng.primes(8)[5:8]
+                assert [int(x) for x in tc] == [det_mod_p(M, int(p)) for p in primes], n
+        assert not np.any(eng.det_large_residues(C, 0, 2))
+
+
 def test_c5_standin_256_blocked_and_sharded_crt(eng):
     from linalg_solver_b200 import dist as lsx_dist
     g = golden_io.load("c5_standins")

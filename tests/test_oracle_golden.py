@@ -149,3 +149,20 @@ def test_c5_standins_bareiss():
         rng = np.random.Generator(np.random.PCG64(c["seed"]))
         A = rng.integers(-5, 6, size=(c["n"], c["n"]), dtype=np.int64).tolist()
         assert ref_port.bareiss_det(A) == int(c["det"])
+
+
+def test_det_mod_p_oracle_pinned_to_standins():
+    """oracle/det_mod_p.py (numpy modular elimination, the config 5 checker) against the exact DomainMatrix
+    determinants, for table primes and a tiny prime (zero pivots, swaps)."""
+    import numpy as np
+    from oracle.det_mod_p import det_mod_p
+    from tests.device_model import prime_table
+    g = golden_io.load("c5_standins")
+    primes = prime_table(3) + [7, 65537]
+    for c in g["cases"]:
+        rng = np.random.Generator(np.random.PCG64(c["seed"]))
+        A = rng.integers(-5, 6, size=(c["n"], c["n"]), dtype=np.int64)
+        for p in primes:
+            assert det_mod_p(A, p) == int(c["det"]) % p
+    S = np.array([[1, 2, 3], [2, 4, 6], [1, 0, 1]])
+    assert det_mod_p(S, primes[0]) == 0
