@@ -57,7 +57,18 @@ __global__ void k_load(const int32_t* __restrict__ A, LargeArgs a) {
     const uint32_t p = a.primes[g].p;
     uint32_t* Wg = a.W + (int64_t)g * nn;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += (int64_t)gridDim.x * blockDim.x)
-        Wg[i] = word_of_int_any(A[i], p);
+    {
+        const int32_t v = A[i];
+        if (p > (1u << 30)) {                      // |v| <= 2^31 < 2p: two conditional corrections, no division
+            int64_t t = v;
+            if (t < 0) t += p;
+            if (t < 0) t += p;
+            if (t >= (int64_t)p) t -= p;
+            Wg[i] = (uint32_t)t;
+        } else {
+            Wg[i] = word_of_int_any(v, p);         // tiny test primes
+        }
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         a.detM[g] = a.primes[g].one;
         a.flags[g] = 0;
@@ -366,6 +377,68 @@ __global__ void __launch_bounds__(256) k_gemm_int(LargeArgs a, int r0, int r1, i
     }
 }
 
+// Same update for a tall, narrow region (inside a 32-column panel: K <= 16, at most 16 columns): one thread
+// per row keeps its L entries and its C entries in registers, U (K x width) sits in shared memory.
+constexpr int NARROW = 16;
+__global__ void __launch_bounds__(128) k_gemm_narrow(LargeArgs a, int r0, int r1, int c0, int c1, int k0, int K) {
+    __shared__ uint32_t Us[NARROW][NARROW];
+    const int n = a.n, g = blockIdx.y, tid = threadIdx.x, wd = c1 - c0;
+    const uint32_t p = a.primes[g].p, pinv = a.primes[g].pinv;
+    uint32_t* Wg = a.W + (int64_t)g * n * n;
+    for (int e = tid; e < NARROW * NARROW; e += 128) {
+        const int k = e / NARROW, j = e % NARROW;
+        Us[k][j] = (k < K && j < wd) ? Wg[(int64_t)(k0 + k) * n + c0 + j] : 0u;
+    }
+    __syncthreads();
+    const int r = r0 + blockIdx.x * 128 + tid;
+    if (r >= r1) return;
+    uint32_t* row = Wg + (int64_t)r * n;
+    uint32_t l[NARROW];
+    uint64_t acc[NARROW];
+    const bool vec = (n & 3) == 0 && (k0 & 3) == 0 && (c0 & 3) == 0 && (K & 3) == 0 && (wd & 3) == 0;
+    if (vec) {
+#pragma unroll
+        for (int k = 0; k < NARROW; k += 4)
+            if (k < K) {
+                const uint4 v = *reinterpret_cast<const uint4*>(row + k0 + k);
+                l[k] = v.x, l[k + 1] = v.y, l[k + 2] = v.z, l[k + 3] = v.w;
+            } else {
+                l[k] = l[k + 1] = l[k + 2] = l[k + 3] = 0u;
+            }
+#pragma unroll
+        for (int j = 0; j < NARROW; j += 4)
+            if (j < wd) {
+                const uint4 v = *reinterpret_cast<const uint4*>(row + c0 + j);
+                acc[j] = (uint64_t)v.x << 32, acc[j + 1] = (uint64_t)v.y << 32, acc[j + 2] = (uint64_t)v.z << 32,
+                acc[j + 3] = (uint64_t)v.w << 32;
+            } else {
+                acc[j] = acc[j + 1] = acc[j + 2] = acc[j + 3] = 0ull;
+            }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NARROW; ++k) l[k] = k < K ? row[k0 + k] : 0u;
+#pragma unroll
+        for (int j = 0; j < NARROW; ++j) acc[j] = j < wd ? (uint64_t)row[c0 + j] << 32 : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < NARROW; ++k)
+        if (k < K) {
+#pragma unroll
+            for (int j = 0; j < NARROW; ++j) acc[j] = mac_lazy(acc[j], l[k], Us[k][j], p);
+        }
+    if (vec) {
+#pragma unroll
+        for (int j = 0; j < NARROW; j += 4)
+            if (j < wd)
+                *reinterpret_cast<uint4*>(row + c0 + j) = make_uint4(mont_redc(acc[j], p, pinv), mont_redc(acc[j + 1], p, pinv),
+                                                                     mont_redc(acc[j + 2], p, pinv), mont_redc(acc[j + 3], p, pinv));
+    } else {
+#pragma unroll
+        for (int j = 0; j < NARROW; ++j)
+            if (j < wd) row[c0 + j] = mont_redc(acc[j], p, pinv);
+    }
+}
+
 __global__ void k_finish(LargeArgs a, uint32_t* residues) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= a.G) return;
@@ -394,9 +467,10 @@ struct Driver {
     void gemm(int r0, int r1, int c0, int c1, int k0, int K) {
         if (r1 <= r0 || c1 <= c0) return;
         cudaStream_t st = ctx->stream;
-        if (use_tc && K % lsx_tc::KC == 0 && K <= lsx_tc::MAX_K) {
+        if (use_tc && lsx_tc::depth_ok(K)) {
             lsx_tc::Region g{};
             g.n = n, g.r0 = r0, g.r1 = r1, g.c0 = c0, g.c1 = c1, g.k0 = k0, g.K = K;
+            g.kc = std::min(K, lsx_tc::KC);
             g.row_tiles = (r1 - r0 + lsx_tc::TM - 1) / lsx_tc::TM;
             g.col_tiles = (c1 - c0 + lsx_tc::TN - 1) / lsx_tc::TN;
             const int units = g.row_tiles * a.G;
@@ -415,6 +489,11 @@ struct Driver {
             ctx->launches += 3;
             return;
         }
+        if (K <= NARROW && c1 - c0 <= NARROW) {   // tall and narrow: one thread per row
+            k_gemm_narrow<<<dim3((r1 - r0 + 127) / 128, a.G), 128, 0, st>>>(a, r0, r1, c0, c1, k0, K);
+            ctx->launches++;
+            return;
+        }
         for (int kk = 0; kk < K; kk += KI) {      // integer pipe, at most 64 deep per launch
             const int kd = std::min(KI, K - kk);
             const size_t smem = (size_t)(KI * (GM + 4) + KI * GN) * 4;
@@ -431,7 +510,7 @@ struct Driver {
     // columns [ca, cb): U = L11^-1 * A for the diagonal block [k0, k0 + w)
     void trsm(int k0, int w, int ca, int cb) {
         if (cb <= ca || w <= 0) return;
-        if (w <= KI) {
+        if (w <= (use_tc ? 32 : KI)) {
             const size_t smem = (size_t)(KI * KI + KI * 128) * 4;
             k_trsm<<<dim3((cb - ca + 127) / 128, a.G), 128, smem, ctx->stream>>>(a, k0, w, ca, cb);
             ctx->launches++;

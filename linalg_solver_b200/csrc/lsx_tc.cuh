@@ -26,7 +26,7 @@ namespace lsx_tc {
 
 constexpr int TM = 128;            // rows per CTA tile (= TMEM lanes)
 constexpr int TN = 64;             // columns per accumulator tile
-constexpr int KC = 64;             // contraction bytes per smem stage
+constexpr int KC = 64;             // contraction bytes per smem stage (32 when K == 32)
 constexpr int A_CHUNK = 4 * TM * KC;   // 32768 B: four byte planes of a 128 x 64 slice
 constexpr int B_CHUNK = 4 * TN * KC;   // 16384 B
 constexpr int STAGES = 4;
@@ -38,7 +38,8 @@ struct Region {
     int n;            // order of W (row stride in words)
     int r0, r1;       // rows of C updated
     int c0, c1;       // columns of C updated
-    int k0, K;        // contraction range; K is a multiple of 64, at most MAX_K
+    int k0, K;        // contraction range; K is 32 or a multiple of 64, at most MAX_K
+    int kc;           // contraction bytes per stage: min(K, 64)
     int row_tiles;    // ceil((r1 - r0) / 128)
     int col_tiles;    // ceil((c1 - c0) / 64)
     int tiles_per_cta;  // column tiles handled by one CTA
@@ -46,12 +47,13 @@ struct Region {
 
 inline size_t a_plane_bytes(const Region& g) { return (size_t)g.row_tiles * g.K * 4 * TM; }   // per prime
 inline size_t b_plane_bytes(const Region& g) { return (size_t)g.col_tiles * g.K * 4 * TN; }   // per prime
-inline size_t smem_bytes(int K) { return (size_t)(K / KC) * A_CHUNK + (size_t)STAGES * B_CHUNK + 256; }
+inline size_t smem_bytes(int K) { return (size_t)K * 4 * TM + (size_t)STAGES * B_CHUNK + 256; }
+inline bool depth_ok(int K) { return K == 32 || (K % KC == 0 && K >= KC && K <= MAX_K); }
 
 #ifdef __CUDACC__
 
 // ---- byte-plane split ---------------------------------------------------------------------------------
-// A planes of prime g, row tile ti:  [K/64][plane a][k16 = 4][row = 128][16 B]
+// A planes of prime g, row tile ti:  [K/kc][plane a][k16 = kc/16][row = 128][16 B]
 __global__ void __launch_bounds__(256) k_tc_split_a(const uint32_t* __restrict__ W, uint8_t* __restrict__ AP, Region g) {
     const int q_per = g.K / 16;                       // 16-byte k groups
     const int64_t per_prime = (int64_t)g.row_tiles * TM * q_per;
@@ -79,8 +81,9 @@ __global__ void __launch_bounds__(256) k_tc_split_a(const uint32_t* __restrict__
 #pragma unroll
         for (int i = 0; i < 16; ++i) w[i] = 0u;
     }
-    uint8_t* dst = AP + ((int64_t)prime * g.row_tiles + ti) * ((int64_t)g.K * 4 * TM) + (int64_t)(q / 4) * A_CHUNK +
-                   (q % 4) * (TM * 16) + r * 16;
+    const int qc = g.kc / 16;                          // 16-byte groups per stage
+    uint8_t* dst = AP + ((int64_t)prime * g.row_tiles + ti) * ((int64_t)g.K * 4 * TM) + (int64_t)(q / qc) * (4 * TM * g.kc) +
+                   (q % qc) * (TM * 16) + r * 16;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         uint32_t o[4];
@@ -88,11 +91,11 @@ __global__ void __launch_bounds__(256) k_tc_split_a(const uint32_t* __restrict__
         for (int i = 0; i < 4; ++i)
             o[i] = ((w[4 * i] >> (8 * a)) & 255u) | (((w[4 * i + 1] >> (8 * a)) & 255u) << 8) |
                    (((w[4 * i + 2] >> (8 * a)) & 255u) << 16) | (((w[4 * i + 3] >> (8 * a)) & 255u) << 24);
-        *reinterpret_cast<uint4*>(dst + a * (4 * TM * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(dst + a * (TM * g.kc)) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
-// B planes of prime g, column tile tj:  [K/64][plane b][k16 = 4][col = 64][16 B]   (U transposed: K-major)
+// B planes of prime g, column tile tj:  [K/kc][plane b][k16 = kc/16][col = 64][16 B]   (U transposed: K-major)
 __global__ void __launch_bounds__(256) k_tc_split_b(const uint32_t* __restrict__ W, uint8_t* __restrict__ BP, Region g) {
     const int q_per = g.K / 16;
     const int64_t per_prime = (int64_t)g.col_tiles * TN * q_per;
@@ -112,8 +115,9 @@ __global__ void __launch_bounds__(256) k_tc_split_b(const uint32_t* __restrict__
 #pragma unroll
         for (int i = 0; i < 16; ++i) w[i] = 0u;
     }
-    uint8_t* dst = BP + ((int64_t)prime * g.col_tiles + tj) * ((int64_t)g.K * 4 * TN) + (int64_t)(q / 4) * B_CHUNK +
-                   (q % 4) * (TN * 16) + c * 16;
+    const int qc = g.kc / 16;
+    uint8_t* dst = BP + ((int64_t)prime * g.col_tiles + tj) * ((int64_t)g.K * 4 * TN) + (int64_t)(q / qc) * (4 * TN * g.kc) +
+                   (q % qc) * (TN * 16) + c * 16;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
         uint32_t o[4];
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(256) k_tc_split_b(const uint32_t* __restrict__
         for (int i = 0; i < 4; ++i)
             o[i] = ((w[4 * i] >> (8 * b)) & 255u) | (((w[4 * i + 1] >> (8 * b)) & 255u) << 8) |
                    (((w[4 * i + 2] >> (8 * b)) & 255u) << 16) | (((w[4 * i + 3] >> (8 * b)) & 255u) << 24);
-        *reinterpret_cast<uint4*>(dst + b * (4 * TN * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(dst + b * (TN * g.kc)) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -206,10 +210,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
     const int tj0 = blockIdx.y * g.tiles_per_cta;
     const int tj1 = min(g.col_tiles, tj0 + g.tiles_per_cta);
     const int ntiles = tj1 - tj0;
-    const int kchunks = g.K / KC;
+    const int kchunks = g.K / g.kc;
+    const uint32_t a_chunk = 4u * TM * g.kc, b_chunk = 4u * TN * g.kc;   // bytes per stage
+    const uint32_t a_plane = TM * g.kc, b_plane = TN * g.kc;             // bytes per byte plane inside a stage
+    const int ksteps = g.kc / 32;                                        // MMA K = 32 bytes
 
     uint8_t* smA = smem;
-    uint8_t* smB = smem + (size_t)kchunks * A_CHUNK;
+    uint8_t* smB = smem + (size_t)g.K * 4 * TM;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)STAGES * B_CHUNK);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
     const uint32_t bar_a_full = smem_u32(bars + 0);
@@ -245,16 +252,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
         // ===== copy producer =====
         if (lane == 0) {
             const uint8_t* srcA = a.AP + ((int64_t)prime * g.row_tiles + ti) * ((int64_t)g.K * 4 * TM);
-            mbar_expect_tx(bar_a_full, (uint32_t)(kchunks * A_CHUNK));
+            mbar_expect_tx(bar_a_full, (uint32_t)kchunks * a_chunk);
             for (int kc = 0; kc < kchunks; ++kc)
-                bulk_g2s(smem_u32(smA + (size_t)kc * A_CHUNK), srcA + (size_t)kc * A_CHUNK, A_CHUNK, bar_a_full);
+                bulk_g2s(smem_u32(smA + (size_t)kc * a_chunk), srcA + (size_t)kc * a_chunk, a_chunk, bar_a_full);
             int stage = 0, phase = 0;
             for (int t = 0; t < ntiles; ++t) {
                 const uint8_t* srcB = a.BP + ((int64_t)prime * g.col_tiles + tj0 + t) * ((int64_t)g.K * 4 * TN);
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(bar_b_full + 8 * stage, B_CHUNK);
-                    bulk_g2s(smem_u32(smB + (size_t)stage * B_CHUNK), srcB + (size_t)kc * B_CHUNK, B_CHUNK,
+                    mbar_expect_tx(bar_b_full + 8 * stage, b_chunk);
+                    bulk_g2s(smem_u32(smB + (size_t)stage * B_CHUNK), srcB + (size_t)kc * b_chunk, b_chunk,
                              bar_b_full + 8 * stage);
                     if (++stage == STAGES) stage = 0, phase ^= 1;
                 }
@@ -280,16 +287,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(bar_b_full + 8 * stage, phase);
                     tc_fence_after();
-#pragma unroll
-                    for (int s = 0; s < 2; ++s) {
+                    for (int s = 0; s < ksteps; ++s) {
 #pragma unroll
                         for (int pa = 0; pa < 4; ++pa) {
                             const uint64_t ad =
-                                smem_desc(smA_u + kc * A_CHUNK + pa * (4 * TM * 16) + s * (2 * TM * 16), a_lbo, a_sbo);
+                                smem_desc(smA_u + kc * a_chunk + pa * a_plane + s * (2 * TM * 16), a_lbo, a_sbo);
 #pragma unroll
                             for (int pb = 0; pb < 4; ++pb) {
                                 const uint64_t bd = smem_desc(
-                                    smB_u + stage * B_CHUNK + pb * (4 * TN * 16) + s * (2 * TN * 16), b_lbo, b_sbo);
+                                    smB_u + stage * B_CHUNK + pb * b_plane + s * (2 * TN * 16), b_lbo, b_sbo);
                                 const uint32_t first = (kc == 0 && s == 0 && (pa == 0 || pb == 3)) ? 0u : 1u;
                                 tc_mma_i8(tmem_base + (uint32_t)((pa + pb) * TN), ad, bd, idesc, first);
                             }
@@ -312,53 +318,56 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
         uint32_t* Wg = a.W + (int64_t)prime * g.n * g.n;
         const bool vec_ok = (g.n & 3) == 0 && (g.c0 & 3) == 0;
         for (int t = 0; t < ntiles; ++t) {
+            // C does not depend on the MMAs: fetch both 16-column chunks of this row BEFORE waiting for the
+            // accumulators, so the HBM/L2 latency hides behind the tensor-core phase of the tile.
+            const int colb = g.c0 + (tj0 + t) * TN + half * 32;
+            uint32_t* cp = Wg + (int64_t)row * g.n + colb;
+            const bool live = row < g.r1 && colb < g.c1;
+            const bool full = live && vec_ok && colb + 32 <= g.c1;
+            uint32_t cv[32];
+            if (full) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(cp + 4 * i);
+                    cv[4 * i] = v.x, cv[4 * i + 1] = v.y, cv[4 * i + 2] = v.z, cv[4 * i + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) cv[i] = (live && colb + i < g.c1) ? cp[i] : 0u;
+            }
             mbar_wait(bar_acc_full, (uint32_t)(t & 1));
             tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 const int cl = half * 32 + ch * 16;              // first column of the chunk inside the tile
                 uint32_t q[7][16];
 #pragma unroll
                 for (int s = 0; s < 7; ++s) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * TN + cl), q[s]);
                 tmem_wait_ld();
-                const int col = g.c0 + (tj0 + t) * TN + cl;
-                if (row < g.r1 && col < g.c1) {
-                    uint32_t* cp = Wg + (int64_t)row * g.n + col;
-                    uint32_t cv[16];
-                    const bool full = vec_ok && col + 16 <= g.c1;
-                    if (full) {
+                if (ch == 1) {                                   // every accumulator word of this warp is in registers:
+                    tc_fence_before();                           // hand TMEM back so the next tile's MMAs overlap the rest
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_acc_empty);
+                }
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint4 v = *reinterpret_cast<const uint4*>(cp + 4 * i);
-                            cv[4 * i] = v.x, cv[4 * i + 1] = v.y, cv[4 * i + 2] = v.z, cv[4 * i + 3] = v.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) cv[i] = col + i < g.c1 ? cp[i] : 0u;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        uint64_t acc = (uint64_t)q[0][i] + ((uint64_t)q[1][i] << 8) + ((uint64_t)q[2][i] << 16) +
-                                       ((uint64_t)q[3][i] << 24) + (uint64_t)q[4][i] * c4 + (uint64_t)q[5][i] * c5 +
-                                       (uint64_t)q[6][i] * c6;
-                        const uint32_t r = mont_redc(acc, p, pinv);
-                        const uint32_t o = cv[i] + r;
-                        cv[i] = min(o, o - p);
-                    }
-                    if (full) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            *reinterpret_cast<uint4*>(cp + 4 * i) = make_uint4(cv[4 * i], cv[4 * i + 1], cv[4 * i + 2], cv[4 * i + 3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (col + i < g.c1) cp[i] = cv[i];
-                    }
+                for (int i = 0; i < 16; ++i) {
+                    uint64_t acc = (uint64_t)q[0][i] + ((uint64_t)q[1][i] << 8) + ((uint64_t)q[2][i] << 16) +
+                                   ((uint64_t)q[3][i] << 24) + (uint64_t)q[4][i] * c4 + (uint64_t)q[5][i] * c5 +
+                                   (uint64_t)q[6][i] * c6;
+                    const uint32_t r = mont_redc(acc, p, pinv);
+                    const uint32_t o = cv[ch * 16 + i] + r;
+                    cv[ch * 16 + i] = min(o, o - p);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acc_empty);
+            if (full) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<uint4*>(cp + 4 * i) = make_uint4(cv[4 * i], cv[4 * i + 1], cv[4 * i + 2], cv[4 * i + 3]);
+            } else if (live) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (colb + i < g.c1) cp[i] = cv[i];
+            }
         }
     }
     tc_fence_before();

@@ -53,6 +53,7 @@ int main(int argc, char** argv) {
     g.r1 = g.c1 = n;
     g.k0 = k0;
     g.K = K;
+    g.kc = K < KC ? K : KC;
     g.row_tiles = (g.r1 - g.r0 + TM - 1) / TM;
     g.col_tiles = (g.c1 - g.c0 + TN - 1) / TN;
     g.tiles_per_cta = g.col_tiles;
