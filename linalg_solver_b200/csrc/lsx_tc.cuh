@@ -161,6 +161,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -268,43 +277,47 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread =====
-        if (lane == 0) {
-            // instruction descriptor: D = s32 (2 << 4), A = B = u8 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-            const uint32_t idesc = (2u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            uint32_t a_lbo = TM * 16, b_lbo = TN * 16, a_sbo = 128, b_sbo = 128;
-            if (a.swap_lbo_sbo) {
-                uint32_t t0 = a_lbo; a_lbo = a_sbo; a_sbo = t0;
-                t0 = b_lbo; b_lbo = b_sbo; b_sbo = t0;
-            }
-            const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
-            mbar_wait(bar_a_full, 0);
+        // ===== MMA issuer: the whole warp walks the pipeline (uniform control flow keeps the descriptors in
+        // uniform registers), one elected lane issues the tcgen05 instructions =====
+        // instruction descriptor: D = s32 (2 << 4), A = B = u8 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+        const uint32_t idesc = (2u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+        uint32_t a_lbo = TM * 16, b_lbo = TN * 16, a_sbo = 128, b_sbo = 128;
+        if (a.swap_lbo_sbo) {
+            uint32_t t0 = a_lbo; a_lbo = a_sbo; a_sbo = t0;
+            t0 = b_lbo; b_lbo = b_sbo; b_sbo = t0;
+        }
+        const uint64_t adesc0 = smem_desc(smem_u32(smA), a_lbo, a_sbo);   // + (byte offset >> 4) per operand slice
+        const uint64_t bdesc0 = smem_desc(smem_u32(smB), b_lbo, b_sbo);
+        mbar_wait(bar_a_full, 0);
+        tc_fence_after();
+        int stage = 0, phase = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            mbar_wait(bar_acc_empty, (uint32_t)((t & 1) ^ 1));
             tc_fence_after();
-            int stage = 0, phase = 0;
-            for (int t = 0; t < ntiles; ++t) {
-                mbar_wait(bar_acc_empty, (uint32_t)((t & 1) ^ 1));
+            for (int kc = 0; kc < kchunks; ++kc) {
+                mbar_wait(bar_b_full + 8 * stage, phase);
                 tc_fence_after();
-                for (int kc = 0; kc < kchunks; ++kc) {
-                    mbar_wait(bar_b_full + 8 * stage, phase);
-                    tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t ad_st = adesc0 + ((uint32_t)kc * a_chunk >> 4);
+                    const uint64_t bd_st = bdesc0 + ((uint32_t)stage * B_CHUNK >> 4);
                     for (int s = 0; s < ksteps; ++s) {
+                        const uint32_t fresh = (kc | s) == 0 ? 0u : 1u;    // 0: first write of the accumulators
 #pragma unroll
                         for (int pa = 0; pa < 4; ++pa) {
-                            const uint64_t ad =
-                                smem_desc(smA_u + kc * a_chunk + pa * a_plane + s * (2 * TM * 16), a_lbo, a_sbo);
+                            const uint64_t ad = ad_st + (((uint32_t)pa * a_plane + (uint32_t)s * (2 * TM * 16)) >> 4);
 #pragma unroll
                             for (int pb = 0; pb < 4; ++pb) {
-                                const uint64_t bd = smem_desc(
-                                    smB_u + stage * B_CHUNK + pb * b_plane + s * (2 * TN * 16), b_lbo, b_sbo);
-                                const uint32_t first = (kc == 0 && s == 0 && (pa == 0 || pb == 3)) ? 0u : 1u;
-                                tc_mma_i8(tmem_base + (uint32_t)((pa + pb) * TN), ad, bd, idesc, first);
+                                const uint64_t bd = bd_st + (((uint32_t)pb * b_plane + (uint32_t)s * (2 * TN * 16)) >> 4);
+                                tc_mma_i8(tmem_base + (uint32_t)((pa + pb) * TN), ad, bd, idesc,
+                                          (pa == 0 || pb == 3) ? fresh : 1u);
                             }
                         }
                     }
                     tc_commit(bar_b_empty + 8 * stage);          // frees the stage when these MMAs have read it
-                    if (++stage == STAGES) stage = 0, phase ^= 1;
+                    if (kc == kchunks - 1) tc_commit(bar_acc_full);   // accumulators of tile t complete
                 }
-                tc_commit(bar_acc_full);                         // accumulators of tile t complete
+                __syncwarp();
+                if (++stage == STAGES) stage = 0, phase ^= 1;
             }
         }
     } else {
