@@ -321,6 +321,42 @@ __global__ void __launch_bounds__(128) k_trsm(LargeArgs a, int k0, int nb, int c
     }
 }
 
+// Same solve for nb <= 32 with the column in REGISTERS: all 32 loads are issued up front, the multipliers
+// come from shared memory as broadcast 16-byte loads (4 multiply-adds per load), fully unrolled.
+constexpr int TS = 32;
+__global__ void __launch_bounds__(128) k_trsm32(LargeArgs a, int k0, int nb, int ca, int cb) {
+    __shared__ __align__(16) uint32_t Ln[TS][TS];
+    const int n = a.n, g = blockIdx.y, tid = threadIdx.x;
+    const uint32_t p = a.primes[g].p, pinv = a.primes[g].pinv;
+    uint32_t* Wg = a.W + (int64_t)g * n * n;
+    for (int e = tid; e < TS * TS; e += 128) {
+        const int i = e / TS, t = e % TS;
+        Ln[i][t] = (i < nb && t < i) ? Wg[(int64_t)(k0 + i) * n + k0 + t] : 0u;
+    }
+    __syncthreads();
+    const int c = ca + blockIdx.x * 128 + tid;
+    if (c >= cb) return;
+    uint32_t u[TS];
+#pragma unroll
+    for (int i = 0; i < TS; ++i) u[i] = i < nb ? Wg[(int64_t)(k0 + i) * n + c] : 0u;
+#pragma unroll
+    for (int i = 1; i < TS; ++i) {
+        uint64_t acc = (uint64_t)u[i] << 32;
+#pragma unroll
+        for (int t4 = 0; t4 < i; t4 += 4) {
+            const uint4 l = *reinterpret_cast<const uint4*>(&Ln[i][t4]);     // entries at t >= i are zero
+            acc = mac_lazy(acc, l.x, u[t4], p);
+            if (t4 + 1 < i) acc = mac_lazy(acc, l.y, u[t4 + 1], p);
+            if (t4 + 2 < i) acc = mac_lazy(acc, l.z, u[t4 + 2], p);
+            if (t4 + 3 < i) acc = mac_lazy(acc, l.w, u[t4 + 3], p);
+        }
+        u[i] = mont_redc(acc, p, pinv);
+    }
+#pragma unroll
+    for (int i = 1; i < TS; ++i)
+        if (i < nb) Wg[(int64_t)(k0 + i) * n + c] = u[i];
+}
+
 // C[i][j] = redc((C[i][j] << 32) + sum_k Lneg[i][k] * U[k][j])  on rows [r0, r1) x cols [c0, c1),
 // Lneg = W[.][k0 .. k0 + K), U = W[k0 .. k0 + K)[.], K <= 64: integer pipe.
 __global__ void __launch_bounds__(256) k_gemm_int(LargeArgs a, int r0, int r1, int c0, int c1, int k0, int K) {
@@ -473,18 +509,21 @@ struct Driver {
             g.kc = std::min(K, lsx_tc::KC);
             g.row_tiles = (r1 - r0 + lsx_tc::TM - 1) / lsx_tc::TM;
             g.col_tiles = (c1 - c0 + lsx_tc::TN - 1) / lsx_tc::TN;
-            const int units = g.row_tiles * a.G;
-            int groups = std::min(g.col_tiles, std::max(1, (2 * ctx->sm_count + units - 1) / units));
-            g.tiles_per_cta = (g.col_tiles + groups - 1) / groups;
-            groups = (g.col_tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
+            // tall and narrow (inside a panel): keep the one or two column tiles resident and stream the rows
+            g.b_stationary = (g.col_tiles <= 2 && g.row_tiles > 2) ? 1 : 0;
+            const int fixed = g.b_stationary ? g.col_tiles : g.row_tiles, looped = g.b_stationary ? g.row_tiles : g.col_tiles;
+            const int units = fixed * a.G;
+            int groups = std::min(looped, std::max(1, (2 * ctx->sm_count + units - 1) / units));
+            g.tiles_per_cta = (looped + groups - 1) / groups;
+            groups = (looped + g.tiles_per_cta - 1) / g.tiles_per_cta;
             const int64_t ta = (int64_t)g.row_tiles * lsx_tc::TM * (K / 16), tb = (int64_t)g.col_tiles * lsx_tc::TN * (K / 16);
             lsx_tc::k_tc_split_a<<<dim3((unsigned)((ta + 255) / 256), a.G), 256, 0, st>>>(a.W, AP, g);
             lsx_tc::k_tc_split_b<<<dim3((unsigned)((tb + 255) / 256), a.G), 256, 0, st>>>(a.W, BP, g);
             lsx_tc::GemmArgs ga{};
-            ga.W = a.W, ga.AP = AP, ga.BP = BP, ga.primes = a.primes, ga.g = g, ga.swap_lbo_sbo = 0;
+            ga.W = a.W, ga.AP = AP, ga.BP = BP, ga.primes = a.primes, ga.g = g, ga.debug = 0;
             const bool big = K == NB_OUT;
             if (big) lsx_timing_begin(ctx);
-            lsx_tc::k_gemm_tc<<<dim3(g.row_tiles, groups, a.G), lsx_tc::THREADS, lsx_tc::smem_bytes(K), st>>>(ga);
+            lsx_tc::k_gemm_tc<<<dim3(fixed, groups, a.G), lsx_tc::THREADS, lsx_tc::smem_bytes(K, g.b_stationary), st>>>(ga);
             if (big) lsx_timing_end(ctx);
             ctx->launches += 3;
             return;
@@ -510,7 +549,12 @@ struct Driver {
     // columns [ca, cb): U = L11^-1 * A for the diagonal block [k0, k0 + w)
     void trsm(int k0, int w, int ca, int cb) {
         if (cb <= ca || w <= 0) return;
-        if (w <= (use_tc ? 32 : KI)) {
+        if (w <= TS) {
+            k_trsm32<<<dim3((cb - ca + 127) / 128, a.G), 128, 0, ctx->stream>>>(a, k0, w, ca, cb);
+            ctx->launches++;
+            return;
+        }
+        if (!use_tc && w <= KI) {
             const size_t smem = (size_t)(KI * KI + KI * 128) * 4;
             k_trsm<<<dim3((cb - ca + 127) / 128, a.G), 128, smem, ctx->stream>>>(a, k0, w, ca, cb);
             ctx->launches++;
@@ -587,7 +631,7 @@ int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_b
     LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_gemm_int, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm));
     if (use_tc)
         LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(lsx_tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)lsx_tc::smem_bytes(lsx_tc::MAX_K)));
+                                               (int)std::max(lsx_tc::smem_bytes(lsx_tc::MAX_K, 0), lsx_tc::smem_bytes(lsx_tc::MAX_K, 1))));
     for (int g0 = 0; g0 < count; g0 += G) {
         const int Gc = std::min(G, count - g0);
         Driver d{};

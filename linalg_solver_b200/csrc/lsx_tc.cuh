@@ -15,10 +15,11 @@
 // accumulators with tcgen05.ld, forms  S = sum_t Q_t * (2^(8t) mod p)  < 2^60 in 64 bits and finishes with
 // one Montgomery reduction:  C + REDC(S) mod p  — bit-identical to the integer-pipe k_gemm.
 //
-// CTA = (prime g, 128-row tile, a contiguous group of 64-column tiles).  The A planes of the row tile stay
-// resident in shared memory for the whole CTA; B planes stream through a ring of 16 KB stages filled by
-// cp.async.bulk (TMA engine, SASS UBLKCP) and released by tcgen05.commit.  Warp 0 = TMEM allocator + copy
-// producer, warp 1 = MMA issuer (one lane), warps 2..9 = epilogue (two warps per TMEM lane quadrant).
+// CTA = (prime g, 128-row tile, a contiguous group of 64-column tiles) or, for tall narrow regions, (prime,
+// 64-column tile, group of row tiles).  The planes of the fixed tile stay resident in shared memory for the
+// whole CTA; the other operand streams through a ring of stages filled by cp.async.bulk (TMA engine, SASS
+// UBLKCP) and released by tcgen05.commit.  Warp 0 = TMEM allocator + copy producer, warp 1 = MMA issuer
+// (one elected lane), warps 2..9 = epilogue (two warps per TMEM lane quadrant).
 #pragma once
 #include "lsx_internal.h"
 
@@ -29,7 +30,8 @@ constexpr int TN = 64;             // columns per accumulator tile
 constexpr int KC = 64;             // contraction bytes per smem stage (32 when K == 32)
 constexpr int A_CHUNK = 4 * TM * KC;   // 32768 B: four byte planes of a 128 x 64 slice
 constexpr int B_CHUNK = 4 * TN * KC;   // 16384 B
-constexpr int STAGES = 4;
+constexpr int STAGES_A = 6;        // ring slots when the A planes are stationary (16 KB B slots)
+constexpr int STAGES_B = 4;        // ring slots when the B planes are stationary (32 KB A slots)
 constexpr int THREADS = 320;
 constexpr int TMEM_COLS = 512;     // 7 accumulators x 64 columns = 448, rounded to a power of two
 constexpr int MAX_K = 256;
@@ -42,12 +44,16 @@ struct Region {
     int kc;           // contraction bytes per stage: min(K, 64)
     int row_tiles;    // ceil((r1 - r0) / 128)
     int col_tiles;    // ceil((c1 - c0) / 64)
-    int tiles_per_cta;  // column tiles handled by one CTA
+    int tiles_per_cta;  // tiles of the looped dimension handled by one CTA
+    int b_stationary;   // 0: CTA keeps the A planes of one row tile and loops over column tiles; 1: the reverse
 };
 
 inline size_t a_plane_bytes(const Region& g) { return (size_t)g.row_tiles * g.K * 4 * TM; }   // per prime
 inline size_t b_plane_bytes(const Region& g) { return (size_t)g.col_tiles * g.K * 4 * TN; }   // per prime
-inline size_t smem_bytes(int K) { return (size_t)K * 4 * TM + (size_t)STAGES * B_CHUNK + 256; }
+inline size_t smem_bytes(int K, int b_stationary) {
+    return b_stationary ? (size_t)K * 4 * TN + (size_t)STAGES_B * A_CHUNK + 256
+                        : (size_t)K * 4 * TM + (size_t)STAGES_A * B_CHUNK + 256;
+}
 inline bool depth_ok(int K) { return K == 32 || (K % KC == 0 && K >= KC && K <= MAX_K); }
 
 #ifdef __CUDACC__
@@ -208,41 +214,59 @@ struct GemmArgs {
     const uint8_t* BP;          // byte planes of U, see k_tc_split_b
     const PrimeRec* primes;     // [G]
     Region g;
-    int swap_lbo_sbo;           // test hook: exchange the two descriptor strides
+    int debug;                  // test hooks: bit 0 exchanges the two descriptor strides, bit 1 skips the epilogue
 };
 
+// Tile loop of one CTA.
+//   g.b_stationary == 0: CTA = (row tile blockIdx.x, column-tile group blockIdx.y); the A planes of the row
+//                        tile stay in shared memory, B planes stream through the ring (wide regions).
+//   g.b_stationary == 1: CTA = (column tile blockIdx.x, row-tile group blockIdx.y); the B planes stay, A planes
+//                        stream (tall and narrow regions inside a panel: one or two column tiles in all).
+// The 16 byte-plane products of a tile are issued in TWO passes over the resident K chunks: first the ten
+// products of weight 2^0 .. 2^24 into accumulators 0..3 ("low"), then the six of weight 2^32 .. 2^48 into
+// accumulators 4..6 ("high").  The epilogue drains the low accumulators while the tensor pipe works on the
+// high pass, and the high ones while it works on the low pass of the NEXT tile, so the accumulators are
+// double-buffered in effect without needing more than 448 TMEM columns.
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const Region& g = a.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ti = blockIdx.x, prime = blockIdx.z;
-    const int tj0 = blockIdx.y * g.tiles_per_cta;
-    const int tj1 = min(g.col_tiles, tj0 + g.tiles_per_cta);
-    const int ntiles = tj1 - tj0;
-    const int kchunks = g.K / g.kc;
-    const uint32_t a_chunk = 4u * TM * g.kc, b_chunk = 4u * TN * g.kc;   // bytes per stage
-    const uint32_t a_plane = TM * g.kc, b_plane = TN * g.kc;             // bytes per byte plane inside a stage
+    const int prime = blockIdx.z;
+    const bool bst = g.b_stationary != 0;
+    const int fixed_tile = blockIdx.x;                                   // row tile (A stationary) or column tile
+    const int loop_tiles = bst ? g.row_tiles : g.col_tiles;
+    const int t0 = blockIdx.y * g.tiles_per_cta;
+    const int ntiles = min(loop_tiles, t0 + g.tiles_per_cta) - t0;
+    const int kchunks = g.K / g.kc;                                      // <= 4 <= ring slots
+    const uint32_t a_chunk = 4u * TM * g.kc, b_chunk = 4u * TN * g.kc;   // bytes per K chunk (four byte planes)
+    const uint32_t a_plane = TM * g.kc, b_plane = TN * g.kc;             // bytes per byte plane inside a chunk
     const int ksteps = g.kc / 32;                                        // MMA K = 32 bytes
+    const uint32_t st_chunk = bst ? b_chunk : a_chunk;                   // stationary operand, per chunk
+    const uint32_t rg_chunk = bst ? a_chunk : b_chunk;                   // streamed operand, per chunk
+    const uint32_t rg_stride = bst ? (uint32_t)A_CHUNK : (uint32_t)B_CHUNK;   // ring slot size
+    const uint32_t STAGES = bst ? STAGES_B : STAGES_A;
 
-    uint8_t* smA = smem;
-    uint8_t* smB = smem + (size_t)g.K * 4 * TM;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)STAGES * B_CHUNK);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-    const uint32_t bar_a_full = smem_u32(bars + 0);
-    const uint32_t bar_acc_full = smem_u32(bars + 1);
-    const uint32_t bar_acc_empty = smem_u32(bars + 2);
-    const uint32_t bar_b_full = smem_u32(bars + 4);              // [STAGES]
-    const uint32_t bar_b_empty = smem_u32(bars + 4 + STAGES);    // [STAGES]
+    uint8_t* smS = smem;                                                 // stationary planes: kchunks * st_chunk
+    uint8_t* smR = smem + (size_t)kchunks * st_chunk;                    // ring: STAGES slots
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smR + (size_t)STAGES * rg_stride);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    const uint32_t bar_s_full = smem_u32(bars + 0);
+    const uint32_t bar_lo_full = smem_u32(bars + 1), bar_lo_empty = smem_u32(bars + 2);
+    const uint32_t bar_hi_full = smem_u32(bars + 3), bar_hi_empty = smem_u32(bars + 4);
+    const uint32_t bar_r_full = smem_u32(bars + 6);                      // [STAGES]
+    const uint32_t bar_r_empty = smem_u32(bars + 6 + STAGES_A);          // [STAGES]
 
-    if (ntiles <= 0) return;                                     // uniform per CTA
+    if (ntiles <= 0) return;                                             // uniform per CTA
     if (warp == 0) {
         if (lane == 0) {
-            mbar_init(bar_a_full, 1);
-            mbar_init(bar_acc_full, 1);
-            mbar_init(bar_acc_empty, 8);
-            for (int s = 0; s < STAGES; ++s) {
-                mbar_init(bar_b_full + 8 * s, 1);
-                mbar_init(bar_b_empty + 8 * s, 1);
+            mbar_init(bar_s_full, 1);
+            mbar_init(bar_lo_full, 1);
+            mbar_init(bar_lo_empty, 8);
+            mbar_init(bar_hi_full, 1);
+            mbar_init(bar_hi_empty, 8);
+            for (uint32_t s = 0; s < STAGES; ++s) {
+                mbar_init(bar_r_full + 8 * s, 1);
+                mbar_init(bar_r_empty + 8 * s, 1);
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -260,19 +284,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
     if (warp == 0) {
         // ===== copy producer =====
         if (lane == 0) {
-            const uint8_t* srcA = a.AP + ((int64_t)prime * g.row_tiles + ti) * ((int64_t)g.K * 4 * TM);
-            mbar_expect_tx(bar_a_full, (uint32_t)kchunks * a_chunk);
+            const uint8_t* baseA = a.AP + (int64_t)prime * g.row_tiles * ((int64_t)g.K * 4 * TM);
+            const uint8_t* baseB = a.BP + (int64_t)prime * g.col_tiles * ((int64_t)g.K * 4 * TN);
+            const uint8_t* srcS = bst ? baseB + (int64_t)fixed_tile * ((int64_t)g.K * 4 * TN)
+                                      : baseA + (int64_t)fixed_tile * ((int64_t)g.K * 4 * TM);
+            mbar_expect_tx(bar_s_full, (uint32_t)kchunks * st_chunk);
             for (int kc = 0; kc < kchunks; ++kc)
-                bulk_g2s(smem_u32(smA + (size_t)kc * a_chunk), srcA + (size_t)kc * a_chunk, a_chunk, bar_a_full);
-            int stage = 0, phase = 0;
+                bulk_g2s(smem_u32(smS + (size_t)kc * st_chunk), srcS + (size_t)kc * st_chunk, st_chunk, bar_s_full);
+            uint32_t cnt = 0;
             for (int t = 0; t < ntiles; ++t) {
-                const uint8_t* srcB = a.BP + ((int64_t)prime * g.col_tiles + tj0 + t) * ((int64_t)g.K * 4 * TN);
-                for (int kc = 0; kc < kchunks; ++kc) {
-                    mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(bar_b_full + 8 * stage, b_chunk);
-                    bulk_g2s(smem_u32(smB + (size_t)stage * B_CHUNK), srcB + (size_t)kc * b_chunk, b_chunk,
-                             bar_b_full + 8 * stage);
-                    if (++stage == STAGES) stage = 0, phase ^= 1;
+                const uint8_t* srcR = bst ? baseA + (int64_t)(t0 + t) * ((int64_t)g.K * 4 * TM)
+                                          : baseB + (int64_t)(t0 + t) * ((int64_t)g.K * 4 * TN);
+                for (int kc = 0; kc < kchunks; ++kc, ++cnt) {
+                    const uint32_t slot = cnt % STAGES, phase = (cnt / STAGES) & 1u;
+                    mbar_wait(bar_r_empty + 8 * slot, phase ^ 1u);
+                    mbar_expect_tx(bar_r_full + 8 * slot, rg_chunk);
+                    bulk_g2s(smem_u32(smR + (size_t)slot * rg_stride), srcR + (size_t)kc * rg_chunk, rg_chunk,
+                             bar_r_full + 8 * slot);
                 }
             }
         }
@@ -282,42 +310,51 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
         // instruction descriptor: D = s32 (2 << 4), A = B = u8 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
         const uint32_t idesc = (2u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
         uint32_t a_lbo = TM * 16, b_lbo = TN * 16, a_sbo = 128, b_sbo = 128;
-        if (a.swap_lbo_sbo) {
-            uint32_t t0 = a_lbo; a_lbo = a_sbo; a_sbo = t0;
-            t0 = b_lbo; b_lbo = b_sbo; b_sbo = t0;
+        if (a.debug & 1) {
+            uint32_t x = a_lbo; a_lbo = a_sbo; a_sbo = x;
+            x = b_lbo; b_lbo = b_sbo; b_sbo = x;
         }
-        const uint64_t adesc0 = smem_desc(smem_u32(smA), a_lbo, a_sbo);   // + (byte offset >> 4) per operand slice
-        const uint64_t bdesc0 = smem_desc(smem_u32(smB), b_lbo, b_sbo);
-        mbar_wait(bar_a_full, 0);
+        // operand bases: + (byte offset >> 4) selects chunk / plane / K step
+        const uint64_t adesc0 = smem_desc(smem_u32(bst ? smR : smS), a_lbo, a_sbo);
+        const uint64_t bdesc0 = smem_desc(smem_u32(bst ? smS : smR), b_lbo, b_sbo);
+        const uint32_t a_step = bst ? rg_stride : a_chunk;               // distance between K chunks of A
+        const uint32_t b_step = bst ? b_chunk : rg_stride;
+        mbar_wait(bar_s_full, 0);
         tc_fence_after();
-        int stage = 0, phase = 0;
-        for (int t = 0; t < ntiles; ++t) {
-            mbar_wait(bar_acc_empty, (uint32_t)((t & 1) ^ 1));
-            tc_fence_after();
-            for (int kc = 0; kc < kchunks; ++kc) {
-                mbar_wait(bar_b_full + 8 * stage, phase);
+        uint32_t cnt = 0;
+        for (int t = 0; t < ntiles; ++t, cnt += kchunks) {
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                mbar_wait(pass ? bar_hi_empty : bar_lo_empty, (uint32_t)((t & 1) ^ 1));
                 tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t ad_st = adesc0 + ((uint32_t)kc * a_chunk >> 4);
-                    const uint64_t bd_st = bdesc0 + ((uint32_t)stage * B_CHUNK >> 4);
-                    for (int s = 0; s < ksteps; ++s) {
-                        const uint32_t fresh = (kc | s) == 0 ? 0u : 1u;    // 0: first write of the accumulators
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    const uint32_t slot = (cnt + kc) % STAGES, phase = ((cnt + kc) / STAGES) & 1u;
+                    if (pass == 0) {
+                        mbar_wait(bar_r_full + 8 * slot, phase);
+                        tc_fence_after();
+                    }
+                    if (elect_one()) {
+                        const uint64_t ad_c = adesc0 + (((bst ? slot : (uint32_t)kc) * a_step) >> 4);
+                        const uint64_t bd_c = bdesc0 + (((bst ? (uint32_t)kc : slot) * b_step) >> 4);
+                        for (int s = 0; s < ksteps; ++s) {
+                            const uint32_t fresh = (kc | s) == 0 ? 0u : 1u;   // 0: first write of the accumulators
 #pragma unroll
-                        for (int pa = 0; pa < 4; ++pa) {
-                            const uint64_t ad = ad_st + (((uint32_t)pa * a_plane + (uint32_t)s * (2 * TM * 16)) >> 4);
+                            for (int pa = 0; pa < 4; ++pa) {
+                                const uint64_t ad = ad_c + (((uint32_t)pa * a_plane + (uint32_t)s * (2 * TM * 16)) >> 4);
 #pragma unroll
-                            for (int pb = 0; pb < 4; ++pb) {
-                                const uint64_t bd = bd_st + (((uint32_t)pb * b_plane + (uint32_t)s * (2 * TN * 16)) >> 4);
-                                tc_mma_i8(tmem_base + (uint32_t)((pa + pb) * TN), ad, bd, idesc,
-                                          (pa == 0 || pb == 3) ? fresh : 1u);
+                                for (int pb = 0; pb < 4; ++pb) {
+                                    if ((pa + pb >= 4) != (pass == 1)) continue;
+                                    const uint64_t bd = bd_c + (((uint32_t)pb * b_plane + (uint32_t)s * (2 * TN * 16)) >> 4);
+                                    tc_mma_i8(tmem_base + (uint32_t)((pa + pb) * TN), ad, bd, idesc,
+                                              (pa == 0 || pb == 3) ? fresh : 1u);
+                                }
                             }
                         }
+                        if (pass == 1) tc_commit(bar_r_empty + 8 * slot);    // slot free once both passes have read it
+                        if (kc == kchunks - 1) tc_commit(pass ? bar_hi_full : bar_lo_full);
                     }
-                    tc_commit(bar_b_empty + 8 * stage);          // frees the stage when these MMAs have read it
-                    if (kc == kchunks - 1) tc_commit(bar_acc_full);   // accumulators of tile t complete
+                    __syncwarp();
                 }
-                __syncwarp();
-                if (++stage == STAGES) stage = 0, phase ^= 1;
             }
         }
     } else {
@@ -327,13 +364,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
         const uint32_t p = P.p, pinv = P.pinv;
         const uint64_t c4 = P.one;                               // 2^32 mod p
         const uint64_t c5 = (c4 << 8) % p, c6 = (c5 << 8) % p;   // 2^40, 2^48 mod p
-        const int row = g.r0 + ti * TM + quad * 32 + lane;
         uint32_t* Wg = a.W + (int64_t)prime * g.n * g.n;
         const bool vec_ok = (g.n & 3) == 0 && (g.c0 & 3) == 0;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32);
         for (int t = 0; t < ntiles; ++t) {
-            // C does not depend on the MMAs: fetch both 16-column chunks of this row BEFORE waiting for the
+            const int ti = bst ? t0 + t : fixed_tile, tj = bst ? fixed_tile : t0 + t;
+            const int row = g.r0 + ti * TM + quad * 32 + lane;
+            // C does not depend on the MMAs: fetch the 32 columns of this row BEFORE waiting for the
             // accumulators, so the HBM/L2 latency hides behind the tensor-core phase of the tile.
-            const int colb = g.c0 + (tj0 + t) * TN + half * 32;
+            const int colb = g.c0 + tj * TN + half * 32;
             uint32_t* cp = Wg + (int64_t)row * g.n + colb;
             const bool live = row < g.r1 && colb < g.c1;
             const bool full = live && vec_ok && colb + 32 <= g.c1;
@@ -348,28 +387,49 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) cv[i] = (live && colb + i < g.c1) ? cp[i] : 0u;
             }
-            mbar_wait(bar_acc_full, (uint32_t)(t & 1));
+            // ---- low accumulators (weights 2^0, 2^8, 2^16, 2^24): exact 64-bit partial sums ----
+            uint64_t lo[32];
+            mbar_wait(bar_lo_full, (uint32_t)(t & 1));
             tc_fence_after();
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
-                const int cl = half * 32 + ch * 16;              // first column of the chunk inside the tile
-                uint32_t q[7][16];
+                uint32_t q[4][16];
 #pragma unroll
-                for (int s = 0; s < 7; ++s) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * TN + cl), q[s]);
+                for (int s = 0; s < 4; ++s) tmem_ld16(lane_base + (uint32_t)(s * TN + ch * 16), q[s]);
                 tmem_wait_ld();
-                if (ch == 1) {                                   // every accumulator word of this warp is in registers:
-                    tc_fence_before();                           // hand TMEM back so the next tile's MMAs overlap the rest
+                if (ch == 1) {                                   // this warp's low words are in registers: hand the
+                    tc_fence_before();                           // low accumulators back to the MMA issuer
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_acc_empty);
+                    if (lane == 0) mbar_arrive(bar_lo_empty);
                 }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    uint64_t acc = (uint64_t)q[0][i] + ((uint64_t)q[1][i] << 8) + ((uint64_t)q[2][i] << 16) +
-                                   ((uint64_t)q[3][i] << 24) + (uint64_t)q[4][i] * c4 + (uint64_t)q[5][i] * c5 +
-                                   (uint64_t)q[6][i] * c6;
-                    const uint32_t r = mont_redc(acc, p, pinv);
-                    const uint32_t o = cv[ch * 16 + i] + r;
-                    cv[ch * 16 + i] = min(o, o - p);
+                for (int i = 0; i < 16; ++i)
+                    lo[ch * 16 + i] = (uint64_t)q[0][i] + ((uint64_t)q[1][i] << 8) + ((uint64_t)q[2][i] << 16) +
+                                      ((uint64_t)q[3][i] << 24);
+            }
+            // ---- high accumulators (weights 2^32, 2^40, 2^48), one Montgomery reduction, C update ----
+            mbar_wait(bar_hi_full, (uint32_t)(t & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t q[3][16];
+#pragma unroll
+                for (int s = 0; s < 3; ++s) tmem_ld16(lane_base + (uint32_t)((4 + s) * TN + ch * 16), q[s]);
+                tmem_wait_ld();
+                if (ch == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_hi_empty);
+                }
+                if (!(a.debug & 2)) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint64_t acc = lo[ch * 16 + i] + (uint64_t)q[0][i] * c4 + (uint64_t)q[1][i] * c5 +
+                                             (uint64_t)q[2][i] * c6;
+                        const uint32_t r = mont_redc(acc, p, pinv);
+                        const uint32_t o = cv[ch * 16 + i] + r;
+                        cv[ch * 16 + i] = min(o, o - p);
+                    }
                 }
             }
             if (full) {

@@ -42,6 +42,8 @@ int main(int argc, char** argv) {
     const int K = argc > 4 ? atoi(argv[4]) : 64;
     const int swap = argc > 5 ? atoi(argv[5]) : 0;
     const int reps = argc > 6 ? atoi(argv[6]) : 3;
+    const int bst = argc > 7 ? atoi(argv[7]) : 0;       // 1: B-stationary CTAs
+    const int cols = argc > 8 ? atoi(argv[8]) : 0;      // restrict the region to this many columns (0: all)
     using namespace lsx_tc;
     std::vector<uint32_t> tab;
     lsx_fill_prime_table(tab, G);
@@ -56,7 +58,12 @@ int main(int argc, char** argv) {
     g.kc = K < KC ? K : KC;
     g.row_tiles = (g.r1 - g.r0 + TM - 1) / TM;
     g.col_tiles = (g.c1 - g.c0 + TN - 1) / TN;
-    g.tiles_per_cta = g.col_tiles;
+    if (cols > 0 && g.c0 + cols < g.c1) {
+        g.c1 = g.c0 + cols;
+        g.col_tiles = (g.c1 - g.c0 + TN - 1) / TN;
+    }
+    g.b_stationary = bst;
+    g.tiles_per_cta = bst ? g.row_tiles : g.col_tiles;
     if (g.row_tiles <= 0 || g.col_tiles <= 0) {
         printf("{\"error\": \"empty region\"}\n");
         return 2;
@@ -85,7 +92,7 @@ int main(int argc, char** argv) {
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     CK(cudaEventElapsedTime(&ms_ref, e0, e1));
-    const size_t smem = smem_bytes(K);
+    const size_t smem = smem_bytes(K, bst);
     CK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GemmArgs a{};
     a.W = dW;
@@ -93,7 +100,7 @@ int main(int argc, char** argv) {
     a.BP = dB;
     a.primes = dP;
     a.g = g;
-    a.swap_lbo_sbo = swap;
+    a.debug = swap;
     for (int rep = 0; rep < reps; ++rep) {
         CK(cudaMemcpy(dW, h.data(), words * 4, cudaMemcpyHostToDevice));
         CK(cudaEventRecord(e0));
@@ -104,7 +111,7 @@ int main(int argc, char** argv) {
         CK(cudaDeviceSynchronize());
         CK(cudaEventElapsedTime(&ms_split, e0, e1));
         CK(cudaEventRecord(e0));
-        k_gemm_tc<<<dim3(g.row_tiles, (g.col_tiles + g.tiles_per_cta - 1) / g.tiles_per_cta, G), THREADS, smem>>>(a);
+        k_gemm_tc<<<dim3(bst ? g.col_tiles : g.row_tiles, 1, G), THREADS, smem>>>(a);
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
         CK(cudaEventElapsedTime(&ms_tc, e0, e1));
@@ -119,7 +126,8 @@ int main(int argc, char** argv) {
             ++bad;
         }
     const double macs = (double)G * (g.r1 - g.r0) * (double)(g.c1 - g.c0) * K;
-    printf("{\"n\": %d, \"G\": %d, \"k0\": %d, \"K\": %d, \"swap\": %d, \"mismatches\": %zu, \"first_bad\": %zu, "
+    printf("{\"bst\": %d, \"cols\": %d, ", bst, g.c1 - g.c0);
+    printf("\"n\": %d, \"G\": %d, \"k0\": %d, \"K\": %d, \"swap\": %d, \"mismatches\": %zu, \"first_bad\": %zu, "
            "\"first_bad_rc\": [%zu, %zu], \"got\": %u, \"ref\": %u, \"ms_ref\": %.3f, \"ms_split\": %.3f, \"ms_tc\": %.3f, "
            "\"mod_mac_per_s\": %.4g, \"int8_tops\": %.1f}\n",
            n, G, k0, K, swap, bad, first_bad, (first_bad % ((size_t)n * n)) / n, first_bad % n, got[first_bad], ref[first_bad],
