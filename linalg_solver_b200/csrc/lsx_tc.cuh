@@ -42,14 +42,25 @@ struct Region {
     int c0, c1;       // columns of C updated
     int k0, K;        // contraction range; K is 32 or a multiple of 64, at most MAX_K
     int kc;           // contraction bytes per stage: min(K, 64)
-    int row_tiles;    // ceil((r1 - r0) / 128)
-    int col_tiles;    // ceil((c1 - c0) / 64)
+    int trans;        // 0: TMEM lanes (M, 128 per tile) are rows of C and TMEM columns (N, 64 per tile) are columns;
+                      // 1: the product is formed transposed (M = columns of C, N = rows), so that the 32 lanes of an
+                      //    epilogue warp touch 32 CONSECUTIVE words of one row of C: coalesced C traffic
+    int m_tiles;      // tiles of 128 along the M dimension
+    int n_tiles;      // tiles of 64 along the N dimension
     int tiles_per_cta;  // tiles of the looped dimension handled by one CTA
-    int b_stationary;   // 0: CTA keeps the A planes of one row tile and loops over column tiles; 1: the reverse
+    int b_stationary;   // 0: CTA keeps the M-operand planes of one M tile and loops over N tiles; 1: the reverse
+    __host__ __device__ int m0() const { return trans ? c0 : r0; }
+    __host__ __device__ int m1() const { return trans ? c1 : r1; }
+    __host__ __device__ int j0() const { return trans ? r0 : c0; }
+    __host__ __device__ int j1() const { return trans ? r1 : c1; }
+    void set_tiles() {
+        m_tiles = (m1() - m0() + TM - 1) / TM;
+        n_tiles = (j1() - j0() + TN - 1) / TN;
+    }
 };
 
-inline size_t a_plane_bytes(const Region& g) { return (size_t)g.row_tiles * g.K * 4 * TM; }   // per prime
-inline size_t b_plane_bytes(const Region& g) { return (size_t)g.col_tiles * g.K * 4 * TN; }   // per prime
+inline size_t a_plane_bytes(const Region& g) { return (size_t)g.m_tiles * g.K * 4 * TM; }   // per prime
+inline size_t b_plane_bytes(const Region& g) { return (size_t)g.n_tiles * g.K * 4 * TN; }   // per prime
 inline size_t smem_bytes(int K, int b_stationary) {
     return b_stationary ? (size_t)K * 4 * TN + (size_t)STAGES_B * A_CHUNK + 256
                         : (size_t)K * 4 * TM + (size_t)STAGES_A * B_CHUNK + 256;
@@ -59,37 +70,48 @@ inline bool depth_ok(int K) { return K == 32 || (K % KC == 0 && K >= KC && K <= 
 #ifdef __CUDACC__
 
 // ---- byte-plane split ---------------------------------------------------------------------------------
-// A planes of prime g, row tile ti:  [K/kc][plane a][k16 = kc/16][row = 128][16 B]
-__global__ void __launch_bounds__(256) k_tc_split_a(const uint32_t* __restrict__ W, uint8_t* __restrict__ AP, Region g) {
+// Planes of one operand, prime g, tile t of width TILE along the operand's own dimension (index idx):
+//     [tile][K/kc][plane][k16 = kc/16][idx = TILE][16 B]          (no-swizzle K-major core matrices)
+// from_l != 0: element (idx, k) = W[idx][k0 + k]   (rows of L: 16 consecutive words per thread)
+// from_l == 0: element (idx, k) = W[k0 + k][idx]   (columns of U: strided in k, coalesced across idx)
+template <int TILE>
+__global__ void __launch_bounds__(256) k_tc_split(const uint32_t* __restrict__ W, uint8_t* __restrict__ planes, Region g,
+                                                  int i0, int i1, int tiles, int from_l) {
     const int q_per = g.K / 16;                       // 16-byte k groups
-    const int64_t per_prime = (int64_t)g.row_tiles * TM * q_per;
+    const int64_t per_prime = (int64_t)tiles * TILE * q_per;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= per_prime) return;
     const int prime = blockIdx.y;
-    const int r = (int)(t % TM);
-    const int q = (int)((t / TM) % q_per);
-    const int ti = (int)(t / ((int64_t)TM * q_per));
-    const int row = g.r0 + ti * TM + r;
+    const int r = (int)(t % TILE);
+    const int q = (int)((t / TILE) % q_per);
+    const int ti = (int)(t / ((int64_t)TILE * q_per));
+    const int idx = i0 + ti * TILE + r;
     uint32_t w[16];
-    if (row < g.r1) {
-        const uint32_t* src = W + ((int64_t)prime * g.n + row) * g.n + g.k0 + q * 16;
-        if ((g.n & 3) == 0 && (g.k0 & 3) == 0) {
+    if (idx < i1) {
+        if (from_l) {
+            const uint32_t* src = W + ((int64_t)prime * g.n + idx) * g.n + g.k0 + q * 16;
+            if ((g.n & 3) == 0 && (g.k0 & 3) == 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint4 v = *reinterpret_cast<const uint4*>(src + 4 * i);
-                w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(src + 4 * i);
+                    w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] = src[i];
             }
         } else {
+            const uint32_t* src = W + ((int64_t)prime * g.n + g.k0 + q * 16) * g.n + idx;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) w[i] = src[i];
+            for (int i = 0; i < 16; ++i) w[i] = src[(int64_t)i * g.n];
         }
     } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) w[i] = 0u;
     }
     const int qc = g.kc / 16;                          // 16-byte groups per stage
-    uint8_t* dst = AP + ((int64_t)prime * g.row_tiles + ti) * ((int64_t)g.K * 4 * TM) + (int64_t)(q / qc) * (4 * TM * g.kc) +
-                   (q % qc) * (TM * 16) + r * 16;
+    uint8_t* dst = planes + ((int64_t)prime * tiles + ti) * ((int64_t)g.K * 4 * TILE) + (int64_t)(q / qc) * (4 * TILE * g.kc) +
+                   (q % qc) * (TILE * 16) + r * 16;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         uint32_t o[4];
@@ -97,42 +119,14 @@ __global__ void __launch_bounds__(256) k_tc_split_a(const uint32_t* __restrict__
         for (int i = 0; i < 4; ++i)
             o[i] = ((w[4 * i] >> (8 * a)) & 255u) | (((w[4 * i + 1] >> (8 * a)) & 255u) << 8) |
                    (((w[4 * i + 2] >> (8 * a)) & 255u) << 16) | (((w[4 * i + 3] >> (8 * a)) & 255u) << 24);
-        *reinterpret_cast<uint4*>(dst + a * (TM * g.kc)) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(dst + a * (TILE * g.kc)) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
-
-// B planes of prime g, column tile tj:  [K/kc][plane b][k16 = kc/16][col = 64][16 B]   (U transposed: K-major)
-__global__ void __launch_bounds__(256) k_tc_split_b(const uint32_t* __restrict__ W, uint8_t* __restrict__ BP, Region g) {
-    const int q_per = g.K / 16;
-    const int64_t per_prime = (int64_t)g.col_tiles * TN * q_per;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= per_prime) return;
-    const int prime = blockIdx.y;
-    const int c = (int)(t % TN);
-    const int q = (int)((t / TN) % q_per);
-    const int tj = (int)(t / ((int64_t)TN * q_per));
-    const int col = g.c0 + tj * TN + c;
-    uint32_t w[16];
-    if (col < g.c1) {
-        const uint32_t* src = W + ((int64_t)prime * g.n + g.k0 + q * 16) * g.n + col;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = src[(int64_t)i * g.n];
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = 0u;
-    }
-    const int qc = g.kc / 16;
-    uint8_t* dst = BP + ((int64_t)prime * g.col_tiles + tj) * ((int64_t)g.K * 4 * TN) + (int64_t)(q / qc) * (4 * TN * g.kc) +
-                   (q % qc) * (TN * 16) + c * 16;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        uint32_t o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            o[i] = ((w[4 * i] >> (8 * b)) & 255u) | (((w[4 * i + 1] >> (8 * b)) & 255u) << 8) |
-                   (((w[4 * i + 2] >> (8 * b)) & 255u) << 16) | (((w[4 * i + 3] >> (8 * b)) & 255u) << 24);
-        *reinterpret_cast<uint4*>(dst + b * (TN * g.kc)) = make_uint4(o[0], o[1], o[2], o[3]);
-    }
+// M-operand planes (128 per tile) and N-operand planes (64 per tile) of a region, all primes of the group
+inline void launch_split(const uint32_t* W, uint8_t* AP, uint8_t* BP, const Region& g, int G, cudaStream_t st) {
+    const int64_t ta = (int64_t)g.m_tiles * TM * (g.K / 16), tb = (int64_t)g.n_tiles * TN * (g.K / 16);
+    k_tc_split<TM><<<dim3((unsigned)((ta + 255) / 256), G), 256, 0, st>>>(W, AP, g, g.m0(), g.m1(), g.m_tiles, g.trans ? 0 : 1);
+    k_tc_split<TN><<<dim3((unsigned)((tb + 255) / 256), G), 256, 0, st>>>(W, BP, g, g.j0(), g.j1(), g.n_tiles, g.trans ? 1 : 0);
 }
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -214,7 +208,6 @@ struct GemmArgs {
     const uint8_t* BP;          // byte planes of U, see k_tc_split_b
     const PrimeRec* primes;     // [G]
     Region g;
-    int debug;                  // test hooks: bit 0 exchanges the two descriptor strides, bit 1 skips the epilogue
 };
 
 // Tile loop of one CTA.
@@ -227,14 +220,18 @@ struct GemmArgs {
 // accumulators 4..6 ("high").  The epilogue drains the low accumulators while the tensor pipe works on the
 // high pass, and the high ones while it works on the low pass of the NEXT tile, so the accumulators are
 // double-buffered in effect without needing more than 448 TMEM columns.
-__global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
+// DBG (timing experiments of tools/tc_gemm_test only; the library instantiates DBG = 0):
+//   bit 0 exchange the descriptor strides, bit 1 skip the epilogue arithmetic, bit 2 skip the TMEM loads,
+//   bit 3 issue the products of a pass in plain (pa, pb) order instead of the accumulator-spaced order
+template <int DBG, int TRANS>
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const Region& g = a.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int prime = blockIdx.z;
     const bool bst = g.b_stationary != 0;
     const int fixed_tile = blockIdx.x;                                   // row tile (A stationary) or column tile
-    const int loop_tiles = bst ? g.row_tiles : g.col_tiles;
+    const int loop_tiles = bst ? g.m_tiles : g.n_tiles;
     const int t0 = blockIdx.y * g.tiles_per_cta;
     const int ntiles = min(loop_tiles, t0 + g.tiles_per_cta) - t0;
     const int kchunks = g.K / g.kc;                                      // <= 4 <= ring slots
@@ -284,8 +281,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
     if (warp == 0) {
         // ===== copy producer =====
         if (lane == 0) {
-            const uint8_t* baseA = a.AP + (int64_t)prime * g.row_tiles * ((int64_t)g.K * 4 * TM);
-            const uint8_t* baseB = a.BP + (int64_t)prime * g.col_tiles * ((int64_t)g.K * 4 * TN);
+            const uint8_t* baseA = a.AP + (int64_t)prime * g.m_tiles * ((int64_t)g.K * 4 * TM);
+            const uint8_t* baseB = a.BP + (int64_t)prime * g.n_tiles * ((int64_t)g.K * 4 * TN);
             const uint8_t* srcS = bst ? baseB + (int64_t)fixed_tile * ((int64_t)g.K * 4 * TN)
                                       : baseA + (int64_t)fixed_tile * ((int64_t)g.K * 4 * TM);
             mbar_expect_tx(bar_s_full, (uint32_t)kchunks * st_chunk);
@@ -310,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
         // instruction descriptor: D = s32 (2 << 4), A = B = u8 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
         const uint32_t idesc = (2u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
         uint32_t a_lbo = TM * 16, b_lbo = TN * 16, a_sbo = 128, b_sbo = 128;
-        if (a.debug & 1) {
+        if (DBG & 1) {
             uint32_t x = a_lbo; a_lbo = a_sbo; a_sbo = x;
             x = b_lbo; b_lbo = b_sbo; b_sbo = x;
         }
@@ -336,21 +333,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
                     if (elect_one()) {
                         const uint64_t ad_c = adesc0 + (((bst ? slot : (uint32_t)kc) * a_step) >> 4);
                         const uint64_t bd_c = bdesc0 + (((bst ? (uint32_t)kc : slot) * b_step) >> 4);
+                        // products of this pass, ordered so that consecutive MMAs accumulate into DIFFERENT
+                        // accumulators (the same one comes back after two or more others)
+                        constexpr int NLO = 10, NHI = 6;
+                        constexpr int lo_pa[NLO] = {0, 0, 1, 0, 1, 2, 0, 3, 1, 2}, lo_pb[NLO] = {3, 2, 2, 1, 1, 1, 0, 0, 0, 0};
+                        constexpr int hi_pa[NHI] = {1, 2, 2, 3, 3, 3}, hi_pb[NHI] = {3, 3, 2, 3, 1, 2};
+                        constexpr int lo_pa_n[NLO] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3}, lo_pb_n[NLO] = {0, 1, 2, 3, 0, 1, 2, 0, 1, 0};
+                        constexpr int hi_pa_n[NHI] = {1, 2, 2, 3, 3, 3}, hi_pb_n[NHI] = {3, 2, 3, 1, 2, 3};
                         for (int s = 0; s < ksteps; ++s) {
                             const uint32_t fresh = (kc | s) == 0 ? 0u : 1u;   // 0: first write of the accumulators
+                            const uint64_t ad_s = ad_c + (((uint32_t)s * (2 * TM * 16)) >> 4);
+                            const uint64_t bd_s = bd_c + (((uint32_t)s * (2 * TN * 16)) >> 4);
+                            if (DBG & 16) {                       // experiment: all 16 products in the first pass
+                                if (pass == 0) {
 #pragma unroll
-                            for (int pa = 0; pa < 4; ++pa) {
-                                const uint64_t ad = ad_c + (((uint32_t)pa * a_plane + (uint32_t)s * (2 * TM * 16)) >> 4);
+                                    for (int pa = 0; pa < 4; ++pa) {
 #pragma unroll
-                                for (int pb = 0; pb < 4; ++pb) {
-                                    if ((pa + pb >= 4) != (pass == 1)) continue;
-                                    const uint64_t bd = bd_c + (((uint32_t)pb * b_plane + (uint32_t)s * (2 * TN * 16)) >> 4);
-                                    tc_mma_i8(tmem_base + (uint32_t)((pa + pb) * TN), ad, bd, idesc,
-                                              (pa == 0 || pb == 3) ? fresh : 1u);
+                                        for (int pb = 0; pb < 4; ++pb)
+                                            tc_mma_i8(tmem_base + (uint32_t)((pa + pb) * TN), ad_s + (((uint32_t)pa * a_plane) >> 4),
+                                                      bd_s + (((uint32_t)pb * b_plane) >> 4), idesc, (pa == 0 || pb == 3) ? fresh : 1u);
+                                    }
                                 }
+                                continue;
+                            }
+#pragma unroll
+                            for (int i = 0; i < (pass ? NHI : NLO); ++i) {
+                                const int pa = pass ? ((DBG & 8) ? hi_pa_n[i % NHI] : hi_pa[i % NHI])
+                                                    : ((DBG & 8) ? lo_pa_n[i % NLO] : lo_pa[i % NLO]);
+                                const int pb = pass ? ((DBG & 8) ? hi_pb_n[i % NHI] : hi_pb[i % NHI])
+                                                    : ((DBG & 8) ? lo_pb_n[i % NLO] : lo_pb[i % NLO]);
+                                // first product into an accumulator: plane 0 of A (weights 0..3) or plane 3 of B (4..6)
+                                tc_mma_i8(tmem_base + (uint32_t)((pa + pb) * TN), ad_s + (((uint32_t)pa * a_plane) >> 4),
+                                          bd_s + (((uint32_t)pb * b_plane) >> 4), idesc, (pa == 0 || pb == 3) ? fresh : 1u);
                             }
                         }
-                        if (pass == 1) tc_commit(bar_r_empty + 8 * slot);    // slot free once both passes have read it
+                        if ((DBG & 16) ? pass == 0 : pass == 1) tc_commit(bar_r_empty + 8 * slot);    // slot free once both passes have read it
                         if (kc == kchunks - 1) tc_commit(pass ? bar_hi_full : bar_lo_full);
                     }
                     __syncwarp();
@@ -365,17 +382,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
         const uint64_t c4 = P.one;                               // 2^32 mod p
         const uint64_t c5 = (c4 << 8) % p, c6 = (c5 << 8) % p;   // 2^40, 2^48 mod p
         uint32_t* Wg = a.W + (int64_t)prime * g.n * g.n;
-        const bool vec_ok = (g.n & 3) == 0 && (g.c0 & 3) == 0;
+        const bool vec_ok = !TRANS && (g.n & 3) == 0 && (g.c0 & 3) == 0;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32);
+        const int m0 = g.m0(), m1 = g.m1(), j0 = g.j0(), j1 = g.j1();
         for (int t = 0; t < ntiles; ++t) {
             const int ti = bst ? t0 + t : fixed_tile, tj = bst ? fixed_tile : t0 + t;
-            const int row = g.r0 + ti * TM + quad * 32 + lane;
-            // C does not depend on the MMAs: fetch the 32 columns of this row BEFORE waiting for the
-            // accumulators, so the HBM/L2 latency hides behind the tensor-core phase of the tile.
-            const int colb = g.c0 + tj * TN + half * 32;
-            uint32_t* cp = Wg + (int64_t)row * g.n + colb;
-            const bool live = row < g.r1 && colb < g.c1;
-            const bool full = live && vec_ok && colb + 32 <= g.c1;
+            const int m = m0 + ti * TM + quad * 32 + lane;          // this thread's TMEM lane
+            const int jb = j0 + tj * TN + half * 32;                // its 32 TMEM columns
+            // element i of the thread is C[m][jb + i] (trans == 0: 32 consecutive words, 16-byte accesses) or
+            // C[jb + i][m] (trans == 1: word accesses, the warp's 32 lanes side by side in one row: coalesced)
+            uint32_t* cp = TRANS ? Wg + (int64_t)jb * g.n + m : Wg + (int64_t)m * g.n + jb;
+            const int64_t estride = TRANS ? g.n : 1;
+            const bool live = !(DBG & 32) && m < m1 && jb < j1;
+            const bool full = live && vec_ok && jb + 32 <= j1;
+            // C does not depend on the MMAs: fetch it BEFORE waiting for the accumulators, so the HBM/L2
+            // latency hides behind the tensor-core phase of the tile.
             uint32_t cv[32];
             if (full) {
 #pragma unroll
@@ -385,9 +406,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) cv[i] = (live && colb + i < g.c1) ? cp[i] : 0u;
+                for (int i = 0; i < 32; ++i) cv[i] = (live && jb + i < j1) ? cp[i * estride] : 0u;
             }
-            // ---- low accumulators (weights 2^0, 2^8, 2^16, 2^24): exact 64-bit partial sums ----
+            // ---- low accumulators (weights 2^0, 2^8, 2^16, 2^24): exact 64-bit partial sums; C goes into the
+            // high word (C * 2^32 + low sum, low sum < 2^51), which frees the registers of the prefetch ----
             uint64_t lo[32];
             mbar_wait(bar_lo_full, (uint32_t)(t & 1));
             tc_fence_after();
@@ -395,7 +417,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
             for (int ch = 0; ch < 2; ++ch) {
                 uint32_t q[4][16];
 #pragma unroll
-                for (int s = 0; s < 4; ++s) tmem_ld16(lane_base + (uint32_t)(s * TN + ch * 16), q[s]);
+                for (int s = 0; s < 4; ++s) {
+                    if (DBG & 4) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) q[s][i] = 0u;
+                    } else {
+                        tmem_ld16(lane_base + (uint32_t)(s * TN + ch * 16), q[s]);
+                    }
+                }
                 tmem_wait_ld();
                 if (ch == 1) {                                   // this warp's low words are in registers: hand the
                     tc_fence_before();                           // low accumulators back to the MMA issuer
@@ -405,30 +434,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
                     lo[ch * 16 + i] = (uint64_t)q[0][i] + ((uint64_t)q[1][i] << 8) + ((uint64_t)q[2][i] << 16) +
-                                      ((uint64_t)q[3][i] << 24);
+                                      ((uint64_t)q[3][i] << 24) + ((uint64_t)cv[ch * 16 + i] << 32);
             }
-            // ---- high accumulators (weights 2^32, 2^40, 2^48), one Montgomery reduction, C update ----
+            // ---- high accumulators (weights 2^32, 2^40, 2^48), one Montgomery reduction ----
             mbar_wait(bar_hi_full, (uint32_t)(t & 1));
             tc_fence_after();
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 uint32_t q[3][16];
 #pragma unroll
-                for (int s = 0; s < 3; ++s) tmem_ld16(lane_base + (uint32_t)((4 + s) * TN + ch * 16), q[s]);
+                for (int s = 0; s < 3; ++s) {
+                    if (DBG & 4) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) q[s][i] = 0u;
+                    } else {
+                        tmem_ld16(lane_base + (uint32_t)((4 + s) * TN + ch * 16), q[s]);
+                    }
+                }
                 tmem_wait_ld();
                 if (ch == 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_hi_empty);
                 }
-                if (!(a.debug & 2)) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint64_t acc = lo[ch * 16 + i] + (uint64_t)q[0][i] * c4 + (uint64_t)q[1][i] * c5 +
-                                             (uint64_t)q[2][i] * c6;
-                        const uint32_t r = mont_redc(acc, p, pinv);
-                        const uint32_t o = cv[ch * 16 + i] + r;
-                        cv[ch * 16 + i] = min(o, o - p);
+                for (int i = 0; i < 16; ++i) {
+                    if (DBG & 2) {
+                        cv[ch * 16 + i] = (uint32_t)(lo[ch * 16 + i] >> 32) + q[0][i];
+                    } else {
+                        // C * 2^32 + S  with S < 2^60: bring the sum below p * 2^32 (one conditional subtraction of
+                        // p * 2^32, as in mac_lazy), then REDC gives (C + S / 2^32) mod p in [0, p)
+                        uint64_t acc = lo[ch * 16 + i] + (uint64_t)q[0][i] * c4 + (uint64_t)q[1][i] * c5 + (uint64_t)q[2][i] * c6;
+                        uint32_t hi = (uint32_t)(acc >> 32);
+                        hi = min(hi, hi - p);
+                        acc = ((uint64_t)hi << 32) | (uint32_t)acc;
+                        cv[ch * 16 + i] = mont_redc(acc, p, pinv);
                     }
                 }
             }
@@ -439,7 +479,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
             } else if (live) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                    if (colb + i < g.c1) cp[i] = cv[i];
+                    if (jb + i < j1) cp[i * estride] = cv[i];
             }
         }
     }
@@ -450,6 +490,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(GemmArgs a) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
+
+// the library's instantiation
+constexpr auto k_gemm_tc = k_gemm_tc_t<0, 0>;
+constexpr auto k_gemm_tc_trans = k_gemm_tc_t<0, 1>;
 
 #endif  // __CUDACC__
 

@@ -44,6 +44,8 @@ int main(int argc, char** argv) {
     const int reps = argc > 6 ? atoi(argv[6]) : 3;
     const int bst = argc > 7 ? atoi(argv[7]) : 0;       // 1: B-stationary CTAs
     const int cols = argc > 8 ? atoi(argv[8]) : 0;      // restrict the region to this many columns (0: all)
+    const int trans = argc > 9 ? atoi(argv[9]) : 0;     // 1: transposed product (coalesced C traffic)
+    const int rows = argc > 10 ? atoi(argv[10]) : 0;    // restrict the region to this many rows (0: all)
     using namespace lsx_tc;
     std::vector<uint32_t> tab;
     lsx_fill_prime_table(tab, G);
@@ -56,15 +58,13 @@ int main(int argc, char** argv) {
     g.k0 = k0;
     g.K = K;
     g.kc = K < KC ? K : KC;
-    g.row_tiles = (g.r1 - g.r0 + TM - 1) / TM;
-    g.col_tiles = (g.c1 - g.c0 + TN - 1) / TN;
-    if (cols > 0 && g.c0 + cols < g.c1) {
-        g.c1 = g.c0 + cols;
-        g.col_tiles = (g.c1 - g.c0 + TN - 1) / TN;
-    }
+    if (cols > 0 && g.c0 + cols < g.c1) g.c1 = g.c0 + cols;
+    if (rows > 0 && g.r0 + rows < g.r1) g.r1 = g.r0 + rows;
+    g.trans = trans;
+    g.set_tiles();
     g.b_stationary = bst;
-    g.tiles_per_cta = bst ? g.row_tiles : g.col_tiles;
-    if (g.row_tiles <= 0 || g.col_tiles <= 0) {
+    g.tiles_per_cta = bst ? g.m_tiles : g.n_tiles;
+    if (g.m_tiles <= 0 || g.n_tiles <= 0) {
         printf("{\"error\": \"empty region\"}\n");
         return 2;
     }
@@ -93,25 +93,31 @@ int main(int argc, char** argv) {
     CK(cudaDeviceSynchronize());
     CK(cudaEventElapsedTime(&ms_ref, e0, e1));
     const size_t smem = smem_bytes(K, bst);
-    CK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kern)(GemmArgs) = trans ? k_gemm_tc_t<0, 1> : k_gemm_tc_t<0, 0>;
+    switch (swap) {
+        case 1: kern = k_gemm_tc_t<1, 0>; break;
+        case 2: kern = k_gemm_tc_t<2, 0>; break;
+        case 6: kern = k_gemm_tc_t<6, 0>; break;
+        case 8: kern = k_gemm_tc_t<8, 0>; break;
+        case 54: kern = k_gemm_tc_t<54, 0>; break;
+        default: break;
+    }
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GemmArgs a{};
     a.W = dW;
     a.AP = dA;
     a.BP = dB;
     a.primes = dP;
     a.g = g;
-    a.debug = swap;
     for (int rep = 0; rep < reps; ++rep) {
         CK(cudaMemcpy(dW, h.data(), words * 4, cudaMemcpyHostToDevice));
         CK(cudaEventRecord(e0));
-        const int64_t ta = (int64_t)g.row_tiles * TM * (K / 16), tb = (int64_t)g.col_tiles * TN * (K / 16);
-        k_tc_split_a<<<dim3((unsigned)((ta + 255) / 256), G), 256>>>(dW, dA, g);
-        k_tc_split_b<<<dim3((unsigned)((tb + 255) / 256), G), 256>>>(dW, dB, g);
+        launch_split(dW, dA, dB, g, G, 0);
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
         CK(cudaEventElapsedTime(&ms_split, e0, e1));
         CK(cudaEventRecord(e0));
-        k_gemm_tc<<<dim3(bst ? g.col_tiles : g.row_tiles, 1, G), THREADS, smem>>>(a);
+        kern<<<dim3(bst ? g.n_tiles : g.m_tiles, 1, G), THREADS, smem>>>(a);
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
         CK(cudaEventElapsedTime(&ms_tc, e0, e1));
@@ -126,7 +132,7 @@ int main(int argc, char** argv) {
             ++bad;
         }
     const double macs = (double)G * (g.r1 - g.r0) * (double)(g.c1 - g.c0) * K;
-    printf("{\"bst\": %d, \"cols\": %d, ", bst, g.c1 - g.c0);
+    printf("{\"bst\": %d, \"trans\": %d, \"rows\": %d, \"cols\": %d, ", bst, trans, g.r1 - g.r0, g.c1 - g.c0);
     printf("\"n\": %d, \"G\": %d, \"k0\": %d, \"K\": %d, \"swap\": %d, \"mismatches\": %zu, \"first_bad\": %zu, "
            "\"first_bad_rc\": [%zu, %zu], \"got\": %u, \"ref\": %u, \"ms_ref\": %.3f, \"ms_split\": %.3f, \"ms_tc\": %.3f, "
            "\"mod_mac_per_s\": %.4g, \"int8_tops\": %.1f}\n",
