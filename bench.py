@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the exact elimination hot path (BASELINE.json metric: exact det/RREF matrices/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4inv]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4inv|c5]
 
 A step is one pass of the hot path over one batch of synthetic matrices.  The default workload is
 BASELINE.json configs[1]: 2^20 random 8x8 integer matrices (entries uniform in [-5,5], the
@@ -14,6 +14,10 @@ ranks); `e2e` is the same metric through the C-ABI with HOST buffers (pinned), h
 inside the timed region; `roofline` is for the dominant kernel (device-timed inside the library);
 `cpu_baseline` is the CPU oracle (port of the reference's algorithm) on this box's host cores.
 `--impl reference` times that CPU port alone on all host cores, same config/metric.
+
+`--workload c5` is BASELINE.json configs[4]: ONE 4096 x 4096 integer determinant, multi-modular, the primes
+sharded over the ranks (strong scaling), one all-gather of the residues before the CRT; its metric is
+seconds per determinant and its roofline is the tensor pipe (tcgen05 int8-split trailing update).
 """
 import argparse
 import json
@@ -384,18 +388,221 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+
+# ------------------------------------------------------------------------------------- config 5
+C5_N, C5_SEED, C5_ABS = 4096, 20260005, 5
+C5_DESC = "single 4096x4096 integer determinant (entries uniform [-5,5], PCG64(20260005)), multi-modular, sharded by prime"
+C5_METRIC = "seconds per exact 4096x4096 determinant"
+
+
+def c5_matrix(n=C5_N):
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(C5_SEED))
+    return rng.integers(-C5_ABS, C5_ABS + 1, size=(n, n), dtype=np.int32)
+
+
+def _c5_cpu_one(item):
+    from oracle.det_mod_p import det_mod_p
+    A, p = item
+    return det_mod_p(A, p)
+
+
+def c5_cpu_baseline(n_primes, sample_n=1280):
+    """oracle/det_mod_p.py (numpy int64 Gaussian elimination modulo p, the forward sweep of reference
+    linalg.py:547-609) on a bounded sample: the leading sample_n x sample_n block, one prime per host core in
+    parallel; scaled to the full job by (n / sample_n)^3 per prime and n_primes / cores."""
+    from multiprocessing import get_context
+    from tests.device_model import prime_table
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    A = c5_matrix()[:sample_n, :sample_n].copy()
+    primes = prime_table(cores)
+    ctx = get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_c5_cpu_one, [(A[:64, :64], p) for p in primes], chunksize=1)     # start the workers
+        t0 = time.perf_counter()
+        pool.map(_c5_cpu_one, [(A, p) for p in primes], chunksize=1)
+        dt = time.perf_counter() - t0
+    per_prime_core_s = dt * (C5_N / sample_n) ** 3               # one prime at full size on one core
+    seconds = per_prime_core_s * n_primes / cores
+    return {"value": seconds, "unit": "s", "cores": cores, "kind": "port",
+            "sample": "det mod p of the leading %dx%d block for %d primes in parallel (oracle/det_mod_p.py, numpy int64 "
+                      "elimination, %.1f s), scaled by (4096/%d)^3 per prime and %d primes / %d cores (extrapolated)"
+                      % (sample_n, sample_n, cores, dt, sample_n, n_primes, cores)}
+
+
+def c5_tensor_ops(n, n_primes_local, block=256):
+    """int8 tensor operations (2 per multiply-add, 16 byte-plane products per residue multiply-add) of the
+    depth-256 trailing updates of the blocked LU for n_primes_local primes."""
+    macs = 0
+    k0 = 0
+    while k0 + block < n:
+        rest = n - k0 - block
+        macs += rest * rest * block
+        k0 += block
+    return 2 * 16 * macs * n_primes_local
+
+
+def run_c5_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from linalg_solver_b200 import _lib  # noqa: F401  (prime count comes from the same plan function)
+    import ctypes
+    k, bits = ctypes.c_int(), ctypes.c_double()
+    _lib.lib.lsx_det_large_prime_count(C5_N, C5_ABS, ctypes.byref(k), ctypes.byref(bits))
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb = c5_cpu_baseline(k.value)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    val = statistics.mean(vals)
+    cb["value"] = val
+    print(json.dumps({
+        "impl": "reference", "metric": C5_METRIC, "value": val, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int64 residues modulo 31-bit primes (numpy)", "data": "synthetic",
+        "config": {"workload": C5_DESC, "primes": k.value, "step": "bounded sample on the host CPU, extrapolated"},
+        "cpu_baseline": cb, "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def run_c5(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from linalg_solver_b200 import Engine
+    from linalg_solver_b200 import dist as lsx_dist
+
+    n_primes, bits = Engine.det_large_prime_count(C5_N, C5_ABS)
+    cpu = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu:
+        cpu = c5_cpu_baseline(n_primes)                           # before CUDA init (fork pool)
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Engine(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    A_host = torch.from_numpy(c5_matrix()).pin_memory()
+    A = A_host.to(dev)
+    # parity before timing: the blocked tensor-core path against the numpy oracle on a 512 x 512 block, two primes
+    if rank == 0:
+        from oracle.det_mod_p import det_mod_p
+        small = A_host[:512, :512].contiguous().numpy()
+        got = eng.det_large_residues(torch.from_numpy(small).to(dev), 0, 2).cpu().numpy().astype(np.uint32)
+        want = [det_mod_p(small, int(p)) for p in eng.primes(2)]
+        assert [int(x) for x in got] == want, "blocked LU residues differ from oracle/det_mod_p.py"
+
+    def step():
+        return lsx_dist.det_large_sharded(eng, A, C5_ABS)
+
+    words = None
+    for _ in range(args.warmup):
+        words, _ = step()
+    barrier()
+    b, e = lsx_dist.shard_range(n_primes, rank, world)
+    launches0 = eng.launch_count
+    eng.timing_enable(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        words, _ = step()
+    ev1.record()
+    barrier()
+    t1 = time.perf_counter()
+    ms_total = ev0.elapsed_time(ev1)
+    kernel_ms = eng.timing_read()
+    eng.timing_enable(False)
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop(t0, t1)
+
+    # ---- end to end: host matrix -> H2D -> residues -> all-gather -> CRT -> limbs back on the host ----
+    e2e_steps = max(3, min(args.steps, 5))
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        A_d = A_host.to(dev, non_blocking=True)
+        w, _ = lsx_dist.det_large_sharded(eng, A_d, C5_ABS)
+        w_host = w.cpu()
+    e2e_ms = (time.perf_counter() - e0) * 1e3 / e2e_steps
+    assert torch.equal(w_host, words.cpu())
+
+    stats = torch.tensor([ms_total, e2e_ms, float(launches), sum(kernel_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    ms_step = float(stats[0]) / args.steps
+    e2e_ms = float(stats[1])
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        # int8 tensor peak is not in MEASURED_PEAKS.json: twice the measured dense bf16 rate (B200: int8 = 2 x bf16)
+        bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak = 2.0 * bf16
+        k_s = float(stats[3]) / args.steps * 1e-3                 # depth-256 tensor updates of one step (slowest rank)
+        ops = c5_tensor_ops(C5_N, e - b)
+        achieved = ops / k_s / 1e12 if k_s > 0 else 0.0
+        limbs = int(bits + 2) // 32 + 1
+        from linalg_solver_b200.convert import limbs_to_ints
+        det = limbs_to_ints(words.cpu().numpy().astype(np.uint32).reshape(1, -1))[0]
+        line = {
+            "metric": C5_METRIC, "value": ms_step * 1e-3, "unit": "s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32 residues modulo 31-bit primes; trailing update as u8 x u8 -> s32 tcgen05 MMA",
+            "data": "synthetic",
+            "config": {"workload": C5_DESC, "primes": n_primes, "primes_per_gpu": e - b, "limbs": limbs,
+                       "sharding": "by prime, one all-gather of %d residues (%d B) before the CRT" % (n_primes, 4 * n_primes),
+                       "l2": "residue matrices of one prime group (64 MiB per prime) far exceed the 126 MB L2",
+                       "det_bits": int(abs(det)).bit_length(), "det_mod_1e9": int(det % 10**9)},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "kernel_ms": k_s * 1e3, "kernel": "lsx_tc::k_gemm_tc (depth-256 trailing updates)",
+                         "kernel_launches_per_step": len(kernel_ms) // max(1, args.steps),
+                         "ops": "int8 tensor ops: 2 x 16 byte-plane products per residue multiply-add",
+                         "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 dense = 2 x bf16 on B200; int8 itself not measured)"
+                                        if peaks else "fallback 2 x 1400"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_ms * 1e-3, "unit": "s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(A_host.numel() * 4),
+                    "d2h_bytes_per_step": int(limbs * 4),
+                    "path": "pinned host matrix -> device, linalg_solver_b200.dist.det_large_sharded (lsx_det_large_residues, "
+                            "all-gather, lsx_crt_signed), limbs back to the host"},
+            "gpu_launches": int(stats[2]),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload == "c5":
+        (run_c5_reference if args.impl == "reference" else run_c5)(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_ours(args)

@@ -336,7 +336,7 @@ def gen_c5():
     from sympy.polys.matrices import DomainMatrix
     from sympy import ZZ
     out = []
-    for n, seed in [(64, 2026000564), (128, 2026000528), (256, 2026000556)]:
+    for n, seed in [(64, 2026000564), (128, 2026000528), (256, 2026000556), (384, 2026000538), (512, 2026000551)]:   # 384/512: 1.5 / 6 minutes
         rng = np.random.Generator(np.random.PCG64(seed))
         A = rng.integers(-5, 6, size=(n, n), dtype=np.int64)
         dm = DomainMatrix([[ZZ(int(x)) for x in row] for row in A.tolist()], (n, n), ZZ)

@@ -429,6 +429,19 @@ def test_c5_standin_256_blocked_and_sharded_crt(eng):
     assert K == eng.det_large_prime_count(256, 5)[0]
 
 
+@pytest.mark.parametrize("n", [384, 512])
+def test_c5_standins_blocked_tensor_path_exact(eng, n):
+    """Full config 5 route (blocked LU with tcgen05 updates -> residues -> CRT) against the exact DomainMatrix
+    determinants of the 384 and 512 stand-ins."""
+    from linalg_solver_b200 import dist as lsx_dist
+    g = golden_io.load("c5_standins")
+    c = [x for x in g["cases"] if x["n"] == n][0]
+    rng = np.random.Generator(np.random.PCG64(c["seed"]))
+    A = rng.integers(-5, 6, size=(n, n), dtype=np.int64).astype(np.int32)
+    words, K = lsx_dist.det_large_sharded(eng, A, 5)
+    assert limbs_to_ints(words) == int(c["det"])
+
+
 def test_subwarp_kernel_equals_tile_path(eng, monkeypatch):
     """Fused sub-warp kernel (row per lane, all primes + CRT in one launch) against the tile path, word
     for word, over every lane-group size, ragged shapes, rank-deficient inputs and all operations."""
