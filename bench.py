@@ -40,10 +40,13 @@ WORKLOADS = {
            16, 1 << 18, 2964),
     "c4inv": ("2^12 (of 2^16) x 64x64 inverse via [A|I] row_reduce(bar_col=64), entries uniform [-5,5]", 64, 1 << 12,
               196912),
+    "c4ker": ("2^12 (of 2^16) x kernel basis of 64x64 A = B(64x48) C(48x64) (rank 48, dim 16), entries of B, C uniform [-5,5]",
+              64, 1 << 12, 98644),
 }
 SEED = 20260002
 METRIC = {"c1": "exact det+rank+RREF matrices/sec", "c2": "exact det+inverse matrices/sec",
-          "c3": "exact find_preimage_of systems/sec", "c4inv": "exact inverse matrices/sec"}
+          "c3": "exact find_preimage_of systems/sec", "c4inv": "exact inverse matrices/sec",
+          "c4ker": "exact kernel bases/sec"}
 
 
 def make_inputs(n, batch, seed, workload="c2"):
@@ -58,6 +61,10 @@ def make_inputs(n, batch, seed, workload="c2"):
         b = np.einsum("bij,bj->bi", A, x0)
         b[1::2] = rng.integers(-5, 6, size=b[1::2].shape)          # odd systems: random rhs (inconsistent w.h.p.)
         return {"A": A.astype(np.int32), "b": b.astype(np.int32)}
+    if workload == "c4ker":
+        Bm = rng.integers(-5, 6, size=(batch, 64, 48), dtype=np.int64)
+        Cm = rng.integers(-5, 6, size=(batch, 48, 64), dtype=np.int64)
+        return {"A": np.einsum("bik,bkj->bij", Bm, Cm).astype(np.int32), "b": np.zeros((batch, 64), dtype=np.int32)}
     return {"A": rng.integers(-5, 6, size=(batch, n, n), dtype=np.int32)}
 
 
@@ -72,12 +79,15 @@ def _cpu_one(item):
     if wl == "c3":
         res = ref_port.find_preimage_of(a, b)
         return None if res is None else res[0][0].numerator
+    if wl == "c4ker":
+        res = ref_port.kernel(a)
+        return len(res[1]) if res and res[1] else 0
     inv = ref_port.inverse(a)
     det = ref_port.determinant(a) if wl == "c2" else None
     return (det.numerator if det is not None else None), (None if inv is None else inv[0][0].numerator)
 
 
-CPU_PER_CORE = {"c1": 4096, "c2": 2048, "c3": 64, "c4inv": 1}
+CPU_PER_CORE = {"c1": 4096, "c2": 2048, "c3": 64, "c4inv": 1, "c4ker": 1}
 
 
 def cpu_baseline(workload, per_core, seed):
@@ -194,6 +204,8 @@ class Job:
         elif workload == "c3":
             bmax = int(data["b"].max()), int(-data["b"].min())
             self.plans = (eng.plan_solve(16, 16, 250, max(bmax), 10, 6),)
+        elif workload == "c4ker":
+            self.plans = (eng.plan_solve(64, 64, int(abs(data["A"]).max()), 0, 48, 16),)
         else:
             self.plans = (eng.plan_inverse(n, 5),)
         self.res = self.run(self.dev)                         # allocates the outputs; reused by every step
@@ -205,7 +217,7 @@ class Job:
             o = out or (None, None, None)
             return (e.det_batch(A, plan=self.plans[0], out=o[0]), e.rank_batch(A, plan=self.plans[1], out=o[1]),
                     e.rref_batch(A, 3, plan=self.plans[2], out=o[2]))
-        if self.wl == "c3":
+        if self.wl in ("c3", "c4ker"):
             return (e.solve_batch(A, src["b"], plan=self.plans[0], out=out[0] if out else None),)
         return (e.inverse_batch(A, plan=self.plans[0], out=out[0] if out else None),)
 
@@ -253,6 +265,13 @@ class Job:
                 R, piv = ref_port.row_reduce(A[i])
                 assert dets[i] == ref_port.bareiss_det(A[i]) and int(rk.rank[i]) == ref_port.rank(A[i])
                 assert [[Fraction(x, den[i]) for x in row] for row in num[i]] == R
+        elif self.wl == "c4ker":
+            (r,) = self.res
+            den, gens = limbs_to_ints(r.den[:1])[0], limbs_to_ints(r.generators[:1])[0]
+            want = ref_port.kernel(A[0])
+            kdim = 64 - int(r.rank[0])
+            assert int(r.status[0]) == 0 and kdim == len(want[1])                  # want[1]: kdim generators of length 64
+            assert [[Fraction(gens[i][c], den) for i in range(64)] for c in range(kdim)] == want[1]
         elif self.wl == "c3":
             (r,) = self.res
             b = self.host["b"][:k].tolist()

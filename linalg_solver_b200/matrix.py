@@ -4,7 +4,8 @@ surface for the elimination path, served by the GPU engine.
 Mirrors reference linalg_solver/linalg.py: container and validation (11-58), ``zero/identity/
 diagonal/new_vector/transpose`` (409-422, 482-489), ``AffineSubspace`` (491-522), ``NoSolution``
 (524-532), ``row_reduce`` (534-630), ``find_preimage_of`` (632-680, 870-999), ``inverse`` (682-743),
-``rank`` (745-747), ``kernel`` (749-756) and the entry of ``determinant`` (183-207).  Same names,
+``rank`` (745-747), ``kernel`` (749-756), the entry of ``determinant`` (183-207) and the eigen-callers that
+sit on them (``eigenvalues`` 424-480, ``find_eigenspace`` 758-770, ``diagonalize`` 833-863).  Same names,
 argument meaning, return shapes and error texts; the arithmetic runs in liblsx (there is no CPU
 fallback) and the reference's LaTeX ``Logger`` output is bypassed: ``row_reduce`` returns empty
 lists for its two log results, which the reference's own callers accept (linalg.py:1009-1010).
@@ -331,6 +332,104 @@ class Matrix:
         for i in range(self.rows):
             items[i][i] = items[i][i] - eigenvalue
         return Matrix(items).kernel()
+
+
+    # ---- eigen-callers on the device engine --------------------
+    def characteristic_polynomial(self) -> List[Any]:
+        """Coefficients ``[c_0, ..., c_n]`` of ``det(A - lambda I) = sum c_k lambda^k`` (exact rationals).
+
+        The reference expands this determinant over ``Polynomial`` entries through its planner
+        (linalg.py:424-445, determinant.py:761-803).  Here it is n + 1 integer determinants
+        ``det(A - t I)``, t = 0..n, in ONE batched device call (``lsx_det_batch``), followed by exact Newton
+        interpolation on the host: a polynomial of degree n is fixed by n + 1 values.
+        """
+        if self.rows != self.cols:
+            raise ValueError("Eigenvalues require a square matrix")
+        n = self.rows
+        kind = _kind_of(self.items)
+        grid, D = _to_int_grid(self.items)                       # grid = D * A
+        pts = list(range(n + 1))
+        batch = np.repeat(grid[None].astype(np.int64), n + 1, axis=0)
+        for k, t in enumerate(pts):
+            batch[k, range(n), range(n)] -= D * t                # D * (A - t I)
+        if np.abs(batch).max(initial=0) > _INT32_MAX:
+            raise OverflowError("entries of A - t I do not fit the device's int32 input")
+        res = default_engine().det_batch(batch.astype(np.int32))
+        for st in res.status:
+            _raise_on_status(int(st))
+        vals = [Fraction(v, D ** n) for v in limbs_to_ints(res.det)]          # det(A - t I)
+        # Newton divided differences on the nodes 0..n, then expansion to monomial coefficients
+        dd = list(vals)
+        for j in range(1, n + 1):
+            for i in range(n, j - 1, -1):
+                dd[i] = (dd[i] - dd[i - 1]) / (pts[i] - pts[i - j])
+        coeffs = [Fraction(0)] * (n + 1)
+        for i in range(n, -1, -1):                               # Horner: coeffs = coeffs * (x - pts[i]) + dd[i]
+            nxt = [Fraction(0)] * (n + 1)
+            for k in range(n):
+                nxt[k + 1] += coeffs[k]
+                nxt[k] -= coeffs[k] * pts[i]
+            nxt[0] += dd[i]
+            coeffs = nxt
+        return [_wrap("sympy" if kind == "sympy" else "fraction", c.numerator, c.denominator) for c in coeffs]
+
+    def eigenvalues(self, real_only: bool = False):
+        """``{root: algebraic multiplicity}`` of the characteristic polynomial (reference linalg.py:424-480; its
+        LaTeX log is bypassed).  Root finding is sympy's, as the reference's ``radical_roots`` ends there too."""
+        import sympy
+        lam = sympy.Symbol("lambda")
+        coeffs = self.characteristic_polynomial()
+        poly = sympy.Poly(sum(sympy.Rational(*_pq_of(c)) * lam ** k for k, c in enumerate(coeffs)), lam)
+        roots = sympy.roots(poly)
+        if real_only:
+            roots = {r: m for r, m in roots.items() if r.is_real is True}
+        return roots
+
+    def eigenvalues_with_geometric_multiplicities(self):
+        """Reference linalg.py:808-818: eigenvalue -> (algebraic, geometric multiplicity); the geometric one is
+        the dimension of ``find_eigenspace`` (device ``kernel``) for rational eigenvalues."""
+        result = {}
+        for eig, alg in self.eigenvalues().items():
+            try:
+                space = self.find_eigenspace(eig)
+                geom = space.dim() if hasattr(space, "dim") else 0
+            except TypeError:                                    # irrational eigenvalue: not on the device path
+                geom = None
+            result[eig] = (alg, geom)
+        return result
+
+    class DiagonalizationResult:
+        """Reference linalg.py:772-806 (``cformat`` omitted: logging is bypassed)."""
+
+        def __init__(self, eig_mults, success, P=None, P_inv=None, D=None):
+            self.eigenvalue_multiplicities = eig_mults
+            self.success = success
+            self.P, self.P_inv, self.D = P, P_inv, D
+
+        def __repr__(self):
+            return ("DiagonalizationResult(success=%s, eigenvalue_multiplicities=%s, P=%s, P_inv=%s, D=%s)"
+                    % (self.success, self.eigenvalue_multiplicities, self.P, self.P_inv, self.D))
+
+    def diagonalize(self):
+        """Reference linalg.py:833-863: eigenspaces through ``kernel`` and ``P.inverse()`` on the device."""
+        if self.rows != self.cols:
+            raise ValueError("Matrix must be square to diagonalize.")
+        n = self.rows
+        eig_mults = self.eigenvalues_with_geometric_multiplicities()
+        basis_vectors = []
+        for eig, (_, geom) in eig_mults.items():
+            if geom is None:
+                return Matrix.DiagonalizationResult(eig_mults, False)
+            space = self.find_eigenspace(eig)
+            if hasattr(space, "basis"):
+                basis_vectors.extend(space.basis())
+        if len(basis_vectors) != n:
+            return Matrix.DiagonalizationResult(eig_mults, False)
+        P = Matrix([list(col) for col in zip(*basis_vectors)])
+        P_inv = P.inverse()
+        if isinstance(P_inv, Matrix.NoSolution):
+            return Matrix.DiagonalizationResult(eig_mults, False)
+        return Matrix.DiagonalizationResult(eig_mults, True, P, P_inv, P_inv * self * P)
 
 
 def _raise_on_status(st):

@@ -156,3 +156,47 @@ def test_find_eigenspace_and_mul():
         Matrix([[1, 2, 3]]).find_eigenspace(1)
     P = Matrix([[1, 2], [3, 4]]) * Matrix([[0, 1], [1, 0]])
     assert P.items == [[2, 1], [4, 3]] and (Matrix([[1, 2]]) * 3).items == [[3, 6]]
+
+
+def test_characteristic_polynomial_matches_sympy():
+    """det(A - lambda I) from n + 1 batched device determinants + interpolation against
+    sympy's exact characteristic polynomial, for integer and fractional entries."""
+    import random
+    import sympy
+    from linalg_solver_b200 import Matrix
+    rnd = random.Random(8)
+    lam = sympy.Symbol("lambda")
+    for n in (1, 2, 3, 5, 8, 12):
+        items = [[rnd.randint(-5, 5) for _ in range(n)] for _ in range(n)]
+        if n == 5:
+            items = [[Fraction(x, rnd.choice([1, 2, 3])) for x in row] for row in items]
+        coeffs = Matrix(items).characteristic_polynomial()
+        want = sympy.Poly((sympy.Matrix(items) - lam * sympy.eye(n)).det(method="berkowitz"), lam).all_coeffs()[::-1]
+        assert [pq(c) for c in coeffs] == [pq(sympy.Rational(w)) for w in want], n
+
+
+def test_eigenvalues_and_diagonalize_on_the_device():
+    """Reference linalg.py:424-480, 808-863: eigenvalues with multiplicities, eigenspaces through kernel(),
+    P^-1 through inverse(); a diagonalizable matrix built as P D P^-1 and a Jordan block that is not."""
+    import sympy
+    from linalg_solver_b200 import Matrix
+    P = sympy.Matrix([[1, 2, 0, 1], [0, 1, 3, 0], [1, 0, 1, 1], [2, 1, 0, 3]])
+    assert P.det() != 0
+    D = sympy.diag(2, 2, -1, 5)
+    A = P * D * P.inv()
+    M = Matrix([[sympy.Rational(A[i, j]) for j in range(4)] for i in range(4)])
+    assert M.eigenvalues() == {sympy.Integer(2): 2, sympy.Integer(-1): 1, sympy.Integer(5): 1}
+    mult = M.eigenvalues_with_geometric_multiplicities()
+    assert mult[sympy.Integer(2)] == (2, 2) and mult[sympy.Integer(5)] == (1, 1)
+    res = M.diagonalize()
+    assert res.success
+    Dm = res.D.items
+    assert all(Dm[i][j] == 0 for i in range(4) for j in range(4) if i != j)
+    assert sorted(Dm[i][i] for i in range(4)) == [-1, 2, 2, 5]
+    assert (res.P_inv * res.P).items == Matrix.identity(4).items
+    J = Matrix([[3, 1, 0], [0, 3, 1], [0, 0, 3]])
+    assert J.eigenvalues() == {sympy.Integer(3): 3}
+    rj = J.diagonalize()
+    assert not rj.success and rj.eigenvalue_multiplicities[sympy.Integer(3)] == (3, 1)
+    with pytest.raises(ValueError):
+        Matrix([[1, 2, 3], [4, 5, 6]]).diagonalize()
