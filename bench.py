@@ -449,6 +449,17 @@ def c5_cpu_baseline(n_primes, sample_n=1280):
                       % (sample_n, sample_n, cores, dt, sample_n, n_primes, cores)}
 
 
+def c5_prime_count_numpy():
+    """Prime count of lsx_det_large_prime_count_for, recomputed on the host (same formula)."""
+    import math
+    import numpy as np
+    A = c5_matrix().astype(np.int64)
+    rows = 0.5 * np.log2((A * A).sum(axis=1).astype(np.float64)).sum()
+    cols = 0.5 * np.log2((A * A).sum(axis=0).astype(np.float64)).sum()
+    bits = min(rows, cols) * (1.0 + 1e-9) + 1e-6
+    return max(1, math.ceil((bits + 1.0 + 1e-6) / 30.999))
+
+
 def c5_tensor_ops(n, n_primes_local, block=256):
     """int8 tensor operations (2 per multiply-add, 16 byte-plane products per residue multiply-add) of the
     depth-256 trailing updates of the blocked LU for n_primes_local primes."""
@@ -466,8 +477,7 @@ def run_c5_reference(args):
         return
     from linalg_solver_b200 import _lib  # noqa: F401  (prime count comes from the same plan function)
     import ctypes
-    k, bits = ctypes.c_int(), ctypes.c_double()
-    _lib.lib.lsx_det_large_prime_count(C5_N, C5_ABS, ctypes.byref(k), ctypes.byref(bits))
+    k = ctypes.c_int(c5_prime_count_numpy())
     vals = []
     cb = None
     for i in range(args.warmup + args.steps):
@@ -495,10 +505,10 @@ def run_c5(args):
     from linalg_solver_b200 import Engine
     from linalg_solver_b200 import dist as lsx_dist
 
-    n_primes, bits = Engine.det_large_prime_count(C5_N, C5_ABS)
+    worst_primes, _ = Engine.det_large_prime_count(C5_N, C5_ABS)   # worst case for |entries| <= 5: 1100 primes
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu:
-        cpu = c5_cpu_baseline(n_primes)                           # before CUDA init (fork pool)
+        cpu = c5_cpu_baseline(c5_prime_count_numpy())             # before CUDA init (fork pool)
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -521,8 +531,12 @@ def run_c5(args):
         want = [det_mod_p(small, int(p)) for p in eng.primes(2)]
         assert [int(x) for x in got] == want, "blocked LU residues differ from oracle/det_mod_p.py"
 
+    # Hadamard bound from the actual row/column norms of A (rigorous, about 8 % fewer primes than the worst case)
+    n_primes, bits = eng.det_large_prime_count_for(A)
+    assert n_primes == c5_prime_count_numpy() and n_primes <= worst_primes
+
     def step():
-        return lsx_dist.det_large_sharded(eng, A, C5_ABS)
+        return lsx_dist.det_large_sharded(eng, A)
 
     words = None
     for _ in range(args.warmup):
@@ -554,7 +568,7 @@ def run_c5(args):
     e0 = time.perf_counter()
     for _ in range(e2e_steps):
         A_d = A_host.to(dev, non_blocking=True)
-        w, _ = lsx_dist.det_large_sharded(eng, A_d, C5_ABS)
+        w, _ = lsx_dist.det_large_sharded(eng, A_d)
         w_host = w.cpu()
     e2e_ms = (time.perf_counter() - e0) * 1e3 / e2e_steps
     assert torch.equal(w_host, words.cpu())
@@ -584,7 +598,9 @@ def run_c5(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32 residues modulo 31-bit primes; trailing update as u8 x u8 -> s32 tcgen05 MMA",
             "data": "synthetic",
-            "config": {"workload": C5_DESC, "primes": n_primes, "primes_per_gpu": e - b, "limbs": limbs,
+            "config": {"workload": C5_DESC, "primes": n_primes, "primes_worst_case_bound": worst_primes,
+                       "bound": "Hadamard with the actual row/column norms, log2 = %.1f" % bits,
+                       "primes_per_gpu": e - b, "limbs": limbs,
                        "sharding": "by prime, one all-gather of %d residues (%d B) before the CRT" % (n_primes, 4 * n_primes),
                        "l2": "residue matrices of one prime group (64 MiB per prime) far exceed the 126 MB L2",
                        "det_bits": int(abs(det)).bit_length(), "det_mod_1e9": int(det % 10**9)},

@@ -182,6 +182,14 @@ int lsx_solve_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, const 
 /* Number of primes the determinant of an n x n matrix with |entries| <= a_abs_max needs. */
 int lsx_det_large_prime_count(int n, int64_t a_abs_max, int* n_primes, double* log2_bound);
 /*
+ * Same, from the matrix itself: Hadamard's bound with the ACTUAL row and column norms,
+ * |det A| <= min(prod_i ||row_i||_2, prod_j ||col_j||_2), which for random entries is a few per cent tighter
+ * than n * log2(sqrt(n) * a_abs_max) and still rigorous (every rank must use the same count: the bound only
+ * depends on A).  A: [n][n] int32 in `mem`.  A zero row or column gives n_primes = 1, log2_bound = 0.
+ */
+int lsx_det_large_prime_count_for(lsx_ctx* ctx, const int32_t* A, int n, int mem, int* n_primes,
+                                  double* log2_bound);
+/*
  * det(A) mod p for the primes [prime_begin, prime_begin + prime_count) of the table.
  * A: [n][n] int32.  residues: [prime_count] uint32 (plain residues), primes_out (may be
  * NULL): the primes used.  Ranks shard the prime range and all-gather `residues`.

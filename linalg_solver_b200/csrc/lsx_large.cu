@@ -4,6 +4,7 @@
 // The reference has no feasible route for this size (its determinant is a plan search over
 // sparsity patterns, determinant.rs:575-665, or an n! sum, linalg.py:264-345); the value is the
 // signed product of the forward-sweep pivots of linalg.py:547-609, computed here modulo each prime.
+#include <algorithm>
 #include <cmath>
 
 #include "lsx_internal.h"
@@ -100,9 +101,67 @@ __global__ void __launch_bounds__(1024) k_garner_big(const PrimeRec* primes, con
     }
 }
 
+// sums of squares of the rows ([0, n)) and of the columns ([n, 2n)) of an n x n int32 matrix
+__global__ void k_sq_norms(const int32_t* __restrict__ A, int n, unsigned long long* __restrict__ out) {
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const bool is_col = i >= n;
+    const int idx = is_col ? i - n : i;
+    unsigned long long s = 0;
+    for (int t = tid; t < n; t += blockDim.x) {
+        const long long v = is_col ? A[(int64_t)t * n + idx] : A[(int64_t)idx * n + t];
+        s += (unsigned long long)(v * v);
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ unsigned long long part[8];
+    if ((tid & 31) == 0) part[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
+        out[i] = tot;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int lsx_det_large_prime_count_for(lsx_ctx* ctx, const int32_t* A, int n, int mem, int* n_primes, double* log2_bound) {
+    if (!ctx) return LSX_ERR_NULL;
+    if (!A || !n_primes) return lsx_fail(ctx, LSX_ERR_NULL, "det_large_prime_count_for: NULL buffer");
+    if (n < 1) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "det_large_prime_count_for: bad n");
+    std::vector<unsigned long long> sq((size_t)2 * n, 0ull);
+    if (mem == LSX_MEM_HOST) {
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                const long long v = A[(int64_t)i * n + j];
+                sq[i] += (unsigned long long)(v * v);
+                sq[n + j] += (unsigned long long)(v * v);
+            }
+    } else {
+        LSX_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        int rc = lsx_ws_reserve(ctx, (size_t)2 * n * 8);
+        if (rc != LSX_OK) return rc;
+        k_sq_norms<<<2 * n, 256, 0, ctx->stream>>>(A, n, (unsigned long long*)ctx->d_ws);
+        ctx->launches++;
+        LSX_CUDA_TRY(ctx, cudaMemcpyAsync(sq.data(), ctx->d_ws, (size_t)2 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        LSX_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    double rows = 0.0, cols = 0.0;
+    bool zero = false;
+    for (int i = 0; i < n; ++i) {
+        if (sq[i] == 0 || sq[n + i] == 0) zero = true;
+        else rows += 0.5 * std::log2((double)sq[i]), cols += 0.5 * std::log2((double)sq[n + i]);
+    }
+    // a relative slack far above the rounding error of 2n logarithms and their sum keeps the bound rigorous
+    const double bits = zero ? 0.0 : std::min(rows, cols) * (1.0 + 1e-9) + 1e-6;
+    int K, L;
+    lsx_bits_to_plan(bits, &K, &L);
+    if (K > LSX_TABLE_PRIMES) return LSX_ERR_BOUND;
+    *n_primes = K;
+    if (log2_bound) *log2_bound = bits;
+    return LSX_OK;
+}
 
 int lsx_det_large_prime_count(int n, int64_t a_abs_max, int* n_primes, double* log2_bound) {
     if (n < 1 || a_abs_max < 0 || !n_primes) return LSX_ERR_BAD_SHAPE;

@@ -44,16 +44,21 @@ def all_gather_residues(local, total: int, group=None):
     return torch.cat(parts) if parts else out
 
 
-def det_large_sharded(engine, A, a_abs_max: int, group=None):
+def det_large_sharded(engine, A, a_abs_max: int = None, group=None):
     """Determinant of one large integer matrix, primes sharded over the ranks of `group`.
 
     Returns (det_words, n_primes): `det_words` is the signed determinant as little-endian 32-bit
-    words (two's complement) on every rank.
+    words (two's complement) on every rank.  The prime count comes from the worst-case Hadamard bound of
+    `a_abs_max` when it is given, else from the row/column norms of A itself (every rank holds the same A,
+    so every rank derives the same count).
     """
     import torch.distributed as dist
 
     n = A.shape[0]
-    K, bits = engine.det_large_prime_count(n, a_abs_max)
+    if a_abs_max is None:
+        K, bits = engine.det_large_prime_count_for(A)
+    else:
+        K, bits = engine.det_large_prime_count(n, a_abs_max)
     if dist.is_available() and dist.is_initialized():
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     else:

@@ -440,6 +440,18 @@ def test_c5_standins_blocked_tensor_path_exact(eng, n):
     A = rng.integers(-5, 6, size=(n, n), dtype=np.int64).astype(np.int32)
     words, K = lsx_dist.det_large_sharded(eng, A, 5)
     assert limbs_to_ints(words) == int(c["det"])
+    # prime count from the matrix's own row/column norms: fewer primes, same determinant
+    words2, K2 = lsx_dist.det_large_sharded(eng, A)
+    assert K2 < K and K2 == eng.det_large_prime_count_for(torch_or_np(A))[0]
+    assert limbs_to_ints(words2) == int(c["det"])
+    Z = A.copy()
+    Z[:, 7] = 0
+    assert eng.det_large_prime_count_for(Z) == (1, 0.0)
+
+
+def torch_or_np(A):
+    import torch
+    return torch.from_numpy(A).cuda()
 
 
 def test_subwarp_kernel_equals_tile_path(eng, monkeypatch):
