@@ -185,6 +185,21 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint6
         : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// TS form: the A operand (128 lanes x 8 columns = 128 rows x 32 bytes) comes from TMEM
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared memory -> TMEM: 128 rows x 256 bits described by a K-major matrix descriptor (same core-matrix layout
+// as an MMA operand slice) into 128 lanes x 8 columns
+__device__ __forceinline__ void tc_cp_128x256b(uint32_t tmem_dst, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -223,7 +238,11 @@ struct GemmArgs {
 // DBG (timing experiments of tools/tc_gemm_test only; the library instantiates DBG = 0):
 //   bit 0 exchange the descriptor strides, bit 1 skip the epilogue arithmetic, bit 2 skip the TMEM loads,
 //   bit 3 issue the products of a pass in plain (pa, pb) order instead of the accumulator-spaced order
-template <int DBG, int TRANS>
+// TRANS: transposed product (see Region::trans).
+// TS:    the A operand of every K step is first copied shared memory -> TMEM (tcgen05.cp, the 64 columns the
+//        accumulators leave free hold two K steps of four byte planes) and the MMAs take it from there, so each
+//        plane slice is read from shared memory once per pass instead of once per product.
+template <int DBG, int TRANS, int TS>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const Region& g = a.g;
@@ -305,7 +324,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
         // ===== MMA issuer: the whole warp walks the pipeline (uniform control flow keeps the descriptors in
         // uniform registers), one elected lane issues the tcgen05 instructions =====
         // instruction descriptor: D = s32 (2 << 4), A = B = u8 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-        const uint32_t idesc = (2u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+        // (DBG bit 4, timing only: N = 128 per instruction into three shared accumulators -- wrong results)
+        const uint32_t idesc = (2u << 4) | ((uint32_t)(((DBG & 16) ? 2 * TN : TN) >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
         uint32_t a_lbo = TM * 16, b_lbo = TN * 16, a_sbo = 128, b_sbo = 128;
         if (DBG & 1) {
             uint32_t x = a_lbo; a_lbo = a_sbo; a_sbo = x;
@@ -318,7 +338,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
         const uint32_t b_step = bst ? b_chunk : rg_stride;
         mbar_wait(bar_s_full, 0);
         tc_fence_after();
-        uint32_t cnt = 0;
+        uint32_t cnt = 0, kstep_ctr = 0;
         for (int t = 0; t < ntiles; ++t, cnt += kchunks) {
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
@@ -344,17 +364,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
                             const uint32_t fresh = (kc | s) == 0 ? 0u : 1u;   // 0: first write of the accumulators
                             const uint64_t ad_s = ad_c + (((uint32_t)s * (2 * TM * 16)) >> 4);
                             const uint64_t bd_s = bd_c + (((uint32_t)s * (2 * TN * 16)) >> 4);
-                            if (DBG & 16) {                       // experiment: all 16 products in the first pass
-                                if (pass == 0) {
+                            // TS: stage the byte planes of A this pass needs into the free TMEM columns (two buffers
+                            // of 4 x 8 columns, alternating per K step; tcgen05.cp and tcgen05.mma run in issue order)
+                            const uint32_t a_tm = tmem_base + 7u * TN + (uint32_t)((kstep_ctr & 1u) * 32u);
+                            if (TS) {
 #pragma unroll
-                                    for (int pa = 0; pa < 4; ++pa) {
-#pragma unroll
-                                        for (int pb = 0; pb < 4; ++pb)
-                                            tc_mma_i8(tmem_base + (uint32_t)((pa + pb) * TN), ad_s + (((uint32_t)pa * a_plane) >> 4),
-                                                      bd_s + (((uint32_t)pb * b_plane) >> 4), idesc, (pa == 0 || pb == 3) ? fresh : 1u);
-                                    }
-                                }
-                                continue;
+                                for (int pa = (pass ? 1 : 0); pa < 4; ++pa)
+                                    tc_cp_128x256b(a_tm + (uint32_t)(pa * 8), ad_s + (((uint32_t)pa * a_plane) >> 4));
+                                ++kstep_ctr;
                             }
 #pragma unroll
                             for (int i = 0; i < (pass ? NHI : NLO); ++i) {
@@ -363,11 +380,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
                                 const int pb = pass ? ((DBG & 8) ? hi_pb_n[i % NHI] : hi_pb[i % NHI])
                                                     : ((DBG & 8) ? lo_pb_n[i % NLO] : lo_pb[i % NLO]);
                                 // first product into an accumulator: plane 0 of A (weights 0..3) or plane 3 of B (4..6)
-                                tc_mma_i8(tmem_base + (uint32_t)((pa + pb) * TN), ad_s + (((uint32_t)pa * a_plane) >> 4),
-                                          bd_s + (((uint32_t)pb * b_plane) >> 4), idesc, (pa == 0 || pb == 3) ? fresh : 1u);
+                                const uint32_t acc_flag = (pa == 0 || pb == 3) ? fresh : 1u;
+                                const uint64_t bd = bd_s + (((uint32_t)pb * b_plane) >> 4);
+                                if (DBG & 16)   // B read from the (large) stationary region so that 128 rows stay inside smem
+                                    tc_mma_i8(tmem_base + (uint32_t)(((pa + pb) % 3) * 2 * TN), ad_s + (((uint32_t)pa * a_plane) >> 4),
+                                              smem_desc(smem_u32(smS) + (uint32_t)pb * b_plane, b_lbo, b_sbo), idesc, 1u);
+                                else if (TS)
+                                    tc_mma_i8_ts(tmem_base + (uint32_t)((pa + pb) * TN), a_tm + (uint32_t)(pa * 8), bd, idesc, acc_flag);
+                                else
+                                    tc_mma_i8(tmem_base + (uint32_t)((pa + pb) * TN), ad_s + (((uint32_t)pa * a_plane) >> 4), bd,
+                                              idesc, acc_flag);
                             }
                         }
-                        if ((DBG & 16) ? pass == 0 : pass == 1) tc_commit(bar_r_empty + 8 * slot);    // slot free once both passes have read it
+                        if (pass == 1) tc_commit(bar_r_empty + 8 * slot);    // slot free once both passes have read it
                         if (kc == kchunks - 1) tc_commit(pass ? bar_hi_full : bar_lo_full);
                     }
                     __syncwarp();
@@ -393,7 +418,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
             // C[jb + i][m] (trans == 1: word accesses, the warp's 32 lanes side by side in one row: coalesced)
             uint32_t* cp = TRANS ? Wg + (int64_t)jb * g.n + m : Wg + (int64_t)m * g.n + jb;
             const int64_t estride = TRANS ? g.n : 1;
-            const bool live = !(DBG & 32) && m < m1 && jb < j1;
+            const bool live = m < m1 && jb < j1;
             const bool full = live && vec_ok && jb + 32 <= j1;
             // C does not depend on the MMAs: fetch it BEFORE waiting for the accumulators, so the HBM/L2
             // latency hides behind the tensor-core phase of the tile.
@@ -492,8 +517,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
 }
 
 // the library's instantiation
-constexpr auto k_gemm_tc = k_gemm_tc_t<0, 0>;
-constexpr auto k_gemm_tc_trans = k_gemm_tc_t<0, 1>;
+constexpr auto k_gemm_tc = k_gemm_tc_t<0, 0, 0>;
+constexpr auto k_gemm_tc_trans = k_gemm_tc_t<0, 1, 0>;
+constexpr auto k_gemm_tc_ts = k_gemm_tc_t<0, 0, 1>;
 
 #endif  // __CUDACC__
 

@@ -93,13 +93,14 @@ int main(int argc, char** argv) {
     CK(cudaDeviceSynchronize());
     CK(cudaEventElapsedTime(&ms_ref, e0, e1));
     const size_t smem = smem_bytes(K, bst);
-    void (*kern)(GemmArgs) = trans ? k_gemm_tc_t<0, 1> : k_gemm_tc_t<0, 0>;
+    const int ts = argc > 11 ? atoi(argv[11]) : 0;      // 1: A operand staged through TMEM (tcgen05.cp + TS-form MMA)
+    void (*kern)(GemmArgs) = ts ? k_gemm_tc_t<0, 0, 1> : (trans ? k_gemm_tc_t<0, 1, 0> : k_gemm_tc_t<0, 0, 0>);
     switch (swap) {
-        case 1: kern = k_gemm_tc_t<1, 0>; break;
-        case 2: kern = k_gemm_tc_t<2, 0>; break;
-        case 6: kern = k_gemm_tc_t<6, 0>; break;
-        case 8: kern = k_gemm_tc_t<8, 0>; break;
-        case 54: kern = k_gemm_tc_t<54, 0>; break;
+        case 1: kern = k_gemm_tc_t<1, 0, 0>; break;
+        case 2: kern = k_gemm_tc_t<2, 0, 0>; break;
+        case 6: kern = ts ? k_gemm_tc_t<6, 0, 1> : k_gemm_tc_t<6, 0, 0>; break;
+        case 8: kern = k_gemm_tc_t<8, 0, 0>; break;
+        case 22: kern = k_gemm_tc_t<22, 0, 0>; break;
         default: break;
     }
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -132,7 +133,7 @@ int main(int argc, char** argv) {
             ++bad;
         }
     const double macs = (double)G * (g.r1 - g.r0) * (double)(g.c1 - g.c0) * K;
-    printf("{\"bst\": %d, \"trans\": %d, \"rows\": %d, \"cols\": %d, ", bst, trans, g.r1 - g.r0, g.c1 - g.c0);
+    printf("{\"ts\": %d, \"bst\": %d, \"trans\": %d, \"rows\": %d, \"cols\": %d, ", ts, bst, trans, g.r1 - g.r0, g.c1 - g.c0);
     printf("\"n\": %d, \"G\": %d, \"k0\": %d, \"K\": %d, \"swap\": %d, \"mismatches\": %zu, \"first_bad\": %zu, "
            "\"first_bad_rc\": [%zu, %zu], \"got\": %u, \"ref\": %u, \"ms_ref\": %.3f, \"ms_split\": %.3f, \"ms_tc\": %.3f, "
            "\"mod_mac_per_s\": %.4g, \"int8_tops\": %.1f}\n",
