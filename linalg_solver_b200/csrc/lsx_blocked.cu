@@ -16,7 +16,7 @@
 //   k_swap      row swaps of a pivot range applied to a column range (left L columns and right columns)
 //   k_trsm      unit-lower triangular solve with a <= 64-wide diagonal block held in shared memory
 //   gemm()      C -= L * U on a rectangular region: contraction depth 64 / 128 / 256 -> tcgen05 int8-split
-//               tensor-core kernel (lsx_tc.cuh: byte planes, 7 TMEM accumulators, cp.async.bulk staging);
+//               tensor-core kernel (lsx_tc.cuh: stacked byte planes, 7 TMEM accumulators x 2 tiles, cp.async.bulk staging);
 //               smaller depths (8 / 16 / 32, inside a 64-column panel) -> k_gemm_int on the integer pipe
 //               (64-bit accumulators, lazy high-word reduction, one REDC at the end)
 //   k_finish    sign, zero flag, Montgomery -> plain residue
@@ -493,7 +493,6 @@ struct Driver {
     uint8_t* AP;          // byte planes for the tensor-core update (lsx_tc.cuh)
     uint8_t* BP;
     bool use_tc;
-    bool tc_trans;
     int n;
 
     static int left_width(int w) {               // largest power of two below w (w > NB_BASE)
@@ -508,13 +507,10 @@ struct Driver {
             lsx_tc::Region g{};
             g.n = n, g.r0 = r0, g.r1 = r1, g.c0 = c0, g.c1 = c1, g.k0 = k0, g.K = K;
             g.kc = std::min(K, lsx_tc::KC);
-            // Transposed product (TMEM lanes = columns of C): the epilogue's C traffic is coalesced, which matters
-            // because global accesses and the tensor core's operand reads share the L1/shared-memory data pipe.
-            g.trans = tc_trans ? 1 : 0;
             g.set_tiles();
-            // CTA keeps the planes of one tile of the SHORT dimension's partner resident and loops over the long
-            // one: N-stationary when there are at most two N tiles (or few of them and many M tiles)
-            g.b_stationary = (g.n_tiles <= 2 && g.m_tiles > 2) ? 1 : 0;
+            // tall and narrow (inside a panel: at most 128 columns): keep the B planes of one 32-column tile
+            // resident and stream the row tiles; otherwise keep the A planes of a row tile and stream columns
+            g.b_stationary = (g.n_tiles <= 4 && g.m_tiles > 2) ? 1 : 0;
             const int fixed = g.b_stationary ? g.n_tiles : g.m_tiles, looped = g.b_stationary ? g.m_tiles : g.n_tiles;
             const int units = fixed * a.G;
             int groups = std::min(looped, std::max(1, (2 * ctx->sm_count + units - 1) / units));
@@ -525,8 +521,7 @@ struct Driver {
             ga.W = a.W, ga.AP = AP, ga.BP = BP, ga.primes = a.primes, ga.g = g;
             const bool big = K == NB_OUT;
             if (big) lsx_timing_begin(ctx);
-            (g.trans ? lsx_tc::k_gemm_tc_trans : lsx_tc::k_gemm_tc)<<<dim3(fixed, groups, a.G), lsx_tc::THREADS,
-                                                                      lsx_tc::smem_bytes(K, g.b_stationary), st>>>(ga);
+            lsx_tc::k_gemm_tc<<<dim3(fixed, groups, a.G), lsx_tc::THREADS, lsx_tc::smem_bytes(K, g.b_stationary), st>>>(ga);
             if (big) lsx_timing_end(ctx);
             ctx->launches += 3;
             return;
@@ -608,8 +603,8 @@ int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_b
         return (mb < 64 ? 64 : mb) << 20;
     }();
     const bool use_tc = !getenv("LSX_NO_TC");
-    const size_t rt = (size_t)(n + lsx_tc::TM - 1) / lsx_tc::TM;
-    const size_t ap_per = rt * lsx_tc::TM * 4 * NB_OUT, bp_per = ap_per;   // byte planes per prime (either operand, either dimension)
+    const size_t rt = (size_t)(n + lsx_tc::TM - 1) / lsx_tc::TM, ct = (size_t)(n + lsx_tc::TN - 1) / lsx_tc::TN;
+    const size_t ap_per = rt * lsx_tc::TM * 4 * NB_OUT, bp_per = ct * lsx_tc::TN * 4 * NB_OUT;   // byte planes per prime
     const size_t per = (size_t)n * n * 4 + (size_t)n * 4 + 64 + (use_tc ? ap_per + bp_per : 0);
     // groups of about one prime per SM, evenly sized, within the workspace budget
     int G = (int)std::min<size_t>((size_t)count, std::max<size_t>(1, budget / per));
@@ -636,7 +631,6 @@ int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_b
     {
         const int smax = (int)std::max(lsx_tc::smem_bytes(lsx_tc::MAX_K, 0), lsx_tc::smem_bytes(lsx_tc::MAX_K, 1));
         LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(lsx_tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
-        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(lsx_tc::k_gemm_tc_trans, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
     }
     for (int g0 = 0; g0 < count; g0 += G) {
         const int Gc = std::min(G, count - g0);
@@ -652,7 +646,6 @@ int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_b
         d.AP = (uint8_t*)(base + o_ap);
         d.BP = (uint8_t*)(base + o_bp);
         d.use_tc = use_tc;
-        d.tc_trans = getenv("LSX_TC_TRANS") != nullptr;   // transposed product: same speed on the big update, slower in panels
         d.n = n;
         k_load<<<dim3(ctx->sm_count * 2, Gc), 256, 0, ctx->stream>>>(dA, d.a);
         ctx->launches++;

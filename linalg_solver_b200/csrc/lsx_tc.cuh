@@ -8,32 +8,44 @@
 // pivots at once, and the only genuinely GEMM-shaped piece of the path.
 //
 // 31-bit residues do not fit a tensor-core operand, so each word is split into four unsigned bytes
-// (k_tc_split_a / k_tc_split_b, written straight in the no-swizzle K-major core-matrix layout tcgen05
-// wants) and the 16 byte-plane products are issued as `tcgen05.mma.kind::i8` (u8 x u8 -> s32) into SEVEN
-// TMEM accumulators Q_t, t = a + b the byte weight: Q_t = sum_{a+b=t} La * Ub^T.  Every Q_t stays below
-// 4 * K * 255^2 < 2^26 for K <= 256, so the s32 accumulation is exact.  The epilogue reads the seven
-// accumulators with tcgen05.ld, forms  S = sum_t Q_t * (2^(8t) mod p)  < 2^60 in 64 bits and finishes with
-// one Montgomery reduction:  C + REDC(S) mod p  — bit-identical to the integer-pipe k_gemm.
+// (k_tc_split, written straight in the no-swizzle K-major core-matrix layout tcgen05 wants) and the 16
+// byte-plane products La * Ub^T accumulate, by weight t = a + b, into SEVEN s32 TMEM accumulators
+// Q_t = sum_{a+b=t} La * Ub^T.  Every Q_t stays below 4 * K * 255^2 < 2^26 for K <= 256, so the s32
+// accumulation is exact.  The epilogue reads the seven accumulators with tcgen05.ld, forms
+// S = sum_t Q_t * (2^(8t) mod p) < 2^60 in 64 bits and finishes with one Montgomery reduction:
+// C + REDC(S) mod p  -- bit-identical to the integer-pipe k_gemm_int.
 //
-// CTA = (prime g, 128-row tile, a contiguous group of 64-column tiles) or, for tall narrow regions, (prime,
-// 64-column tile, group of row tiles).  The planes of the fixed tile stay resident in shared memory for the
+// Instruction shape (the point of this layout; measurements in profiles/r01i_tc_gemm_experiments.md): a
+// tcgen05.mma of M = 128, N, K = 32 costs about (4096 + 32 N) B / 110 B/clk of operand fetch, so the 16
+// products issued as 16 instructions of N = 64 run at half the tensor peak.  Here the four byte planes of
+// the B tile are STACKED along N in shared memory ([k16][plane b][column][16 B]): one instruction per A
+// plane a with N = 4 * TN covers the accumulators a .. a+3, which are adjacent in TMEM -- 4 instructions
+// per K step instead of 16, each long enough to be MAC bound.  (The very first K step of a tile splits
+// three of them so that every accumulator's first write has accumulate = 0.)  With TN = 32 the seven
+// accumulators take 224 columns, so TWO tiles fit TMEM and the epilogue of one tile overlaps the MMAs of
+// the next.
+//
+// CTA = (prime g, 128-row tile, a contiguous group of 32-column tiles) or, for tall narrow regions, (prime,
+// 32-column tile, group of row tiles).  The planes of the fixed tile stay resident in shared memory for the
 // whole CTA; the other operand streams through a ring of stages filled by cp.async.bulk (TMA engine, SASS
 // UBLKCP) and released by tcgen05.commit.  Warp 0 = TMEM allocator + copy producer, warp 1 = MMA issuer
-// (one elected lane), warps 2..9 = epilogue (two warps per TMEM lane quadrant).
+// (converged warp, one elected lane), warps 2..9 = epilogue (two warps per TMEM lane quadrant, 16 columns each).
 #pragma once
 #include "lsx_internal.h"
 
 namespace lsx_tc {
 
-constexpr int TM = 128;            // rows per CTA tile (= TMEM lanes)
-constexpr int TN = 64;             // columns per accumulator tile
+constexpr int TM = 128;            // rows per tile (= TMEM lanes)
+constexpr int TN = 32;             // columns per tile; the MMA N is 4 * TN = 128 (four stacked byte planes)
 constexpr int KC = 64;             // contraction bytes per smem stage (32 when K == 32)
 constexpr int A_CHUNK = 4 * TM * KC;   // 32768 B: four byte planes of a 128 x 64 slice
-constexpr int B_CHUNK = 4 * TN * KC;   // 16384 B
-constexpr int STAGES_A = 6;        // ring slots when the A planes are stationary (16 KB B slots)
+constexpr int B_CHUNK = 4 * TN * KC;   // 8192 B
+constexpr int STAGES_A = 8;        // ring slots when the A planes are stationary (8 KB B slots)
 constexpr int STAGES_B = 4;        // ring slots when the B planes are stationary (32 KB A slots)
 constexpr int THREADS = 320;
-constexpr int TMEM_COLS = 512;     // 7 accumulators x 64 columns = 448, rounded to a power of two
+constexpr int ACC_COLS = 7 * TN;   // 224 TMEM columns per tile
+constexpr int ACC_STRIDE = 256;    // second accumulator buffer
+constexpr int TMEM_COLS = 512;
 constexpr int MAX_K = 256;
 
 struct Region {
@@ -42,20 +54,13 @@ struct Region {
     int c0, c1;       // columns of C updated
     int k0, K;        // contraction range; K is 32 or a multiple of 64, at most MAX_K
     int kc;           // contraction bytes per stage: min(K, 64)
-    int trans;        // 0: TMEM lanes (M, 128 per tile) are rows of C and TMEM columns (N, 64 per tile) are columns;
-                      // 1: the product is formed transposed (M = columns of C, N = rows), so that the 32 lanes of an
-                      //    epilogue warp touch 32 CONSECUTIVE words of one row of C: coalesced C traffic
-    int m_tiles;      // tiles of 128 along the M dimension
-    int n_tiles;      // tiles of 64 along the N dimension
+    int m_tiles;      // tiles of 128 rows
+    int n_tiles;      // tiles of 32 columns
     int tiles_per_cta;  // tiles of the looped dimension handled by one CTA
-    int b_stationary;   // 0: CTA keeps the M-operand planes of one M tile and loops over N tiles; 1: the reverse
-    __host__ __device__ int m0() const { return trans ? c0 : r0; }
-    __host__ __device__ int m1() const { return trans ? c1 : r1; }
-    __host__ __device__ int j0() const { return trans ? r0 : c0; }
-    __host__ __device__ int j1() const { return trans ? r1 : c1; }
+    int b_stationary;   // 0: CTA keeps the A planes of one row tile and loops over column tiles; 1: the reverse
     void set_tiles() {
-        m_tiles = (m1() - m0() + TM - 1) / TM;
-        n_tiles = (j1() - j0() + TN - 1) / TN;
+        m_tiles = (r1 - r0 + TM - 1) / TM;
+        n_tiles = (c1 - c0 + TN - 1) / TN;
     }
 };
 
@@ -70,48 +75,10 @@ inline bool depth_ok(int K) { return K == 32 || (K % KC == 0 && K >= KC && K <= 
 #ifdef __CUDACC__
 
 // ---- byte-plane split ---------------------------------------------------------------------------------
-// Planes of one operand, prime g, tile t of width TILE along the operand's own dimension (index idx):
-//     [tile][K/kc][plane][k16 = kc/16][idx = TILE][16 B]          (no-swizzle K-major core matrices)
-// from_l != 0: element (idx, k) = W[idx][k0 + k]   (rows of L: 16 consecutive words per thread)
-// from_l == 0: element (idx, k) = W[k0 + k][idx]   (columns of U: strided in k, coalesced across idx)
-template <int TILE>
-__global__ void __launch_bounds__(256) k_tc_split(const uint32_t* __restrict__ W, uint8_t* __restrict__ planes, Region g,
-                                                  int i0, int i1, int tiles, int from_l) {
-    const int q_per = g.K / 16;                       // 16-byte k groups
-    const int64_t per_prime = (int64_t)tiles * TILE * q_per;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= per_prime) return;
-    const int prime = blockIdx.y;
-    const int r = (int)(t % TILE);
-    const int q = (int)((t / TILE) % q_per);
-    const int ti = (int)(t / ((int64_t)TILE * q_per));
-    const int idx = i0 + ti * TILE + r;
-    uint32_t w[16];
-    if (idx < i1) {
-        if (from_l) {
-            const uint32_t* src = W + ((int64_t)prime * g.n + idx) * g.n + g.k0 + q * 16;
-            if ((g.n & 3) == 0 && (g.k0 & 3) == 0) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(src + 4 * i);
-                    w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) w[i] = src[i];
-            }
-        } else {
-            const uint32_t* src = W + ((int64_t)prime * g.n + g.k0 + q * 16) * g.n + idx;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) w[i] = src[(int64_t)i * g.n];
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = 0u;
-    }
-    const int qc = g.kc / 16;                          // 16-byte groups per stage
-    uint8_t* dst = planes + ((int64_t)prime * tiles + ti) * ((int64_t)g.K * 4 * TILE) + (int64_t)(q / qc) * (4 * TILE * g.kc) +
-                   (q % qc) * (TILE * 16) + r * 16;
+// A planes (rows of L), prime g, row tile ti:      [K/kc][plane a][k16 = kc/16][row = 128][16 B]
+// B planes (columns of U), prime g, column tile tj: [K/kc][k16 = kc/16][plane b][col = 32][16 B]
+// (both no-swizzle K-major core matrices; the B planes are stacked along N inside each 16-byte K group)
+__device__ __forceinline__ void split_store(uint8_t* dst, int plane_stride, const uint32_t (&w)[16]) {
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         uint32_t o[4];
@@ -119,14 +86,69 @@ __global__ void __launch_bounds__(256) k_tc_split(const uint32_t* __restrict__ W
         for (int i = 0; i < 4; ++i)
             o[i] = ((w[4 * i] >> (8 * a)) & 255u) | (((w[4 * i + 1] >> (8 * a)) & 255u) << 8) |
                    (((w[4 * i + 2] >> (8 * a)) & 255u) << 16) | (((w[4 * i + 3] >> (8 * a)) & 255u) << 24);
-        *reinterpret_cast<uint4*>(dst + a * (TILE * g.kc)) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(dst + a * plane_stride) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
-// M-operand planes (128 per tile) and N-operand planes (64 per tile) of a region, all primes of the group
+__global__ void __launch_bounds__(256) k_tc_split_a(const uint32_t* __restrict__ W, uint8_t* __restrict__ AP, Region g) {
+    const int q_per = g.K / 16;                       // 16-byte k groups
+    const int64_t per_prime = (int64_t)g.m_tiles * TM * q_per;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per_prime) return;
+    const int prime = blockIdx.y;
+    const int r = (int)(t % TM);
+    const int q = (int)((t / TM) % q_per);
+    const int ti = (int)(t / ((int64_t)TM * q_per));
+    const int row = g.r0 + ti * TM + r;
+    uint32_t w[16];
+    if (row < g.r1) {
+        const uint32_t* src = W + ((int64_t)prime * g.n + row) * g.n + g.k0 + q * 16;
+        if ((g.n & 3) == 0 && (g.k0 & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint4 v = *reinterpret_cast<const uint4*>(src + 4 * i);
+                w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = src[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = 0u;
+    }
+    const int qc = g.kc / 16;                          // 16-byte groups per stage
+    uint8_t* dst = AP + ((int64_t)prime * g.m_tiles + ti) * ((int64_t)g.K * 4 * TM) + (int64_t)(q / qc) * (4 * TM * g.kc) +
+                   (q % qc) * (TM * 16) + r * 16;
+    split_store(dst, TM * g.kc, w);
+}
+__global__ void __launch_bounds__(256) k_tc_split_b(const uint32_t* __restrict__ W, uint8_t* __restrict__ BP, Region g) {
+    const int q_per = g.K / 16;
+    const int64_t per_prime = (int64_t)g.n_tiles * TN * q_per;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per_prime) return;
+    const int prime = blockIdx.y;
+    const int c = (int)(t % TN);
+    const int q = (int)((t / TN) % q_per);
+    const int tj = (int)(t / ((int64_t)TN * q_per));
+    const int col = g.c0 + tj * TN + c;
+    uint32_t w[16];
+    if (col < g.c1) {
+        const uint32_t* src = W + ((int64_t)prime * g.n + g.k0 + q * 16) * g.n + col;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = src[(int64_t)i * g.n];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = 0u;
+    }
+    const int qc = g.kc / 16;
+    uint8_t* dst = BP + ((int64_t)prime * g.n_tiles + tj) * ((int64_t)g.K * 4 * TN) + (int64_t)(q / qc) * (4 * TN * g.kc) +
+                   (q % qc) * (4 * TN * 16) + c * 16;
+    split_store(dst, TN * 16, w);
+}
 inline void launch_split(const uint32_t* W, uint8_t* AP, uint8_t* BP, const Region& g, int G, cudaStream_t st) {
     const int64_t ta = (int64_t)g.m_tiles * TM * (g.K / 16), tb = (int64_t)g.n_tiles * TN * (g.K / 16);
-    k_tc_split<TM><<<dim3((unsigned)((ta + 255) / 256), G), 256, 0, st>>>(W, AP, g, g.m0(), g.m1(), g.m_tiles, g.trans ? 0 : 1);
-    k_tc_split<TN><<<dim3((unsigned)((tb + 255) / 256), G), 256, 0, st>>>(W, BP, g, g.j0(), g.j1(), g.n_tiles, g.trans ? 1 : 0);
+    k_tc_split_a<<<dim3((unsigned)((ta + 255) / 256), G), 256, 0, st>>>(W, AP, g);
+    k_tc_split_b<<<dim3((unsigned)((tb + 255) / 256), G), 256, 0, st>>>(W, BP, g);
 }
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -225,24 +247,9 @@ struct GemmArgs {
     Region g;
 };
 
-// Tile loop of one CTA.
-//   g.b_stationary == 0: CTA = (row tile blockIdx.x, column-tile group blockIdx.y); the A planes of the row
-//                        tile stay in shared memory, B planes stream through the ring (wide regions).
-//   g.b_stationary == 1: CTA = (column tile blockIdx.x, row-tile group blockIdx.y); the B planes stay, A planes
-//                        stream (tall and narrow regions inside a panel: one or two column tiles in all).
-// The 16 byte-plane products of a tile are issued in TWO passes over the resident K chunks: first the ten
-// products of weight 2^0 .. 2^24 into accumulators 0..3 ("low"), then the six of weight 2^32 .. 2^48 into
-// accumulators 4..6 ("high").  The epilogue drains the low accumulators while the tensor pipe works on the
-// high pass, and the high ones while it works on the low pass of the NEXT tile, so the accumulators are
-// double-buffered in effect without needing more than 448 TMEM columns.
 // DBG (timing experiments of tools/tc_gemm_test only; the library instantiates DBG = 0):
-//   bit 0 exchange the descriptor strides, bit 1 skip the epilogue arithmetic, bit 2 skip the TMEM loads,
-//   bit 3 issue the products of a pass in plain (pa, pb) order instead of the accumulator-spaced order
-// TRANS: transposed product (see Region::trans).
-// TS:    the A operand of every K step is first copied shared memory -> TMEM (tcgen05.cp, the 64 columns the
-//        accumulators leave free hold two K steps of four byte planes) and the MMAs take it from there, so each
-//        plane slice is read from shared memory once per pass instead of once per product.
-template <int DBG, int TRANS, int TS>
+//   bit 1 skip the epilogue arithmetic, bit 2 skip the TMEM loads
+template <int DBG>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const Region& g = a.g;
@@ -253,9 +260,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
     const int loop_tiles = bst ? g.m_tiles : g.n_tiles;
     const int t0 = blockIdx.y * g.tiles_per_cta;
     const int ntiles = min(loop_tiles, t0 + g.tiles_per_cta) - t0;
-    const int kchunks = g.K / g.kc;                                      // <= 4 <= ring slots
+    const int kchunks = g.K / g.kc;                                      // <= 4
     const uint32_t a_chunk = 4u * TM * g.kc, b_chunk = 4u * TN * g.kc;   // bytes per K chunk (four byte planes)
-    const uint32_t a_plane = TM * g.kc, b_plane = TN * g.kc;             // bytes per byte plane inside a chunk
+    const uint32_t a_plane = TM * g.kc;                                  // bytes per A byte plane inside a chunk
     const int ksteps = g.kc / 32;                                        // MMA K = 32 bytes
     const uint32_t st_chunk = bst ? b_chunk : a_chunk;                   // stationary operand, per chunk
     const uint32_t rg_chunk = bst ? a_chunk : b_chunk;                   // streamed operand, per chunk
@@ -265,21 +272,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
     uint8_t* smS = smem;                                                 // stationary planes: kchunks * st_chunk
     uint8_t* smR = smem + (size_t)kchunks * st_chunk;                    // ring: STAGES slots
     uint64_t* bars = reinterpret_cast<uint64_t*>(smR + (size_t)STAGES * rg_stride);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
     const uint32_t bar_s_full = smem_u32(bars + 0);
-    const uint32_t bar_lo_full = smem_u32(bars + 1), bar_lo_empty = smem_u32(bars + 2);
-    const uint32_t bar_hi_full = smem_u32(bars + 3), bar_hi_empty = smem_u32(bars + 4);
-    const uint32_t bar_r_full = smem_u32(bars + 6);                      // [STAGES]
-    const uint32_t bar_r_empty = smem_u32(bars + 6 + STAGES_A);          // [STAGES]
+    const uint32_t bar_acc_full = smem_u32(bars + 2);                    // [2]
+    const uint32_t bar_acc_empty = smem_u32(bars + 4);                   // [2]
+    const uint32_t bar_r_full = smem_u32(bars + 8);                      // [STAGES]
+    const uint32_t bar_r_empty = smem_u32(bars + 8 + STAGES_A);          // [STAGES]
 
     if (ntiles <= 0) return;                                             // uniform per CTA
     if (warp == 0) {
         if (lane == 0) {
             mbar_init(bar_s_full, 1);
-            mbar_init(bar_lo_full, 1);
-            mbar_init(bar_lo_empty, 8);
-            mbar_init(bar_hi_full, 1);
-            mbar_init(bar_hi_empty, 8);
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(bar_acc_full + 8 * b, 1);
+                mbar_init(bar_acc_empty + 8 * b, 8);
+            }
             for (uint32_t s = 0; s < STAGES; ++s) {
                 mbar_init(bar_r_full + 8 * s, 1);
                 mbar_init(bar_r_empty + 8 * s, 1);
@@ -324,187 +331,128 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
         // ===== MMA issuer: the whole warp walks the pipeline (uniform control flow keeps the descriptors in
         // uniform registers), one elected lane issues the tcgen05 instructions =====
         // instruction descriptor: D = s32 (2 << 4), A = B = u8 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-        // (DBG bit 4, timing only: N = 128 per instruction into three shared accumulators -- wrong results)
-        const uint32_t idesc = (2u << 4) | ((uint32_t)(((DBG & 16) ? 2 * TN : TN) >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-        uint32_t a_lbo = TM * 16, b_lbo = TN * 16, a_sbo = 128, b_sbo = 128;
-        if (DBG & 1) {
-            uint32_t x = a_lbo; a_lbo = a_sbo; a_sbo = x;
-            x = b_lbo; b_lbo = b_sbo; b_sbo = x;
-        }
-        // operand bases: + (byte offset >> 4) selects chunk / plane / K step
-        const uint64_t adesc0 = smem_desc(smem_u32(bst ? smR : smS), a_lbo, a_sbo);
-        const uint64_t bdesc0 = smem_desc(smem_u32(bst ? smS : smR), b_lbo, b_sbo);
+        const uint32_t idesc0 = (2u << 4) | ((uint32_t)(TM >> 4) << 24);
+        const uint32_t idesc_n4 = idesc0 | ((uint32_t)((4 * TN) >> 3) << 17);     // all four planes: N = 128
+        const uint32_t idesc_n3 = idesc0 | ((uint32_t)((3 * TN) >> 3) << 17);     // planes 0..2:     N = 96
+        const uint32_t idesc_n1 = idesc0 | ((uint32_t)(TN >> 3) << 17);           // plane 3 alone:   N = 32
+        // operand bases: + (byte offset >> 4) selects chunk / plane / K step.  A: LBO (next 16-byte K group) =
+        // 128 rows * 16 B; B: the four stacked planes make 4 * TN rows per K group.  SBO (next 8 rows) = 128 B.
+        const uint64_t adesc0 = smem_desc(smem_u32(bst ? smR : smS), TM * 16, 128);
+        const uint64_t bdesc0 = smem_desc(smem_u32(bst ? smS : smR), 4 * TN * 16, 128);
         const uint32_t a_step = bst ? rg_stride : a_chunk;               // distance between K chunks of A
         const uint32_t b_step = bst ? b_chunk : rg_stride;
         mbar_wait(bar_s_full, 0);
         tc_fence_after();
-        uint32_t cnt = 0, kstep_ctr = 0;
+        uint32_t cnt = 0;
         for (int t = 0; t < ntiles; ++t, cnt += kchunks) {
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                mbar_wait(pass ? bar_hi_empty : bar_lo_empty, (uint32_t)((t & 1) ^ 1));
+            const uint32_t buf = (uint32_t)t & 1u, use = (uint32_t)t >> 1;
+            mbar_wait(bar_acc_empty + 8 * buf, (use & 1u) ^ 1u);         // the epilogue has drained this buffer
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + buf * ACC_STRIDE;
+            for (int kc = 0; kc < kchunks; ++kc) {
+                const uint32_t slot = (cnt + kc) % STAGES, phase = ((cnt + kc) / STAGES) & 1u;
+                mbar_wait(bar_r_full + 8 * slot, phase);
                 tc_fence_after();
-                for (int kc = 0; kc < kchunks; ++kc) {
-                    const uint32_t slot = (cnt + kc) % STAGES, phase = ((cnt + kc) / STAGES) & 1u;
-                    if (pass == 0) {
-                        mbar_wait(bar_r_full + 8 * slot, phase);
-                        tc_fence_after();
-                    }
-                    if (elect_one()) {
-                        const uint64_t ad_c = adesc0 + (((bst ? slot : (uint32_t)kc) * a_step) >> 4);
-                        const uint64_t bd_c = bdesc0 + (((bst ? (uint32_t)kc : slot) * b_step) >> 4);
-                        // products of this pass, ordered so that consecutive MMAs accumulate into DIFFERENT
-                        // accumulators (the same one comes back after two or more others)
-                        constexpr int NLO = 10, NHI = 6;
-                        constexpr int lo_pa[NLO] = {0, 0, 1, 0, 1, 2, 0, 3, 1, 2}, lo_pb[NLO] = {3, 2, 2, 1, 1, 1, 0, 0, 0, 0};
-                        constexpr int hi_pa[NHI] = {1, 2, 2, 3, 3, 3}, hi_pb[NHI] = {3, 3, 2, 3, 1, 2};
-                        constexpr int lo_pa_n[NLO] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3}, lo_pb_n[NLO] = {0, 1, 2, 3, 0, 1, 2, 0, 1, 0};
-                        constexpr int hi_pa_n[NHI] = {1, 2, 2, 3, 3, 3}, hi_pb_n[NHI] = {3, 2, 3, 1, 2, 3};
-                        for (int s = 0; s < ksteps; ++s) {
-                            const uint32_t fresh = (kc | s) == 0 ? 0u : 1u;   // 0: first write of the accumulators
-                            const uint64_t ad_s = ad_c + (((uint32_t)s * (2 * TM * 16)) >> 4);
-                            const uint64_t bd_s = bd_c + (((uint32_t)s * (2 * TN * 16)) >> 4);
-                            // TS: stage the byte planes of A this pass needs into the free TMEM columns (two buffers
-                            // of 4 x 8 columns, alternating per K step; tcgen05.cp and tcgen05.mma run in issue order)
-                            const uint32_t a_tm = tmem_base + 7u * TN + (uint32_t)((kstep_ctr & 1u) * 32u);
-                            if (TS) {
+                if (elect_one()) {
+                    const uint64_t ad_c = adesc0 + (((bst ? slot : (uint32_t)kc) * a_step) >> 4);
+                    const uint64_t bd_c = bdesc0 + (((bst ? (uint32_t)kc : slot) * b_step) >> 4);
+                    for (int s = 0; s < ksteps; ++s) {
+                        const uint64_t ad_s = ad_c + (((uint32_t)s * (2 * TM * 16)) >> 4);
+                        const uint64_t bd_s = bd_c + (((uint32_t)s * (2 * 4 * TN * 16)) >> 4);
+                        if ((kc | s) == 0) {
+                            // first K step of the tile: every accumulator's first write must not accumulate.
+                            // plane a = 0 writes accumulators 0..3 fresh; for a = 1, 2, 3 the planes b = 0..2
+                            // accumulate into a..a+2 (already written) and b = 3 opens accumulator a + 3.
+                            tc_mma_i8(d0, ad_s, bd_s, idesc_n4, 0u);
 #pragma unroll
-                                for (int pa = (pass ? 1 : 0); pa < 4; ++pa)
-                                    tc_cp_128x256b(a_tm + (uint32_t)(pa * 8), ad_s + (((uint32_t)pa * a_plane) >> 4));
-                                ++kstep_ctr;
+                            for (int pa = 1; pa < 4; ++pa) {
+                                const uint64_t ad = ad_s + (((uint32_t)pa * a_plane) >> 4);
+                                tc_mma_i8(d0 + (uint32_t)(pa * TN), ad, bd_s, idesc_n3, 1u);
+                                tc_mma_i8(d0 + (uint32_t)((pa + 3) * TN), ad, bd_s + ((3u * TN * 16) >> 4), idesc_n1, 0u);
                             }
+                        } else {
 #pragma unroll
-                            for (int i = 0; i < (pass ? NHI : NLO); ++i) {
-                                const int pa = pass ? ((DBG & 8) ? hi_pa_n[i % NHI] : hi_pa[i % NHI])
-                                                    : ((DBG & 8) ? lo_pa_n[i % NLO] : lo_pa[i % NLO]);
-                                const int pb = pass ? ((DBG & 8) ? hi_pb_n[i % NHI] : hi_pb[i % NHI])
-                                                    : ((DBG & 8) ? lo_pb_n[i % NLO] : lo_pb[i % NLO]);
-                                // first product into an accumulator: plane 0 of A (weights 0..3) or plane 3 of B (4..6)
-                                const uint32_t acc_flag = (pa == 0 || pb == 3) ? fresh : 1u;
-                                const uint64_t bd = bd_s + (((uint32_t)pb * b_plane) >> 4);
-                                if (DBG & 16)   // B read from the (large) stationary region so that 128 rows stay inside smem
-                                    tc_mma_i8(tmem_base + (uint32_t)(((pa + pb) % 3) * 2 * TN), ad_s + (((uint32_t)pa * a_plane) >> 4),
-                                              smem_desc(smem_u32(smS) + (uint32_t)pb * b_plane, b_lbo, b_sbo), idesc, 1u);
-                                else if (TS)
-                                    tc_mma_i8_ts(tmem_base + (uint32_t)((pa + pb) * TN), a_tm + (uint32_t)(pa * 8), bd, idesc, acc_flag);
-                                else
-                                    tc_mma_i8(tmem_base + (uint32_t)((pa + pb) * TN), ad_s + (((uint32_t)pa * a_plane) >> 4), bd,
-                                              idesc, acc_flag);
-                            }
+                            for (int pa = 0; pa < 4; ++pa)
+                                tc_mma_i8(d0 + (uint32_t)(pa * TN), ad_s + (((uint32_t)pa * a_plane) >> 4), bd_s, idesc_n4, 1u);
                         }
-                        if (pass == 1) tc_commit(bar_r_empty + 8 * slot);    // slot free once both passes have read it
-                        if (kc == kchunks - 1) tc_commit(pass ? bar_hi_full : bar_lo_full);
                     }
-                    __syncwarp();
+                    tc_commit(bar_r_empty + 8 * slot);                   // frees the slot when these MMAs have read it
+                    if (kc == kchunks - 1) tc_commit(bar_acc_full + 8 * buf);
                 }
+                __syncwarp();
             }
         }
     } else {
-        // ===== epilogue: 8 warps; warp w reads TMEM lanes 32 * (w % 4) .. + 31, half of the 64 columns =====
+        // ===== epilogue: 8 warps; warp w reads TMEM lanes 32 * (w % 4) .. + 31, 16 of the 32 columns =====
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const PrimeRec P = a.primes[prime];
         const uint32_t p = P.p, pinv = P.pinv;
         const uint64_t c4 = P.one;                               // 2^32 mod p
         const uint64_t c5 = (c4 << 8) % p, c6 = (c5 << 8) % p;   // 2^40, 2^48 mod p
         uint32_t* Wg = a.W + (int64_t)prime * g.n * g.n;
-        const bool vec_ok = !TRANS && (g.n & 3) == 0 && (g.c0 & 3) == 0;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32);
-        const int m0 = g.m0(), m1 = g.m1(), j0 = g.j0(), j1 = g.j1();
+        const bool vec_ok = (g.n & 3) == 0 && (g.c0 & 3) == 0;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 16);
         for (int t = 0; t < ntiles; ++t) {
+            const uint32_t buf = (uint32_t)t & 1u, use = (uint32_t)t >> 1;
             const int ti = bst ? t0 + t : fixed_tile, tj = bst ? fixed_tile : t0 + t;
-            const int m = m0 + ti * TM + quad * 32 + lane;          // this thread's TMEM lane
-            const int jb = j0 + tj * TN + half * 32;                // its 32 TMEM columns
-            // element i of the thread is C[m][jb + i] (trans == 0: 32 consecutive words, 16-byte accesses) or
-            // C[jb + i][m] (trans == 1: word accesses, the warp's 32 lanes side by side in one row: coalesced)
-            uint32_t* cp = TRANS ? Wg + (int64_t)jb * g.n + m : Wg + (int64_t)m * g.n + jb;
-            const int64_t estride = TRANS ? g.n : 1;
-            const bool live = m < m1 && jb < j1;
-            const bool full = live && vec_ok && jb + 32 <= j1;
+            const int row = g.r0 + ti * TM + quad * 32 + lane;
+            const int colb = g.c0 + tj * TN + half * 16;
+            uint32_t* cp = Wg + (int64_t)row * g.n + colb;
+            const bool live = row < g.r1 && colb < g.c1;
+            const bool full = live && vec_ok && colb + 16 <= g.c1;
             // C does not depend on the MMAs: fetch it BEFORE waiting for the accumulators, so the HBM/L2
             // latency hides behind the tensor-core phase of the tile.
-            uint32_t cv[32];
+            uint32_t cv[16];
             if (full) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     const uint4 v = *reinterpret_cast<const uint4*>(cp + 4 * i);
                     cv[4 * i] = v.x, cv[4 * i + 1] = v.y, cv[4 * i + 2] = v.z, cv[4 * i + 3] = v.w;
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) cv[i] = (live && jb + i < j1) ? cp[i * estride] : 0u;
+                for (int i = 0; i < 16; ++i) cv[i] = (live && colb + i < g.c1) ? cp[i] : 0u;
             }
-            // ---- low accumulators (weights 2^0, 2^8, 2^16, 2^24): exact 64-bit partial sums; C goes into the
-            // high word (C * 2^32 + low sum, low sum < 2^51), which frees the registers of the prefetch ----
-            uint64_t lo[32];
-            mbar_wait(bar_lo_full, (uint32_t)(t & 1));
+            mbar_wait(bar_acc_full + 8 * buf, use & 1u);
             tc_fence_after();
+            uint32_t q[7][16];
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                uint32_t q[4][16];
+            for (int s = 0; s < 7; ++s) {
+                if (DBG & 4) {
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    if (DBG & 4) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) q[s][i] = 0u;
-                    } else {
-                        tmem_ld16(lane_base + (uint32_t)(s * TN + ch * 16), q[s]);
-                    }
+                    for (int i = 0; i < 16; ++i) q[s][i] = 0u;
+                } else {
+                    tmem_ld16(lane_base + buf * ACC_STRIDE + (uint32_t)(s * TN), q[s]);
                 }
-                tmem_wait_ld();
-                if (ch == 1) {                                   // this warp's low words are in registers: hand the
-                    tc_fence_before();                           // low accumulators back to the MMA issuer
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_lo_empty);
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    lo[ch * 16 + i] = (uint64_t)q[0][i] + ((uint64_t)q[1][i] << 8) + ((uint64_t)q[2][i] << 16) +
-                                      ((uint64_t)q[3][i] << 24) + ((uint64_t)cv[ch * 16 + i] << 32);
             }
-            // ---- high accumulators (weights 2^32, 2^40, 2^48), one Montgomery reduction ----
-            mbar_wait(bar_hi_full, (uint32_t)(t & 1));
-            tc_fence_after();
+            tmem_wait_ld();
+            tc_fence_before();                                   // all accumulator words of this warp are in registers:
+            __syncwarp();                                        // hand the buffer back (the MMAs of tile t + 2 reuse it)
+            if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                uint32_t q[3][16];
-#pragma unroll
-                for (int s = 0; s < 3; ++s) {
-                    if (DBG & 4) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) q[s][i] = 0u;
-                    } else {
-                        tmem_ld16(lane_base + (uint32_t)((4 + s) * TN + ch * 16), q[s]);
-                    }
-                }
-                tmem_wait_ld();
-                if (ch == 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_hi_empty);
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (DBG & 2) {
-                        cv[ch * 16 + i] = (uint32_t)(lo[ch * 16 + i] >> 32) + q[0][i];
-                    } else {
-                        // C * 2^32 + S  with S < 2^60: bring the sum below p * 2^32 (one conditional subtraction of
-                        // p * 2^32, as in mac_lazy), then REDC gives (C + S / 2^32) mod p in [0, p)
-                        uint64_t acc = lo[ch * 16 + i] + (uint64_t)q[0][i] * c4 + (uint64_t)q[1][i] * c5 + (uint64_t)q[2][i] * c6;
-                        uint32_t hi = (uint32_t)(acc >> 32);
-                        hi = min(hi, hi - p);
-                        acc = ((uint64_t)hi << 32) | (uint32_t)acc;
-                        cv[ch * 16 + i] = mont_redc(acc, p, pinv);
-                    }
+            for (int i = 0; i < 16; ++i) {
+                if (DBG & 2) {
+                    cv[i] += q[0][i] + q[6][i];
+                } else {
+                    // C * 2^32 + S  with S < 2^60: bring the sum below p * 2^32 (one conditional subtraction of
+                    // p * 2^32, as in mac_lazy), then REDC gives (C + S / 2^32) mod p in [0, p)
+                    uint64_t acc = ((uint64_t)cv[i] << 32) + (uint64_t)q[0][i] + ((uint64_t)q[1][i] << 8) +
+                                   ((uint64_t)q[2][i] << 16) + ((uint64_t)q[3][i] << 24) + (uint64_t)q[4][i] * c4 +
+                                   (uint64_t)q[5][i] * c5 + (uint64_t)q[6][i] * c6;
+                    uint32_t hi = (uint32_t)(acc >> 32);
+                    hi = min(hi, hi - p);
+                    acc = ((uint64_t)hi << 32) | (uint32_t)acc;
+                    cv[i] = mont_redc(acc, p, pinv);
                 }
             }
             if (full) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < 4; ++i)
                     *reinterpret_cast<uint4*>(cp + 4 * i) = make_uint4(cv[4 * i], cv[4 * i + 1], cv[4 * i + 2], cv[4 * i + 3]);
             } else if (live) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (jb + i < j1) cp[i * estride] = cv[i];
+                for (int i = 0; i < 16; ++i)
+                    if (colb + i < g.c1) cp[i] = cv[i];
             }
         }
     }
@@ -517,9 +465,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
 }
 
 // the library's instantiation
-constexpr auto k_gemm_tc = k_gemm_tc_t<0, 0, 0>;
-constexpr auto k_gemm_tc_trans = k_gemm_tc_t<0, 1, 0>;
-constexpr auto k_gemm_tc_ts = k_gemm_tc_t<0, 0, 1>;
+constexpr auto k_gemm_tc = k_gemm_tc_t<0>;
 
 #endif  // __CUDACC__
 

@@ -1,7 +1,7 @@
 // Stand-alone check + timing of the tensor-core trailing update (lsx_tc.cuh) against a naive integer kernel.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I linalg_solver_b200/csrc \
 //        tools/tc_gemm_test.cu linalg_solver_b200/csrc/lsx_primes.cpp -o tools/tc_gemm_test
-//   tools/tc_gemm_test n G k0 K [swap] [reps]
+//   tools/tc_gemm_test n G k0 K [dbg] [reps] [b_stationary] [cols] [rows]
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -44,8 +44,7 @@ int main(int argc, char** argv) {
     const int reps = argc > 6 ? atoi(argv[6]) : 3;
     const int bst = argc > 7 ? atoi(argv[7]) : 0;       // 1: B-stationary CTAs
     const int cols = argc > 8 ? atoi(argv[8]) : 0;      // restrict the region to this many columns (0: all)
-    const int trans = argc > 9 ? atoi(argv[9]) : 0;     // 1: transposed product (coalesced C traffic)
-    const int rows = argc > 10 ? atoi(argv[10]) : 0;    // restrict the region to this many rows (0: all)
+    const int rows = argc > 9 ? atoi(argv[9]) : 0;      // restrict the region to this many rows (0: all)
     using namespace lsx_tc;
     std::vector<uint32_t> tab;
     lsx_fill_prime_table(tab, G);
@@ -60,7 +59,6 @@ int main(int argc, char** argv) {
     g.kc = K < KC ? K : KC;
     if (cols > 0 && g.c0 + cols < g.c1) g.c1 = g.c0 + cols;
     if (rows > 0 && g.r0 + rows < g.r1) g.r1 = g.r0 + rows;
-    g.trans = trans;
     g.set_tiles();
     g.b_stationary = bst;
     g.tiles_per_cta = bst ? g.m_tiles : g.n_tiles;
@@ -93,16 +91,9 @@ int main(int argc, char** argv) {
     CK(cudaDeviceSynchronize());
     CK(cudaEventElapsedTime(&ms_ref, e0, e1));
     const size_t smem = smem_bytes(K, bst);
-    const int ts = argc > 11 ? atoi(argv[11]) : 0;      // 1: A operand staged through TMEM (tcgen05.cp + TS-form MMA)
-    void (*kern)(GemmArgs) = ts ? k_gemm_tc_t<0, 0, 1> : (trans ? k_gemm_tc_t<0, 1, 0> : k_gemm_tc_t<0, 0, 0>);
-    switch (swap) {
-        case 1: kern = k_gemm_tc_t<1, 0, 0>; break;
-        case 2: kern = k_gemm_tc_t<2, 0, 0>; break;
-        case 6: kern = ts ? k_gemm_tc_t<6, 0, 1> : k_gemm_tc_t<6, 0, 0>; break;
-        case 8: kern = k_gemm_tc_t<8, 0, 0>; break;
-        case 22: kern = k_gemm_tc_t<22, 0, 0>; break;
-        default: break;
-    }
+    void (*kern)(GemmArgs) = k_gemm_tc_t<0>;
+    if (swap == 2) kern = k_gemm_tc_t<2>;       // no epilogue arithmetic
+    if (swap == 6) kern = k_gemm_tc_t<6>;       // no TMEM loads, no arithmetic: the MMA pipeline alone
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GemmArgs a{};
     a.W = dW;
@@ -133,7 +124,7 @@ int main(int argc, char** argv) {
             ++bad;
         }
     const double macs = (double)G * (g.r1 - g.r0) * (double)(g.c1 - g.c0) * K;
-    printf("{\"ts\": %d, \"bst\": %d, \"trans\": %d, \"rows\": %d, \"cols\": %d, ", ts, bst, trans, g.r1 - g.r0, g.c1 - g.c0);
+    printf("{\"bst\": %d, \"rows\": %d, \"cols\": %d, ", bst, g.r1 - g.r0, g.c1 - g.c0);
     printf("\"n\": %d, \"G\": %d, \"k0\": %d, \"K\": %d, \"swap\": %d, \"mismatches\": %zu, \"first_bad\": %zu, "
            "\"first_bad_rc\": [%zu, %zu], \"got\": %u, \"ref\": %u, \"ms_ref\": %.3f, \"ms_split\": %.3f, \"ms_tc\": %.3f, "
            "\"mod_mac_per_s\": %.4g, \"int8_tops\": %.1f}\n",
