@@ -608,7 +608,7 @@ def run_c5(args):
                          "traffic": None, "kernel_ms": k_s * 1e3, "kernel": "lsx_tc::k_gemm_tc (depth-256 trailing updates)",
                          "kernel_launches_per_step": len(kernel_ms) // max(1, args.steps),
                          "ops": "int8 tensor ops: 2 x 16 byte-plane products per residue multiply-add",
-                         "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 dense = 2 x bf16 on B200; int8 itself not measured)"
+                         "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops_sustained (nominal int8 : bf16 ratio; the MMA-only stream of this kernel measures 2.41e15 op/s, profiles/r01i)"
                                         if peaks else "fallback 2 x 1400"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_ms * 1e-3, "unit": "s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(A_host.numel() * 4),
