@@ -171,7 +171,10 @@ def test_characteristic_polynomial_matches_sympy():
         if n == 5:
             items = [[Fraction(x, rnd.choice([1, 2, 3])) for x in row] for row in items]
         coeffs = Matrix(items).characteristic_polynomial()
-        want = sympy.Poly((sympy.Matrix(items) - lam * sympy.eye(n)).det(method="berkowitz"), lam).all_coeffs()[::-1]
+        # sympy's charpoly is det(lambda I - A); det(A - lambda I) = (-1)^n times it
+        sm = sympy.Matrix([[sympy.Rational(x.numerator, x.denominator) if isinstance(x, Fraction) else x for x in row]
+                           for row in items])
+        want = [(-1) ** n * w for w in sm.charpoly(lam).all_coeffs()[::-1]]
         assert [pq(c) for c in coeffs] == [pq(sympy.Rational(w)) for w in want], n
 
 
