@@ -449,6 +449,43 @@ def test_c5_standins_blocked_tensor_path_exact(eng, n):
     assert eng.det_large_prime_count_for(Z) == (1, 0.0)
 
 
+def _planted(n, seed):
+    """A = L U with unit-lower L and upper U (entries in {-1, 0, 1}, diagonal of U in +-{1, 2, 3}): the determinant
+    is the product of U's diagonal (planted matrices with known determinant).  The product
+    runs in float64 BLAS, exact because every entry of A is below n."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    L = np.tril(rng.integers(-1, 2, size=(n, n)), -1).astype(np.float64) + np.eye(n)
+    U = np.triu(rng.integers(-1, 2, size=(n, n)), 1).astype(np.float64)
+    d = rng.choice(np.array([-3, -2, -1, 1, 2, 3]), size=n)
+    U[np.arange(n), np.arange(n)] = d
+    A = L @ U
+    assert np.abs(A).max() < 2**31
+    det = 1
+    for x in d.tolist():
+        det *= int(x)
+    return A.astype(np.int32), det
+
+
+def test_c5_full_size_planted_determinant_exact(eng):
+    """BASELINE.json configs[4] at its full size, 4096 x 4096: exact determinant of a planted matrix through the
+    blocked tensor-core LU, the data-dependent Hadamard bound and the CRT."""
+    from linalg_solver_b200 import dist as lsx_dist
+    A, det = _planted(4096, 4096)
+    words, K = lsx_dist.det_large_sharded(eng, torch_or_np(A))
+    assert K > 200
+    assert limbs_to_ints(words.cpu().numpy()) == det
+
+
+def test_blocked_lu_beyond_the_register_panel(eng):
+    """More than 4096 rows: the first base panels take the global-memory fallback (k_panel_gmem); residues of a
+    planted matrix for three primes, n not a multiple of 8."""
+    n = 4100 + 3
+    A, det = _planted(n, 7)
+    res = eng.det_large_residues(torch_or_np(A), 2, 3).cpu().numpy()
+    primes = eng.primes(5)[2:5]
+    assert [int(x) for x in res] == [det % int(p) for p in primes]
+
+
 def torch_or_np(A):
     import torch
     return torch.from_numpy(A).cuda()
