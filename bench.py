@@ -235,12 +235,17 @@ class Job:
             outs.append(type(r)(plan=r.plan, **{k: kw.get(k) for k in vars(r) if k != "plan"}))
         self.host_out = tuple(outs)
         self.host_np = {k: v.numpy() for k, v in self.host.items()}
+        if self.wl == "c2":
+            # entries are in [-5, 5]: the end-to-end call ships them as int8 (lsx_inverse_batch_i8), a quarter
+            # of the host-to-device bytes of the int32 container; the results are the same words
+            self.host_i8 = self.host["A"].to(torch.int8).pin_memory()
+            self.host_np = {"A": self.host_i8.numpy()}
 
     def step_e2e(self):
         self.run(self.host_np, self.host_out)                 # returns when the results are in host memory
 
     def h2d_bytes(self):
-        return int(sum(v.numpy().nbytes for v in self.host.values()))
+        return int(sum(v.nbytes for v in self.host_np.values()))
 
     def d2h_bytes(self):
         return int(sum(v.nbytes for r in self.host_out for _, v in self._fields(r)))
@@ -397,7 +402,8 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "matrices/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": job.h2d_bytes(), "d2h_bytes_per_step": job.d2h_bytes(),
-                    "path": "lsx_*_batch(mem=LSX_MEM_HOST) via ctypes, pinned host buffers"},
+                    "path": "lsx_*_batch(mem=LSX_MEM_HOST) via ctypes, pinned host buffers"
+                            + (" (int8 input container: lsx_inverse_batch_i8)" if args.workload == "c2" else "")},
             "gpu_launches": int(stats[2]),
             "clocks": clocks,
         }

@@ -154,6 +154,15 @@ int lsx_rref_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, int64_t
 int lsx_inverse_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, int64_t batch,
                       int mem, uint32_t* adj, uint32_t* det, int32_t* status);
 
+/*
+ * Same with the input matrices as int8 ([batch][n][n] bytes, for entries in [-127, 127]): a quarter of the
+ * host-to-device traffic of the call, which matters because LSX_MEM_HOST calls on small matrices are PCIe bound.
+ * Served by the fused register-resident kernel only (n <= 8 and one prime / one limb in the plan); other plans
+ * return LSX_ERR_UNSUPPORTED and the caller widens to int32.
+ */
+int lsx_inverse_batch_i8(lsx_ctx* ctx, const lsx_plan* plan, const int8_t* A, int64_t batch,
+                         int mem, uint32_t* adj, uint32_t* det, int32_t* status);
+
 /* determinant (and rank, may be NULL).  A: [batch][n][n].  det: [batch][limbs]. */
 int lsx_det_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, int64_t batch,
                   int mem, uint32_t* det, int32_t* rank, int32_t* status);

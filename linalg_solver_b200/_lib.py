@@ -64,6 +64,7 @@ SIGNATURES = {
     "lsx_plan_solve": (_i, [_i, _i, _i64, _i64, _i, _i, _pp]),
     "lsx_rref_batch": (_i, [_vp, _pp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
     "lsx_inverse_batch": (_i, [_vp, _pp, _vp, _i64, _i, _vp, _vp, _vp]),
+    "lsx_inverse_batch_i8": (_i, [_vp, _pp, _vp, _i64, _i, _vp, _vp, _vp]),
     "lsx_det_batch": (_i, [_vp, _pp, _vp, _i64, _i, _vp, _vp, _vp]),
     "lsx_rank_batch": (_i, [_vp, _pp, _vp, _i64, _i, _vp, _vp]),
     "lsx_solve_batch": (_i, [_vp, _pp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

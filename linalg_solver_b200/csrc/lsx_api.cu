@@ -295,7 +295,7 @@ ElimJob slice_job(const ElimJob& job, int64_t b0, int64_t cnt) {
     const int nvars = job.n - 1;
     ElimJob c = job;
     c.batch = cnt;
-    c.A = job.A + b0 * m * job.n_in;
+    c.A = job.in_i8 ? (const int32_t*)((const int8_t*)job.A + b0 * m * job.n_in) : job.A + b0 * m * job.n_in;
     if (job.bvec) c.bvec = job.bvec + b0 * m;
     if (job.num) {
         const int64_t per = job.op == LSX_OP_INVERSE ? (int64_t)m * m : (int64_t)m * job.n;
@@ -321,6 +321,7 @@ int run_chunks(lsx_ctx* ctx, const ElimJob& job) {
     int rc = lsx_run_small(ctx, job, &handled);
     if (rc != LSX_OK) return rc;
     if (handled) return LSX_OK;
+    if (job.in_i8) return lsx_fail(ctx, LSX_ERR_UNSUPPORTED, "int8 input is served by the fused small-matrix inverse only");
     rc = lsx_run_subwarp(ctx, job, &handled);
     if (rc != LSX_OK) return rc;
     if (handled) return LSX_OK;
@@ -492,6 +493,26 @@ int lsx_inverse_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, int6
     const size_t L4 = (size_t)j.L * 4;
     Buf bufs[] = {
         {A, nullptr, (size_t)j.m * j.m * 4, (void**)&j.A, true},
+        {nullptr, adj, (size_t)j.m * j.m * L4, (void**)&j.num, false},
+        {nullptr, det, L4, (void**)&j.den, false},
+    };
+    return run_job(ctx, j, mem, bufs, 3, status);
+}
+
+int lsx_inverse_batch_i8(lsx_ctx* ctx, const lsx_plan* plan, const int8_t* A, int64_t batch, int mem, uint32_t* adj,
+                         uint32_t* det, int32_t* status) {
+    int rc = check_plan(ctx, plan, LSX_OP_INVERSE);
+    if (rc != LSX_OK) return rc;
+    if (plan->n != 2 * plan->m || plan->bar_col != plan->m)
+        return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "inverse plan must be n x 2n with bar n");
+    if (batch > 0 && (!A || !adj || !det || !status)) return lsx_fail(ctx, LSX_ERR_NULL, "inverse: NULL buffer");
+    ElimJob j = job_from_plan(plan, batch);
+    j.n_in = j.m;
+    j.right_identity = 1;
+    j.in_i8 = 1;
+    const size_t L4 = (size_t)j.L * 4;
+    Buf bufs[] = {
+        {A, nullptr, (size_t)j.m * j.m, (void**)&j.A, true},
         {nullptr, adj, (size_t)j.m * j.m * L4, (void**)&j.num, false},
         {nullptr, det, L4, (void**)&j.den, false},
     };

@@ -108,6 +108,7 @@ struct ElimJob {
     int64_t batch = 0;
     int m = 0, n_in = 0, n = 0, bar = 0;
     int right_identity = 0;         // columns n_in..n-1 are the identity
+    int in_i8 = 0;                  // A holds int8 entries (fused small inverse only)
     int64_t a_abs_max = 0, b_abs_max = 0;
     int max_rank = 0;
     int op = 0;

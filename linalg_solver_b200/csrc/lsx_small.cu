@@ -53,7 +53,7 @@ __device__ __forceinline__ uint32_t mont_inverse(uint32_t a, const PrimeRec& P) 
     return mont_mul(mont_sqn(x29, 2, p, pinv), a, p, pinv);
 }
 
-template <int N, int HEAD>
+template <int N, int HEAD, bool I8>
 __global__ void __launch_bounds__(TPM_THREADS, LSX_TPM_MINB)
 k_inv_tpm(const int32_t* __restrict__ A, int64_t batch, PrimeRec P, int a_abs_max, int32_t* __restrict__ adj,
           int32_t* __restrict__ det, int32_t* __restrict__ status) {
@@ -66,7 +66,24 @@ k_inv_tpm(const int32_t* __restrict__ A, int64_t batch, PrimeRec P, int a_abs_ma
     const uint32_t p = P.p, pinv = P.pinv;
 
     // ---- coalesced load of the block's matrices into shared memory ----
-    {
+    if (I8) {
+        // int8 entries: 16 per 16-byte load when the block's bytes allow it
+        const int8_t* src = reinterpret_cast<const int8_t*>(A) + tile0 * E;
+        if ((E % 16) == 0) {
+            const int4* src4 = reinterpret_cast<const int4*>(src);
+            const int n16 = (int)(nwords >> 4);
+            for (int g = tid; g < n16; g += TPM_THREADS) {
+                const int4 v = __ldg(src4 + g);
+                const int w = g * 16;
+                uint32_t* d = sm + (w / E) * ST + (w % E);
+                const int q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 16; ++i) d[i] = (uint32_t)(int32_t)(int8_t)(q[i >> 2] >> (8 * (i & 3)));
+            }
+        } else {
+            for (int w = tid; w < (int)nwords; w += TPM_THREADS) sm[(w / E) * ST + (w % E)] = (uint32_t)(int32_t)__ldg(src + w);
+        }
+    } else {
         const int32_t* src = A + tile0 * E;
         if ((E % 4) == 0) {
             const int4* src4 = reinterpret_cast<const int4*>(src);
@@ -289,15 +306,15 @@ int head_steps_for(int n, int64_t a_abs_max) {
     return h;
 }
 
-template <int N, int HEAD>
+template <int N, int HEAD, bool I8>
 int launch_inv_tpm_h(lsx_ctx* ctx, const ElimJob& job) {
     const size_t smem = (size_t)TPM_THREADS * TpmSmem<N>::STRIDE * 4;
     if (smem > 48 * 1024)
-        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_inv_tpm<N, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_inv_tpm<N, HEAD, I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((job.batch + TPM_THREADS - 1) / TPM_THREADS);
     const PrimeRec P = lsx_make_prime_rec(ctx->primes[0]);
     lsx_timing_begin(ctx);
-    k_inv_tpm<N, HEAD><<<grid, TPM_THREADS, smem, ctx->stream>>>(job.A, job.batch, P, (int)job.a_abs_max,
+    k_inv_tpm<N, HEAD, I8><<<grid, TPM_THREADS, smem, ctx->stream>>>(job.A, job.batch, P, (int)job.a_abs_max,
                                                                  (int32_t*)job.num, (int32_t*)job.den, job.status);
     lsx_timing_end(ctx);
     ctx->launches++;
@@ -311,8 +328,9 @@ int launch_inv_tpm(lsx_ctx* ctx, const ElimJob& job) {
     constexpr int HMAX = N - 1 < 3 ? N - 1 : 3;
     const char* e = getenv("LSX_TPM_HEAD");
     const int want = e ? atoi(e) : HMAX;
-    if (HMAX > 0 && want >= HMAX && head_steps_for(N, job.a_abs_max) >= HMAX) return launch_inv_tpm_h<N, HMAX>(ctx, job);
-    return launch_inv_tpm_h<N, 0>(ctx, job);
+    const bool head = HMAX > 0 && want >= HMAX && head_steps_for(N, job.a_abs_max) >= HMAX;
+    if (job.in_i8) return head ? launch_inv_tpm_h<N, HMAX, true>(ctx, job) : launch_inv_tpm_h<N, 0, true>(ctx, job);
+    return head ? launch_inv_tpm_h<N, HMAX, false>(ctx, job) : launch_inv_tpm_h<N, 0, false>(ctx, job);
 }
 
 }  // namespace

@@ -135,12 +135,26 @@ class Engine:
     def set_stream(self, cuda_stream_ptr):
         self._check(lib.lsx_set_stream(self._ctx, cuda_stream_ptr))
 
-    def _prep_in(self, x, ndim, name):
-        """-> (array, pointer, mem, like) for an int32 input."""
+    @staticmethod
+    def _is_i8(x):
         if _is_torch(x):
             import torch
-            if x.dtype != torch.int32:
-                raise TypeError("%s must be int32, got %s" % (name, x.dtype))
+            return x.dtype == torch.int8
+        return isinstance(x, np.ndarray) and x.dtype == np.int8
+
+    @staticmethod
+    def _widen(x):
+        if _is_torch(x):
+            import torch
+            return x.to(torch.int32)
+        return x.astype(np.int32)
+
+    def _prep_in(self, x, ndim, name, i8=False):
+        """-> (array, pointer, mem, like) for an int32 input (int8 when i8: lsx_inverse_batch_i8)."""
+        if _is_torch(x):
+            import torch
+            if x.dtype != (torch.int8 if i8 else torch.int32):
+                raise TypeError("%s must be %s, got %s" % (name, "int8" if i8 else "int32", x.dtype))
             if x.dim() != ndim:
                 raise ValueError("%s must have %d dimensions" % (name, ndim))
             x = x.contiguous()
@@ -155,6 +169,11 @@ class Engine:
             self.set_stream(None)
             return x, x.data_ptr(), _lib.MEM_HOST, x
         a = np.ascontiguousarray(x)
+        if i8:
+            if a.ndim != ndim:
+                raise ValueError("%s must have %d dimensions" % (name, ndim))
+            self.set_stream(None)
+            return a, a.ctypes.data, _lib.MEM_HOST, None
         if a.dtype != np.int32:
             if not np.issubdtype(a.dtype, np.integer):
                 raise TypeError("%s must be an integer array" % name)
@@ -240,7 +259,12 @@ class Engine:
     def inverse_batch(self, A, a_abs_max=None, plan=None, out=None) -> InverseResult:
         """A^-1 = adj / det through [A|I] (reference linalg.py:704-743); singular matrices get
         status ST_SINGULAR (the reference returns ``NoSolution()``)."""
-        A, pA, mem, like = self._prep_in(A, 3, "A")
+        i8 = self._is_i8(A)
+        if i8 and plan is None:
+            plan = self.plan_inverse(A.shape[-1], self._absmax(A) if a_abs_max is None else a_abs_max)
+        if i8 and not (A.shape[-1] <= 8 and plan.limbs == 1):
+            A, i8 = self._widen(A), False                        # int8 is served by the fused small kernel only
+        A, pA, mem, like = self._prep_in(A, 3, "A", i8=i8)
         B, n, n2 = A.shape
         if n != n2:
             raise ValueError("Matrix must be square to invert.")
@@ -253,6 +277,13 @@ class Engine:
             status = self._alloc(like, (B,), np.int32)
         else:
             adj, det, status = out.adj, out.det, out.status
+        if i8:
+            rc = lib.lsx_inverse_batch_i8(self._ctx, ctypes.byref(plan), pA, B, mem, self._ptr(adj), self._ptr(det),
+                                          self._ptr(status))
+            if rc != _lib.ERR_UNSUPPORTED:
+                self._check(rc)
+                return InverseResult(adj, det, status, plan)
+            A, pA, mem, like = self._prep_in(self._widen(A), 3, "A")      # plan outside the fused kernel: widen
         self._check(lib.lsx_inverse_batch(self._ctx, ctypes.byref(plan), pA, B, mem, self._ptr(adj), self._ptr(det),
                                           self._ptr(status)))
         return InverseResult(adj, det, status, plan)

@@ -449,6 +449,27 @@ def test_c5_standins_blocked_tensor_path_exact(eng, n):
     assert eng.det_large_prime_count_for(Z) == (1, 0.0)
 
 
+def test_inverse_int8_input_container(eng):
+    """lsx_inverse_batch_i8: the same matrices in an int8 container give the same words as int32, from host and
+    from device memory, for every size of the fused kernel; larger sizes are widened by the Python layer."""
+    import torch
+    rng = np.random.Generator(np.random.PCG64(88))
+    for n in (1, 2, 3, 5, 7, 8):
+        A = rng.integers(-5, 6, size=(301, n, n), dtype=np.int32)
+        A[7] = 0                                              # singular
+        want = eng.inverse_batch(A, a_abs_max=5)
+        got = eng.inverse_batch(A.astype(np.int8), a_abs_max=5)
+        for k in ("adj", "det", "status"):
+            assert np.array_equal(getattr(want, k), getattr(got, k)), (n, k)
+        dev = eng.inverse_batch(torch.from_numpy(A.astype(np.int8)).cuda(), a_abs_max=5)
+        assert np.array_equal(dev.adj.cpu().numpy().view(np.uint32), want.adj)       # torch holds the words as int32
+        assert np.array_equal(dev.status.cpu().numpy(), want.status)
+    B = rng.integers(-5, 6, size=(9, 16, 16), dtype=np.int32)
+    w16 = eng.inverse_batch(B, a_abs_max=5)
+    g16 = eng.inverse_batch(B.astype(np.int8), a_abs_max=5)
+    assert np.array_equal(w16.adj, g16.adj) and np.array_equal(w16.det, g16.det)
+
+
 def _planted(n, seed):
     """A = L U with unit-lower L and upper U (entries in {-1, 0, 1}, diagonal of U in +-{1, 2, 3}): the determinant
     is the product of U's diagonal (planted matrices with known determinant).  The product
