@@ -219,6 +219,14 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
         uint32_t S = P.one, Q = P.one, X = 1u;
         int pi = 0;
         bool neg = false, tri = true;          // tri: no column skipped so far (pi == j)
+        // [A|I]: the identity column of a physical row that has not been a pivot row yet is still a unit column
+        // (its one entry carries the common scale S, the rest is zero), so whole 16-column blocks of the right
+        // part need no update until one of their rows is used.  rb_on = number of right blocks maintained so far;
+        // a block is switched on by writing the current scale into its 16 diagonal cells (the cells are raw words
+        // that lose a factor R per step while S is a Montgomery word: the cell value is S / R).
+        const bool lazy_id = a.right_identity && (a.n_in & 15) == 0 && n == a.n_in + m;
+        const int nleft = a.n_in >> 4;         // 16-column blocks of the left part
+        int rb_on = 0;
         uint8_t* prof = a.prof + ((int64_t)kslot * a.cap + slot) * bar;
         for (int j = 0; j < bar; ++j) {
             if (pi >= m) {
@@ -261,6 +269,19 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
             }
             neg ^= src != pi;
             const int prp = perm[src];         // physical row of the pivot (perm is swapped after the barrier)
+            if (lazy_id) {
+                // the pivot row's own identity column (n_in + prp) becomes active now, with every block before it
+                while (rb_on <= (prp >> 4)) {
+                    if (tx == ty) {            // the diagonal cell (r, n_in + r) of row r = ty + 16 * rb_on
+#pragma unroll
+                        for (int ia = 0; ia < RA; ++ia)
+#pragma unroll
+                            for (int ib = 0; ib < CB; ++ib)
+                                if (ia == rb_on && ib == nleft + rb_on && ty + 16 * ia < m) W[ia][ib] = mont_redc((uint64_t)S, p, pinv);
+                    }
+                    ++rb_on;
+                }
+            }
             // 3. publish the pivot row
             if (ty == (prp & 15)) {
                 switch (prp >> 4) {
@@ -289,9 +310,10 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
             __syncthreads();
             // 4. update (register resident)
             const int b0 = tri ? ((j + 1) >> 4) : 0;        // blocks left of the pivot column are finished
+            const int b1 = lazy_id ? nleft + rb_on : CB;    // right blocks that are still pure unit columns
 #pragma unroll
             for (int ib = 0; ib < CB; ++ib) {
-                if (ib >= b0) {
+                if (ib >= b0 && ib < b1) {
                     const uint32_t pc = prow[tx + 16 * ib];
 #pragma unroll
                     for (int ia = 0; ia < RA; ++ia) W[ia][ib] = mont_fma2(xs[ia], W[ia][ib], ys[ia], pc, p, pinv);
@@ -307,6 +329,19 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
             }
             ++pi;
             __syncthreads();                   // prow / colbuf / perm are rewritten by the next column
+        }
+        if (lazy_id) {
+            // rank-deficient input: blocks never switched on still hold the initial ones; give them the final scale
+            while (rb_on < ((m + 15) >> 4)) {
+                if (tx == ty) {
+#pragma unroll
+                    for (int ia = 0; ia < RA; ++ia)
+#pragma unroll
+                        for (int ib = 0; ib < CB; ++ib)
+                            if (ia == rb_on && ib == nleft + rb_on && ty + 16 * ia < m) W[ia][ib] = mont_redc((uint64_t)S, p, pinv);
+                }
+                ++rb_on;
+            }
         }
         // ---- one inversion, scale to N = d * RREF (plain residues), rows in logical order ----
         if (tid < m) inv[perm[tid]] = (uint8_t)tid;

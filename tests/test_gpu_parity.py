@@ -570,7 +570,7 @@ def test_register_tiled_kernel_equals_smem_kernel(eng, monkeypatch):
         y = f()
         monkeypatch.delenv("LSX_DISABLE_TILE_REG")
         return x, y
-    for m, n, bar in [(34, 34, 34), (40, 41, 40), (33, 70, 33), (64, 64, 64), (64, 65, 64), (50, 100, 50),
+    for m, n, bar in [(34, 34, 34), (48, 48, 48), (40, 41, 40), (33, 70, 33), (64, 64, 64), (64, 65, 64), (50, 100, 50),
                       (64, 128, 64), (100, 90, 60), (80, 80, 80), (20, 40, 15)]:
         B = 9
         mats = np.zeros((B, m, n), dtype=np.int32)
