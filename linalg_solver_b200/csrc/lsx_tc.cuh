@@ -392,17 +392,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
         uint32_t* Wg = a.W + (int64_t)prime * g.n * g.n;
         const bool vec_ok = (g.n & 3) == 0 && (g.c0 & 3) == 0;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 16);
-        for (int t = 0; t < ntiles; ++t) {
-            const uint32_t buf = (uint32_t)t & 1u, use = (uint32_t)t >> 1;
+        // Tile t of this thread: 16 consecutive words of one row of C.
+        auto tile_ptr = [&](int t, bool& live, bool& full) -> uint32_t* {
             const int ti = bst ? t0 + t : fixed_tile, tj = bst ? fixed_tile : t0 + t;
             const int row = g.r0 + ti * TM + quad * 32 + lane;
             const int colb = g.c0 + tj * TN + half * 16;
-            uint32_t* cp = Wg + (int64_t)row * g.n + colb;
-            const bool live = row < g.r1 && colb < g.c1;
-            const bool full = live && vec_ok && colb + 16 <= g.c1;
-            // C does not depend on the MMAs: fetch it BEFORE waiting for the accumulators, so the HBM/L2
-            // latency hides behind the tensor-core phase of the tile.
-            uint32_t cv[16];
+            live = t < ntiles && row < g.r1 && colb < g.c1;
+            full = live && vec_ok && colb + 16 <= g.c1;
+            return Wg + (int64_t)row * g.n + colb;
+        };
+        // C does not depend on the MMAs, and a warp handles its tiles one after the other: the loads of a tile are
+        // issued TWO tiles ahead (three register buffers), so their HBM/L2 latency (about as long as a whole tile
+        // takes) is hidden instead of being paid once per tile.
+        auto load_c = [&](int t, uint32_t (&cv)[16]) {
+            bool live, full;
+            const uint32_t* cp = tile_ptr(t, live, full);
             if (full) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -410,9 +414,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
                     cv[4 * i] = v.x, cv[4 * i + 1] = v.y, cv[4 * i + 2] = v.z, cv[4 * i + 3] = v.w;
                 }
             } else {
+                const int colb = g.c0 + (bst ? fixed_tile : t0 + t) * TN + half * 16;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) cv[i] = (live && colb + i < g.c1) ? cp[i] : 0u;
             }
+        };
+        auto process = [&](int t, uint32_t (&cv)[16]) {
+            const uint32_t buf = (uint32_t)t & 1u, use = (uint32_t)t >> 1;
             mbar_wait(bar_acc_full + 8 * buf, use & 1u);
             tc_fence_after();
             uint32_t q[7][16];
@@ -445,14 +453,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
                     cv[i] = mont_redc(acc, p, pinv);
                 }
             }
+            bool live, full;
+            uint32_t* cp = tile_ptr(t, live, full);
             if (full) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     *reinterpret_cast<uint4*>(cp + 4 * i) = make_uint4(cv[4 * i], cv[4 * i + 1], cv[4 * i + 2], cv[4 * i + 3]);
             } else if (live) {
+                const int colb = g.c0 + (bst ? fixed_tile : t0 + t) * TN + half * 16;
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
                     if (colb + i < g.c1) cp[i] = cv[i];
+            }
+        };
+        uint32_t cva[16], cvb[16], cvc[16];
+        load_c(0, cva);
+        load_c(1, cvb);
+        for (int t = 0; t < ntiles; t += 3) {
+            load_c(t + 2, cvc);
+            process(t, cva);
+            if (t + 1 < ntiles) {
+                load_c(t + 3, cva);
+                process(t + 1, cvb);
+            }
+            if (t + 2 < ntiles) {
+                load_c(t + 4, cvb);
+                process(t + 2, cvc);
             }
         }
     }
