@@ -92,6 +92,12 @@ __device__ __forceinline__ uint32_t pivot_scale(uint32_t piv, const PrimeRec& P,
 }
 
 // ---- base panel in registers: rows [k0, n) x columns [k0, k0 + nb), nb <= 8, n - k0 <= LU8_T * LU8_RPT ----
+// The eight pivot steps run FRACTION-FREE (row <- piv * row - f * pivot_row, no division), so the Fermat inversion
+// -- a serial chain of ~60 Montgomery products that every warp would wait for -- is needed once per panel instead
+// of once per column: at step j every row from j on carries the common factor S_j = piv'_0 ... piv'_{j-1}, the true
+// multiplier is l = f / piv'_j (same step, same factor), the true pivot row is row'_j / S_j and the true pivot is
+// piv'_j / S_j.  One inversion of the product of all piv' gives every 1 / piv'_j and 1 / S_j (Montgomery's trick);
+// a final pass rescales each register once.
 __global__ void __launch_bounds__(LU8_T) k_lu8(LargeArgs a, int k0, int nb) {
     __shared__ uint32_t rowbuf[2][NB_BASE];      // [0]: old row j, [1]: pivot row (old row src)
     __shared__ int red[LU8_T / 32];
@@ -119,10 +125,11 @@ __global__ void __launch_bounds__(LU8_T) k_lu8(LargeArgs a, int k0, int nb) {
             for (int c = 0; c < NB_BASE; ++c) v[i][c] = 0u;
         }
     }
-    uint32_t detM = a.detM[g];
     int flags = a.flags[g];
+    uint32_t pivw[NB_BASE];                      // piv'_j as Montgomery words (R for a column without pivot)
 #pragma unroll
     for (int jj = 0; jj < NB_BASE; ++jj) {
+        pivw[jj] = P.one;
         if (jj < nb) {                                            // uniform
             const int j = k0 + jj;
             // ---- pivot search: first row >= j with a non-zero entry in column jj ----
@@ -171,27 +178,73 @@ __global__ void __launch_bounds__(LU8_T) k_lu8(LargeArgs a, int k0, int nb) {
             uint32_t prow[NB_BASE];
 #pragma unroll
             for (int c = 0; c < NB_BASE; ++c) prow[c] = rowbuf[1][c];
-            uint32_t pivM;
-            const uint32_t cscale = pivot_scale(prow[jj], P, &pivM);   // every thread, redundantly: no broadcast
             if (tid == 0) {
                 a.piv_row[(int64_t)g * n + j] = src;
                 if (zero_col) flags |= 2;
-                else detM = mont_mul(detM, pivM, p, pinv);
                 if (src != j) flags ^= 1;
             }
+            // fraction-free step: row <- piv * row - f * pivot_row for the rows below (a zero column changes nothing)
+            const uint32_t pm = zero_col ? P.one : mont_mul(prow[jj], P.r2, p, pinv);      // word of piv'
+            pivw[jj] = pm;
 #pragma unroll
             for (int i = 0; i < LU8_RPT; ++i) {
                 const int r = k0 + tid + i * LU8_T;
                 if (r > j && r < n) {
-                    const uint32_t lm = mont_mul(v[i][jj], cscale, p, pinv);
-                    const uint32_t ln = lm ? p - lm : 0u;
+                    const uint32_t f = v[i][jj];
+                    const uint32_t nf = mont_mul(f ? p - f : 0u, P.r2, p, pinv);            // word of -f
 #pragma unroll
-                    for (int c = jj + 1; c < NB_BASE; ++c)
-                        v[i][c] = mont_redc(mac_lazy((uint64_t)v[i][c] << 32, ln, prow[c], p), p, pinv);
-                    v[i][jj] = ln;
+                    for (int c = jj + 1; c < NB_BASE; ++c) v[i][c] = mont_fma2(pm, v[i][c], nf, prow[c], p, pinv);
                 }
             }
             __syncthreads();                                      // rowbuf / red are reused by the next column
+        }
+    }
+    // ---- one inversion for the whole panel: ip[j] = word of 1 / (piv'_0 ... piv'_j) ----
+    uint32_t pre[NB_BASE];                       // pre[j] = word of piv'_0 ... piv'_j
+    pre[0] = pivw[0];
+#pragma unroll
+    for (int j = 1; j < NB_BASE; ++j) pre[j] = mont_mul(pre[j - 1], pivw[j], p, pinv);
+    uint32_t inv = P.one;                        // Fermat, not unrolled (code size)
+    {
+        const uint32_t e = p - 2u, base = pre[NB_BASE - 1];
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; --bit) {
+            inv = mont_mul(inv, inv, p, pinv);
+            if ((e >> bit) & 1u) inv = mont_mul(inv, base, p, pinv);
+        }
+    }
+    // cl[j] = (1 / piv'_j) * R^2  (multiplier of column j:  mont_mul(p - f, cl[j]) = (-f / piv'_j) * R)
+    // cu[j] = (1 / S_j) * R       (pivot row j and everything right of its pivot: mont_mul(v, cu[j]) = v / S_j)
+    uint32_t cl[NB_BASE], cu[NB_BASE];
+    uint32_t detM = a.detM[g];
+#pragma unroll
+    for (int j = NB_BASE - 1; j >= 0; --j) {
+        // inv = word of 1 / pre[j]
+        const uint32_t sinv = j ? mont_mul(inv, pivw[j], p, pinv) : P.one;          // word of 1 / pre[j-1] = 1 / S_j
+        const uint32_t pinvw = j ? mont_mul(inv, pre[j - 1], p, pinv) : inv;        // word of 1 / piv'_j
+        cl[j] = mont_mul(pinvw, P.r2, p, pinv);
+        cu[j] = sinv;
+        if (j < nb && tid == 0 && !(flags & 2)) detM = mont_mul(detM, mont_mul(pivw[j], sinv, p, pinv), p, pinv);
+        inv = sinv;
+    }
+    // ---- rescale: column c of row k0 + q is a multiplier if q > c, else part of pivot row q (or of a row above) ----
+#pragma unroll
+    for (int i = 0; i < LU8_RPT; ++i) {
+        const int q = tid + i * LU8_T;           // row index inside the panel's row range
+#pragma unroll
+        for (int c = 0; c < NB_BASE; ++c) {
+            if (c < nb) {
+                if (q > c) {
+                    const uint32_t f = v[i][c];
+                    v[i][c] = mont_mul(f ? p - f : 0u, cl[c], p, pinv);
+                } else {
+                    uint32_t cs = cu[0];
+#pragma unroll
+                    for (int t = 1; t < NB_BASE; ++t)
+                        if (t == q) cs = cu[t];
+                    v[i][c] = mont_mul(v[i][c], cs, p, pinv);
+                }
+            }
         }
     }
 #pragma unroll
