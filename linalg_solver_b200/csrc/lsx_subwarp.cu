@@ -113,7 +113,10 @@ __device__ __noinline__ void crt_entry(const uint32_t* res, int res_stride, cons
     store_limbs<KT>(dst, acc, L, negate, zero_out);
 }
 
-__device__ __forceinline__ void crt_entry_any(const uint32_t* res, int res_stride, const uint32_t* scale, int scale_stride,
+// NOT inlined on purpose: the kernel calls it from ten places and every inlined copy carries three Garner
+// instantiations; inlined, k_subwarp<16,17> was 9 500 instructions (152 KB) and ncu's top stall was the
+// instruction fetch ("no_instruction").
+__device__ __noinline__ void crt_entry_any(const uint32_t* res, int res_stride, const uint32_t* scale, int scale_stride,
                                               int K, int L, SwTables T, uint32_t* dst, bool negate, bool zero_out) {
     if (K <= 1) crt_entry<1>(res, res_stride, scale, scale_stride, K, L, T, dst, negate, zero_out);
     else if (K <= 4) crt_entry<4>(res, res_stride, scale, scale_stride, K, L, T, dst, negate, zero_out);
