@@ -187,6 +187,24 @@ int lsx_solve_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, const 
                     uint32_t* generators, int32_t* pivot_col, int32_t* rank,
                     int32_t* status);
 
+/* ---- step trace of row_reduce (reference linalg.py:544-629: intermediate_matrices / intermediate_steps) ------ */
+/* Upper bound on the number of recorded steps: per pivot S, N, E (below) and E (above). */
+int lsx_rref_trace_max_ops(int m, int n, int bar_col);
+/*
+ * Replays row_reduce of ONE m x n matrix (m * n <= 4096) modulo the first n_primes table primes in exactly the
+ * reference's operation order and records every step the reference records:
+ *   ops       [n_primes][max_ops][4] int32   kind (1 = S row swap: a, b = the two rows; 2 = N normalisation of row a;
+ *                                            3 = E elimination below the pivot of column a; 4 = E above), a, b, 0
+ *   frames    [n_primes][max_ops][m][n]      residues (plain, in [0, p)) of the matrix after each step
+ *   n_ops     [n_primes]                     number of recorded steps (identical for all primes unless a prime divides
+ *                                            an intermediate value: the caller compares the logs)
+ *   pivot_col [n_primes][min(m, bar_col)]    pivot column of row k, -1 padded
+ * The caller lifts the residues to rationals (CRT + rational reconstruction); every intermediate entry is a
+ * quotient of minors of A, so n_primes follows from twice the Hadamard bound.  Not a throughput path.
+ */
+int lsx_rref_trace(lsx_ctx* ctx, const int32_t* A, int m, int n, int bar_col, int n_primes, int mem,
+                   int32_t* ops, uint32_t* frames, int32_t* n_ops, int32_t* pivot_col);
+
 /* ---- one large determinant, shardable by prime ------------------------------------------ */
 /* Number of primes the determinant of an n x n matrix with |entries| <= a_abs_max needs. */
 int lsx_det_large_prime_count(int n, int64_t a_abs_max, int* n_primes, double* log2_bound);

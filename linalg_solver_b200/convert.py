@@ -56,3 +56,34 @@ def reduce_pq(num, den):
 def fraction_grid(num_rows, den):
     """Rows of integer numerators over one denominator -> rows of Fractions."""
     return [[Fraction(x, den) for x in row] for row in num_rows]
+
+
+# ---- residues -> rationals (step traces: every intermediate entry is a quotient of minors) ---------------
+def crt_basis(primes):
+    """(M, [c_k]) with x = sum r_k * c_k mod M for residues r_k modulo the given primes."""
+    M = 1
+    for p in primes:
+        M *= int(p)
+    coef = []
+    for p in primes:
+        p = int(p)
+        Mk = M // p
+        coef.append(Mk * pow(Mk % p, p - 2, p))
+    return M, coef
+
+
+def rational_reconstruct(x, M, bound):
+    """The fraction a / b with |a|, b <= bound and a = b * x (mod M), or None (Wang's algorithm: the extended
+    Euclidean sequence of (M, x) is stopped at the first remainder not above ``bound``).  Unique when 2 bound^2 < M."""
+    r0, r1, t0, t1 = M, x % M, 0, 1
+    while r1 > bound:
+        q = r0 // r1
+        r0, r1 = r1, r0 - q * r1
+        t0, t1 = t1, t0 - q * t1
+    if t1 == 0 or abs(t1) > bound:
+        return None
+    if t1 < 0:
+        r1, t1 = -r1, -t1
+    if gcd(r1, t1) != 1:
+        return None
+    return Fraction(r1, t1)

@@ -349,6 +349,80 @@ class Engine:
                                         self._ptr(gens), self._ptr(piv), self._ptr(rank), self._ptr(status)))
         return SolveResult(den, part, gens, piv, rank, status, plan)
 
+    # ---- step trace of row_reduce (reference linalg.py:544-629) -----------------------------
+    def rref_trace(self, A, bar_col):
+        """Steps and exact intermediate matrices of ``row_reduce`` for ONE small integer matrix.
+
+        Returns ``(frames, ops, pivots)``: ``ops`` is the list of ``(kind, a, b)`` the reference records (1 = S swap
+        of rows a and b, 2 = N normalisation of row a, 3 / 4 = E elimination below / above the pivot of column a),
+        ``frames[t]`` the matrix (rows of ``Fraction``) after ``ops[t]``, ``pivots`` the (row, column) list.  The
+        device replays the reference's operation order modulo K primes (``lsx_rref_trace``); K follows from twice
+        the Hadamard bound of the minors (every intermediate entry is a quotient of two of them) plus one check
+        prime, the logs of all primes must agree, and the residues are lifted by CRT + rational reconstruction.
+        """
+        import math
+        from .convert import crt_basis, rational_reconstruct
+        A = np.ascontiguousarray(np.asarray(A, dtype=np.int64))
+        if A.ndim != 2:
+            raise ValueError("A must have 2 dimensions")
+        m, n = A.shape
+        if A.size and np.abs(A).max() > 2**31 - 1:
+            raise OverflowError("A has entries outside int32")
+        amax = max(1, int(np.abs(A).max()) if A.size else 1)
+        r = min(m, n)
+        log2h = r * (0.5 * math.log2(r) + math.log2(amax)) if r else 0.0          # Hadamard bound of any minor
+        max_ops = lib.lsx_rref_trace_max_ops(m, n, bar_col)
+        if max_ops < 0:
+            raise LsxError(max_ops, "rref_trace: bad shape")
+        a32 = A.astype(np.int32)
+        slots = min(m, bar_col)
+        self.set_stream(None)
+        # Forward-sweep entries are quotients of two minors, but the backward sweep combines such quotients, so the
+        # size of an intermediate entry is not bounded by one Hadamard bound: start from 2 H^2 < M and double the
+        # prime count until every entry reconstructs AND agrees with one more prime that took no part in the lift.
+        K = int(math.ceil((2.0 * log2h + 2.0) / 30.99)) + 1
+        while True:
+            Kc = K + 1                                            # the last prime only checks
+            ops = np.zeros((Kc, max_ops, 4), dtype=np.int32)
+            frames = np.zeros((Kc, max_ops, m, n), dtype=np.uint32)
+            n_ops = np.zeros(Kc, dtype=np.int32)
+            piv = np.zeros((Kc, slots), dtype=np.int32)
+            self._check(lib.lsx_rref_trace(self._ctx, a32.ctypes.data, m, n, bar_col, Kc, _lib.MEM_HOST, ops.ctypes.data,
+                                           frames.ctypes.data, n_ops.ctypes.data, piv.ctypes.data))
+            T = int(n_ops[0])
+            if not (np.all(n_ops == T) and np.all(ops[:, :T] == ops[0, :T]) and np.all(piv == piv[0])):
+                raise RuntimeError("liblsx: the primes disagree on the step log (a prime divides an intermediate value)")
+            primes = [int(p) for p in self.primes(Kc)]
+            M, coef = crt_basis(primes[:K])
+            bound = math.isqrt((M - 1) // 2)
+            pc = primes[K]
+            out, ok = [], True
+            for t in range(T):
+                grid = []
+                for i in range(m):
+                    row = []
+                    for j in range(n):
+                        x = sum(int(frames[k, t, i, j]) * coef[k] for k in range(K)) % M
+                        v = rational_reconstruct(x, M, bound)
+                        if v is None or v.denominator % pc == 0 or \
+                                (v.numerator * pow(v.denominator, pc - 2, pc) - int(frames[K, t, i, j])) % pc != 0:
+                            ok = False
+                            break
+                        row.append(v)
+                    if not ok:
+                        break
+                    grid.append(row)
+                if not ok:
+                    break
+                out.append(grid)
+            if ok:
+                break
+            if K > 256:
+                raise RuntimeError("liblsx: rational reconstruction of the step trace did not converge")
+            K *= 2
+        pivots = [(k, int(piv[0, k])) for k in range(slots) if piv[0, k] >= 0]
+        return out, [tuple(int(x) for x in ops[0, t, :3]) for t in range(T)], pivots
+
     # ---- one large determinant, by prime ----------------------------------------------------
     @staticmethod
     def det_large_prime_count(n, a_abs_max):

@@ -201,15 +201,27 @@ class Matrix:
             return "NoSolution()"
 
     # ---- the elimination path -----------------------------------------------------------------
-    def row_reduce(self, bar_col: int = None):
+    # step descriptions of the reference's log (linalg.py:556-559, 581, 603, 627)
+    _STEP_TEXT = {1: ("S", r"Výměna řádků $R_{%d}$ a $R_{%d}$"), 2: ("N", r"Normalizace pivotního řádku %s"),
+                  3: ("E", r"Eliminace prvků pod pivotem ve sloupci %s"), 4: ("E", r"Eliminace nad pivotem ve sloupci %s")}
+
+    def row_reduce(self, bar_col: int = None, trace: bool = False):
         """Reduced row echelon form on the columns left of ``bar_col`` (reference linalg.py:534-630).
 
-        Returns ``(A, pivots, intermediate_matrices, intermediate_steps)``; the two log lists are
-        empty on the device path.  ``bar_col`` falsy means ``cols - 1`` exactly as linalg.py:543.
+        Returns ``(A, pivots, intermediate_matrices, intermediate_steps)``.  ``bar_col`` falsy means ``cols - 1``
+        exactly as linalg.py:543.  By default the two log lists are empty (the batched device path does not keep
+        intermediate states).  With ``trace=True`` (integer or rational entries, rows * cols <= 4096) the device
+        replays the reference's operation order and the lists are filled like the reference fills them:
+        ``intermediate_steps`` holds the same ``(label, description)`` pairs (S / N / E + running number,
+        linalg.py:556-561, 580-582, 601-605, 626-628) and ``intermediate_matrices`` holds the input followed by
+        the matrix after every step -- as exact matrices (lists of rows), not as the LaTeX strings the reference
+        renders from them: the LaTeX ``Logger`` stays outside the device path.
         """
         m, n = self.rows, self.cols
         bar = bar_col or n - 1
         kind = _kind_of(self.items)
+        if trace and n > 0 and bar > 0:
+            return self._row_reduce_trace(min(bar, n), kind)
         if n == 0 or bar <= 0:
             # nothing to pivot on: the loop of linalg.py:547 never runs
             return [list(r) for r in self.items], [], [], []
@@ -230,6 +242,21 @@ class Matrix:
             d_i = den if i < rank else den * D
             out.append([_wrap(kind, *reduce_pq(x, d_i)) for x in num[i]])
         return out, pivots, [], []
+
+    def _row_reduce_trace(self, bar, kind):
+        grid, D = _to_int_grid(self.items)                       # grid = D * A: the same row operations, frames / D
+        frames, ops, pivots = default_engine().rref_trace(grid, bar)
+        # the input scaled by D has the same steps except that "pivot == 1" is "pivot == D": only D == 1 is served
+        if D != 1:
+            raise TypeError("row_reduce(trace=True) takes integer entries")
+        wrap = lambda f: [[_wrap(kind, x.numerator, x.denominator) for x in row] for row in f]
+        start = [[_wrap(kind, *_pq_of(x)) for x in row] for row in self.items]
+        mats = [start] + [wrap(f) for f in frames]
+        steps = []
+        for t, (k, a, b) in enumerate(ops):
+            letter, text = Matrix._STEP_TEXT[k]
+            steps.append(("%s%d" % (letter, t), text % ((a + 1, b + 1) if k == 1 else (a + 1,))))
+        return mats[-1], pivots, mats, steps
 
     def rank(self) -> int:
         """Reference linalg.py:745-747."""

@@ -9,7 +9,7 @@ come from the reference's own ``RandomMatrixBuilder`` under fixed seeds and are
 rationalised with ``sympy.Rational`` exactly as reference main.py:20-31 does,
 because raw ints make ``row_reduce`` fall into floats (linalg.py:574).
 
-Usage:  python oracle/gen_golden.py [c1 c2 c3 c4 edge c5]   (default: all)
+Usage:  python oracle/gen_golden.py [c1 c2 c3 c4 edge c5 trace]   (default: all)
 """
 import os
 import random
@@ -329,6 +329,60 @@ def gen_edge():
         "rref_cases": r, "system_cases": s, "inverse_cases": i})
 
 
+# ----------------------------------------------------------------------------- step traces
+def trace_case(arg):
+    """The reference's own row_reduce with its frame renderer wrapped: every call of
+    make_latex_augmented_matrix(A, bar_col) inside linalg.py:534-630 is one recorded frame, so the exact rational
+    intermediate matrices come from the unmodified reference (the LaTeX it returns is not kept)."""
+    import copy
+    import linalg_solver.linalg as L
+    items, bar = arg
+    frames = []
+    orig = L.make_latex_augmented_matrix
+
+    def spy(A, bar_col=None, **kw):
+        frames.append(pq_grid(copy.deepcopy(A)))
+        return orig(A, bar_col=bar_col, **kw)
+
+    L.make_latex_augmented_matrix = spy
+    try:
+        M = Matrix(rat(items))
+        R, piv, mats, steps = M.row_reduce(bar) if bar is not None else M.row_reduce()
+    finally:
+        L.make_latex_augmented_matrix = orig
+    assert len(frames) == len(mats) == len(steps) + 1
+    return {"A": items, "bar_col": bar, "steps": [list(x) for x in steps], "frames": frames,
+            "rref": pq_grid(R), "pivots": [list(x) for x in piv]}
+
+
+def gen_trace():
+    rnd = random.Random(20260033)
+    cases = []
+    for m, n in [(1, 2), (2, 2), (2, 3), (3, 3), (3, 4), (4, 4), (4, 5), (3, 6), (5, 4), (5, 6), (6, 6), (6, 7), (8, 9)]:
+        for rep in range(12):
+            if rep % 4 == 3:                                      # low rank
+                rk = max(1, min(m, n) - 1 - rep % 2)
+                Bm = [[rnd.randint(-3, 3) for _ in range(rk)] for _ in range(m)]
+                Cm = [[rnd.randint(-3, 3) for _ in range(n)] for _ in range(rk)]
+                items = [[sum(Bm[i][k] * Cm[k][j] for k in range(rk)) for j in range(n)] for i in range(m)]
+            else:
+                items = [[rnd.randint(-5, 5) for _ in range(n)] for _ in range(m)]
+            if rep % 4 == 1:
+                items[0][0] = 0                                   # forces a swap (or a skipped column)
+                if m > 1 and rep % 8 == 5:
+                    items[1][0] = 0
+            if rep % 4 == 2 and m > 1:
+                items[0][0] = 1                                   # pivot already one: no N step
+            bar = [None, n, max(1, n - 1), min(n, m)][rep % 4]
+            cases.append((items, bar))
+    with Pool(NPROC) as pool:
+        out = pool.map(trace_case, cases, chunksize=4)
+    golden_io.save("trace_small", {
+        "about": "reference Matrix.row_reduce (linalg.py:534-630) with its frame renderer wrapped: step labels/descriptions "
+                 "(intermediate_steps) and the exact rational intermediate matrices behind intermediate_matrices",
+        "cases": out})
+
+
 # ----------------------------------------------------------------------------- C5 stand-ins
 def gen_c5():
     """No reference route can compute these; third-party cross-oracle only."""
@@ -346,7 +400,7 @@ def gen_c5():
         "cases": out})
 
 
-ALL = {"c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "edge": gen_edge, "c5": gen_c5}
+ALL = {"c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "edge": gen_edge, "c5": gen_c5, "trace": gen_trace}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(ALL)

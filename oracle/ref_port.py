@@ -78,6 +78,72 @@ def row_reduce(items, bar_col=None):
     return A, pivots
 
 
+# step descriptions of the reference (linalg.py:556-559, 581, 603, 627): part of its observable output
+STEP_SWAP = r"Výměna řádků $R_{%d}$ a $R_{%d}$"
+STEP_NORM = r"Normalizace pivotního řádku %s"
+STEP_ELIM_DOWN = r"Eliminace prvků pod pivotem ve sloupci %s"
+STEP_ELIM_UP = r"Eliminace nad pivotem ve sloupci %s"
+
+
+def row_reduce_trace(items, bar_col=None):
+    """``row_reduce`` with the reference's step log (linalg.py:544-629).
+
+    Returns ``(R, pivots, frames, steps)``: ``frames[0]`` is the input, ``frames[t + 1]`` the matrix after
+    ``steps[t] = (label, description)``.  A step is recorded exactly when the reference records one: a row swap
+    (S, 551-562), a normalisation that changed the pivot row, i.e. pivot != 1 (N, 569-584), an elimination below
+    with at least one non-zero factor (E, 586-606) and, in reverse pivot order, an elimination above with at
+    least one non-zero factor (E, 611-628).  Labels are the kind letter followed by the running step number.
+    """
+    A = _frac_rows(items)
+    m, n = len(A), len(A[0])
+    bar = bar_col or n - 1
+    frames = [[row[:] for row in A]]
+    steps = []
+
+    def record(kind, text):
+        steps.append(("%s%d" % (kind, len(steps)), text))
+        frames.append([row[:] for row in A])
+
+    pivots = []
+    pi = pj = 0
+    while pi < m and pj < bar:
+        if A[pi][pj] == 0:
+            src = next((i for i in range(pi + 1, m) if A[i][pj] != 0), None)
+            if src is None:
+                pj += 1
+                continue
+            A[pi], A[src] = A[src], A[pi]
+            record("S", STEP_SWAP % (pi + 1, src + 1))
+        lead = A[pi][pj]
+        if lead != 1:
+            for j in range(pj, n):
+                A[pi][j] = A[pi][j] / lead
+            record("N", STEP_NORM % (pi + 1))
+        hit = False
+        for k in range(pi + 1, m):
+            f = A[k][pj]
+            if f != 0:
+                hit = True
+                for j in range(pj, n):
+                    A[k][j] -= f * A[pi][j]
+        if hit:
+            record("E", STEP_ELIM_DOWN % (pj + 1))
+        pivots.append((pi, pj))
+        pi += 1
+        pj += 1
+    for r, c in reversed(pivots):
+        hit = False
+        for k in range(r):
+            f = A[k][c]
+            if f != 0:
+                hit = True
+                for j in range(c, n):
+                    A[k][j] -= f * A[r][j]
+        if hit:
+            record("E", STEP_ELIM_UP % (c + 1))
+    return A, pivots, frames, steps
+
+
 def forward_profile(items, bar_col):
     """Forward sweep only; returns (pivots, source_rows, sign, pivot_values).
 

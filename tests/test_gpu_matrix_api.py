@@ -203,3 +203,24 @@ def test_eigenvalues_and_diagonalize_on_the_device():
     assert not rj.success and rj.eigenvalue_multiplicities[sympy.Integer(3)] == (3, 1)
     with pytest.raises(ValueError):
         Matrix([[1, 2, 3], [4, 5, 6]]).diagonalize()
+
+
+def test_row_reduce_trace_matches_reference_steps_and_frames():
+    """row_reduce(trace=True): step labels, descriptions and every intermediate matrix against the frames of the
+    unmodified reference (tests/golden/trace_small)."""
+    from linalg_solver_b200 import Matrix
+    g = golden_io.load("trace_small")
+    seen = set()
+    for c in g["cases"]:
+        M = Matrix(rat(c["A"]))
+        R, piv, mats, steps = M.row_reduce(c["bar_col"], trace=True) if c["bar_col"] is not None else M.row_reduce(trace=True)
+        assert [list(s) for s in steps] == c["steps"], (c["A"], c["bar_col"])
+        assert [[pq(x) for row in f for x in row] for f in mats] == c["frames"]
+        assert [pq(x) for row in R for x in row] == c["rref"] and [list(p) for p in piv] == c["pivots"]
+        seen |= {s[0][0] for s in steps}
+    assert seen == {"S", "N", "E"}
+    # the default call keeps its empty log lists and agrees with the traced result
+    M = Matrix(rat(g["cases"][40]["A"]))
+    R0, p0, f0, s0 = M.row_reduce()
+    R1, p1, f1, s1 = M.row_reduce(trace=True)
+    assert f0 == [] and s0 == [] and R0 == R1 and p0 == p1 and len(f1) == len(s1) + 1

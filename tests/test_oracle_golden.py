@@ -166,3 +166,17 @@ def test_det_mod_p_oracle_pinned_to_standins():
             assert det_mod_p(A, p) == int(c["det"]) % p
     S = np.array([[1, 2, 3], [2, 4, 6], [1, 0, 1]])
     assert det_mod_p(S, primes[0]) == 0
+
+
+def test_row_reduce_trace_pinned_to_reference_frames():
+    """oracle row_reduce_trace (step labels, descriptions and every intermediate matrix) against the frames the
+    unmodified reference produced (tests/golden/trace_small, generated by oracle/gen_golden.py trace)."""
+    g = golden_io.load("trace_small")
+    kinds = set()
+    for c in g["cases"]:
+        R, piv, frames, steps = ref_port.row_reduce_trace(c["A"], c["bar_col"])
+        assert [list(s) for s in steps] == c["steps"], c["A"]
+        assert [pq_list(f) for f in frames] == c["frames"]
+        assert pq_list(R) == c["rref"] and [list(p) for p in piv] == c["pivots"]
+        kinds |= {s[0][0] for s in steps}
+    assert kinds == {"S", "N", "E"}
