@@ -51,23 +51,30 @@ struct LargeArgs {
     int n, G;
 };
 
+// any int32 into [0, p) for p > 2^30: |v| <= 2^31 < 2p, two conditional corrections, no division
+__device__ __forceinline__ uint32_t residue_of(int32_t v, uint32_t p) {
+    int64_t t = v;
+    if (t < 0) t += p;
+    if (t < 0) t += p;
+    if (t >= (int64_t)p) t -= p;
+    return (uint32_t)t;
+}
 __global__ void k_load(const int32_t* __restrict__ A, LargeArgs a) {
     const int64_t nn = (int64_t)a.n * a.n;
     const int g = blockIdx.y;
     const uint32_t p = a.primes[g].p;
     uint32_t* Wg = a.W + (int64_t)g * nn;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += (int64_t)gridDim.x * blockDim.x)
-    {
-        const int32_t v = A[i];
-        if (p > (1u << 30)) {                      // |v| <= 2^31 < 2p: two conditional corrections, no division
-            int64_t t = v;
-            if (t < 0) t += p;
-            if (t < 0) t += p;
-            if (t >= (int64_t)p) t -= p;
-            Wg[i] = (uint32_t)t;
-        } else {
-            Wg[i] = word_of_int_any(v, p);         // tiny test primes
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > (1u << 30) && (nn & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) {   // 16-byte accesses
+        const int4* A4 = reinterpret_cast<const int4*>(A);
+        uint4* W4 = reinterpret_cast<uint4*>(Wg);
+        for (int64_t i = t0; i < (nn >> 2); i += stride) {
+            const int4 v = __ldg(A4 + i);
+            W4[i] = make_uint4(residue_of(v.x, p), residue_of(v.y, p), residue_of(v.z, p), residue_of(v.w, p));
         }
+    } else {
+        for (int64_t i = t0; i < nn; i += stride)
+            Wg[i] = p > (1u << 30) ? residue_of(A[i], p) : word_of_int_any(A[i], p);      // tiny test primes
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         a.detM[g] = a.primes[g].one;
