@@ -279,9 +279,16 @@ class Matrix:
             raise ValueError("Determinant requires a square matrix")
         kind = _kind_of(self.items)
         grid, D = _to_int_grid(self.items)
-        res = default_engine().det_batch(grid[None])
-        _raise_on_status(int(res.status[0]))
-        d = limbs_to_ints(res.det[0])
+        if n > 64:
+            # one large matrix: residues modulo many primes (tile kernel up to n ~ 220, blocked tensor-core LU above),
+            # sharded by prime over the ranks when torch.distributed is initialised, then one CRT
+            from .dist import det_large_sharded
+            words, _ = det_large_sharded(default_engine(), grid)
+            d = limbs_to_ints(np.asarray(words).reshape(1, -1))[0]
+        else:
+            res = default_engine().det_batch(grid[None])
+            _raise_on_status(int(res.status[0]))
+            d = limbs_to_ints(res.det[0])
         return _wrap(kind, *reduce_pq(d, D ** n))
 
     def inverse(self, log_matrices: bool = False, log_steps: bool = False, log_result: bool = False):

@@ -224,3 +224,17 @@ def test_row_reduce_trace_matches_reference_steps_and_frames():
     R0, p0, f0, s0 = M.row_reduce()
     R1, p1, f1, s1 = M.row_reduce(trace=True)
     assert f0 == [] and s0 == [] and R0 == R1 and p0 == p1 and len(f1) == len(s1) + 1
+
+
+def test_determinant_of_a_large_matrix_goes_through_the_by_prime_route():
+    """Matrix.determinant() beyond the batched kernels (n > 64): residues + CRT, exact against the DomainMatrix
+    stand-ins (128: tile kernel per prime, 256: blocked tensor-core LU)."""
+    import numpy as np
+    from linalg_solver_b200 import Matrix
+    g = golden_io.load("c5_standins")
+    for c in g["cases"]:
+        if c["n"] not in (128, 256):
+            continue
+        rng = np.random.Generator(np.random.PCG64(c["seed"]))
+        A = rng.integers(-5, 6, size=(c["n"], c["n"]), dtype=np.int64)
+        assert Matrix(A.tolist()).determinant() == int(c["det"])
