@@ -449,6 +449,61 @@ def test_c5_standins_blocked_tensor_path_exact(eng, n):
     assert eng.det_large_prime_count_for(Z) == (1, 0.0)
 
 
+def test_random_differential_against_the_oracle(eng):
+    """Randomised differential test: shapes up to 12 x 14, entries up to +-60, every rank from 0 to full, random
+    bar_col; rref, rank, determinant, inverse and find_preimage_of through the C-ABI against oracle/ref_port.py
+    (itself pinned to the reference's goldens)."""
+    import random
+    rnd = random.Random(20260018)
+    rng = np.random.Generator(np.random.PCG64(20260018))
+    for trial in range(60):
+        m, n = rnd.randint(1, 12), rnd.randint(1, 14)
+        B = 7
+        amp = rnd.choice([2, 5, 60])
+        mats = np.zeros((B, m, n), dtype=np.int32)
+        for i in range(B):
+            rk = rnd.randint(0, min(m, n))
+            if rk == min(m, n) or rk == 0:
+                mats[i] = rng.integers(-amp, amp + 1, size=(m, n)) if rk else 0
+            else:
+                mats[i] = rng.integers(-3, 4, size=(m, rk)) @ rng.integers(-3, 4, size=(rk, n))
+        bar = rnd.randint(1, n)
+        res = eng.rref_batch(mats, bar)
+        num, den = limbs_to_ints(res.num), limbs_to_ints(res.den)
+        rks = eng.rank_batch(mats).rank
+        for i in range(B):
+            R, piv = ref_port.row_reduce(mats[i].tolist(), bar)
+            assert int(res.status[i]) & ~32 == 0
+            assert [(k, int(res.pivot_col[i][k])) for k in range(int(res.rank[i]))] == piv, (m, n, bar)
+            assert pq_grid_from_num(num[i], den[i]) == pq_of_fracs(R), (m, n, bar, mats[i].tolist())
+            assert int(rks[i]) == ref_port.rank(mats[i].tolist())
+        if m == n:
+            inv = eng.inverse_batch(mats)
+            adj, det = limbs_to_ints(inv.adj), limbs_to_ints(inv.det)
+            dets = limbs_to_ints(eng.det_batch(mats).det)
+            for i in range(B):
+                want = ref_port.inverse(mats[i].tolist())
+                assert dets[i] == det[i] == ref_port.bareiss_det(mats[i].tolist())
+                if want is None:
+                    assert int(inv.status[i]) & 1
+                else:
+                    assert pq_grid_from_num(adj[i], det[i]) == pq_of_fracs(want)
+        b = rng.integers(-amp, amp + 1, size=(B, m), dtype=np.int32)
+        b[::2] = np.einsum("bij,bj->bi", mats[::2].astype(np.int64), rng.integers(-3, 4, size=(len(mats[::2]), n))).astype(np.int32)
+        sol = eng.solve_batch(mats, b)
+        for i in range(B):
+            want = ref_port.find_preimage_of(mats[i].tolist(), b[i].tolist())
+            got = affine_pq(sol, i, n, "logged")
+            if want is None:
+                assert got["status"] == "nosolution", (m, n)
+            else:
+                part, gens = want
+                assert got["status"] == "ok" and got["particular"] == [[x.numerator, x.denominator] for x in part]
+                k = n - int(sol.rank[i])
+                flat = [[gens[t][r].numerator, gens[t][r].denominator] for r in range(n) for t in range(k)] if k else []
+                assert got["generators"] == flat
+
+
 def test_inverse_int8_input_container(eng):
     """lsx_inverse_batch_i8: the same matrices in an int8 container give the same words as int32, from host and
     from device memory, for every size of the fused kernel; larger sizes are widened by the Python layer."""
