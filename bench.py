@@ -43,6 +43,12 @@ WORKLOADS = {
     "c4ker": ("2^12 (of 2^16) x kernel basis of 64x64 A = B(64x48) C(48x64) (rank 48, dim 16), entries of B, C uniform [-5,5]",
               64, 1 << 12, 98644),
 }
+# ALGORITHMIC modular multiply-subtracts per matrix and prime (Gauss-Jordan on m x n with pivots
+# in columns c_k costs sum_k m * (n - c_k)); the integer-pipe roofline is the measured mont_mul rate
+# (profiles/r01_ubench_int.jsonl: 12.0 per SM per clock)
+ALG_OPS = {"c2": 8 * sum(16 - k for k in range(8)), "c3": 16 * sum(17 - k for k in range(10)),
+           "c4inv": 64 * sum(128 - k for k in range(64)), "c4ker": 64 * sum(65 - k for k in range(48))}
+MONT_MUL_PER_SM_CLK = 12.0
 SEED = 20260002
 METRIC = {"c1": "exact det+rank+RREF matrices/sec", "c2": "exact det+inverse matrices/sec",
           "c3": "exact find_preimage_of systems/sec", "c4inv": "exact inverse matrices/sec",
@@ -387,6 +393,16 @@ def run_ours(args):
         except Exception:
             pass
         plan = job.plans[-1]
+        int_pipe = None
+        if args.workload in ALG_OPS:
+            sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+            ip_peak = MONT_MUL_PER_SM_CLK * 148 * sm_mhz * 1e6
+            # the fused 8x8 kernel runs ONE prime (exact int64 determinant); the other kernels run the plan's primes
+            n_pr = 1 if args.workload == "c2" else int(plan.n_primes)
+            ip_ach = ALG_OPS[args.workload] * n_pr * batch / (k_ms * 1e-3)
+            int_pipe = {"algorithmic_ops_per_matrix": ALG_OPS[args.workload] * n_pr, "achieved": ip_ach, "peak": ip_peak,
+                        "unit": "modular multiply-subtracts/s", "frac": ip_ach / ip_peak,
+                        "peak_source": "measured mont_mul rate 12.0 per SM per clock (profiles/r01_ubench_int.jsonl) x 148 SMs x max SM clock"}
         line = {
             "metric": METRIC[args.workload], "value": value, "unit": "matrices/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -397,7 +413,7 @@ def run_ours(args):
                        "l2": "inputs+outputs per step (%.0f MB) vs the 126 MB L2" % ((alg_bytes * batch) / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel_ms": k_ms, "kernel_launches_per_step": per_step,
-                         "algorithmic_bytes_per_matrix": alg_bytes,
+                         "algorithmic_bytes_per_matrix": alg_bytes, "int_pipe": int_pipe,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"},
             "cpu_baseline": cpu,
             "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "matrices/s", "ms_per_step": e2e_ms,
