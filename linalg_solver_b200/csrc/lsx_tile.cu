@@ -843,8 +843,12 @@ int lsx_run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const
             k_assemble<4><<<gridn, bs, 0, ctx->stream>>>(aa);
         else if (K <= 8)
             k_assemble<8><<<gridn, bs, 0, ctx->stream>>>(aa);
+        else if (K <= 12)                       // 64 x 64 inverse: 12 primes
+            k_assemble<12><<<gridn, bs, 0, ctx->stream>>>(aa);
         else if (K <= 16)
             k_assemble<16><<<gridn, bs, 0, ctx->stream>>>(aa);
+        else if (K <= 24)                       // 64 x 64 kernel basis: 21 primes (the Horner loop is KT wide)
+            k_assemble<24><<<gridn, bs, 0, ctx->stream>>>(aa);
         else
             k_assemble<32><<<gridn, bs, 0, ctx->stream>>>(aa);
         ctx->launches++;
