@@ -552,6 +552,25 @@ def test_c5_full_size_planted_determinant_exact(eng):
     assert limbs_to_ints(words.cpu().numpy()) == det
 
 
+def test_c5_full_size_matrix_against_cpu_residues(eng):
+    """BASELINE.json configs[4], the very matrix bench.py times (4096 x 4096, PCG64(20260005), entries in [-5, 5]):
+    det mod p for two table primes OUTSIDE the CRT set, computed on the CPU by oracle/det_mod_p.py (numpy int64
+    elimination, ~6 minutes per prime; tools/gen_c5_residues.py, stored in tests/golden/c5_full_residues), against
+    (i) the device residues for those primes and (ii) the exact CRT determinant reduced modulo them."""
+    from linalg_solver_b200 import dist as lsx_dist
+    g = golden_io.load("c5_full_residues")
+    rng = np.random.Generator(np.random.PCG64(g["seed"]))
+    A = torch_or_np(rng.integers(-5, 6, size=(g["n"], g["n"]), dtype=np.int32))
+    words, K = lsx_dist.det_large_sharded(eng, A)
+    det = limbs_to_ints(words.cpu().numpy())
+    for e in g["entries"]:
+        assert K <= e["prime_index"]                          # an independent prime: not part of the lift
+        assert int(eng.primes(e["prime_index"] + 1)[-1]) == e["prime"]
+        got = eng.det_large_residues(A, e["prime_index"], 1).cpu().numpy().view(np.uint32)
+        assert int(got[0]) == e["residue"]
+        assert det % e["prime"] == e["residue"]
+
+
 def test_blocked_lu_beyond_the_register_panel(eng):
     """More than 4096 rows: the first base panels take the global-memory fallback (k_panel_gmem); residues of a
     planted matrix for three primes, n not a multiple of 8."""
