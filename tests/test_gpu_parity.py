@@ -205,6 +205,71 @@ def test_c2_full_size_properties(eng):
     assert sing.sum() > 0 or True
 
 
+def _limbs_mod(t, q):
+    """Signed multi-limb integers (torch int32 words, two's complement, last dim = limbs) reduced modulo a prime
+    q < 2^20, on the tensor's device, as float64-exact integers."""
+    import torch
+    w = t.to(torch.int64) & 0xffffffff
+    L = w.shape[-1]
+    acc = torch.zeros(w.shape[:-1], dtype=torch.int64, device=w.device)
+    for l in range(L - 1, -1, -1):
+        acc = (acc * ((1 << 32) % q) + w[..., l] % q) % q
+    neg = w[..., L - 1] >= (1 << 31)
+    acc = torch.where(neg, (acc - pow(2, 32 * L, q)) % q, acc)
+    return acc.to(torch.float64)
+
+
+def test_c3_full_size_properties(eng):
+    """BASELINE.json configs[2] at its full size (2^18 systems): A * particular == den * b for the consistent
+    half, A * generators == 0 everywhere, every odd (random right-hand side) system of rank-10 A is inconsistent or
+    satisfies the equations; all checked modulo a prime outside the table, on the device."""
+    import torch
+    import bench
+    q = 1048573
+    data = bench.make_inputs(16, 1 << 18, 20260003, "c3")
+    A = torch.from_numpy(data["A"]).cuda()
+    b = torch.from_numpy(data["b"]).cuda()
+    res = eng.solve_batch(A, b, a_abs_max=250, b_abs_max=int(np.abs(data["b"]).max()), max_rank=10, gen_cap=6)
+    st = res.status
+    assert int((st & ~(2 | 32)).count_nonzero()) == 0
+    ok = (st & 2) == 0
+    assert bool(ok[0::2].all())                                  # b = A x0 is consistent
+    assert int(ok[1::2].count_nonzero()) < 64                    # random b: inconsistent with overwhelming probability
+    assert bool((res.rank == 10).all())
+    Aq = (A.to(torch.float64) % q)
+    part = _limbs_mod(res.particular, q)                         # [B, 16]
+    den = _limbs_mod(res.den, q)                                 # [B]
+    gens = _limbs_mod(res.generators, q)                         # [B, 16, 6]
+    lhs = torch.einsum("bij,bj->bi", Aq, part) % q
+    rhs = (den[:, None] * (b.to(torch.float64) % q)) % q
+    assert bool((lhs[ok] == rhs[ok]).all())
+    assert bool(((torch.einsum("bij,bjk->bik", Aq, gens) % q)[ok] == 0).all())
+    assert bool((den[ok] != 0).all())
+
+
+def test_c4_full_size_properties(eng):
+    """BASELINE.json configs[3] at its full size (2^16 matrices 64 x 64, 11-limb results): A * adj == det * I modulo
+    a prime outside the table for every matrix, in chunks of 2^13, on the device."""
+    import torch
+    q = 1048573
+    rng = np.random.Generator(np.random.PCG64(20260004))
+    eye = torch.eye(64, dtype=torch.float64, device="cuda")
+    nsing = 0
+    for chunk in range(8):
+        A = torch.from_numpy(rng.integers(-5, 6, size=(1 << 13, 64, 64), dtype=np.int32)).cuda()
+        res = eng.inverse_batch(A, a_abs_max=5)
+        assert res.plan.limbs == 11 and int((res.status & ~(1 | 32)).count_nonzero()) == 0
+        adj = _limbs_mod(res.adj, q)
+        det = _limbs_mod(res.det, q)
+        prod = torch.matmul(A.to(torch.float64) % q, adj) % q
+        want = (det[:, None, None] * eye[None]) % q
+        sing = (res.status & 1) != 0
+        nsing += int(sing.count_nonzero())
+        assert bool((prod[~sing] == want[~sing]).all())
+        del A, res, adj, det, prod, want
+    assert nsing < 8                                            # random 64 x 64 integer matrices are almost never singular
+
+
 # ------------------------------------------------------------------ config 3: 16x17 rank-10 systems
 def test_c3_golden(eng):
     g = golden_io.load("c3_16x17")
