@@ -244,7 +244,7 @@ def test_c3_full_size_properties(eng):
     rhs = (den[:, None] * (b.to(torch.float64) % q)) % q
     assert bool((lhs[ok] == rhs[ok]).all())
     assert bool(((torch.einsum("bij,bjk->bik", Aq, gens) % q)[ok] == 0).all())
-    assert bool((den[ok] != 0).all())
+    assert bool((res.den != 0).any(dim=-1)[ok].all())            # exact words: a non-zero integer may vanish modulo q
 
 
 def test_c4_full_size_properties(eng):
@@ -268,6 +268,29 @@ def test_c4_full_size_properties(eng):
         assert bool((prod[~sing] == want[~sing]).all())
         del A, res, adj, det, prod, want
     assert nsing < 8                                            # random 64 x 64 integer matrices are almost never singular
+
+
+def test_c4_kernel_basis_full_size_properties(eng):
+    """BASELINE.json configs[3], second half, at its full size: 2^16 products B(64x48) C(48x64); the device kernel
+    basis has 16 generators with A G == 0 and den on the free positions, modulo an independent prime."""
+    import torch
+    import bench
+    q = 1048573
+    for chunk in range(16):
+        data = bench.make_inputs(64, 1 << 12, 20260040 + chunk, "c4ker")
+        A = torch.from_numpy(data["A"]).cuda()
+        z = torch.zeros((1 << 12, 64), dtype=torch.int32, device="cuda")
+        res = eng.solve_batch(A, z, a_abs_max=int(np.abs(data["A"]).max()), b_abs_max=0, max_rank=48, gen_cap=16)
+        assert int((res.status & ~32).count_nonzero()) == 0 and bool((res.rank == 48).all())
+        gens = _limbs_mod(res.generators, q)                     # [B, 64, 16]
+        den = _limbs_mod(res.den, q)
+        assert bool(((torch.matmul(A.to(torch.float64) % q, gens) % q) == 0).all())
+        assert int(_limbs_mod(res.particular, q).count_nonzero()) == 0
+        # den is a non-zero integer and every generator column has a non-zero entry (exact words, not residues:
+        # a non-zero integer may vanish modulo q)
+        assert bool((res.den != 0).any(dim=-1).all())
+        assert bool((res.generators != 0).any(dim=-1).any(dim=1).all())
+        del A, res, gens, den
 
 
 # ------------------------------------------------------------------ config 3: 16x17 rank-10 systems
