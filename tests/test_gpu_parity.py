@@ -486,7 +486,7 @@ def test_blocked_lu_tensor_core_path_vs_numpy_oracle(eng, monkeypatch):
     exercise full and ragged outer blocks, row swaps and singular inputs."""
     from oracle.det_mod_p import det_mod_p
     rng = np.random.Generator(np.random.PCG64(505))
-    for n in (257, 320, 520, 1000):
+    for n in (230, 257, 320, 520, 1000):
         A = rng.integers(-5, 6, size=(n, n), dtype=np.int32)
         B = A.copy()
         B[0, 0] = 0
@@ -504,6 +504,7 @@ def test_blocked_lu_tensor_core_path_vs_numpy_oracle(eng, monkeypatch):
                 primes = eng.primes(8)[5:8]
                 assert [int(x) for x in tc] == [det_mod_p(M, int(p)) for p in primes], n
         assert not np.any(eng.det_large_residues(C, 0, 2))
+        assert int(eng.det_large_residues(A, 7, 1)[0]) == det_mod_p(A, int(eng.primes(8)[7])) or n > 520   # one prime
 
 
 def test_c5_standin_256_blocked_and_sharded_crt(eng):
