@@ -593,6 +593,43 @@ def test_random_differential_against_the_oracle(eng):
                 assert got["generators"] == flat
 
 
+def test_rref_trace_device_memory_equals_host_memory(eng):
+    """lsx_rref_trace with LSX_MEM_DEVICE buffers (enqueue only) against the LSX_MEM_HOST call: same op log, frames,
+    step counts and pivot columns for every prime."""
+    import ctypes
+    import torch
+    from linalg_solver_b200 import _lib
+    rng = np.random.Generator(np.random.PCG64(12))
+    for m, n, bar in [(3, 4, 3), (6, 7, 6), (5, 9, 4), (12, 12, 12)]:
+        A = rng.integers(-5, 6, size=(m, n), dtype=np.int32)
+        A[0, 0] = 0
+        K = 5
+        max_ops = _lib.lib.lsx_rref_trace_max_ops(m, n, bar)
+        slots = min(m, bar)
+        h_ops = np.zeros((K, max_ops, 4), np.int32)
+        h_fr = np.zeros((K, max_ops, m, n), np.uint32)
+        h_n = np.zeros(K, np.int32)
+        h_pc = np.zeros((K, slots), np.int32)
+        ctx = eng._ctx
+        eng.set_stream(None)
+        assert _lib.lib.lsx_rref_trace(ctx, A.ctypes.data, m, n, bar, K, _lib.MEM_HOST, h_ops.ctypes.data, h_fr.ctypes.data,
+                                       h_n.ctypes.data, h_pc.ctypes.data) == 0
+        dA = torch.from_numpy(A).cuda()
+        d_ops = torch.zeros((K, max_ops, 4), dtype=torch.int32, device="cuda")
+        d_fr = torch.zeros((K, max_ops, m, n), dtype=torch.int32, device="cuda")
+        d_n = torch.zeros(K, dtype=torch.int32, device="cuda")
+        d_pc = torch.zeros((K, slots), dtype=torch.int32, device="cuda")
+        eng.set_stream(torch.cuda.current_stream().cuda_stream or 1)
+        assert _lib.lib.lsx_rref_trace(ctx, dA.data_ptr(), m, n, bar, K, _lib.MEM_DEVICE, d_ops.data_ptr(), d_fr.data_ptr(),
+                                       d_n.data_ptr(), d_pc.data_ptr()) == 0
+        torch.cuda.synchronize()
+        T = int(h_n[0])
+        assert T > 0 and np.array_equal(d_n.cpu().numpy(), h_n) and np.array_equal(d_pc.cpu().numpy(), h_pc)
+        assert np.array_equal(d_ops.cpu().numpy()[:, :T], h_ops[:, :T])
+        assert np.array_equal(d_fr.cpu().numpy().view(np.uint32)[:, :T], h_fr[:, :T])
+    assert _lib.lib.lsx_rref_trace_max_ops(3, 4, 9) < 0          # bar_col beyond n
+
+
 def test_inverse_int8_input_container(eng):
     """lsx_inverse_batch_i8: the same matrices in an int8 container give the same words as int32, from host and
     from device memory, for every size of the fused kernel; larger sizes are widened by the Python layer."""
