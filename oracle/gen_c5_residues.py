@@ -1,5 +1,5 @@
 """tests/golden/c5_full_residues: det(A) mod p of the config 5 matrix (bench.c5_matrix(): 4096 x 4096, PCG64(20260005))
-for two table primes beyond the CRT set, by oracle/det_mod_p.py on the CPU (about 6 minutes per prime)."""
+for two table primes beyond the CRT set, by oracle/det_mod_p.py on the CPU (about 11 minutes per prime on one core)."""
 import json
 import os
 import sys

@@ -681,7 +681,7 @@ def test_c5_full_size_planted_determinant_exact(eng):
 def test_c5_full_size_matrix_against_cpu_residues(eng):
     """BASELINE.json configs[4], the very matrix bench.py times (4096 x 4096, PCG64(20260005), entries in [-5, 5]):
     det mod p for two table primes OUTSIDE the CRT set, computed on the CPU by oracle/det_mod_p.py (numpy int64
-    elimination, ~6 minutes per prime; oracle/gen_c5_residues.py, stored in tests/golden/c5_full_residues), against
+    elimination, ~11 minutes per prime; oracle/gen_c5_residues.py, stored in tests/golden/c5_full_residues), against
     (i) the device residues for those primes and (ii) the exact CRT determinant reduced modulo them."""
     from linalg_solver_b200 import dist as lsx_dist
     g = golden_io.load("c5_full_residues")
