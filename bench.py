@@ -1,7 +1,14 @@
 #!/usr/bin/env python
 """Benchmark of the exact elimination hot path (BASELINE.json metric: exact det/RREF matrices/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4inv|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4inv|c4ker|c5]
+                    [--extra c1,c3,c4inv,c4ker,c5 | none]
+
+The ONE JSON line of a default run carries the headline workload (c2) at the top level and a `workloads` object
+with a full sub-record (value, ms_per_step, roofline, e2e, clocks, gpu_launches) for every other BASELINE.json
+config: c1, c3, c4inv and c4ker at their full 2^16, and c5 (seconds per 4096 x 4096 determinant with the primes
+sharded over the run's N ranks and one all-gather of residues), so the driver's N = 1/2/4/8 runs evidence the
+by-prime path too.  `--workload X` alone prints only X; `--extra` picks the sub-records.
 
 A step is one pass of the hot path over one batch of synthetic matrices.  The default workload is
 BASELINE.json configs[1]: 2^20 random 8x8 integer matrices (entries uniform in [-5,5], the
@@ -38,11 +45,14 @@ WORKLOADS = {
     "c2": ("2^20 x 8x8 det + inverse via [A|I] row_reduce(bar_col=8), entries uniform [-5,5]", 8, 1 << 20, 556),
     "c3": ("2^18 x find_preimage_of on 16x17 [A|b], A = B(16x10) C(10x16) rank 10, entries of B, C uniform [-5,5]",
            16, 1 << 18, 2964),
-    "c4inv": ("2^12 (of 2^16) x 64x64 inverse via [A|I] row_reduce(bar_col=64), entries uniform [-5,5]", 64, 1 << 12,
-              196912),
-    "c4ker": ("2^12 (of 2^16) x kernel basis of 64x64 A = B(64x48) C(48x64) (rank 48, dim 16), entries of B, C uniform [-5,5]",
-              64, 1 << 12, 98644),
+    "c4inv": ("2^16 x 64x64 inverse via [A|I] row_reduce(bar_col=64), entries uniform [-5,5]", 64, 1 << 16, 196912),
+    "c4ker": ("2^16 x kernel basis of 64x64 A = B(64x48) C(48x64) (rank 48, dim 16), entries of B, C uniform [-5,5]",
+              64, 1 << 16, 98644),
 }
+EXTRA_DEFAULT = ["c1", "c3", "c4inv", "c4ker", "c5"]
+# end-to-end (host buffer) calls per step: the 64x64 workloads stream their 2^16 matrices through the C-ABI in 8 calls
+# of 2^13 that reuse one set of pinned result buffers (11.8 GB of adjugates per step would otherwise be pinned per rank)
+E2E_CALLS = {"c4inv": 8, "c4ker": 8}
 # ALGORITHMIC modular multiply-subtracts per matrix and prime (Gauss-Jordan on m x n with pivots
 # in columns c_k costs sum_k m * (n - c_k)); the integer-pipe roofline is the measured mont_mul rate
 # (profiles/r01_ubench_int.jsonl: 12.0 per SM per clock)
@@ -191,245 +201,6 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------- GPU arm
-class Job:
-    """One workload bound to an engine: device-resident step, host-buffer (end-to-end) step, oracle check."""
-
-    def __init__(self, eng, workload, rank, dev):
-        import numpy as np
-        import torch
-        self.eng, self.wl, self.np, self.torch = eng, workload, np, torch
-        desc, n, batch, _ = WORKLOADS[workload]
-        self.n, self.batch = n, batch
-        # by-matrix sharding: every rank owns an independent batch (its own seed), no collective on the data path
-        data = make_inputs(n, batch, SEED + 1000 * rank, workload)
-        self.host = {k: torch.from_numpy(v).pin_memory() for k, v in data.items()}
-        self.dev = {k: v.to(dev) for k, v in self.host.items()}
-        if workload == "c1":
-            self.plans = (eng.plan_det(4, 5), eng.plan_rank(4, 4, 5), eng.plan_rref(4, 4, 3, 5, 5))
-        elif workload == "c3":
-            bmax = int(data["b"].max()), int(-data["b"].min())
-            self.plans = (eng.plan_solve(16, 16, 250, max(bmax), 10, 6),)
-        elif workload == "c4ker":
-            self.plans = (eng.plan_solve(64, 64, int(abs(data["A"]).max()), 0, 48, 16),)
-        else:
-            self.plans = (eng.plan_inverse(n, 5),)
-        self.res = self.run(self.dev)                         # allocates the outputs; reused by every step
-        self.host_out = None
-
-    def run(self, src, out=None):
-        e, A = self.eng, src["A"]
-        if self.wl == "c1":
-            o = out or (None, None, None)
-            return (e.det_batch(A, plan=self.plans[0], out=o[0]), e.rank_batch(A, plan=self.plans[1], out=o[1]),
-                    e.rref_batch(A, 3, plan=self.plans[2], out=o[2]))
-        if self.wl in ("c3", "c4ker"):
-            return (e.solve_batch(A, src["b"], plan=self.plans[0], out=out[0] if out else None),)
-        return (e.inverse_batch(A, plan=self.plans[0], out=out[0] if out else None),)
-
-    def step_device(self):
-        self.run(self.dev, self.res)
-
-    def _fields(self, r):
-        return [(k, v) for k, v in vars(r).items() if k != "plan" and v is not None]
-
-    def make_host_outputs(self):
-        torch = self.torch
-        outs = []
-        for r in self.res:
-            kw = {k: torch.empty(tuple(v.shape), dtype=torch.int32).pin_memory().numpy() for k, v in self._fields(r)}
-            outs.append(type(r)(plan=r.plan, **{k: kw.get(k) for k in vars(r) if k != "plan"}))
-        self.host_out = tuple(outs)
-        self.host_np = {k: v.numpy() for k, v in self.host.items()}
-        if self.wl == "c2":
-            # entries are in [-5, 5]: the end-to-end call ships them as int8 (lsx_inverse_batch_i8), a quarter
-            # of the host-to-device bytes of the int32 container; the results are the same words
-            self.host_i8 = self.host["A"].to(torch.int8).pin_memory()
-            self.host_np = {"A": self.host_i8.numpy()}
-
-    def step_e2e(self):
-        self.run(self.host_np, self.host_out)                 # returns when the results are in host memory
-
-    def h2d_bytes(self):
-        return int(sum(v.nbytes for v in self.host_np.values()))
-
-    def d2h_bytes(self):
-        return int(sum(v.nbytes for r in self.host_out for _, v in self._fields(r)))
-
-    def check_e2e_equals_device(self):
-        np = self.np
-        for rh, rd in zip(self.host_out, self.res):
-            for (k, vh), (_, vd) in zip(self._fields(rh), self._fields(rd)):
-                assert np.array_equal(vh.reshape(-1)[:4096], vd.reshape(-1)[:4096].cpu().numpy()), k
-
-    def check_against_oracle(self):
-        """A few units of this very batch against the CPU oracle (untimed)."""
-        from fractions import Fraction
-        from linalg_solver_b200.convert import limbs_to_ints
-        from oracle import ref_port
-        k = 8 if self.n <= 16 else 1
-        A = self.host["A"][:k].tolist()
-        if self.wl == "c1":
-            d, rk, rr = self.res
-            dets, num, den = limbs_to_ints(d.det[:k]), limbs_to_ints(rr.num[:k]), limbs_to_ints(rr.den[:k])
-            for i in range(k):
-                R, piv = ref_port.row_reduce(A[i])
-                assert dets[i] == ref_port.bareiss_det(A[i]) and int(rk.rank[i]) == ref_port.rank(A[i])
-                assert [[Fraction(x, den[i]) for x in row] for row in num[i]] == R
-        elif self.wl == "c4ker":
-            (r,) = self.res
-            den, gens = limbs_to_ints(r.den[:1])[0], limbs_to_ints(r.generators[:1])[0]
-            want = ref_port.kernel(A[0])
-            kdim = 64 - int(r.rank[0])
-            assert int(r.status[0]) == 0 and kdim == len(want[1])                  # want[1]: kdim generators of length 64
-            assert [[Fraction(gens[i][c], den) for i in range(64)] for c in range(kdim)] == want[1]
-        elif self.wl == "c3":
-            (r,) = self.res
-            b = self.host["b"][:k].tolist()
-            den, part = limbs_to_ints(r.den[:k]), limbs_to_ints(r.particular[:k])
-            for i in range(k):
-                want = ref_port.find_preimage_of(A[i], b[i])
-                if want is None:
-                    assert int(r.status[i]) & 2
-                else:
-                    assert int(r.status[i]) == 0 and [Fraction(x, den[i]) for x in part[i]] == want[0]
-        else:
-            (r,) = self.res
-            adj, det = limbs_to_ints(r.adj[:k]), limbs_to_ints(r.det[:k])
-            for i in range(k):
-                want = ref_port.inverse(A[i])
-                got = None if det[i] == 0 else [[Fraction(x, det[i]) for x in row] for row in adj[i]]
-                assert got == want and det[i] == ref_port.bareiss_det(A[i]), "device result differs from the oracle"
-
-
-def run_ours(args):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    desc, n, batch, alg_bytes = WORKLOADS[args.workload]
-
-    cpu = None
-    if rank == 0 and args.gpus == 1 and not args.no_cpu:
-        cpu, _ = cpu_baseline(args.workload, 8 * CPU_PER_CORE[args.workload], SEED)   # before CUDA init (fork pool)
-
-    import torch
-    import torch.distributed as dist
-    from linalg_solver_b200 import Engine
-
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    eng = Engine(local)
-
-    def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize(dev)
-
-    job = Job(eng, args.workload, rank, dev)
-    torch.cuda.synchronize(dev)
-    if rank == 0:
-        job.check_against_oracle()
-
-    for _ in range(args.warmup):
-        job.step_device()
-    barrier()
-    launches0 = eng.launch_count
-    eng.timing_enable(True)
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.25)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        job.step_device()
-    ev1.record()
-    barrier()
-    t1 = time.perf_counter()
-    ms_total = ev0.elapsed_time(ev1)
-    kernel_ms = eng.timing_read()
-    eng.timing_enable(False)
-    launches = eng.launch_count - launches0
-    clocks = sampler.stop(t0, t1)
-
-    # ---- end to end through the C-ABI with host buffers (pinned): H2D + kernels + D2H per step ----
-    job.make_host_outputs()
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        job.step_e2e()
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        job.step_e2e()
-    torch.cuda.synchronize(dev)
-    e2e_ms = (time.perf_counter() - e0) * 1e3 / e2e_steps
-    job.check_e2e_equals_device()
-
-    # ---- reduce over ranks: the slowest rank defines the step ----
-    stats = torch.tensor([ms_total, e2e_ms, float(launches)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(stats[0]), float(stats[1])
-    ms_step = ms_total / args.steps
-    value = world * batch / (ms_step * 1e-3)
-
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        # dominant kernel = the elimination kernel(s) of a step (device-timed inside the library)
-        per_step = max(1, len(kernel_ms) // args.steps) if kernel_ms else 1
-        k_ms = sum(kernel_ms) / args.steps if kernel_ms else ms_step
-        achieved = alg_bytes * batch / (k_ms * 1e-3) / 1e9
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tr.get(args.workload, {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-        plan = job.plans[-1]
-        int_pipe = None
-        if args.workload in ALG_OPS:
-            sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
-            ip_peak = MONT_MUL_PER_SM_CLK * 148 * sm_mhz * 1e6
-            # the fused 8x8 kernel runs ONE prime (exact int64 determinant); the other kernels run the plan's primes
-            n_pr = 1 if args.workload == "c2" else int(plan.n_primes)
-            ip_ach = ALG_OPS[args.workload] * n_pr * batch / (k_ms * 1e-3)
-            int_pipe = {"algorithmic_ops_per_matrix": ALG_OPS[args.workload] * n_pr, "achieved": ip_ach, "peak": ip_peak,
-                        "unit": "modular multiply-subtracts/s", "frac": ip_ach / ip_peak,
-                        "peak_source": "measured mont_mul rate 12.0 per SM per clock (profiles/r01_ubench_int.jsonl) x 148 SMs x max SM clock"}
-        line = {
-            "metric": METRIC[args.workload], "value": value, "unit": "matrices/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32 (Montgomery words modulo 31-bit primes)",
-            "data": "synthetic",
-            "config": {"workload": desc, "batch_per_gpu": batch, "primes": int(plan.n_primes), "limbs": int(plan.limbs),
-                       "sharding": "by matrix, no collective",
-                       "l2": "inputs+outputs per step (%.0f MB) vs the 126 MB L2" % ((alg_bytes * batch) / 1e6)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel_ms": k_ms, "kernel_launches_per_step": per_step,
-                         "algorithmic_bytes_per_matrix": alg_bytes, "int_pipe": int_pipe,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"},
-            "cpu_baseline": cpu,
-            "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "matrices/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": job.h2d_bytes(), "d2h_bytes_per_step": job.d2h_bytes(),
-                    "path": "lsx_*_batch(mem=LSX_MEM_HOST) via ctypes, pinned host buffers"
-                            + (" (int8 input container: lsx_inverse_batch_i8)" if args.workload == "c2" else "")},
-            "gpu_launches": int(stats[2]),
-            "clocks": clocks,
-        }
-        print(json.dumps(line), flush=True)
-    eng.close()
-    if world > 1:
-        dist.destroy_process_group()
-
-
-
 # ------------------------------------------------------------------------------------- config 5
 C5_N, C5_SEED, C5_ABS = 4096, 20260005, 5
 C5_DESC = "single 4096x4096 integer determinant (entries uniform [-5,5], PCG64(20260005)), multi-modular, sharded by prime"
@@ -494,6 +265,508 @@ def c5_tensor_ops(n, n_primes_local, block=256):
     return 2 * 16 * macs * n_primes_local
 
 
+# ------------------------------------------------------------------------------------- GPU arm
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def load_counts():
+    """Per-launch counters of the dominant kernels taken from ncu captures of this build (profiles/kernel_counts.json:
+    smsp__inst_executed.sum and dram__bytes_read.sum + dram__bytes_write.sum per launch, with the capture they come
+    from).  They are properties of the binary and the workload, not of the run; the durations they are divided by
+    are measured live."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "kernel_counts.json")))
+    except Exception:
+        return {}
+
+
+class Ctx:
+    """One rank of the run: device, engine, process group."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from linalg_solver_b200 import Engine
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.eng = Engine(self.local)
+        self.peaks = load_peaks()
+        self.counts = load_counts()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(device_ids=[self.local])
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def close(self):
+        self.eng.close()
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+class Job:
+    """One workload bound to an engine: device-resident step, host-buffer (end-to-end) step, oracle check."""
+
+    def __init__(self, ctx, workload):
+        import numpy as np
+        torch = ctx.torch
+        eng, dev = ctx.eng, ctx.dev
+        self.eng, self.wl, self.np, self.torch = eng, workload, np, torch
+        desc, n, batch, _ = WORKLOADS[workload]
+        self.n, self.batch = n, batch
+        # by-matrix sharding: every rank owns an independent batch (its own seed), no collective on the data path
+        data = make_inputs(n, batch, SEED + 1000 * ctx.rank, workload, device=dev)
+        self.dev = {k: (v if hasattr(v, "is_cuda") else torch.from_numpy(v).to(dev)) for k, v in data.items()}
+        self.host = {k: v.cpu().pin_memory() for k, v in self.dev.items()}
+        if workload == "c1":
+            self.plans = (eng.plan_det(4, 5), eng.plan_rank(4, 4, 5), eng.plan_rref(4, 4, 3, 5, 5))
+        elif workload == "c3":
+            self.plans = (eng.plan_solve(16, 16, 250, int(self.dev["b"].abs().max().item()), 10, 6),)
+        elif workload == "c4ker":
+            self.plans = (eng.plan_solve(64, 64, int(self.dev["A"].abs().max().item()), 0, 48, 16),)
+        else:
+            self.plans = (eng.plan_inverse(n, 5),)
+        self.res = self.run(self.dev)                         # allocates the outputs; reused by every step
+        self.host_out = None
+
+    def run(self, src, out=None):
+        e, A = self.eng, src["A"]
+        if self.wl == "c1":
+            o = out or (None, None, None)
+            return (e.det_batch(A, plan=self.plans[0], out=o[0]), e.rank_batch(A, plan=self.plans[1], out=o[1]),
+                    e.rref_batch(A, 3, plan=self.plans[2], out=o[2]))
+        if self.wl in ("c3", "c4ker"):
+            return (e.solve_batch(A, src["b"], plan=self.plans[0], out=out[0] if out else None),)
+        return (e.inverse_batch(A, plan=self.plans[0], out=out[0] if out else None),)
+
+    def step_device(self):
+        self.run(self.dev, self.res)
+
+    def _fields(self, r):
+        return [(k, v) for k, v in vars(r).items() if k != "plan" and v is not None]
+
+    def make_host_outputs(self):
+        torch = self.torch
+        self.e2e_calls = E2E_CALLS.get(self.wl, 1)
+        self.e2e_batch = self.batch // self.e2e_calls
+        outs = []
+        for r in self.res:
+            kw = {k: torch.empty((self.e2e_batch,) + tuple(v.shape[1:]), dtype=torch.int32).pin_memory().numpy()
+                  for k, v in self._fields(r)}
+            outs.append(type(r)(plan=r.plan, **{k: kw.get(k) for k in vars(r) if k != "plan"}))
+        self.host_out = tuple(outs)
+        self.host_np = {k: v.numpy() for k, v in self.host.items()}
+        if self.wl == "c2":
+            # entries are in [-5, 5]: the end-to-end call ships them as int8 (lsx_inverse_batch_i8), a quarter
+            # of the host-to-device bytes of the int32 container; the results are the same words
+            self.host_i8 = self.host["A"].to(torch.int8).pin_memory()
+            self.host_np = {"A": self.host_i8.numpy()}
+
+    def step_e2e(self):
+        """All `batch` matrices from pinned host memory through the C-ABI; returns when the results are in host memory."""
+        eb = self.e2e_batch
+        for c in range(self.e2e_calls):
+            self.run({k: v[c * eb:(c + 1) * eb] for k, v in self.host_np.items()}, self.host_out)
+
+    def h2d_bytes(self):
+        return int(sum(v.nbytes for v in self.host_np.values()))
+
+    def d2h_bytes(self):
+        return int(self.e2e_calls * sum(v.nbytes for r in self.host_out for _, v in self._fields(r)))
+
+    def check_e2e_equals_device(self):
+        np = self.np
+        b0 = (self.e2e_calls - 1) * self.e2e_batch             # the host buffers hold the last call's slice
+        for rh, rd in zip(self.host_out, self.res):
+            for (k, vh), (_, vd) in zip(self._fields(rh), self._fields(rd)):
+                assert np.array_equal(vh.reshape(-1)[:4096], vd[b0:].reshape(-1)[:4096].cpu().numpy()), k
+
+    def check_against_oracle(self):
+        """A few units of this very batch against the CPU oracle (untimed)."""
+        from fractions import Fraction
+        from linalg_solver_b200.convert import limbs_to_ints
+        from oracle import ref_port
+        k = 8 if self.n <= 16 else 1
+        A = self.host["A"][:k].tolist()
+        if self.wl == "c1":
+            d, rk, rr = self.res
+            dets, num, den = limbs_to_ints(d.det[:k]), limbs_to_ints(rr.num[:k]), limbs_to_ints(rr.den[:k])
+            for i in range(k):
+                R, piv = ref_port.row_reduce(A[i])
+                assert dets[i] == ref_port.bareiss_det(A[i]) and int(rk.rank[i]) == ref_port.rank(A[i])
+                assert [[Fraction(x, den[i]) for x in row] for row in num[i]] == R
+        elif self.wl == "c4ker":
+            (r,) = self.res
+            den, gens = limbs_to_ints(r.den[:1])[0], limbs_to_ints(r.generators[:1])[0]
+            want = ref_port.kernel(A[0])
+            kdim = 64 - int(r.rank[0])
+            assert int(r.status[0]) == 0 and kdim == len(want[1])                  # want[1]: kdim generators of length 64
+            assert [[Fraction(gens[i][c], den) for i in range(64)] for c in range(kdim)] == want[1]
+        elif self.wl == "c3":
+            (r,) = self.res
+            b = self.host["b"][:k].tolist()
+            den, part = limbs_to_ints(r.den[:k]), limbs_to_ints(r.particular[:k])
+            for i in range(k):
+                want = ref_port.find_preimage_of(A[i], b[i])
+                if want is None:
+                    assert int(r.status[i]) & 2
+                else:
+                    assert int(r.status[i]) == 0 and [Fraction(x, den[i]) for x in part[i]] == want[0]
+        else:
+            (r,) = self.res
+            adj, det = limbs_to_ints(r.adj[:k]), limbs_to_ints(r.det[:k])
+            for i in range(k):
+                want = ref_port.inverse(A[i])
+                got = None if det[i] == 0 else [[Fraction(x, det[i]) for x in row] for row in adj[i]]
+                assert got == want and det[i] == ref_port.bareiss_det(A[i]), "device result differs from the oracle"
+
+
+def measure_batch(ctx, workload, steps, warmup, cpu):
+    """One by-matrix workload at this run's N ranks -> its record (on rank 0; None elsewhere).  Every rank must call."""
+    torch = ctx.torch
+    eng, dev, world = ctx.eng, ctx.dev, ctx.world
+    desc, n, batch, alg_bytes = WORKLOADS[workload]
+    job = Job(ctx, workload)
+    torch.cuda.synchronize(dev)
+    if ctx.rank == 0:
+        job.check_against_oracle()
+
+    for _ in range(warmup):
+        job.step_device()
+    ctx.barrier()
+    launches0 = eng.launch_count
+    eng.timing_enable(True)
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(steps):
+        job.step_device()
+    ev1.record()
+    ctx.barrier()
+    t1 = time.perf_counter()
+    ms_total = ev0.elapsed_time(ev1)
+    kernel_ms = eng.timing_read()
+    eng.timing_enable(False)
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop(t0, t1)
+
+    # ---- end to end through the C-ABI with host buffers (pinned): H2D + kernels + D2H per step ----
+    job.make_host_outputs()
+    e2e_steps = max(3, min(steps, 10)) if job.e2e_calls == 1 else 3
+    for _ in range(2):
+        job.step_e2e()
+    ctx.barrier()
+    e0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        job.step_e2e()
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - e0) * 1e3 / e2e_steps
+    job.check_e2e_equals_device()
+
+    # ---- reduce over ranks: the slowest rank defines the step ----
+    ms_total, e2e_ms, launches = ctx.max_over_ranks([ms_total, e2e_ms, float(launches)])
+    ms_step = ms_total / steps
+    value = world * batch / (ms_step * 1e-3)
+    h2d, d2h = job.h2d_bytes(), job.d2h_bytes()
+    plan = job.plans[-1]
+    del job
+    torch.cuda.empty_cache()
+    if ctx.rank != 0:
+        return None
+
+    peaks = ctx.peaks
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    sm_run = float(clocks.get("sm_mhz") or sm_max)                # median SM clock sampled during the timed region
+    # dominant kernel = the elimination kernel(s) of a step (device-timed inside the library)
+    per_step = max(1, len(kernel_ms) // steps) if kernel_ms else 1
+    k_ms = sum(kernel_ms) / steps if kernel_ms else ms_step
+    achieved = alg_bytes * batch / (k_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "kernel_ms": k_ms, "kernel_launches_per_step": per_step,
+            "algorithmic_bytes_per_matrix": alg_bytes,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"}
+    cnt = ctx.counts.get(workload)
+    if cnt and cnt.get("batch") == batch:
+        # executed figures: warp instructions of the dominant kernel(s) per step (ncu capture of this build) over
+        # the issue slots the live-timed kernel had: 4 schedulers x SMs x cycles at the SM clock sampled in this run
+        slots = 4.0 * 148 * (k_ms * 1e-3) * sm_run * 1e6
+        roof["traffic"] = cnt.get("dram_bytes_per_step")
+        roof["issue_slots"] = {"warp_instructions_per_step": cnt["warp_inst_per_step"], "slots": slots,
+                               "frac": cnt["warp_inst_per_step"] / slots, "sm_mhz": sm_run,
+                               "source": cnt.get("source")}
+    if workload in ALG_OPS:
+        # ALGORITHMIC count (SURVEY.md section 8d), not executed instructions: the fused 8x8 kernel runs ONE prime and
+        # part of its steps on plain int32, so it executes fewer and cheaper operations than this count
+        n_pr = 1 if workload == "c2" else int(plan.n_primes)
+        ip_peak = MONT_MUL_PER_SM_CLK * 148 * sm_max * 1e6
+        ip_ach = ALG_OPS[workload] * n_pr * batch / (k_ms * 1e-3)
+        roof["algorithmic_int"] = {"ops_per_matrix": ALG_OPS[workload] * n_pr, "achieved": ip_ach, "peak": ip_peak,
+                                   "unit": "algorithmic modular multiply-subtracts/s", "frac": ip_ach / ip_peak,
+                                   "note": "algorithmic operation count over the measured mont_mul rate; NOT a pipe utilisation",
+                                   "peak_source": "measured mont_mul rate 12.0 per SM per clock (profiles/r01_ubench_int.jsonl) x 148 SMs x max SM clock"}
+    return {
+        "metric": METRIC[workload], "value": value, "unit": "matrices/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 (Montgomery words modulo 31-bit primes)",
+        "data": "synthetic",
+        "config": {"workload": desc, "batch_per_gpu": batch, "primes": int(plan.n_primes), "limbs": int(plan.limbs),
+                   "sharding": "by matrix, no collective",
+                   "l2": "inputs+outputs per step (%.0f MB) vs the 126 MB L2" % ((alg_bytes * batch) / 1e6)},
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "matrices/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_calls_per_step": E2E_CALLS.get(workload, 1),
+                "gb_per_s_per_gpu": (h2d + d2h) / (e2e_ms * 1e-3) / 1e9,
+                "path": "lsx_*_batch(mem=LSX_MEM_HOST) via ctypes, pinned host buffers"
+                        + (" (int8 input container: lsx_inverse_batch_i8)" if workload == "c2" else "")},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+
+def c5_total_ops(n, n_primes_local):
+    """int8-equivalent tensor operations of the WHOLE LU (2 n^3 / 3 multiply-adds per prime, 16 byte-plane products
+    per residue multiply-add, 2 operations per multiply-add) -- the whole-step figure next to the dominant kernel's."""
+    return 2 * 16 * (n ** 3 // 3) * n_primes_local
+
+
+def int8_peak(peaks):
+    """Dense int8 tensor peak in TOP/s and where it comes from: the measurement-only probe (tools/int8_peak_probe.py,
+    a library int8 GEMM, never linked into liblsx) when its result is committed, else 2 x the measured bf16 rate."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "int8_peak.json")))
+        return float(d["int8_tops_sustained"]), "profiles/int8_peak.json (measured: %s)" % d.get("how", "library int8 GEMM")
+    except Exception:
+        bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        return 2.0 * bf16, "2 x MEASURED_PEAKS.json bf16_tflops_sustained (nominal int8 : bf16 ratio, not measured)"
+
+
+def measure_c5(ctx, steps, warmup, cpu):
+    """BASELINE.json configs[4] at this run's N ranks: primes sharded over the ranks, one all-gather, CRT on every rank."""
+    import numpy as np
+    torch = ctx.torch
+    from linalg_solver_b200 import Engine
+    from linalg_solver_b200 import dist as lsx_dist
+    eng, dev, world, rank = ctx.eng, ctx.dev, ctx.world, ctx.rank
+
+    worst_primes, _ = Engine.det_large_prime_count(C5_N, C5_ABS)   # worst case for |entries| <= 5: 1100 primes
+    A_host = torch.from_numpy(c5_matrix()).pin_memory()
+    A = A_host.to(dev)
+    # parity before timing: the blocked tensor-core path against the numpy oracle on a 512 x 512 block, two primes
+    if rank == 0:
+        from oracle.det_mod_p import det_mod_p
+        small = A_host[:512, :512].contiguous().numpy()
+        got = eng.det_large_residues(torch.from_numpy(small).to(dev), 0, 2).cpu().numpy().astype(np.uint32)
+        want = [det_mod_p(small, int(p)) for p in eng.primes(2)]
+        assert [int(x) for x in got] == want, "blocked LU residues differ from oracle/det_mod_p.py"
+
+    # Hadamard bound from the actual row/column norms of A (rigorous, about 8 % fewer primes than the worst case)
+    n_primes, bits = eng.det_large_prime_count_for(A)
+    assert n_primes == c5_prime_count_numpy() and n_primes <= worst_primes
+
+    def step():
+        return lsx_dist.det_large_sharded(eng, A)
+
+    words = None
+    for _ in range(warmup):
+        words, _ = step()
+    ctx.barrier()
+    b, e = lsx_dist.shard_range(n_primes, rank, world)
+    launches0 = eng.launch_count
+    eng.timing_enable(True)
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(steps):
+        words, _ = step()
+    ev1.record()
+    ctx.barrier()
+    t1 = time.perf_counter()
+    ms_total = ev0.elapsed_time(ev1)
+    kernel_ms = eng.timing_read()
+    eng.timing_enable(False)
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop(t0, t1)
+
+    # ---- end to end: host matrix -> H2D -> residues -> all-gather -> CRT -> limbs back on the host ----
+    e2e_steps = 3
+    ctx.barrier()
+    e0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        A_d = A_host.to(dev, non_blocking=True)
+        w, _ = lsx_dist.det_large_sharded(eng, A_d)
+        w_host = w.cpu()
+    e2e_ms = (time.perf_counter() - e0) * 1e3 / e2e_steps
+    assert torch.equal(w_host, words.cpu())
+
+    ms_total, e2e_ms, launches, k_sum = ctx.max_over_ranks([ms_total, e2e_ms, float(launches), sum(kernel_ms)])
+    ms_step = ms_total / steps
+    words_host = words.cpu().numpy().astype(np.uint32)
+    del A, words
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peak, peak_src = int8_peak(ctx.peaks)
+    k_s = k_sum / steps * 1e-3                                    # depth-256 tensor updates of one step (slowest rank)
+    ops = c5_tensor_ops(C5_N, e - b)
+    achieved = ops / k_s / 1e12 if k_s > 0 else 0.0
+    whole = c5_total_ops(C5_N, e - b) / (ms_step * 1e-3) / 1e12
+    limbs = int(bits + 2) // 32 + 1
+    from linalg_solver_b200.convert import limbs_to_ints
+    det = limbs_to_ints(words_host.reshape(1, -1))[0]
+    return {
+        "metric": C5_METRIC, "value": ms_step * 1e-3, "unit": "s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32 residues modulo 31-bit primes; trailing update as u8 x u8 -> s32 tcgen05 MMA",
+        "data": "synthetic",
+        "config": {"workload": C5_DESC, "primes": n_primes, "primes_worst_case_bound": worst_primes,
+                   "bound": "Hadamard with the actual row/column norms, log2 = %.1f" % bits,
+                   "primes_per_gpu": e - b, "limbs": limbs,
+                   "sharding": "by prime, one all-gather of %d residues (%d B) before the CRT" % (n_primes, 4 * n_primes),
+                   "all_gather_bytes": 4 * n_primes,
+                   "l2": "residue matrices of one prime group (64 MiB per prime) far exceed the 126 MB L2",
+                   "det_bits": int(abs(det)).bit_length(), "det_mod_1e9": int(det % 10**9)},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "kernel_ms": k_s * 1e3, "kernel": "lsx_tc::k_gemm_tc (depth-256 trailing updates)",
+                     "kernel_share_of_step": k_s * 1e3 / ms_step,
+                     "kernel_launches_per_step": len(kernel_ms) // max(1, steps),
+                     "ops": "int8 tensor ops: 2 x 16 byte-plane products per residue multiply-add",
+                     "whole_step": {"achieved": whole, "frac": whole / peak, "unit": "TFLOP/s",
+                                    "ops": "2 x 16 x n^3/3 per prime over the whole step (panels, solves, splits and "
+                                           "swaps included in the time, only the LU's multiply-adds in the count)"},
+                     "peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_ms * 1e-3, "unit": "s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(A_host.numel() * 4),
+                "d2h_bytes_per_step": int(limbs * 4),
+                "path": "pinned host matrix -> device, linalg_solver_b200.dist.det_large_sharded (lsx_det_large_residues, "
+                        "all-gather, lsx_crt_signed), limbs back to the host"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+
+# ------------------------------------------------------------------------------------- CPU legs
+def cpu_leg(workload, scale=8):
+    """cpu_baseline of one workload (the pinned oracle port on all host cores, bounded sample)."""
+    if workload == "c5":
+        return c5_cpu_baseline(c5_prime_count_numpy())
+    cb, _ = cpu_baseline(workload, scale * CPU_PER_CORE[workload], SEED)
+    ref = reference_unmodified(workload)
+    if ref is not None:
+        cb["reference_unmodified"] = ref
+    return cb
+
+
+def _ref_one(item):
+    """One unit through the UNMODIFIED reference package vendored under oracle/_ref (oracle/build_ref.py)."""
+    import sympy
+    from linalg_solver.linalg import Matrix
+    wl, a, b = item
+    rat = [[sympy.Rational(x) for x in row] for row in a]
+    if wl == "c1":
+        M = Matrix(rat)
+        return M.rank(), len(M.row_reduce()[1])
+    if wl == "c3":
+        res = Matrix(rat).find_preimage_of([sympy.Rational(x) for x in b])
+        return isinstance(res, Matrix.NoSolution)
+    if wl == "c4ker":
+        return Matrix(rat).kernel().generators.cols
+    n = len(a)
+    if wl == "c2":
+        aug = [list(rat[i]) + [sympy.Integer(1 if i == j else 0) for j in range(n)] for i in range(n)]
+        return len(Matrix(aug).row_reduce(bar_col=n)[1])
+    return isinstance(Matrix(rat).inverse(), Matrix.NoSolution)
+
+
+REF_UNITS_PER_CORE = {"c1": 64, "c2": 16, "c3": 2, "c4inv": 1, "c4ker": 0}
+
+
+def reference_unmodified(workload):
+    """The reference's own Python (unmodified, oracle/_ref) on a SMALL sample of the workload, all host cores: how
+    conservative the port-based cpu_baseline is.  None when oracle/_ref was not built (it is git-ignored)."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    per_core = REF_UNITS_PER_CORE.get(workload, 0)
+    if not os.path.isdir(os.path.join(ref_dir, "linalg_solver")) or per_core == 0:
+        return None
+    from multiprocessing import get_context
+    for d in (ref_dir,):
+        if d not in sys.path:
+            sys.path.insert(0, d)
+    try:
+        from linalg_solver.log import global_logger
+        global_logger._auto_print = False
+    except Exception as e:                                        # a broken vendored copy must not sink the bench
+        return {"unavailable": "import of oracle/_ref failed: %r" % (e,)}
+    desc, n, _, _ = WORKLOADS[workload]
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    data = make_inputs(n, cores * per_core, SEED, workload)
+    A = data["A"].tolist()
+    b = data["b"].tolist() if "b" in data else [None] * len(A)
+    sample = [(workload, A[i], b[i]) for i in range(len(A))]
+    calls = {"c1": "Matrix.rank() + row_reduce()", "c2": "row_reduce([A|I], bar_col=8)", "c3": "find_preimage_of(b)",
+             "c4inv": "inverse()", "c4ker": "kernel()"}[workload]
+    ctx = get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_ref_one, sample[:cores], chunksize=1)
+        t0 = time.perf_counter()
+        pool.map(_ref_one, sample, chunksize=1)
+        dt = time.perf_counter() - t0
+    return {"value": len(sample) / dt, "unit": "matrices/s", "cores": cores, "kind": "reference",
+            "sample": "%d units through the unmodified reference (%s on sympy.Rational entries, the Rust planner "
+                      "replaced by oracle/standin), %.1f s" % (len(sample), calls, dt)}
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    main_wl = args.workload
+    extras = [w for w in args.extra_list if w != main_wl]
+    order = [main_wl] + extras
+
+    # CPU legs first (fork pools must precede CUDA initialisation); rank 0 at N = 1 only
+    cpus = {}
+    if rank == 0 and args.gpus == 1 and not args.no_cpu:
+        for w in order:
+            cpus[w] = cpu_leg(w)
+
+    ctx = Ctx(args)
+    sub_steps = max(3, min(args.steps, 10))
+    recs = {}
+    for i, w in enumerate(order):
+        steps = args.steps if i == 0 else (sub_steps if w not in ("c4inv", "c4ker", "c5") else max(3, min(args.steps, 5)))
+        warm = args.warmup if i == 0 else 3
+        rec = measure_c5(ctx, steps, warm, cpus.get(w)) if w == "c5" else measure_batch(ctx, w, steps, warm, cpus.get(w))
+        recs[w] = rec
+    if ctx.rank == 0:
+        line = recs[main_wl]
+        if extras:
+            line["workloads"] = {w: recs[w] for w in extras}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def run_c5_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
@@ -515,135 +788,6 @@ def run_c5_reference(args):
         "config": {"workload": C5_DESC, "primes": k.value, "step": "bounded sample on the host CPU, extrapolated"},
         "cpu_baseline": cb, "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
-
-
-def run_c5(args):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    from linalg_solver_b200 import Engine
-    from linalg_solver_b200 import dist as lsx_dist
-
-    worst_primes, _ = Engine.det_large_prime_count(C5_N, C5_ABS)   # worst case for |entries| <= 5: 1100 primes
-    cpu = None
-    if rank == 0 and args.gpus == 1 and not args.no_cpu:
-        cpu = c5_cpu_baseline(c5_prime_count_numpy())             # before CUDA init (fork pool)
-
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    eng = Engine(local)
-
-    def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize(dev)
-
-    A_host = torch.from_numpy(c5_matrix()).pin_memory()
-    A = A_host.to(dev)
-    # parity before timing: the blocked tensor-core path against the numpy oracle on a 512 x 512 block, two primes
-    if rank == 0:
-        from oracle.det_mod_p import det_mod_p
-        small = A_host[:512, :512].contiguous().numpy()
-        got = eng.det_large_residues(torch.from_numpy(small).to(dev), 0, 2).cpu().numpy().astype(np.uint32)
-        want = [det_mod_p(small, int(p)) for p in eng.primes(2)]
-        assert [int(x) for x in got] == want, "blocked LU residues differ from oracle/det_mod_p.py"
-
-    # Hadamard bound from the actual row/column norms of A (rigorous, about 8 % fewer primes than the worst case)
-    n_primes, bits = eng.det_large_prime_count_for(A)
-    assert n_primes == c5_prime_count_numpy() and n_primes <= worst_primes
-
-    def step():
-        return lsx_dist.det_large_sharded(eng, A)
-
-    words = None
-    for _ in range(args.warmup):
-        words, _ = step()
-    barrier()
-    b, e = lsx_dist.shard_range(n_primes, rank, world)
-    launches0 = eng.launch_count
-    eng.timing_enable(True)
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.25)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        words, _ = step()
-    ev1.record()
-    barrier()
-    t1 = time.perf_counter()
-    ms_total = ev0.elapsed_time(ev1)
-    kernel_ms = eng.timing_read()
-    eng.timing_enable(False)
-    launches = eng.launch_count - launches0
-    clocks = sampler.stop(t0, t1)
-
-    # ---- end to end: host matrix -> H2D -> residues -> all-gather -> CRT -> limbs back on the host ----
-    e2e_steps = max(3, min(args.steps, 5))
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        A_d = A_host.to(dev, non_blocking=True)
-        w, _ = lsx_dist.det_large_sharded(eng, A_d)
-        w_host = w.cpu()
-    e2e_ms = (time.perf_counter() - e0) * 1e3 / e2e_steps
-    assert torch.equal(w_host, words.cpu())
-
-    stats = torch.tensor([ms_total, e2e_ms, float(launches), sum(kernel_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms_step = float(stats[0]) / args.steps
-    e2e_ms = float(stats[1])
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        # int8 tensor peak is not in MEASURED_PEAKS.json: twice the measured dense bf16 rate (B200: int8 = 2 x bf16)
-        bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        peak = 2.0 * bf16
-        k_s = float(stats[3]) / args.steps * 1e-3                 # depth-256 tensor updates of one step (slowest rank)
-        ops = c5_tensor_ops(C5_N, e - b)
-        achieved = ops / k_s / 1e12 if k_s > 0 else 0.0
-        limbs = int(bits + 2) // 32 + 1
-        from linalg_solver_b200.convert import limbs_to_ints
-        det = limbs_to_ints(words.cpu().numpy().astype(np.uint32).reshape(1, -1))[0]
-        line = {
-            "metric": C5_METRIC, "value": ms_step * 1e-3, "unit": "s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong",
-            "vs_baseline": None, "dtype": "u32 residues modulo 31-bit primes; trailing update as u8 x u8 -> s32 tcgen05 MMA",
-            "data": "synthetic",
-            "config": {"workload": C5_DESC, "primes": n_primes, "primes_worst_case_bound": worst_primes,
-                       "bound": "Hadamard with the actual row/column norms, log2 = %.1f" % bits,
-                       "primes_per_gpu": e - b, "limbs": limbs,
-                       "sharding": "by prime, one all-gather of %d residues (%d B) before the CRT" % (n_primes, 4 * n_primes),
-                       "l2": "residue matrices of one prime group (64 MiB per prime) far exceed the 126 MB L2",
-                       "det_bits": int(abs(det)).bit_length(), "det_mod_1e9": int(det % 10**9)},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel_ms": k_s * 1e3, "kernel": "lsx_tc::k_gemm_tc (depth-256 trailing updates)",
-                         "kernel_launches_per_step": len(kernel_ms) // max(1, args.steps),
-                         "ops": "int8 tensor ops: 2 x 16 byte-plane products per residue multiply-add",
-                         "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops_sustained (nominal int8 : bf16 ratio; the MMA-only stream of this kernel measures 2.41e15 op/s, profiles/r01i)"
-                                        if peaks else "fallback 2 x 1400"},
-            "cpu_baseline": cpu,
-            "e2e": {"value": e2e_ms * 1e-3, "unit": "s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(A_host.numel() * 4),
-                    "d2h_bytes_per_step": int(limbs * 4),
-                    "path": "pinned host matrix -> device, linalg_solver_b200.dist.det_large_sharded (lsx_det_large_residues, "
-                            "all-gather, lsx_crt_signed), limbs back to the host"},
-            "gpu_launches": int(stats[2]),
-            "clocks": clocks,
-        }
-        print(json.dumps(line), flush=True)
-    eng.close()
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():

@@ -59,23 +59,51 @@ void lsx_timing_end(lsx_ctx* ctx);
 #define LSX_HD inline
 #endif
 
+// 32 x 32 -> 64 products and the high word of t + m * p, written as PTX on the device.  From plain C the front end
+// sometimes hoists the zero extension of a loop-invariant factor (the prime) and emits a 64 x 64 multiply, which
+// ptxas lowers to IMAD.WIDE plus an add of a zero high word per reduction (`IADD3 R, R, UR(=0)` after every
+// reduction of the unrolled kernels).  The sequences below are the ones ptxas folds into IMAD.WIDE / IMAD.HI.
+LSX_HD uint64_t mul_wide(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    uint64_t r;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+#else
+    return (uint64_t)a * b;
+#endif
+}
+// high 32 bits of t + m * p
+LSX_HD uint32_t mad_wide_hi(uint32_t m, uint32_t p, uint64_t t) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("{\n\t.reg .b64 u;\n\t.reg .b32 lo;\n\tmul.wide.u32 u, %1, %2;\n\tadd.s64 u, u, %3;\n\tmov.b64 {lo, %0}, u;\n\t}"
+        : "=r"(r)
+        : "r"(m), "r"(p), "l"(t));
+    return r;
+#else
+    return (uint32_t)(((uint64_t)m * p + t) >> 32);
+#endif
+}
+
 // REDC of t < 2 p^2 (fits 63 bits): returns t / R mod p in [0, p).
 LSX_HD uint32_t mont_redc(uint64_t t, uint32_t p, uint32_t pinv) {
     uint32_t m = (uint32_t)t * pinv;
-    uint64_t u = t + (uint64_t)m * p;
-    uint32_t r = (uint32_t)(u >> 32);
+    uint32_t r = mad_wide_hi(m, p, t);
     uint32_t s = r - p;
     return r < s ? r : s;               // r in [0, 2p): subtract p once if needed
 }
 LSX_HD uint32_t mont_mul(uint32_t a, uint32_t b, uint32_t p, uint32_t pinv) {
-    return mont_redc((uint64_t)a * b, p, pinv);
+    return mont_redc(mul_wide(a, b), p, pinv);
 }
 // x*a + y*b (one reduction for two products)
 LSX_HD uint32_t mont_fma2(uint32_t x, uint32_t a, uint32_t y, uint32_t b, uint32_t p, uint32_t pinv) {
-    return mont_redc((uint64_t)x * a + (uint64_t)y * b, p, pinv);
+    return mont_redc(mul_wide(x, a) + mul_wide(y, b), p, pinv);
 }
 LSX_HD uint32_t mont_pow(uint32_t a, uint32_t e, uint32_t one, uint32_t p, uint32_t pinv) {
     uint32_t acc = one;
+#ifdef __CUDACC__
+#pragma unroll 1
+#endif
     for (int bit = 31; bit >= 0; --bit) {
         acc = mont_mul(acc, acc, p, pinv);
         if ((e >> bit) & 1u) acc = mont_mul(acc, a, p, pinv);

@@ -1,0 +1,375 @@
+// k_inv_tpm<N, HEAD, I8>: fused inverse + determinant of n x n matrices (n <= 8), ONE launch per batch, one
+// thread per matrix, the matrix resident in N*N registers (reference semantics: linalg.py:682-743 through
+// [A|I] row_reduce(bar_col = n), results as adjugate + determinant).
+//
+// Arithmetic (mirror: tests/device_model.py::inverse_inplace_v2): in-place division-free Gauss-Jordan modulo ONE
+// 31-bit prime.  The launcher takes this path only when the Hadamard bound of every minor of A is below the
+// prime, so zero tests modulo p are exact and the adjugate entries come back exactly by the symmetric lift.
+// The first HEAD pivot steps run on plain int32 (two IMADs per entry) while the entries provably fit; pivot
+// rows stay unscaled and the per-row factor, the sign and the single modular inversion are folded into the
+// multipliers of the LAST pivot step.
+//
+// What this version does to the instruction stream (round 2; ncu of the previous version: 31 % of the executed
+// instructions were selects / moves / compares, profiles/r01b_ncu_full_k_inv_tpm8_v2.txt):
+//   * The adjugate and the determinant do not depend on the pivot order, so the kernel does not reproduce the
+//     reference's "first non-zero row" search with a full physical row swap per step.  It tests the pivot
+//     position and the row below it (a 2-row window: 16 selects per step) and only when a whole warp vote finds
+//     a lane whose window is all zero does it fall into the full search (a rarely taken, warp-uniform branch).
+//   * It eliminates on the TRANSPOSE (held in registers: a renaming at load time).  A row exchange of the
+//     transpose permutes the ROWS of the result, so every result row is written with 16-byte shared-memory
+//     stores at a data-dependent row address instead of 4-byte scatters at data-dependent columns, and the
+//     determinant identity det = sum_c adj[i][c] A[c][i] uses the first pivot row, which is already in registers.
+//   * Tiles are staged with 16-byte shared-memory accesses on a layout whose 16-byte chunk stride per matrix is
+//     odd (conflict-free for the per-matrix vector reads and for the cooperative copies).
+//   * The declared-magnitude check is a min/max scan (3-input min/max), singular and out-of-bound matrices are
+//     zeroed in a rarely taken branch instead of per-element selects, the negated multiplier needs no zero
+//     test (y = p - f is a valid operand of the two-product reduction), and the determinant, which fits int32 by
+//     the launcher's bound, is accumulated with wrapping 32-bit multiply-adds against a column of A that is read
+//     back from the input tile (8 registers less while the elimination runs).
+// Measured (profiles/r02b_*): 3 063 warp instructions per 32 matrices (was 4 760), 202 us per 2^20 matrices (was
+// 263); the kernel is now bound by the fmaheavy pipe (IMAD / IMAD.WIDE / IMAD.HI), 75 % busy.
+#pragma once
+#include "lsx_internal.h"
+
+namespace lsx_inv_small {
+
+#ifndef LSX_TPM_THREADS
+#define LSX_TPM_THREADS 128
+#endif
+#ifndef LSX_TPM_MINB
+#define LSX_TPM_MINB 4
+#endif
+#ifndef LSX_TPM_WINDOW
+#define LSX_TPM_WINDOW 1          // rows below the pivot position tested before the full search
+#endif
+constexpr int TPM_THREADS = LSX_TPM_THREADS;
+
+// Shared-memory tile: one matrix = ST 32-bit words.  With E = N*N a multiple of 4 the matrix is E/4 chunks of
+// 16 bytes and ST/4 is odd (lanes t .. t+7 of a quarter warp then hit 8 different 16-byte bank groups);
+// otherwise ST is odd and all accesses are scalar.
+template <int N>
+struct TpmTile {
+    static constexpr int E = N * N;
+    static constexpr bool VEC = (E % 4) == 0;
+    static constexpr int C = E / 4;
+    static constexpr int ST = VEC ? 4 * (C | 1) : (E | 1);
+    // int8 input tile: bytes per matrix, 16-byte chunks with an odd chunk stride when E is a multiple of 16
+    static constexpr bool VEC8 = (E % 16) == 0;
+    static constexpr int C8 = E / 16;
+    static constexpr int STB = VEC8 ? 16 * (C8 | 1) : E;
+    static constexpr size_t BYTES = (size_t)TPM_THREADS * ST * 4;
+};
+
+__device__ __forceinline__ uint32_t mont_sqn(uint32_t x, int k, uint32_t p, uint32_t pinv) {
+    for (int i = 0; i < k; ++i) x = mont_mul(x, x, p, pinv);
+    return x;
+}
+// a^(p-2): addition chain (30 squarings + 8 products) for p = 2^31 - 1, square-and-multiply otherwise
+__device__ __forceinline__ uint32_t mont_inverse(uint32_t a, const PrimeRec& P) {
+    const uint32_t p = P.p, pinv = P.pinv;
+    if (p != 0x7fffffffu) return mont_pow(a, p - 2u, P.one, p, pinv);
+    const uint32_t x2 = mont_mul(mont_sqn(a, 1, p, pinv), a, p, pinv);
+    const uint32_t x4 = mont_mul(mont_sqn(x2, 2, p, pinv), x2, p, pinv);
+    const uint32_t x8 = mont_mul(mont_sqn(x4, 4, p, pinv), x4, p, pinv);
+    const uint32_t x16 = mont_mul(mont_sqn(x8, 8, p, pinv), x8, p, pinv);
+    const uint32_t x24 = mont_mul(mont_sqn(x16, 8, p, pinv), x8, p, pinv);
+    const uint32_t x28 = mont_mul(mont_sqn(x24, 4, p, pinv), x4, p, pinv);
+    const uint32_t x29 = mont_mul(mont_sqn(x28, 1, p, pinv), a, p, pinv);
+    return mont_mul(mont_sqn(x29, 2, p, pinv), a, p, pinv);
+}
+
+// residue word of a signed value with |a| < p: a >= 0 -> a, a < 0 -> a + p (one add-min instruction)
+__device__ __forceinline__ uint32_t word_of_small(uint32_t a, uint32_t p) { return min(a, a + p); }
+
+// conditional exchange of two register rows (selects: the rows must stay in registers)
+template <int N>
+__device__ __forceinline__ void cswap_rows(bool sw, uint32_t (&x)[N], uint32_t (&y)[N], uint32_t& px, uint32_t& py) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        const uint32_t a = x[c], b = y[c];
+        x[c] = sw ? b : a;
+        y[c] = sw ? a : b;
+    }
+    const uint32_t a = px, b = py;
+    px = sw ? b : a;
+    py = sw ? a : b;
+}
+
+template <int N, int HEAD, bool I8>
+__global__ void __launch_bounds__(TPM_THREADS, LSX_TPM_MINB)
+k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max, int vec_ok,
+          int32_t* __restrict__ adj, int32_t* __restrict__ det, int32_t* __restrict__ status) {
+    using T = TpmTile<N>;
+    constexpr int E = T::E, ST = T::ST;
+    extern __shared__ __align__(16) uint32_t sm[];
+    const int tid = threadIdx.x;
+    const int64_t tile0 = (int64_t)blockIdx.x * TPM_THREADS;           // first matrix of this block
+    const int nmat = (int)min((int64_t)TPM_THREADS, batch - tile0);
+    const uint32_t p = P.p, pinv = P.pinv;
+    const int me = tid < nmat ? tid : 0;                                // idle lanes of the last block redo matrix 0
+
+    uint32_t W[N][N];          // TRANSPOSE of the matrix.  head: two's-complement integers; tail: residue words
+    int vmax = INT32_MIN, vmin = INT32_MAX;
+
+    // ---- coalesced load of the block's matrices into shared memory, then one matrix per thread ----
+    if (I8) {
+        const int8_t* src = reinterpret_cast<const int8_t*>(Ain) + tile0 * E;
+        uint8_t* sm8 = reinterpret_cast<uint8_t*>(sm);
+        constexpr int CC8 = T::C8 > 0 ? T::C8 : 1;
+        if (T::VEC8 && vec_ok) {
+            const int4* src4 = reinterpret_cast<const int4*>(src);
+            for (int g = tid; g < nmat * T::C8; g += TPM_THREADS)
+                *reinterpret_cast<int4*>(sm8 + (g / CC8) * T::STB + (g % CC8) * 16) = __ldg(src4 + g);
+        } else {
+            for (int w = tid; w < nmat * E; w += TPM_THREADS) sm8[(w / E) * T::STB + (w % E)] = (uint8_t)__ldg(src + w);
+        }
+        __syncthreads();
+        const uint8_t* mine = sm8 + me * T::STB;
+        if constexpr (T::VEC8) {
+#pragma unroll
+            for (int q = 0; q < T::C8; ++q) {
+                const int4 v4 = *reinterpret_cast<const int4*>(mine + 16 * q);
+                const int w4[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int e = 16 * q + i;
+                    const int v = (int)(int8_t)(w4[i >> 2] >> (8 * (i & 3)));
+                    vmax = max(vmax, v);
+                    vmin = min(vmin, v);
+                    W[e % N][e / N] = (uint32_t)v;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int v = (int)(int8_t)mine[e];
+                vmax = max(vmax, v);
+                vmin = min(vmin, v);
+                W[e % N][e / N] = (uint32_t)v;
+            }
+        }
+    } else {
+        const int32_t* src = reinterpret_cast<const int32_t*>(Ain) + tile0 * E;
+        if (T::VEC && vec_ok) {
+            constexpr int CC = T::C > 0 ? T::C : 1;
+            const int4* src4 = reinterpret_cast<const int4*>(src);
+#pragma unroll 4
+            for (int g = tid; g < nmat * T::C; g += TPM_THREADS)
+                *reinterpret_cast<int4*>(sm + (g / CC) * ST + (g % CC) * 4) = __ldg(src4 + g);
+        } else {
+            for (int w = tid; w < nmat * E; w += TPM_THREADS) sm[(w / E) * ST + (w % E)] = (uint32_t)__ldg(src + w);
+        }
+        __syncthreads();
+        const uint32_t* mine = sm + me * ST;
+        if (T::VEC) {
+#pragma unroll
+            for (int q = 0; q < T::C; ++q) {
+                const int4 v4 = *reinterpret_cast<const int4*>(mine + 4 * q);
+                const int w4[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int e = 4 * q + i;
+                    vmax = max(vmax, w4[i]);
+                    vmin = min(vmin, w4[i]);
+                    W[e % N][e / N] = (uint32_t)w4[i];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int v = (int)mine[e];
+                vmax = max(vmax, v);
+                vmin = min(vmin, v);
+                W[e % N][e / N] = (uint32_t)v;
+            }
+        }
+    }
+    // entries outside the declared magnitude: the integer head may wrap and the words may leave [0, p); all of
+    // that is well-defined unsigned arithmetic whose results are discarded below (status LSX_ST_BOUND)
+    const bool bound_bad = vmax > a_abs_max || vmin < -a_abs_max;
+
+    uint32_t perm[N];                       // perm[r]: original index of the transpose row now at position r
+#pragma unroll
+    for (int r = 0; r < N; ++r) perm[r] = (uint32_t)r;
+    bool neg = false, singular = false;
+    uint32_t cw[N];                         // per-row multiplier words (what pivot row k still lacks)
+    uint32_t sig = 1u;                      // head: product of the pivots so far (exact integer)
+    uint32_t S = 1u, Q = P.one;
+
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const bool head = j < HEAD;
+        const bool last = j == N - 1;
+        if (j == HEAD) {
+            // ---- switch to residue words: S = sigma_h, Q = word(prod sigma_k), cw[k] = word(sigma_k) ----
+            // cw[k] was stored as the plain integer sigma_k: to Montgomery form, and Q = their product
+            uint32_t qh = P.one;
+#pragma unroll
+            for (int k = 0; k < HEAD; ++k) {
+                cw[k] = mont_mul(word_of_small(cw[k], p), P.r2, p, pinv);
+                qh = k == 0 ? cw[0] : mont_mul(qh, cw[k], p, pinv);
+            }
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < N; ++c) W[r][c] = word_of_small(W[r][c], p);
+            S = word_of_small(sig, p);
+            Q = qh;
+        }
+        // ---- pivot: position j, else a row of the window below it, else (rare, warp vote) any lower row ----
+        if (j + 1 < N) {
+            bool found = W[j][j] != 0u;
+            const int WEND = j + LSX_TPM_WINDOW < N - 1 ? j + LSX_TPM_WINDOW : N - 1;       // last row of the window
+            bool swn[LSX_TPM_WINDOW > 0 ? LSX_TPM_WINDOW : 1];
+#pragma unroll
+            for (int r = j + 1; r <= WEND; ++r) {
+                swn[r - j - 1] = !found && W[r][j] != 0u;
+                found = found || swn[r - j - 1];
+            }
+            if (WEND < N - 1) {
+                if (__any_sync(0xffffffffu, !found)) {
+                    int src = -1;
+#pragma unroll
+                    for (int r = N - 1; r > WEND; --r)
+                        if (W[r][j] != 0u) src = r;
+                    const bool far = !found && src >= 0;
+#pragma unroll
+                    for (int r = WEND + 1; r < N; ++r) cswap_rows<N>(far && r == src, W[j], W[r], perm[j], perm[r]);
+                    neg = neg != far;
+                }
+            }
+#pragma unroll
+            for (int r = j + 1; r <= WEND; ++r) {
+                cswap_rows<N>(swn[r - j - 1], W[j], W[r], perm[j], perm[r]);
+                neg = neg != swn[r - j - 1];
+            }
+        }
+        const uint32_t piv = W[j][j];
+        singular = singular || piv == 0u;   // keep going on garbage: every operation below is total
+        uint32_t prow[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) prow[c] = W[j][c];
+        if (head) {
+            // plain two's-complement integers: W[r][c] = piv * W[r][c] - f * prow[c]
+            const uint32_t nsig = 0u - sig;
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                if (r == j) continue;
+                const uint32_t f = W[r][j];
+#pragma unroll
+                for (int c = 0; c < N; ++c) W[r][c] = (c == j) ? f * nsig : (piv * W[r][c] - f * prow[c]);
+            }
+            W[j][j] = sig;
+            cw[j] = sig;
+            sig *= piv;
+        } else {
+            cw[j] = S;
+            Q = mont_mul(Q, S, p, pinv);
+            uint32_t qinv = 0u;
+            if (last) {
+                qinv = mont_inverse(Q, P);
+                if (neg) qinv = p - qinv;               // Q is a unit unless the matrix is singular (discarded)
+            }
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                if (r == j) {
+                    if (last) {
+                        const uint32_t g = mont_mul(qinv, cw[r], p, pinv);
+#pragma unroll
+                        for (int c = 0; c < N; ++c) W[r][c] = mont_mul(g, c == j ? S : prow[c], p, pinv);
+                    } else {
+                        W[r][j] = S;
+                    }
+                } else {
+                    uint32_t y = p - W[r][j];           // in [1, p]: a valid operand of the two-product reduction
+                    uint32_t x = piv;
+                    if (last) {
+                        const uint32_t g = mont_mul(qinv, cw[r], p, pinv);
+                        x = mont_mul(g, x, p, pinv);
+                        y = mont_mul(g, y, p, pinv);
+                    }
+#pragma unroll
+                    for (int c = 0; c < N; ++c)
+                        W[r][c] = (c == j) ? mont_mul(y, S, p, pinv) : mont_fma2(x, W[r][c], y, prow[c], p, pinv);
+                }
+            }
+            S = mont_mul(S, piv, p, pinv);
+        }
+    }
+    // Column perm[0] of A (= the first pivot row of the transpose as loaded) for the determinant identity below:
+    // read back from the input tile, which is intact until the barrier, instead of living in 8 registers.
+    uint32_t a0[N];
+    if (I8) {
+        const int8_t* mine = reinterpret_cast<const int8_t*>(sm) + me * T::STB;
+#pragma unroll
+        for (int c = 0; c < N; ++c) a0[c] = (uint32_t)(int)mine[c * N + perm[0]];
+    } else {
+        const uint32_t* mine = sm + me * ST;
+#pragma unroll
+        for (int c = 0; c < N; ++c) a0[c] = mine[c * N + perm[0]];
+    }
+
+    // ---- symmetric lift, determinant, rows of the adjugate to shared memory at their permuted position ----
+    if (singular || bound_bad) {            // rare: zeros (the reference returns NoSolution(), linalg.py:725-737)
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int c = 0; c < N; ++c) W[r][c] = 0u;
+    }
+    const uint32_t half = p >> 1;
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            const uint32_t v = W[r][c];
+            W[r][c] = v > half ? v - p : v;
+        }
+    // det = sum_c adj[i][c] * A[c][i] with i = perm[0]: adj[i][c] = W[c][0], A[c][i] = a0[c].  The launcher's bound
+    // (|det| < 2^31) makes the wrapping 32-bit sum exact.
+    uint32_t dsum = 0u;
+#pragma unroll
+    for (int c = 0; c < N; ++c) dsum += a0[c] * W[c][0];
+
+    __syncthreads();                        // everybody has read its input tile: reuse it for the output
+    {
+        uint32_t* mine = sm + me * ST;
+        if (tid < nmat) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                // slot j holds row perm[j] of the adjugate of A: its entries are W[0..N-1][j]
+                uint32_t* orow = mine + perm[j] * N;
+                if (N % 4 == 0) {
+#pragma unroll
+                    for (int q = 0; q < N / 4; ++q)
+                        *reinterpret_cast<uint4*>(orow + 4 * q) =
+                            make_uint4(W[4 * q][j], W[4 * q + 1][j], W[4 * q + 2][j], W[4 * q + 3][j]);
+                } else if (N % 2 == 0) {
+#pragma unroll
+                    for (int q = 0; q < N / 2; ++q)
+                        *reinterpret_cast<uint2*>(orow + 2 * q) = make_uint2(W[2 * q][j], W[2 * q + 1][j]);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < N; ++r) orow[r] = W[r][j];
+                }
+            }
+            det[tile0 + tid] = (int32_t)dsum;
+            status[tile0 + tid] = (singular && !bound_bad ? LSX_ST_SINGULAR : 0) | (bound_bad ? LSX_ST_BOUND : 0);
+        }
+    }
+    __syncthreads();
+    // ---- coalesced store of the adjugates ----
+    {
+        int32_t* dst = adj + tile0 * E;
+        if (T::VEC && vec_ok) {
+            constexpr int CC = T::C > 0 ? T::C : 1;
+            int4* dst4 = reinterpret_cast<int4*>(dst);
+#pragma unroll 4
+            for (int g = tid; g < nmat * T::C; g += TPM_THREADS)
+                dst4[g] = *reinterpret_cast<const int4*>(sm + (g / CC) * ST + (g % CC) * 4);
+        } else {
+            for (int w = tid; w < nmat * E; w += TPM_THREADS) dst[w] = (int32_t)sm[(w / E) * ST + (w % E)];
+        }
+    }
+}
+
+}  // namespace lsx_inv_small

@@ -101,22 +101,24 @@ __global__ void __launch_bounds__(1024) k_garner_big(const PrimeRec* primes, con
     }
 }
 
-// sums of squares of the rows ([0, n)) and of the columns ([n, 2n)) of an n x n int32 matrix
-__global__ void k_sq_norms(const int32_t* __restrict__ A, int n, unsigned long long* __restrict__ out) {
+// sums of squares of the rows ([0, n)) and of the columns ([n, 2n)) of an n x n int32 matrix.  Accumulated in
+// double: a 64-bit integer sum wraps for full-range entries (n = 65 with |a| near 2^31 already exceeds 2^64), and
+// the relative rounding error of n additions (n * 2^-53) is far below the slack the caller adds to the bound.
+__global__ void k_sq_norms(const int32_t* __restrict__ A, int n, double* __restrict__ out) {
     const int i = blockIdx.x, tid = threadIdx.x;
     const bool is_col = i >= n;
     const int idx = is_col ? i - n : i;
-    unsigned long long s = 0;
+    double s = 0.0;
     for (int t = tid; t < n; t += blockDim.x) {
-        const long long v = is_col ? A[(int64_t)t * n + idx] : A[(int64_t)idx * n + t];
-        s += (unsigned long long)(v * v);
+        const double v = (double)(is_col ? A[(int64_t)t * n + idx] : A[(int64_t)idx * n + t]);
+        s += v * v;
     }
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    __shared__ unsigned long long part[8];
+    __shared__ double part[8];
     if ((tid & 31) == 0) part[tid >> 5] = s;
     __syncthreads();
     if (tid == 0) {
-        unsigned long long tot = 0;
+        double tot = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
         out[i] = tot;
     }
@@ -130,19 +132,19 @@ int lsx_det_large_prime_count_for(lsx_ctx* ctx, const int32_t* A, int n, int mem
     if (!ctx) return LSX_ERR_NULL;
     if (!A || !n_primes) return lsx_fail(ctx, LSX_ERR_NULL, "det_large_prime_count_for: NULL buffer");
     if (n < 1) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "det_large_prime_count_for: bad n");
-    std::vector<unsigned long long> sq((size_t)2 * n, 0ull);
+    std::vector<double> sq((size_t)2 * n, 0.0);
     if (mem == LSX_MEM_HOST) {
         for (int i = 0; i < n; ++i)
             for (int j = 0; j < n; ++j) {
-                const long long v = A[(int64_t)i * n + j];
-                sq[i] += (unsigned long long)(v * v);
-                sq[n + j] += (unsigned long long)(v * v);
+                const double v = (double)A[(int64_t)i * n + j];
+                sq[i] += v * v;
+                sq[n + j] += v * v;
             }
     } else {
         LSX_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
         int rc = lsx_ws_reserve(ctx, (size_t)2 * n * 8);
         if (rc != LSX_OK) return rc;
-        k_sq_norms<<<2 * n, 256, 0, ctx->stream>>>(A, n, (unsigned long long*)ctx->d_ws);
+        k_sq_norms<<<2 * n, 256, 0, ctx->stream>>>(A, n, (double*)ctx->d_ws);
         ctx->launches++;
         LSX_CUDA_TRY(ctx, cudaMemcpyAsync(sq.data(), ctx->d_ws, (size_t)2 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
         LSX_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -150,10 +152,11 @@ int lsx_det_large_prime_count_for(lsx_ctx* ctx, const int32_t* A, int n, int mem
     double rows = 0.0, cols = 0.0;
     bool zero = false;
     for (int i = 0; i < n; ++i) {
-        if (sq[i] == 0 || sq[n + i] == 0) zero = true;
-        else rows += 0.5 * std::log2((double)sq[i]), cols += 0.5 * std::log2((double)sq[n + i]);
+        if (sq[i] == 0.0 || sq[n + i] == 0.0) zero = true;
+        else rows += 0.5 * std::log2(sq[i]), cols += 0.5 * std::log2(sq[n + i]);
     }
-    // a relative slack far above the rounding error of 2n logarithms and their sum keeps the bound rigorous
+    // a relative slack far above the rounding error of the double sums of squares (n * 2^-53 each), of 2n
+    // logarithms and of their sum keeps the bound rigorous
     const double bits = zero ? 0.0 : std::min(rows, cols) * (1.0 + 1e-9) + 1e-6;
     int K, L;
     lsx_bits_to_plan(bits, &K, &L);

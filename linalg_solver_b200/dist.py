@@ -44,13 +44,35 @@ def all_gather_residues(local, total: int, group=None):
     return torch.cat(parts) if parts else out
 
 
-def det_large_sharded(engine, A, a_abs_max: int = None, group=None):
+def _gather_any(local, total: int, device_index, group=None):
+    """all_gather_residues for a residue vector in either container: torch tensors go through as they are; a
+    numpy array (host-memory engine call) is wrapped as an int32 tensor -- on the engine's GPU when the group's
+    backend is NCCL, which only moves CUDA tensors -- and comes back as a numpy uint32 array."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not isinstance(local, np.ndarray):
+        return all_gather_residues(local, total, group)
+    t = torch.from_numpy(np.ascontiguousarray(local).view(np.int32).copy())
+    if dist.get_backend(group) == "nccl":
+        t = t.to(torch.device("cuda", device_index))
+    full = all_gather_residues(t, total, group)
+    return full.cpu().numpy().view(np.uint32)
+
+
+def det_large_sharded(engine, A, a_abs_max: int = None, group=None, sharded: bool = True):
     """Determinant of one large integer matrix, primes sharded over the ranks of `group`.
 
     Returns (det_words, n_primes): `det_words` is the signed determinant as little-endian 32-bit
     words (two's complement) on every rank.  The prime count comes from the worst-case Hadamard bound of
     `a_abs_max` when it is given, else from the row/column norms of A itself (every rank holds the same A,
     so every rank derives the same count).
+
+    With `sharded` (the default) and an initialised process group this is a COLLECTIVE: every rank of `group`
+    must call it with the same matrix.  `sharded=False` computes all primes on this rank and never communicates
+    (what ``Matrix.determinant`` does: a method of one object must not turn into an implicit collective).
+    A may be a torch tensor (CUDA: device call) or a numpy array (host call); the result follows the input.
     """
     import torch.distributed as dist
 
@@ -59,12 +81,12 @@ def det_large_sharded(engine, A, a_abs_max: int = None, group=None):
         K, bits = engine.det_large_prime_count_for(A)
     else:
         K, bits = engine.det_large_prime_count(n, a_abs_max)
-    if dist.is_available() and dist.is_initialized():
+    if sharded and dist.is_available() and dist.is_initialized():
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     else:
         rank, world = 0, 1
     b, e = shard_range(K, rank, world)
     local = engine.det_large_residues(A, b, e - b)
-    full = all_gather_residues(local, K, group) if world > 1 else local
+    full = _gather_any(local, K, getattr(engine, "device", 0), group) if world > 1 else local
     limbs = int(bits + 2) // 32 + 1
     return engine.crt_signed(full, limbs), K

@@ -281,9 +281,10 @@ class Matrix:
         grid, D = _to_int_grid(self.items)
         if n > 64:
             # one large matrix: residues modulo many primes (tile kernel up to n ~ 220, blocked tensor-core LU above),
-            # sharded by prime over the ranks when torch.distributed is initialised, then one CRT
+            # then one CRT.  All primes run on this process's GPU: a method of one object is not a collective
+            # (the by-prime multi-GPU route is linalg_solver_b200.dist.det_large_sharded, called by every rank).
             from .dist import det_large_sharded
-            words, _ = det_large_sharded(default_engine(), grid)
+            words, _ = det_large_sharded(default_engine(), grid, sharded=False)
             d = limbs_to_ints(np.asarray(words).reshape(1, -1))[0]
         else:
             res = default_engine().det_batch(grid[None])

@@ -37,6 +37,12 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed, int iters
             if (MODE == 3) a[i] = redc((uint64_t)a[i] * x + (uint64_t)b[i] * y, p, pinv);   // mont_fma2
             if (MODE == 4) d[i] = fma(d[i], 1.0000001, 0.5);                     // DFMA
             if (MODE == 5) a[i] = redc(((uint64_t)a[i] << 32) + (uint64_t)b[i] * y, p, pinv); // mulsub form
+            if (MODE == 6) a[i] = __umulhi(a[i], x) + b[i];                      // IMAD.HI (32-bit addend)
+            if (MODE == 7) { const uint64_t t = (uint64_t)a[i] * x; a[i] = (uint32_t)t ^ (uint32_t)(t >> 32); }  // IMAD.WIDE (no addend) + LOP3
+            if (MODE == 8) a[i] = min(a[i] + x, a[i] ^ y);                       // ALU pipe: LOP3 + VIADDMNMX
+            if (MODE == 9) { a[i] = a[i] * x + y; b[i] = min(b[i] + x, b[i]) ^ a[i]; }   // IMAD + 2 ALU ops per iteration (dual pipe)
+            if (MODE == 10) { const uint64_t t = (uint64_t)a[i] * x + (uint64_t)b[i] * y; a[i] = (uint32_t)(t & 0x7fffffffu) + (uint32_t)(t >> 31); a[i] = min(a[i], a[i] - p); }  // Mersenne-style fold (not exact: rate probe)
+            if (MODE == 11) { a[i] = a[i] > x ? b[i] : a[i]; b[i] = b[i] > y ? a[i] : b[i]; }    // ISETP + SEL pairs
         }
     }
     uint32_t acc = 0;
@@ -85,6 +91,12 @@ int main() {
     run<2>("mont_mul", out, sms, ghz);
     run<3>("mont_fma2", out, sms, ghz);
     run<5>("mont_mulsub_shift", out, sms, ghz);
+    run<6>("imad_hi_plus_add", out, sms, ghz);
+    run<7>("imad_wide_rz_plus_lop", out, sms, ghz);
+    run<8>("alu_lop_viaddmnmx_pairs", out, sms, ghz);
+    run<9>("imad_plus_2alu", out, sms, ghz);
+    run<10>("fma2_mersenne_fold", out, sms, ghz);
+    run<11>("setp_sel_pairs", out, sms, ghz);
     run<4>("dfma", out, sms, ghz);
     cudaFree(out);
     return 0;
