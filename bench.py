@@ -65,10 +65,20 @@ METRIC = {"c1": "exact det+rank+RREF matrices/sec", "c2": "exact det+inverse mat
           "c4ker": "exact kernel bases/sec"}
 
 
-def make_inputs(n, batch, seed, workload="c2"):
-    """-> dict of int32 arrays for one rank's batch."""
+def make_inputs(n, batch, seed, workload="c2", device=None):
+    """-> dict of int32 arrays for one rank's batch.  With `device` (a torch CUDA device) the large rank-deficient
+    products are formed there (float32 batched products of small integers are exact) and returned as device tensors;
+    the factors always come from the same numpy generator, so both routes give the same matrices."""
     import numpy as np
     rng = np.random.Generator(np.random.PCG64(seed))
+
+    def product(Bm, Cm):
+        if device is None or Bm.shape[0] <= 4096:
+            return np.einsum("bik,bkj->bij", Bm.astype(np.int64), Cm.astype(np.int64)).astype(np.int32)
+        import torch
+        out = torch.bmm(torch.from_numpy(Bm).to(device, torch.float32), torch.from_numpy(Cm).to(device, torch.float32))
+        return out.round().to(torch.int32)                        # |entries| <= 48 * 25 < 2^24: exact in float32
+
     if workload == "c3":
         Bm = rng.integers(-5, 6, size=(batch, 16, 10), dtype=np.int64)
         Cm = rng.integers(-5, 6, size=(batch, 10, 16), dtype=np.int64)
@@ -80,8 +90,47 @@ def make_inputs(n, batch, seed, workload="c2"):
     if workload == "c4ker":
         Bm = rng.integers(-5, 6, size=(batch, 64, 48), dtype=np.int64)
         Cm = rng.integers(-5, 6, size=(batch, 48, 64), dtype=np.int64)
-        return {"A": np.einsum("bik,bkj->bij", Bm, Cm).astype(np.int32), "b": np.zeros((batch, 64), dtype=np.int32)}
+        return {"A": product(Bm, Cm), "b": np.zeros((batch, 64), dtype=np.int32)}
     return {"A": rng.integers(-5, 6, size=(batch, n, n), dtype=np.int32)}
+
+
+def plan_of(workload):
+    """The lsx plan of a by-matrix workload (host-only query: prime and limb counts from the Hadamard bound)."""
+    import ctypes
+    from linalg_solver_b200 import _lib
+    p = _lib.Plan()
+    if workload == "c1":
+        rc = _lib.lib.lsx_plan_rref(4, 4, 3, 5, 5, 0, ctypes.byref(p))
+    elif workload == "c3":
+        rc = _lib.lib.lsx_plan_solve(16, 16, 250, 250 * 16 * 5, 10, 6, ctypes.byref(p))
+    elif workload == "c4ker":
+        rc = _lib.lib.lsx_plan_solve(64, 64, 48 * 25, 0, 48, 16, ctypes.byref(p))
+    else:
+        rc = _lib.lib.lsx_plan_inverse(WORKLOADS[workload][1], 5, ctypes.byref(p))
+    assert rc == 0, rc
+    return p
+
+
+def config_for(workload, world):
+    """`config` of a line: the same dict in our arm and in the reference arm."""
+    if workload == "c5":
+        from linalg_solver_b200 import dist as lsx_dist
+        import ctypes
+        from linalg_solver_b200 import _lib
+        k, bits = ctypes.c_int(), ctypes.c_double()
+        assert _lib.lib.lsx_det_large_prime_count(C5_N, C5_ABS, ctypes.byref(k), ctypes.byref(bits)) == 0
+        n_primes = c5_prime_count_numpy()
+        return {"workload": C5_DESC, "primes": n_primes, "primes_worst_case_bound": k.value,
+                "bound": "Hadamard with the actual row/column norms of the matrix",
+                "primes_per_gpu": lsx_dist.shard_sizes(n_primes, world)[0],
+                "sharding": "by prime, one all-gather of %d residues (%d B) before the CRT" % (n_primes, 4 * n_primes),
+                "all_gather_bytes": 4 * n_primes,
+                "l2": "residue matrices of one prime group (64 MiB per prime) far exceed the 126 MB L2"}
+    desc, n, batch, alg_bytes = WORKLOADS[workload]
+    plan = plan_of(workload)
+    return {"workload": desc, "batch_per_gpu": batch, "primes": int(plan.n_primes), "limbs": int(plan.limbs),
+            "sharding": "by matrix, no collective",
+            "l2": "inputs+outputs per step (%.0f MB) vs the 126 MB L2" % ((alg_bytes * batch) / 1e6)}
 
 
 # ------------------------------------------------------------------------------------- CPU arm
@@ -127,30 +176,45 @@ def cpu_baseline(workload, per_core, seed):
                       "%d cores, %.1f s" % (len(sample), workload, seed, cores, dt)}, out
 
 
-def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    desc, n, batch, _ = WORKLOADS[args.workload]
-    per_core = CPU_PER_CORE[args.workload]
+def reference_line(workload, steps, warmup, gpus):
+    """One workload of the reference arm: the CPU implementation of the path on a bounded sample per step."""
+    desc, n, batch, _ = WORKLOADS[workload]
+    per_core = CPU_PER_CORE[workload]
     times = []
     cb = None
-    for i in range(args.warmup + args.steps):
-        cb, _ = cpu_baseline(args.workload, per_core, SEED + i)
-        if i >= args.warmup:
+    for i in range(warmup + steps):
+        cb, _ = cpu_baseline(workload, per_core, SEED + i)
+        if i >= warmup:
             times.append(cb["value"])
     val = statistics.mean(times)
     cb["value"] = val
-    line = {
-        "impl": "reference", "metric": METRIC[args.workload], "value": val, "unit": "matrices/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    ref = reference_unmodified(workload)
+    if ref is not None:
+        cb["reference_unmodified"] = ref
+    return {
+        "impl": "reference", "metric": METRIC[workload], "value": val, "unit": "matrices/s",
+        "n_gpus": gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": 1e3 * per_core * cb["cores"] / val, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "exact rationals (fractions.Fraction)", "data": "synthetic",
-        "config": {"workload": desc, "step": "bounded sample of the workload on the host CPU"},
+        "config": config_for(workload, gpus), "sample_per_step": "bounded sample of the workload on the host CPU",
         "cpu_baseline": cb,
         "e2e": {"value": val, "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    main_wl = args.workload
+    line = run_c5_reference_line(args.steps, args.warmup, args.gpus) if main_wl == "c5" else \
+        reference_line(main_wl, args.steps, args.warmup, args.gpus)
+    extras = [w for w in args.extra_list if w != main_wl]
+    if extras:
+        # one bounded pass each: the sub-records only have to place the CPU side of every config in the same run
+        line["workloads"] = {w: (run_c5_reference_line(1, 0, args.gpus) if w == "c5" else reference_line(w, 1, 0, args.gpus))
+                             for w in extras}
     print(json.dumps(line), flush=True)
 
 
@@ -334,14 +398,11 @@ class Job:
         data = make_inputs(n, batch, SEED + 1000 * ctx.rank, workload, device=dev)
         self.dev = {k: (v if hasattr(v, "is_cuda") else torch.from_numpy(v).to(dev)) for k, v in data.items()}
         self.host = {k: v.cpu().pin_memory() for k, v in self.dev.items()}
+        # declared magnitudes (rigorous for the generator above), the same plans config_for() reports
         if workload == "c1":
-            self.plans = (eng.plan_det(4, 5), eng.plan_rank(4, 4, 5), eng.plan_rref(4, 4, 3, 5, 5))
-        elif workload == "c3":
-            self.plans = (eng.plan_solve(16, 16, 250, int(self.dev["b"].abs().max().item()), 10, 6),)
-        elif workload == "c4ker":
-            self.plans = (eng.plan_solve(64, 64, int(self.dev["A"].abs().max().item()), 0, 48, 16),)
+            self.plans = (eng.plan_det(4, 5), eng.plan_rank(4, 4, 5), plan_of("c1"))
         else:
-            self.plans = (eng.plan_inverse(n, 5),)
+            self.plans = (plan_of(workload),)
         self.res = self.run(self.dev)                         # allocates the outputs; reused by every step
         self.host_out = None
 
@@ -529,9 +590,7 @@ def measure_batch(ctx, workload, steps, warmup, cpu):
         "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 (Montgomery words modulo 31-bit primes)",
         "data": "synthetic",
-        "config": {"workload": desc, "batch_per_gpu": batch, "primes": int(plan.n_primes), "limbs": int(plan.limbs),
-                   "sharding": "by matrix, no collective",
-                   "l2": "inputs+outputs per step (%.0f MB) vs the 126 MB L2" % ((alg_bytes * batch) / 1e6)},
+        "config": config_for(workload, world),
         "roofline": roof,
         "cpu_baseline": cpu,
         "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "matrices/s", "ms_per_step": e2e_ms,
@@ -642,13 +701,8 @@ def measure_c5(ctx, steps, warmup, cpu):
         "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32 residues modulo 31-bit primes; trailing update as u8 x u8 -> s32 tcgen05 MMA",
         "data": "synthetic",
-        "config": {"workload": C5_DESC, "primes": n_primes, "primes_worst_case_bound": worst_primes,
-                   "bound": "Hadamard with the actual row/column norms, log2 = %.1f" % bits,
-                   "primes_per_gpu": e - b, "limbs": limbs,
-                   "sharding": "by prime, one all-gather of %d residues (%d B) before the CRT" % (n_primes, 4 * n_primes),
-                   "all_gather_bytes": 4 * n_primes,
-                   "l2": "residue matrices of one prime group (64 MiB per prime) far exceed the 126 MB L2",
-                   "det_bits": int(abs(det)).bit_length(), "det_mod_1e9": int(det % 10**9)},
+        "config": config_for("c5", world),
+        "result": {"log2_bound": bits, "limbs": limbs, "det_bits": int(abs(det)).bit_length(), "det_mod_1e9": int(det % 10**9)},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": None, "kernel_ms": k_s * 1e3, "kernel": "lsx_tc::k_gemm_tc (depth-256 trailing updates)",
                      "kernel_share_of_step": k_s * 1e3 / ms_step,
@@ -701,7 +755,7 @@ def _ref_one(item):
     return isinstance(Matrix(rat).inverse(), Matrix.NoSolution)
 
 
-REF_UNITS_PER_CORE = {"c1": 64, "c2": 16, "c3": 2, "c4inv": 1, "c4ker": 0}
+REF_UNITS_PER_CORE = {"c1": 256, "c2": 64, "c3": 8, "c4inv": 4, "c4ker": 0}
 
 
 def reference_unmodified(workload):
@@ -767,27 +821,23 @@ def run_ours(args):
     ctx.close()
 
 
-def run_c5_reference(args):
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
-    from linalg_solver_b200 import _lib  # noqa: F401  (prime count comes from the same plan function)
-    import ctypes
-    k = ctypes.c_int(c5_prime_count_numpy())
+def run_c5_reference_line(steps, warmup, gpus):
+    k = c5_prime_count_numpy()
     vals = []
     cb = None
-    for i in range(args.warmup + args.steps):
-        cb = c5_cpu_baseline(k.value)
-        if i >= args.warmup:
+    for i in range(warmup + steps):
+        cb = c5_cpu_baseline(k)
+        if i >= warmup:
             vals.append(cb["value"])
     val = statistics.mean(vals)
     cb["value"] = val
-    print(json.dumps({
-        "impl": "reference", "metric": C5_METRIC, "value": val, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "strong",
+    return {
+        "impl": "reference", "metric": C5_METRIC, "value": val, "unit": "s", "n_gpus": gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "int64 residues modulo 31-bit primes (numpy)", "data": "synthetic",
-        "config": {"workload": C5_DESC, "primes": k.value, "step": "bounded sample on the host CPU, extrapolated"},
+        "config": config_for("c5", gpus), "sample_per_step": "bounded sample on the host CPU, extrapolated",
         "cpu_baseline": cb, "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}), flush=True)
+        "gpu_launches": 0}
 
 
 def main():
@@ -796,14 +846,25 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["c5"],
+                    help="headline workload of the line (default c2, with every other config as a sub-record)")
+    ap.add_argument("--extra", default=None,
+                    help="comma list of workloads reported as sub-records under `workloads`, or none "
+                         "(default: all other configs when --workload is not given, none otherwise)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.workload == "c5":
-        (run_c5_reference if args.impl == "reference" else run_c5)(args)
-    elif args.impl == "reference":
+    if args.extra is None:
+        args.extra_list = list(EXTRA_DEFAULT) if args.workload is None else []
+    else:
+        args.extra_list = [] if args.extra in ("", "none") else [w for w in args.extra.split(",") if w]
+        bad = [w for w in args.extra_list if w not in WORKLOADS and w != "c5"]
+        if bad:
+            ap.error("unknown workload(s) in --extra: %s" % ",".join(bad))
+    if args.workload is None:
+        args.workload = "c2"
+    if args.impl == "reference":
         run_reference_arm(args)
     else:
         run_ours(args)

@@ -204,6 +204,14 @@ int lsx_rref_trace_max_ops(int m, int n, int bar_col);
  */
 int lsx_rref_trace(lsx_ctx* ctx, const int32_t* A, int m, int n, int bar_col, int n_primes, int mem,
                    int32_t* ops, uint32_t* frames, int32_t* n_ops, int32_t* pivot_col);
+/*
+ * Same for a RATIONAL matrix A / D (row_reduce accepts any Fraction matrix, linalg.py:534-630): A holds the integer
+ * numerators over one common denominator D > 0 and den_residues[k] = D mod (k-th table prime) ([n_primes], in `mem`;
+ * NULL means D = 1).  The replay runs on the residues of A / D, so "pivot is 1" is tested on the rational entry as
+ * the reference does.  A prime that divides D reports n_ops[k] = -1 and is to be dropped by the caller.
+ */
+int lsx_rref_trace_q(lsx_ctx* ctx, const int32_t* A, const uint32_t* den_residues, int m, int n, int bar_col,
+                     int n_primes, int mem, int32_t* ops, uint32_t* frames, int32_t* n_ops, int32_t* pivot_col);
 
 /* ---- one large determinant, shardable by prime ------------------------------------------ */
 /* Number of primes the determinant of an n x n matrix with |entries| <= a_abs_max needs. */

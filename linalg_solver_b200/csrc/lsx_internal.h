@@ -101,7 +101,7 @@ LSX_HD uint32_t mont_fma2(uint32_t x, uint32_t a, uint32_t y, uint32_t b, uint32
 }
 LSX_HD uint32_t mont_pow(uint32_t a, uint32_t e, uint32_t one, uint32_t p, uint32_t pinv) {
     uint32_t acc = one;
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
     for (int bit = 31; bit >= 0; --bit) {

@@ -16,6 +16,7 @@ constexpr int TR_MAX_CELLS = 4096;     // m * n words of shared memory
 struct TraceArgs {
     const int32_t* A;        // [m][n]
     const PrimeRec* primes;  // [K]
+    const uint32_t* den;     // [K] residues of the common denominator of the input (NULL: 1)
     int m, n, bar, max_ops;
     int32_t* ops;            // [K][max_ops][4]: kind (1 S, 2 N, 3 E below, 4 E above), a, b, 0
     uint32_t* frames;        // [K][max_ops][m][n] plain residues after each op
@@ -43,7 +44,15 @@ __global__ void __launch_bounds__(TR_THREADS) k_rref_trace(TraceArgs a) {
     const int slots = m < bar ? m : bar;
     int32_t* ops = a.ops + (int64_t)k * a.max_ops * 4;
     uint32_t* frames = a.frames + (int64_t)k * a.max_ops * m * n;
-    for (int e = tid; e < m * n; e += TR_THREADS) W[e] = word_of_int_any(a.A[e], p);
+    // rational input: the matrix is A / D with one common denominator D; its residues are A * D^-1.  A prime that
+    // divides D cannot represent the matrix: it reports n_ops = -1 and the host drops it.
+    const uint32_t dres = a.den ? a.den[k] % p : 1u;
+    if (dres == 0u) {
+        if (tid == 0) a.n_ops[k] = -1;
+        return;
+    }
+    const uint32_t dinv = dres == 1u ? 1u : invmod(dres, p);
+    for (int e = tid; e < m * n; e += TR_THREADS) W[e] = mulmod(word_of_int_any(a.A[e], p), dinv, p);
     for (int e = tid; e < slots; e += TR_THREADS) a.pivot_col[(int64_t)k * slots + e] = -1;
     __syncthreads();
     int step = 0;
@@ -148,8 +157,8 @@ int lsx_rref_trace_max_ops(int m, int n, int bar_col) {
     return 4 * r;          // per pivot at most S, N, E below and, in the backward sweep, E above
 }
 
-int lsx_rref_trace(lsx_ctx* ctx, const int32_t* A, int m, int n, int bar_col, int n_primes, int mem, int32_t* ops,
-                   uint32_t* frames, int32_t* n_ops, int32_t* pivot_col) {
+int lsx_rref_trace_q(lsx_ctx* ctx, const int32_t* A, const uint32_t* den_residues, int m, int n, int bar_col,
+                     int n_primes, int mem, int32_t* ops, uint32_t* frames, int32_t* n_ops, int32_t* pivot_col) {
     if (!ctx) return LSX_ERR_NULL;
     if (!A || !ops || !frames || !n_ops || !pivot_col) return lsx_fail(ctx, LSX_ERR_NULL, "rref_trace: NULL buffer");
     if (m < 1 || n < 1 || bar_col < 1 || bar_col > n || (int64_t)m * n > TR_MAX_CELLS || m > 4096)
@@ -164,14 +173,14 @@ int lsx_rref_trace(lsx_ctx* ctx, const int32_t* A, int m, int n, int bar_col, in
     t.primes = ctx->d_primes;
     t.m = m, t.n = n, t.bar = bar_col, t.max_ops = max_ops;
     if (mem == LSX_MEM_DEVICE) {
-        t.A = A, t.ops = ops, t.frames = frames, t.n_ops = n_ops, t.pivot_col = pivot_col;
+        t.A = A, t.den = den_residues, t.ops = ops, t.frames = frames, t.n_ops = n_ops, t.pivot_col = pivot_col;
         k_rref_trace<<<n_primes, TR_THREADS, 0, ctx->stream>>>(t);
         ctx->launches++;
         LSX_CUDA_TRY(ctx, cudaGetLastError());
         return LSX_OK;
     }
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
-    int rc = lsx_ws_reserve(ctx, up(b_a) + up(b_ops) + up(b_fr) + up(b_n) + up(b_pc));
+    int rc = lsx_ws_reserve(ctx, up(b_a) + up(b_ops) + up(b_fr) + up(b_n) + up(b_pc) + up(b_n));
     if (rc != LSX_OK) return rc;
     char* base = (char*)ctx->d_ws;
     int32_t* dA = (int32_t*)base;
@@ -180,7 +189,12 @@ int lsx_rref_trace(lsx_ctx* ctx, const int32_t* A, int m, int n, int bar_col, in
     t.frames = (uint32_t*)(base + up(b_a) + up(b_ops));
     t.n_ops = (int32_t*)(base + up(b_a) + up(b_ops) + up(b_fr));
     t.pivot_col = (int32_t*)(base + up(b_a) + up(b_ops) + up(b_fr) + up(b_n));
+    uint32_t* d_den = (uint32_t*)(base + up(b_a) + up(b_ops) + up(b_fr) + up(b_n) + up(b_pc));
     LSX_CUDA_TRY(ctx, cudaMemcpyAsync(dA, A, b_a, cudaMemcpyHostToDevice, ctx->stream));
+    if (den_residues) {
+        LSX_CUDA_TRY(ctx, cudaMemcpyAsync(d_den, den_residues, b_n, cudaMemcpyHostToDevice, ctx->stream));
+        t.den = d_den;
+    }
     LSX_CUDA_TRY(ctx, cudaMemsetAsync(t.ops, 0, b_ops, ctx->stream));
     k_rref_trace<<<n_primes, TR_THREADS, 0, ctx->stream>>>(t);
     ctx->launches++;
@@ -191,6 +205,11 @@ int lsx_rref_trace(lsx_ctx* ctx, const int32_t* A, int m, int n, int bar_col, in
     LSX_CUDA_TRY(ctx, cudaMemcpyAsync(pivot_col, t.pivot_col, b_pc, cudaMemcpyDeviceToHost, ctx->stream));
     LSX_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return LSX_OK;
+}
+
+int lsx_rref_trace(lsx_ctx* ctx, const int32_t* A, int m, int n, int bar_col, int n_primes, int mem, int32_t* ops,
+                   uint32_t* frames, int32_t* n_ops, int32_t* pivot_col) {
+    return lsx_rref_trace_q(ctx, A, nullptr, m, n, bar_col, n_primes, mem, ops, frames, n_ops, pivot_col);
 }
 
 }  // extern "C"

@@ -350,17 +350,21 @@ class Engine:
         return SolveResult(den, part, gens, piv, rank, status, plan)
 
     # ---- step trace of row_reduce (reference linalg.py:544-629) -----------------------------
-    def rref_trace(self, A, bar_col):
-        """Steps and exact intermediate matrices of ``row_reduce`` for ONE small integer matrix.
+    def rref_trace(self, A, bar_col, den=1):
+        """Steps and exact intermediate matrices of ``row_reduce`` for ONE small rational matrix ``A / den``.
 
+        ``A`` holds integer numerators, ``den`` their common denominator (1 for an integer matrix).
         Returns ``(frames, ops, pivots)``: ``ops`` is the list of ``(kind, a, b)`` the reference records (1 = S swap
         of rows a and b, 2 = N normalisation of row a, 3 / 4 = E elimination below / above the pivot of column a),
         ``frames[t]`` the matrix (rows of ``Fraction``) after ``ops[t]``, ``pivots`` the (row, column) list.  The
-        device replays the reference's operation order modulo K primes (``lsx_rref_trace``); K follows from twice
-        the Hadamard bound of the minors (every intermediate entry is a quotient of two of them) plus one check
-        prime, the logs of all primes must agree, and the residues are lifted by CRT + rational reconstruction.
+        device replays the reference's operation order modulo table primes (``lsx_rref_trace_q``); K follows from
+        twice the Hadamard bound of the minors (every intermediate entry is a quotient of two of them) plus one check
+        prime.  Primes whose log differs from the majority's (a prime dividing an intermediate value, a lead that is
+        1 only modulo p, a prime dividing ``den``) are dropped and replaced by further table primes; the residues of
+        the agreeing primes are lifted by CRT + rational reconstruction.
         """
         import math
+        from collections import Counter
         from .convert import crt_basis, rational_reconstruct
         A = np.ascontiguousarray(np.asarray(A, dtype=np.int64))
         if A.ndim != 2:
@@ -368,7 +372,10 @@ class Engine:
         m, n = A.shape
         if A.size and np.abs(A).max() > 2**31 - 1:
             raise OverflowError("A has entries outside int32")
-        amax = max(1, int(np.abs(A).max()) if A.size else 1)
+        den = int(den)
+        if den < 1:
+            raise ValueError("den must be a positive integer")
+        amax = max(1, int(np.abs(A).max()) if A.size else 1, den)
         r = min(m, n)
         log2h = r * (0.5 * math.log2(r) + math.log2(amax)) if r else 0.0          # Hadamard bound of any minor
         max_ops = lib.lsx_rref_trace_max_ops(m, n, bar_col)
@@ -381,31 +388,48 @@ class Engine:
         # size of an intermediate entry is not bounded by one Hadamard bound: start from 2 H^2 < M and double the
         # prime count until every entry reconstructs AND agrees with one more prime that took no part in the lift.
         K = int(math.ceil((2.0 * log2h + 2.0) / 30.99)) + 1
+        spare = 0
         while True:
-            Kc = K + 1                                            # the last prime only checks
-            ops = np.zeros((Kc, max_ops, 4), dtype=np.int32)
-            frames = np.zeros((Kc, max_ops, m, n), dtype=np.uint32)
-            n_ops = np.zeros(Kc, dtype=np.int32)
-            piv = np.zeros((Kc, slots), dtype=np.int32)
-            self._check(lib.lsx_rref_trace(self._ctx, a32.ctypes.data, m, n, bar_col, Kc, _lib.MEM_HOST, ops.ctypes.data,
-                                           frames.ctypes.data, n_ops.ctypes.data, piv.ctypes.data))
-            T = int(n_ops[0])
-            if not (np.all(n_ops == T) and np.all(ops[:, :T] == ops[0, :T]) and np.all(piv == piv[0])):
-                raise RuntimeError("liblsx: the primes disagree on the step log (a prime divides an intermediate value)")
-            primes = [int(p) for p in self.primes(Kc)]
-            M, coef = crt_basis(primes[:K])
+            n_req = K + 1 + spare                                  # K lift primes, one check prime, replacements
+            if n_req > _lib.TABLE_PRIMES:
+                raise RuntimeError("liblsx: the step trace ran out of table primes")
+            primes_all = [int(p) for p in self.primes(n_req)]
+            dres = np.array([den % p for p in primes_all], dtype=np.uint32)
+            ops = np.zeros((n_req, max_ops, 4), dtype=np.int32)
+            frames = np.zeros((n_req, max_ops, m, n), dtype=np.uint32)
+            n_ops = np.zeros(n_req, dtype=np.int32)
+            piv = np.zeros((n_req, slots), dtype=np.int32)
+            self._check(lib.lsx_rref_trace_q(self._ctx, a32.ctypes.data, dres.ctypes.data if den != 1 else None, m, n,
+                                             bar_col, n_req, _lib.MEM_HOST, ops.ctypes.data, frames.ctypes.data,
+                                             n_ops.ctypes.data, piv.ctypes.data))
+            # the rational log is the majority's: a bad prime deviates on its own, good primes all agree
+            keys = [None if n_ops[k] < 0 else (int(n_ops[k]), ops[k, :max(0, int(n_ops[k]))].tobytes(), piv[k].tobytes())
+                    for k in range(n_req)]
+            votes = Counter(k for k in keys if k is not None)
+            if not votes:
+                spare = max(2, 2 * spare)
+                continue
+            best, cnt = votes.most_common(1)[0]
+            good = [k for k in range(n_req) if keys[k] == best]
+            if cnt < K + 1 or cnt * 2 <= len([k for k in keys if k is not None]):
+                spare = max(2, 2 * spare)
+                continue
+            lift, chk = good[:K], good[K]
+            T = int(n_ops[lift[0]])
+            primes = [primes_all[k] for k in lift]
+            M, coef = crt_basis(primes)
             bound = math.isqrt((M - 1) // 2)
-            pc = primes[K]
+            pc = primes_all[chk]
             out, ok = [], True
             for t in range(T):
                 grid = []
                 for i in range(m):
                     row = []
                     for j in range(n):
-                        x = sum(int(frames[k, t, i, j]) * coef[k] for k in range(K)) % M
+                        x = sum(int(frames[k, t, i, j]) * c for k, c in zip(lift, coef)) % M
                         v = rational_reconstruct(x, M, bound)
                         if v is None or v.denominator % pc == 0 or \
-                                (v.numerator * pow(v.denominator, pc - 2, pc) - int(frames[K, t, i, j])) % pc != 0:
+                                (v.numerator * pow(v.denominator, pc - 2, pc) - int(frames[chk, t, i, j])) % pc != 0:
                             ok = False
                             break
                         row.append(v)
@@ -420,8 +444,9 @@ class Engine:
             if K > 256:
                 raise RuntimeError("liblsx: rational reconstruction of the step trace did not converge")
             K *= 2
-        pivots = [(k, int(piv[0, k])) for k in range(slots) if piv[0, k] >= 0]
-        return out, [tuple(int(x) for x in ops[0, t, :3]) for t in range(T)], pivots
+        p0 = piv[lift[0]]
+        pivots = [(k, int(p0[k])) for k in range(slots) if p0[k] >= 0]
+        return out, [tuple(int(x) for x in ops[lift[0], t, :3]) for t in range(T)], pivots
 
     # ---- one large determinant, by prime ----------------------------------------------------
     @staticmethod

@@ -244,11 +244,10 @@ class Matrix:
         return out, pivots, [], []
 
     def _row_reduce_trace(self, bar, kind):
-        grid, D = _to_int_grid(self.items)                       # grid = D * A: the same row operations, frames / D
-        frames, ops, pivots = default_engine().rref_trace(grid, bar)
-        # the input scaled by D has the same steps except that "pivot == 1" is "pivot == D": only D == 1 is served
-        if D != 1:
-            raise TypeError("row_reduce(trace=True) takes integer entries")
+        # rational entries: integer numerators over the common denominator D; the device replays the steps on the
+        # residues of grid / D, so "pivot == 1" is tested on the rational entry as the reference does (linalg.py:570)
+        grid, D = _to_int_grid(self.items)
+        frames, ops, pivots = default_engine().rref_trace(grid, bar, den=D)
         wrap = lambda f: [[_wrap(kind, x.numerator, x.denominator) for x in row] for row in f]
         start = [[_wrap(kind, *_pq_of(x)) for x in row] for row in self.items]
         mats = [start] + [wrap(f) for f in frames]
