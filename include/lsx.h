@@ -187,6 +187,18 @@ int lsx_solve_batch(lsx_ctx* ctx, const lsx_plan* plan, const int32_t* A, const 
                     uint32_t* generators, int32_t* pivot_col, int32_t* rank,
                     int32_t* status);
 
+/* ---- lowest terms ------------------------------------------------------------------------------------------ */
+/*
+ * The batched operations return numerators over ONE common denominator per matrix; the reference returns reduced
+ * rationals (true division on Rational entries, linalg.py:574; sympy.Matrix.inv(), linalg.py:698-699).  This call
+ * reduces on the device: for every matrix b and entry i < count
+ *   p[b][i] / q[b][i] = num[b][i] / den[b],  gcd(p, q) = 1,  q > 0      (binary gcd + exact division, multi-limb)
+ *   num [batch][count][limbs], den [batch][limbs]  ->  p, q [batch][count][limbs]   (two's complement words)
+ * num == 0 gives 0 / 1; den == 0 (a matrix flagged singular / inconsistent) gives 0 / 0.  limbs <= 32.
+ */
+int lsx_lowest_terms(lsx_ctx* ctx, const uint32_t* num, const uint32_t* den, int64_t batch, int count,
+                     int limbs, int mem, uint32_t* p, uint32_t* q);
+
 /* ---- step trace of row_reduce (reference linalg.py:544-629: intermediate_matrices / intermediate_steps) ------ */
 /* Upper bound on the number of recorded steps: per pivot S, N, E (below) and E (above). */
 int lsx_rref_trace_max_ops(int m, int n, int bar_col);
@@ -232,6 +244,14 @@ int lsx_det_large_prime_count_for(lsx_ctx* ctx, const int32_t* A, int n, int mem
 int lsx_det_large_residues(lsx_ctx* ctx, const int32_t* A, int n, int prime_begin,
                            int prime_count, int mem, uint32_t* residues,
                            uint32_t* primes_out);
+/*
+ * rank of ONE m x n int32 matrix of any size that fits device memory (reference rank(), linalg.py:745-747, has no
+ * size limit; lsx_rank_batch keeps one residue tile per CTA, m <= 254).  Fraction-free elimination in global memory
+ * modulo groups of table primes; the answer is the largest rank seen, which is the rank over Q once the primes'
+ * product exceeds the Hadamard bound of the minors (full rank modulo one prime ends the loop early).
+ * A follows `mem`; rank and primes_used (may be NULL: how many primes were run) are HOST pointers.
+ */
+int lsx_rank_large(lsx_ctx* ctx, const int32_t* A, int m, int n, int mem, int32_t* rank, int32_t* primes_used);
 /*
  * CRT of `count` residues (for table primes [0, count)) to a signed integer of `limbs`
  * words (two's complement, little endian).  residues/out follow `mem`.

@@ -68,12 +68,14 @@ SIGNATURES = {
     "lsx_det_batch": (_i, [_vp, _pp, _vp, _i64, _i, _vp, _vp, _vp]),
     "lsx_rank_batch": (_i, [_vp, _pp, _vp, _i64, _i, _vp, _vp]),
     "lsx_solve_batch": (_i, [_vp, _pp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lsx_lowest_terms": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "lsx_rref_trace_max_ops": (_i, [_i, _i, _i]),
     "lsx_rref_trace": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "lsx_rref_trace_q": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "lsx_det_large_prime_count": (_i, [_i, _i64, ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_double)]),
     "lsx_det_large_prime_count_for": (_i, [_vp, _vp, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_double)]),
     "lsx_det_large_residues": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "lsx_rank_large": (_i, [_vp, _vp, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "lsx_crt_signed": (_i, [_vp, _vp, _i, _i, _i, _vp]),
 }
 

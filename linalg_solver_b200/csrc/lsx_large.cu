@@ -124,6 +124,102 @@ __global__ void k_sq_norms(const int32_t* __restrict__ A, int n, double* __restr
     }
 }
 
+// ---- rank of one matrix of any size: fraction-free elimination in global memory -----------------------------
+// The batched rank keeps one residue tile per CTA in shared memory (m <= 254).  Beyond that the reference's rank()
+// (linalg.py:745-747) still has to have an answer, so this is the plain route: G primes side by side in HBM
+// ([G][m][n] words), per column one launch that finds each prime's first non-zero row at or below its pivot
+// count (rows are exchanged through a permutation, not physically) and one launch that applies
+// row <- piv * row - f * pivot_row to the rows below on the columns right of the pivot.  Montgomery's R^-1 per
+// update scales whole rows and does not change which entries are zero.  rank over Q = max over primes of the rank
+// modulo p as soon as the primes' product exceeds the Hadamard bound of the minors (a non-zero minor cannot vanish
+// modulo all of them); full rank modulo ONE prime already proves full rank, which ends the loop early.
+__global__ void k_rl_absmax(const int32_t* __restrict__ A, int64_t count, unsigned int* out) {
+    unsigned int m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = A[i];
+        const unsigned int a = v < 0 ? 0u - (unsigned int)v : (unsigned int)v;
+        m = a > m ? a : m;
+    }
+    for (int o = 16; o; o >>= 1) {
+        const unsigned int t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+__global__ void k_rl_load(const int32_t* __restrict__ A, int64_t cells, int m, const PrimeRec* primes, int prime0,
+                          uint32_t* __restrict__ W, int32_t* __restrict__ perm, int32_t* __restrict__ npiv) {
+    const int g = blockIdx.y;
+    const uint32_t p = primes[prime0 + g].p;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x)
+        W[(int64_t)g * cells + i] = word_of_int_any(A[i], p);
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < m; i += blockDim.x) perm[(int64_t)g * m + i] = i;
+        if (threadIdx.x == 0) npiv[g] = 0;
+    }
+}
+
+// one CTA per prime: first row (in permuted order) at or below the pivot count with a non-zero entry in column c
+__global__ void __launch_bounds__(256) k_rl_pivot(const uint32_t* __restrict__ W, int m, int n, int c, int32_t* perm,
+                                                   const int32_t* __restrict__ npiv, int32_t* __restrict__ pinfo) {
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const int r = npiv[g];
+    __shared__ int s_min;
+    if (tid == 0) s_min = INT32_MAX;
+    __syncthreads();
+    int32_t* pm = perm + (int64_t)g * m;
+    const uint32_t* Wg = W + (int64_t)g * m * n;
+    if (r < m) {
+        int best = INT32_MAX;
+        for (int i = r + tid; i < m; i += 256)
+            if (Wg[(int64_t)pm[i] * n + c] != 0u) {
+                best = i;
+                break;                                        // this thread's rows ascend: its first hit is its minimum
+            }
+        if (best != INT32_MAX) atomicMin(&s_min, best);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int src = s_min;
+        if (src == INT32_MAX) {
+            pinfo[2 * g] = -1;                                // no pivot in this column (or the prime is done)
+        } else {
+            const int32_t a = pm[r], b = pm[src];
+            pm[r] = b;
+            pm[src] = a;
+            pinfo[2 * g] = b;                                 // physical pivot row
+            pinfo[2 * g + 1] = r;                             // its position
+        }
+    }
+}
+
+// rows below the pivot: row <- piv * row - f * pivot_row on the columns right of c
+__global__ void __launch_bounds__(256) k_rl_elim(uint32_t* __restrict__ W, int m, int n, int c,
+                                                  const int32_t* __restrict__ perm, int32_t* __restrict__ npiv,
+                                                  const int32_t* __restrict__ pinfo, const PrimeRec* primes, int prime0) {
+    const int g = blockIdx.y;
+    const int prow = pinfo[2 * g];
+    if (prow < 0) return;
+    const int r = pinfo[2 * g + 1];
+    const PrimeRec P = primes[prime0 + g];
+    uint32_t* Wg = W + (int64_t)g * m * n;
+    const uint32_t* pr = Wg + (int64_t)prow * n;
+    const uint32_t piv = pr[c];
+    const int32_t* pm = perm + (int64_t)g * m;
+    // the rows below position r are split over the blocks of the x dimension, one warp per row at a time
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    for (int i = r + 1 + blockIdx.x * warps + warp; i < m; i += gridDim.x * warps) {
+        uint32_t* row = Wg + (int64_t)pm[i] * n;
+        const uint32_t f = row[c];
+        if (f == 0u) continue;
+        const uint32_t y = P.p - f;
+        for (int j = c + 1 + lane; j < n; j += 32) row[j] = mont_fma2(piv, row[j], y, pr[j], P.p, P.pinv);
+        __syncwarp();
+        if (lane == 0) row[c] = 0u;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) npiv[g] = r + 1;
+}
+
 }  // namespace
 
 extern "C" {
@@ -222,6 +318,70 @@ int lsx_det_large_residues(lsx_ctx* ctx, const int32_t* A, int n, int prime_begi
         cudaFree(stage);
     }
     return rc;
+}
+
+int lsx_rank_large(lsx_ctx* ctx, const int32_t* A, int m, int n, int mem, int32_t* rank, int32_t* primes_used) {
+    if (!ctx) return LSX_ERR_NULL;
+    if (!A || !rank) return lsx_fail(ctx, LSX_ERR_NULL, "rank_large: NULL buffer");
+    if (m < 1 || n < 1) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "rank_large: bad shape %d x %d", m, n);
+    if (mem != LSX_MEM_HOST && mem != LSX_MEM_DEVICE) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "bad mem flag %d", mem);
+    LSX_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t cells = (int64_t)m * n;
+    const int full = m < n ? m : n;
+    // group size: about 2 GiB of residues, at least one prime
+    int G = (int)std::max<int64_t>(1, std::min<int64_t>(32, ((int64_t)2 << 30) / (cells * 4)));
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t b_a = up((size_t)cells * 4), b_w = up((size_t)G * cells * 4), b_perm = up((size_t)G * m * 4),
+                 b_small = up((size_t)G * 16 + 64);
+    int rc = lsx_ws_reserve(ctx, b_a + b_w + b_perm + b_small);
+    if (rc != LSX_OK) return rc;
+    char* base = (char*)ctx->d_ws;
+    const int32_t* dA = A;
+    if (mem == LSX_MEM_HOST) {
+        LSX_CUDA_TRY(ctx, cudaMemcpyAsync(base, A, (size_t)cells * 4, cudaMemcpyHostToDevice, ctx->stream));
+        dA = (const int32_t*)base;
+    }
+    uint32_t* W = (uint32_t*)(base + b_a);
+    int32_t* perm = (int32_t*)(base + b_a + b_w);
+    int32_t* npiv = (int32_t*)(base + b_a + b_w + b_perm);
+    int32_t* pinfo = npiv + G;
+    unsigned int* d_amax = (unsigned int*)(pinfo + 2 * G);
+    // declared magnitude = the actual one; the prime count for a rigorous answer follows from the Hadamard bound
+    LSX_CUDA_TRY(ctx, cudaMemsetAsync(d_amax, 0, 4, ctx->stream));
+    k_rl_absmax<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dA, cells, d_amax);
+    ctx->launches++;
+    unsigned int amax = 0;
+    LSX_CUDA_TRY(ctx, cudaMemcpyAsync(&amax, d_amax, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LSX_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    int best = 0, used = 0;
+    if (amax != 0) {
+        const double bits = lsx_log2_minor_bound(m, n, false, (int64_t)amax, 0, false, full);
+        int K, L;
+        lsx_bits_to_plan(bits, &K, &L);
+        if (K > LSX_TABLE_PRIMES) return lsx_fail(ctx, LSX_ERR_BOUND, "rank_large: the bound needs %d primes", K);
+        std::vector<int32_t> h_npiv(G);
+        const int steps = n;
+        const unsigned row_blocks = (unsigned)std::max(1, std::min(ctx->sm_count * 2, (m + 7) / 8));
+        for (int p0 = 0; p0 < K && best < full; p0 += G) {
+            const int g = std::min(G, K - p0);
+            k_rl_load<<<dim3((unsigned)std::min<int64_t>(1024, (cells + 255) / 256), g), 256, 0, ctx->stream>>>(
+                dA, cells, m, ctx->d_primes, p0, W, perm, npiv);
+            ctx->launches++;
+            for (int c = 0; c < steps; ++c) {
+                k_rl_pivot<<<g, 256, 0, ctx->stream>>>(W, m, n, c, perm, npiv, pinfo);
+                k_rl_elim<<<dim3(row_blocks, g), 256, 0, ctx->stream>>>(W, m, n, c, perm, npiv, pinfo, ctx->d_primes, p0);
+                ctx->launches += 2;
+            }
+            LSX_CUDA_TRY(ctx, cudaGetLastError());
+            LSX_CUDA_TRY(ctx, cudaMemcpyAsync(h_npiv.data(), npiv, (size_t)g * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            LSX_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int i = 0; i < g; ++i) best = std::max(best, (int)h_npiv[i]);
+            used += g;
+        }
+    }
+    *rank = best;
+    if (primes_used) *primes_used = used;
+    return LSX_OK;
 }
 
 int lsx_crt_signed(lsx_ctx* ctx, const uint32_t* residues, int count, int limbs, int mem, uint32_t* out) {

@@ -206,31 +206,45 @@ class Engine:
         return int(np.abs(x.astype(np.int64)).max()) if x.size else 0
 
     # ---- plans ----------------------------------------------------------------------------
+    @staticmethod
+    def _check_plan(rc, what):
+        """lsx_plan_* take no ctx, so lsx_last_error has nothing to say about them: explain the code here."""
+        if rc == _lib.OK:
+            return
+        why = {
+            _lib.ERR_BAD_SHAPE: "invalid dimensions, bar_col or magnitudes",
+            _lib.ERR_UNSUPPORTED: "more than 254 rows: the batched kernels keep one residue tile per CTA "
+                                  "(a single large determinant goes through det_large_residues / Matrix.determinant)",
+            _lib.ERR_BOUND: "the Hadamard bound of the declared magnitudes needs more than 32 primes per matrix, the "
+                            "limit of the batched kernels",
+        }.get(rc, "plan query failed")
+        raise LsxError(rc, "%s: %s" % (what, why))
+
     def plan_rref(self, m, n, bar_col, a_abs_max, b_abs_max=None, max_rank=0) -> Plan:
         p = Plan()
-        self._check(lib.lsx_plan_rref(m, n, bar_col, a_abs_max, a_abs_max if b_abs_max is None else b_abs_max,
-                                      max_rank, ctypes.byref(p)))
+        self._check_plan(lib.lsx_plan_rref(m, n, bar_col, a_abs_max, a_abs_max if b_abs_max is None else b_abs_max,
+                                      max_rank, ctypes.byref(p)), "plan_rref(m=%d, n=%d, bar_col=%d)" % (m, n, bar_col))
         return p
 
     def plan_inverse(self, n, a_abs_max) -> Plan:
         p = Plan()
-        self._check(lib.lsx_plan_inverse(n, a_abs_max, ctypes.byref(p)))
+        self._check_plan(lib.lsx_plan_inverse(n, a_abs_max, ctypes.byref(p)), "plan_inverse(n=%d)" % n)
         return p
 
     def plan_det(self, n, a_abs_max) -> Plan:
         p = Plan()
-        self._check(lib.lsx_plan_det(n, a_abs_max, ctypes.byref(p)))
+        self._check_plan(lib.lsx_plan_det(n, a_abs_max, ctypes.byref(p)), "plan_det(n=%d)" % n)
         return p
 
     def plan_rank(self, m, n, a_abs_max) -> Plan:
         p = Plan()
-        self._check(lib.lsx_plan_rank(m, n, a_abs_max, ctypes.byref(p)))
+        self._check_plan(lib.lsx_plan_rank(m, n, a_abs_max, ctypes.byref(p)), "plan_rank(m=%d, n=%d)" % (m, n))
         return p
 
     def plan_solve(self, m, n, a_abs_max, b_abs_max, max_rank=0, gen_cap=None) -> Plan:
         p = Plan()
-        self._check(lib.lsx_plan_solve(m, n, a_abs_max, b_abs_max, max_rank, n if gen_cap is None else gen_cap,
-                                       ctypes.byref(p)))
+        self._check_plan(lib.lsx_plan_solve(m, n, a_abs_max, b_abs_max, max_rank, n if gen_cap is None else gen_cap,
+                                       ctypes.byref(p)), "plan_solve(m=%d, n=%d)" % (m, n))
         return p
 
     # ---- batched operations ---------------------------------------------------------------
@@ -348,6 +362,41 @@ class Engine:
         self._check(lib.lsx_solve_batch(self._ctx, ctypes.byref(plan), pA, pb, B, mem, self._ptr(den), self._ptr(part),
                                         self._ptr(gens), self._ptr(piv), self._ptr(rank), self._ptr(status)))
         return SolveResult(den, part, gens, piv, rank, status, plan)
+
+    # ---- lowest terms (reference results are reduced rationals: linalg.py:574, 698-699) ------
+    def lowest_terms(self, num, den):
+        """``num[b, ..., L] / den[b, L]`` -> ``(p, q)`` of the same shape as ``num`` with ``gcd(p, q) = 1`` and
+        ``q > 0`` for every entry, computed on the device (multi-limb binary gcd + exact division).  ``num == 0``
+        gives ``0 / 1``; a zero denominator (matrix flagged singular / inconsistent) gives ``0 / 0``."""
+        if _is_torch(num):
+            if not _is_torch(den) or num.is_cuda != den.is_cuda:
+                raise ValueError("num and den must live in the same memory space")
+            num, den = num.contiguous(), den.contiguous()
+            mem = _lib.MEM_DEVICE if num.is_cuda else _lib.MEM_HOST
+            like = num if num.is_cuda else None
+            if num.is_cuda:
+                import torch
+                self.set_stream(torch.cuda.current_stream(num.device).cuda_stream or 1)
+            else:
+                num, den = num.numpy(), den.numpy()
+                self.set_stream(None)
+        else:
+            num = np.ascontiguousarray(num)
+            den = np.ascontiguousarray(den)
+            mem, like = _lib.MEM_HOST, None
+            self.set_stream(None)
+        shape = tuple(num.shape)
+        B, L = shape[0], shape[-1]
+        if tuple(den.shape) != (B, L):
+            raise ValueError("den must have shape [batch, limbs] matching num")
+        count = 1
+        for s_ in shape[1:-1]:
+            count *= s_
+        p = self._alloc(like, shape, np.uint32)
+        q = self._alloc(like, shape, np.uint32)
+        self._check(lib.lsx_lowest_terms(self._ctx, self._ptr(num), self._ptr(den), B, count, L, mem, self._ptr(p),
+                                         self._ptr(q)))
+        return p, q
 
     # ---- step trace of row_reduce (reference linalg.py:544-629) -----------------------------
     def rref_trace(self, A, bar_col, den=1):
@@ -479,6 +528,15 @@ class Engine:
         res = self._alloc(like, (prime_count,), np.uint32)
         self._check(lib.lsx_det_large_residues(self._ctx, pA, n, prime_begin, prime_count, mem, self._ptr(res), None))
         return res
+
+    def rank_large(self, A):
+        """Rank of ONE integer matrix of any size that fits device memory (``lsx_rank_large``: the batched rank keeps
+        a tile per CTA, m <= 254).  Returns ``(rank, primes_used)``."""
+        A, pA, mem, _ = self._prep_in(A, 2, "A")
+        m, n = A.shape
+        rank, used = ctypes.c_int(), ctypes.c_int()
+        self._check(lib.lsx_rank_large(self._ctx, pA, m, n, mem, ctypes.byref(rank), ctypes.byref(used)))
+        return rank.value, used.value
 
     def crt_signed(self, residues, limbs):
         """Residues for table primes [0, len) -> signed integer as `limbs` 32-bit words."""

@@ -84,6 +84,18 @@ def _to_int_grid(rows):
     return np.array(grid, dtype=np.int32).reshape(len(rows), len(rows[0]) if rows else 0), D
 
 
+def _lowest(num_words, den_words):
+    """Numerators ``[..., L]`` over one denominator ``[L]`` (packed device results) -> nested lists of lowest-terms
+    ``(p, q)`` pairs with ``q > 0``, reduced on the device (``lsx_lowest_terms``: the reference returns reduced
+    rationals, linalg.py:574, 698-699)."""
+    p, q = default_engine().lowest_terms(np.ascontiguousarray(num_words)[None], np.ascontiguousarray(den_words)[None])
+    P, Q = limbs_to_ints(p[0]), limbs_to_ints(q[0])
+
+    def pairs(a, b):
+        return [pairs(x, y) for x, y in zip(a, b)] if isinstance(a, list) else (a, b)
+    return pairs(P, Q)
+
+
 class Matrix:
     items: List[List[Any]]
 
@@ -232,10 +244,12 @@ class Matrix:
         amax = int(np.abs(grid.astype(np.int64)).max()) if grid.size else 0
         res = eng.rref_batch(grid[None], bar, a_abs_max=amax, b_abs_max=amax)
         _raise_on_status(int(res.status[0]))
-        num = limbs_to_ints(res.num[0])
-        den = limbs_to_ints(res.den[0])
         rank = int(res.rank[0])
         pivots = [(k, int(res.pivot_col[0][k])) for k in range(rank)]
+        if D == 1:                                              # integer input: lowest terms straight from the device
+            return [[_wrap(kind, p, q) for p, q in row] for row in _lowest(res.num[0], res.den[0])], pivots, [], []
+        num = limbs_to_ints(res.num[0])
+        den = limbs_to_ints(res.den[0])
         out = []
         for i in range(m):
             # rows that never became a pivot row keep the scale D of the cleared denominators
@@ -262,7 +276,15 @@ class Matrix:
         if self.cols == 0:
             return 0
         grid, _ = _to_int_grid(self.items)
-        res = default_engine().rank_batch(grid[None])
+        from .engine import LsxError
+        try:
+            res = default_engine().rank_batch(grid[None])
+        except LsxError as e:
+            if e.code not in (_lib.ERR_UNSUPPORTED, _lib.ERR_BOUND):
+                raise
+            # beyond the batched kernels (more than 254 rows, or entries that need more than 32 primes): the
+            # global-memory route has no size limit, only a time one -- like the reference's own rank()
+            return default_engine().rank_large(grid)[0]
         _raise_on_status(int(res.status[0]))
         return int(res.rank[0])
 
@@ -272,8 +294,8 @@ class Matrix:
         n = self.rows
         if n == 0:
             return 1
-        if n == 1 and self.cols == 1:
-            return self.items[0][0]
+        if n == 1:
+            return self.items[0][0]                               # the reference's shortcut for ANY one-row matrix (linalg.py:200)
         if self.rows != self.cols:
             raise ValueError("Determinant requires a square matrix")
         kind = _kind_of(self.items)
@@ -286,9 +308,19 @@ class Matrix:
             words, _ = det_large_sharded(default_engine(), grid, sharded=False)
             d = limbs_to_ints(np.asarray(words).reshape(1, -1))[0]
         else:
-            res = default_engine().det_batch(grid[None])
-            _raise_on_status(int(res.status[0]))
-            d = limbs_to_ints(res.det[0])
+            from .engine import LsxError
+            try:
+                res = default_engine().det_batch(grid[None])
+                _raise_on_status(int(res.status[0]))
+                d = limbs_to_ints(res.det[0])
+            except LsxError as e:
+                if e.code != _lib.ERR_BOUND:
+                    raise
+                # entries so large that the batched kernels' 32 primes do not cover the Hadamard bound: the by-prime
+                # route has the whole table (2048 primes)
+                from .dist import det_large_sharded
+                words, _ = det_large_sharded(default_engine(), grid, sharded=False)
+                d = limbs_to_ints(np.asarray(words).reshape(1, -1))[0]
         return _wrap(kind, *reduce_pq(d, D ** n))
 
     def inverse(self, log_matrices: bool = False, log_steps: bool = False, log_result: bool = False):
@@ -312,9 +344,11 @@ class Matrix:
         if st & _lib.ST_SINGULAR:
             return Matrix.NoSolution()
         _raise_on_status(st)
+        if D == 1:                                              # integer input: lowest terms straight from the device
+            return Matrix([[_wrap(kind, p, q) for p, q in row] for row in _lowest(res.adj[0], res.det[0])])
         adj = limbs_to_ints(res.adj[0])
         det = limbs_to_ints(res.det[0])
-        # (D A)^-1 = adj / det  =>  A^-1 = D adj / det
+        # (D A)^-1 = adj / det  =>  A^-1 = D adj / det  (fractional input: the extra factor D is folded in on the host)
         return Matrix([[_wrap(kind, *reduce_pq(D * adj[i][j], det)) for j in range(n)] for i in range(n)])
 
     def find_preimage_of(self, vec: List[Any], log_matrices: bool = False, log_steps: bool = False,
@@ -339,18 +373,15 @@ class Matrix:
         if st & _lib.ST_INCONSISTENT:
             return Matrix.NoSolution()
         _raise_on_status(st)
-        den = limbs_to_ints(res.den[0])
-        part = limbs_to_ints(res.particular[0])
         rank = int(res.rank[0])
         k = n - rank
-        particular = [_wrap(kind, *reduce_pq(x, den)) for x in part]
-        if not logged:
-            particular = [_wrap("sympy", *reduce_pq(x, den)) for x in part]
+        # x = (D A)^-1 (D b): the common denominator of the inputs cancels, so the device's lowest terms are final
+        particular = [_wrap(kind, p, q) for p, q in _lowest(res.particular[0], res.den[0])]
         if k == 0:
             return Matrix.AffineSubspace(particular, None if logged else Matrix.zero(n, 0))
-        gens = limbs_to_ints(res.generators[0])          # [n][gen_cap]
+        gens = _lowest(res.generators[0], res.den[0])    # [n][gen_cap] pairs
         order = list(range(k)) if logged else sorted(range(k), key=lambda i: "tau%d" % i)
-        gen_items = [[_wrap(kind, *reduce_pq(gens[r][c], den)) for c in order] for r in range(n)]
+        gen_items = [[_wrap(kind, *gens[r][c]) for c in order] for r in range(n)]
         return Matrix.AffineSubspace(particular, Matrix(gen_items))
 
     def kernel(self):

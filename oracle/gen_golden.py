@@ -9,7 +9,7 @@ come from the reference's own ``RandomMatrixBuilder`` under fixed seeds and are
 rationalised with ``sympy.Rational`` exactly as reference main.py:20-31 does,
 because raw ints make ``row_reduce`` fall into floats (linalg.py:574).
 
-Usage:  python oracle/gen_golden.py [c1 c2 c3 c4 edge c5 trace]   (default: all)
+Usage:  python oracle/gen_golden.py [c1 c2 c3 c4 edge c5 trace eig traceq]   (default: all)
 """
 import os
 import random
@@ -383,6 +383,85 @@ def gen_trace():
         "cases": out})
 
 
+# ----------------------------------------------------------------------------- eigen-callers and builders
+EIG_SPECS = [
+    # (kind, N, spec): the reference builder under random.seed(20260060 + index)
+    ("diag", 3, [(2, 1), (-1, 2)]), ("diag", 4, [(1, 2), (3, 2)]), ("diag", 4, [(0, 1), (2, 1), (-3, 2)]),
+    ("diag", 5, [(1, 1), (2, 1), (3, 1), (-1, 2)]), ("diag", 5, [(4, 5)]), ("diag", 6, [(0, 2), (1, 2), (-2, 2)]),
+    ("diag", 6, [(5, 1), (-5, 1), (2, 4)]), ("diag", 8, [(1, 3), (-1, 3), (2, 2)]),
+    ("jordan", 3, [(2, 2), (1, 1)]), ("jordan", 4, [(1, 2), (1, 2)]), ("jordan", 4, [(0, 3), (2, 1)]),
+    ("jordan", 5, [(3, 2), (3, 1), (-1, 2)]), ("jordan", 6, [(1, 3), (2, 3)]), ("jordan", 6, [(-2, 1), (-2, 2), (4, 3)]),
+    ("jordan", 8, [(0, 4), (1, 2), (1, 2)]),
+]
+
+
+def eig_case(arg):
+    idx, (kind, N, spec) = arg
+    seed = 20260060 + idx
+    random.seed(seed)
+    P = quiet(lambda: __import__("linalg_solver.random_matrix", fromlist=["x"]).gen_unimodular_matrix(N))
+    random.seed(seed)
+    b = RandomMatrixBuilder.new().with_size(N, N)
+    b = b.with_eigenvalues(spec) if kind == "diag" else b.with_jordan_blocks(spec)
+    A = quiet(lambda: b.build())                                   # P^-1 D P / P^-1 J P through the reference's inverse
+    eigs = sorted({e for e, _ in spec})
+    spaces, basis = [], []
+    for e in eigs:
+        sp = quiet(lambda: A.find_eigenspace(sympy.Integer(e)))      # kernel -> find_preimage_of default route
+        gens = sp.generators
+        spaces.append({"eig": e, "vec": [pq(x) for x in sp.vec], "dim": int(sp.dim()),
+                       "generators": pq_grid(gens.items) if gens.cols else []})
+        basis.extend(sp.basis())
+    out = {"kind": kind, "N": N, "spec": [list(x) for x in spec], "seed": seed, "unimodular": pq_grid(P.items),
+           "A": pq_grid(A.items), "eigenspaces": spaces}
+    if len(basis) == N:                                            # what diagonalize() does next (linalg.py:852-858)
+        Pm = Matrix([list(col) for col in zip(*basis)])
+        P_inv = quiet(lambda: Pm.inverse())
+        out["P"] = pq_grid(Pm.items)
+        out["P_inv"] = pq_grid(P_inv.items)
+        out["D"] = pq_grid(quiet(lambda: P_inv * A * Pm).items)
+    return out
+
+
+def gen_eig():
+    with Pool(NPROC) as pool:
+        cases = pool.map(eig_case, list(enumerate(EIG_SPECS)), chunksize=1)
+    golden_io.save("eig_builders", {
+        "about": "reference gen_unimodular_matrix, RandomMatrixBuilder.build_diagonalizable / build_jordanized "
+                 "(random_matrix.py:131-167, 233-267) under random.seed(20260060 + index); find_eigenspace "
+                 "(linalg.py:758-770) for every eigenvalue in ascending order; P from the eigenvectors as columns, "
+                 "P.inverse() and P^-1 A P as diagonalize() forms them (linalg.py:852-858)",
+        "cases": cases})
+
+
+# ----------------------------------------------------------------------------- step traces of RATIONAL matrices
+def gen_trace_q():
+    from fractions import Fraction
+    rnd = random.Random(20260034)
+    cases = []
+    for m, n in [(2, 2), (2, 3), (3, 3), (3, 4), (4, 4), (4, 5), (5, 6)]:
+        for rep in range(6):
+            items = [[Fraction(rnd.randint(-6, 6), rnd.choice([1, 2, 3, 4, 6])) for _ in range(n)] for _ in range(m)]
+            if rep % 3 == 1:
+                items[0][0] = Fraction(0)
+            if rep % 3 == 2:
+                items[0][0] = Fraction(1)                          # pivot already one: no N step
+            bar = [None, n, max(1, n - 1)][rep % 3]
+            cases.append(([[[x.numerator, x.denominator] for x in row] for row in items], bar))
+    with Pool(NPROC) as pool:
+        out = pool.map(trace_q_case, cases, chunksize=4)
+    golden_io.save("trace_rational", {
+        "about": "as trace_small, for matrices with fractional entries (row_reduce accepts any exact entries, linalg.py:534-630)",
+        "cases": out})
+
+
+def trace_q_case(arg):
+    items, bar = arg
+    res = trace_case(([[sympy.Rational(p, q) for p, q in row] for row in items], bar))
+    res["A"] = items
+    return res
+
+
 # ----------------------------------------------------------------------------- C5 stand-ins
 def gen_c5():
     """No reference route can compute these; third-party cross-oracle only."""
@@ -400,7 +479,8 @@ def gen_c5():
         "cases": out})
 
 
-ALL = {"c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "edge": gen_edge, "c5": gen_c5, "trace": gen_trace}
+ALL = {"c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "edge": gen_edge, "c5": gen_c5, "trace": gen_trace,
+       "eig": gen_eig, "traceq": gen_trace_q}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(ALL)

@@ -238,3 +238,79 @@ def test_determinant_of_a_large_matrix_goes_through_the_by_prime_route():
         rng = np.random.Generator(np.random.PCG64(c["seed"]))
         A = rng.integers(-5, 6, size=(c["n"], c["n"]), dtype=np.int64)
         assert Matrix(A.tolist()).determinant() == int(c["det"])
+
+
+def test_builders_and_eigen_callers_match_reference_goldens():
+    """SURVEY.md section 8f items 1 and 2 against outputs of the UNMODIFIED reference (tests/golden/eig_builders,
+    oracle/gen_golden.py eig): under the same random.seed our gen_unimodular_matrix / build_diagonalizable /
+    build_jordanized (device inverse of P) give the reference's matrices; find_eigenspace (device kernel) gives the
+    reference's particular vector, generators and dimension for every eigenvalue; and the P, P^-1 and P^-1 A P that
+    diagonalize() forms from them (device inverse) are the reference's."""
+    import random
+    import sympy
+    from linalg_solver_b200 import Matrix, RandomMatrixBuilder
+    from linalg_solver_b200.random_matrix import gen_unimodular_matrix
+    g = golden_io.load("eig_builders")
+    flat = lambda M: [pq(x) for row in M.items for x in row]
+    n_diag = 0
+    for c in g["cases"]:
+        N = c["N"]
+        random.seed(c["seed"])
+        assert flat(gen_unimodular_matrix(N)) == c["unimodular"]
+        random.seed(c["seed"])
+        b = RandomMatrixBuilder.new().with_size(N, N)
+        spec = [tuple(x) for x in c["spec"]]
+        b = b.with_eigenvalues(spec) if c["kind"] == "diag" else b.with_jordan_blocks(spec)
+        A = b.build()
+        assert flat(A) == c["A"], (c["kind"], c["spec"])
+        basis = []
+        for sp_want in c["eigenspaces"]:
+            sp = A.find_eigenspace(sympy.Integer(sp_want["eig"]))
+            assert sp.dim() == sp_want["dim"] and [pq(x) for x in sp.vec] == sp_want["vec"]
+            assert (flat(sp.generators) if sp.generators.cols else []) == sp_want["generators"]
+            basis.extend(sp.basis())
+        assert (len(basis) == N) == ("P" in c)
+        if "P" in c:
+            n_diag += 1
+            P = Matrix([list(col) for col in zip(*basis)])
+            P_inv = P.inverse()
+            assert flat(P) == c["P"] and flat(P_inv) == c["P_inv"] and flat(P_inv * A * P) == c["D"]
+            res = A.diagonalize()
+            assert res.success and sorted(pq(res.D.items[i][i])[0] for i in range(N)) == \
+                sorted(e for e, mlt in spec for _ in range(mlt))
+        else:
+            assert not A.diagonalize().success
+    assert n_diag == 8
+
+
+def test_row_reduce_trace_of_rational_matrices():
+    """row_reduce(trace=True) on Fraction entries (reference linalg.py:534-630 accepts any exact entries): steps and
+    frames against the unmodified reference (tests/golden/trace_rational); the device replays on the residues of
+    numerators / common denominator (lsx_rref_trace_q)."""
+    from linalg_solver_b200 import Matrix
+    g = golden_io.load("trace_rational")
+    seen = set()
+    for c in g["cases"]:
+        M = Matrix([[Fraction(p, q) for p, q in row] for row in c["A"]])
+        R, piv, mats, steps = M.row_reduce(c["bar_col"], trace=True) if c["bar_col"] is not None else M.row_reduce(trace=True)
+        assert [list(s) for s in steps] == c["steps"], (c["A"], c["bar_col"])
+        assert [[pq(x) for row in f for x in row] for f in mats] == c["frames"]
+        assert [pq(x) for row in R for x in row] == c["rref"] and [list(p) for p in piv] == c["pivots"]
+        seen |= {s[0][0] for s in steps}
+    assert seen == {"S", "N", "E"}
+
+
+def test_trace_votes_out_a_bad_prime():
+    """a prime that divides an intermediate value logs different steps; it is dropped and replaced instead
+    of failing the call.  Tiny first primes (5 divides the pivot 5; 7 divides the denominator of a later entry)."""
+    from linalg_solver_b200 import Matrix, default_engine
+    eng = default_engine()
+    A = [[5, 1, 2], [3, 7, 1], [2, 2, 9]]
+    want = Matrix(A).row_reduce(trace=True)
+    eng.debug_set_primes([5, 7, 11])
+    try:
+        got = Matrix(A).row_reduce(trace=True)
+    finally:
+        eng.debug_set_primes([])
+    assert got[1] == want[1] and got[3] == want[3]
+    assert [[pq(x) for row in f for x in row] for f in got[2]] == [[pq(x) for row in f for x in row] for f in want[2]]

@@ -180,3 +180,15 @@ def test_row_reduce_trace_pinned_to_reference_frames():
         assert pq_list(R) == c["rref"] and [list(p) for p in piv] == c["pivots"]
         kinds |= {s[0][0] for s in steps}
     assert kinds == {"S", "N", "E"}
+
+
+def test_row_reduce_trace_of_rational_matrices_pinned():
+    """The oracle's step trace on fractional entries against the unmodified reference (tests/golden/trace_rational)."""
+    from fractions import Fraction
+    g = golden_io.load("trace_rational")
+    for c in g["cases"]:
+        items = [[Fraction(p, q) for p, q in row] for row in c["A"]]
+        R, piv, frames, steps = ref_port.row_reduce_trace(items, c["bar_col"])
+        assert [list(s) for s in steps] == c["steps"], c["A"]
+        assert [pq_list(f) for f in frames] == c["frames"]
+        assert pq_list(R) == c["rref"] and [list(p) for p in piv] == c["pivots"]
