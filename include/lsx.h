@@ -93,6 +93,14 @@ typedef struct lsx_plan {
 int  lsx_abi_version(void);
 int  lsx_create(int device_id, lsx_ctx** out);
 void lsx_destroy(lsx_ctx* ctx);
+/*
+ * One context over several GPUs of this process (distinct device ids).  Batched calls with LSX_MEM_HOST buffers are
+ * sharded BY MATRIX over the GPUs (contiguous slices, one host thread per GPU, no collective); lsx_det_large shards
+ * BY PRIME.  LSX_MEM_DEVICE calls return LSX_ERR_UNSUPPORTED on such a context (device data belongs to one GPU: keep
+ * one single-device context per GPU for it).  Stream, timing and launch-count calls address the first GPU.
+ */
+int  lsx_create_multi(const int* device_ids, int n_dev, lsx_ctx** out);
+int  lsx_device_count(const lsx_ctx* ctx);
 const char* lsx_last_error(const lsx_ctx* ctx);
 /* Run on the caller's CUDA stream (a cudaStream_t passed as void*; NULL = the ctx's own). */
 int  lsx_set_stream(lsx_ctx* ctx, void* cuda_stream);
@@ -252,6 +260,16 @@ int lsx_det_large_residues(lsx_ctx* ctx, const int32_t* A, int n, int prime_begi
  * A follows `mem`; rank and primes_used (may be NULL: how many primes were run) are HOST pointers.
  */
 int lsx_rank_large(lsx_ctx* ctx, const int32_t* A, int m, int n, int mem, int32_t* rank, int32_t* primes_used);
+/*
+ * The whole by-prime determinant behind one call (BASELINE.json configs[4]): Hadamard bound from the row / column
+ * norms -> prime count K; the primes are sharded over the context's GPUs (each gets its own copy of A), the residue
+ * vectors are all-gathered over NVLink (NCCL, loaded at run time; peer copies if it is unavailable), the Garner
+ * CRT runs on the first GPU.  A: [n][n] int32 in HOST memory.  det_words: HOST, room for limbs_cap words; the
+ * signed determinant comes back as *limbs_out little-endian two's-complement words (LSX_ERR_BOUND if limbs_cap is too
+ * small: *limbs_out then says how many are needed).  n_primes_out may be NULL.  Works on a single-device context too.
+ */
+int lsx_det_large(lsx_ctx* ctx, const int32_t* A, int n, int limbs_cap, uint32_t* det_words, int* limbs_out,
+                  int* n_primes_out);
 /*
  * CRT of `count` residues (for table primes [0, count)) to a signed integer of `limbs`
  * words (two's complement, little endian).  residues/out follow `mem`.

@@ -48,6 +48,8 @@ _pp = ctypes.POINTER(Plan)
 SIGNATURES = {
     "lsx_abi_version": (_i, []),
     "lsx_create": (_i, [_i, ctypes.POINTER(_vp)]),
+    "lsx_create_multi": (_i, [ctypes.POINTER(_i), _i, ctypes.POINTER(_vp)]),
+    "lsx_device_count": (_i, [_vp]),
     "lsx_destroy": (None, [_vp]),
     "lsx_last_error": (ctypes.c_char_p, [_vp]),
     "lsx_set_stream": (_i, [_vp, _vp]),
@@ -76,6 +78,7 @@ SIGNATURES = {
     "lsx_det_large_prime_count_for": (_i, [_vp, _vp, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_double)]),
     "lsx_det_large_residues": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "lsx_rank_large": (_i, [_vp, _vp, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    "lsx_det_large": (_i, [_vp, _vp, _i, _i, _vp, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "lsx_crt_signed": (_i, [_vp, _vp, _i, _i, _i, _vp]),
 }
 

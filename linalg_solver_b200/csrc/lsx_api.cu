@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <new>
+#include <thread>
 
 #include "lsx_internal.h"
 
@@ -138,6 +139,9 @@ int lsx_create(int device_id, lsx_ctx** out) {
 
 void lsx_destroy(lsx_ctx* ctx) {
     if (!ctx) return;
+    lsx_multi_release(ctx);
+    for (lsx_ctx* peer : ctx->peers) lsx_destroy(peer);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     if (ctx->d_ws) cudaFree(ctx->d_ws);
@@ -359,6 +363,44 @@ int run_job(lsx_ctx* ctx, ElimJob& job, int mem, Buf* bufs, int nbufs, int32_t* 
     if (job.batch < 0) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "negative batch");
     if (job.batch == 0) return LSX_OK;
     if (job.batch > 0x7fffffffLL) return lsx_fail(ctx, LSX_ERR_BAD_SHAPE, "batch above 2^31-1");
+    if (!ctx->peers.empty()) {
+        // a context over several GPUs (lsx_create_multi): host buffers are sharded BY MATRIX, one host thread per GPU
+        // running this very function on its contiguous slice; matrices are independent, nothing is exchanged
+        if (mem != LSX_MEM_HOST)
+            return lsx_fail(ctx, LSX_ERR_UNSUPPORTED, "a multi-GPU context shards host buffers; device buffers belong to "
+                                                      "one GPU: use one context per GPU for device-resident data");
+        std::vector<lsx_ctx*> dev{ctx};
+        dev.insert(dev.end(), ctx->peers.begin(), ctx->peers.end());
+        const int world = (int)std::min<int64_t>((int64_t)dev.size(), job.batch);
+        std::vector<int> rcs(world, LSX_OK);
+        std::vector<std::thread> th;
+        std::vector<std::vector<lsx_ctx*>> saved(world);
+        for (int d = 0; d < world; ++d) {
+            const int64_t base = job.batch / world, extra = job.batch % world;
+            const int64_t b0 = d * base + std::min<int64_t>(d, extra), cnt = base + (d < extra ? 1 : 0);
+            th.emplace_back([&, d, b0, cnt]() {
+                lsx_ctx* c = dev[d];
+                ElimJob jd = job;
+                jd.batch = cnt;
+                std::vector<Buf> bd(bufs, bufs + nbufs);
+                for (Buf& b : bd) {
+                    if (b.src) b.src = (const char*)b.src + b.per * (size_t)b0;
+                    if (b.dst) b.dst = (char*)b.dst + b.per * (size_t)b0;
+                    if (b.slot) b.slot = (void**)((char*)&jd + ((char*)b.slot - (char*)&job));   // same field of the copy
+                }
+                saved[d].swap(c->peers);                           // the slice runs as a plain single-device call
+                rcs[d] = run_job(c, jd, mem, bd.data(), nbufs, status_user + b0);
+                saved[d].swap(c->peers);
+            });
+        }
+        for (auto& t : th) t.join();
+        for (int d = 0; d < world; ++d)
+            if (rcs[d] != LSX_OK) {
+                if (d) ctx->err = dev[d]->err;
+                return rcs[d];
+            }
+        return LSX_OK;
+    }
     const size_t st_bytes = (size_t)job.batch * 4;
     if (mem == LSX_MEM_DEVICE) {
         for (int i = 0; i < nbufs; ++i)

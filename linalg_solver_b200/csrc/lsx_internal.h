@@ -47,6 +47,10 @@ struct lsx_ctx {
     int tev_used = 0;
     std::vector<cudaEvent_t> tev;        // pairs: [2*i] before, [2*i+1] after
     std::vector<cudaEvent_t> pev;        // events of the host-call pipeline
+    // lsx_create_multi: the other GPUs of this context (each a full single-device ctx, driven by its own host
+    // thread inside a call); empty for a single-device ctx.  nccl: communicators of all devices (lsx_multi.cpp)
+    std::vector<lsx_ctx*> peers;
+    void* nccl = nullptr;
 };
 // Record CUDA events around the dominant kernel of an operation when timing is enabled.
 void lsx_timing_begin(lsx_ctx* ctx);
@@ -168,6 +172,7 @@ int lsx_tile_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_begi
 int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_begin, int count, uint32_t* d_res);
 
 int lsx_ws_reserve(lsx_ctx* ctx, size_t bytes);
+void lsx_multi_release(lsx_ctx* ctx);   // frees the NCCL state of a multi-device ctx (lsx_multi.cu)
 int lsx_fail(lsx_ctx* ctx, int code, const char* fmt, ...);
 #define LSX_CUDA_TRY(ctx, expr)                                                              \
     do {                                                                                     \

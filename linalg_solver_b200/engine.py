@@ -76,13 +76,31 @@ class SolveResult:
 
 
 class Engine:
-    """One lsx context = one GPU + one stream.  Not thread-safe (one thread per Engine)."""
+    """One lsx context = one GPU + one stream.  Not thread-safe (one thread per Engine).
 
-    def __init__(self, device: Optional[int] = None):
+    ``Engine(devices=[0, 1, ...])`` is one context over several GPUs of this process (``lsx_create_multi``): batched
+    calls on host (numpy) arrays are sharded by matrix over the GPUs inside the library and ``det_large`` shards a
+    single large determinant by prime with an NCCL all-gather of the residues; device tensors are not accepted there
+    (they belong to one GPU).  The torch.distributed route (one process per GPU, ``linalg_solver_b200.dist``) is
+    unchanged and is what ``bench.py`` drives under torchrun."""
+
+    def __init__(self, device: Optional[int] = None, devices=None):
+        self._ctx = ctypes.c_void_p()
+        if devices is not None:
+            ids = [int(d) for d in devices]
+            if not ids:
+                raise ValueError("devices must name at least one GPU")
+            self.device, self.devices = ids[0], ids
+            arr = (ctypes.c_int * len(ids))(*ids)
+            rc = lib.lsx_create_multi(arr, len(ids), ctypes.byref(self._ctx))
+            if rc != _lib.OK:
+                self._ctx = None
+                raise LsxError(rc, "lsx_create_multi(devices=%r) failed: CUDA devices are required, there is no CPU "
+                                   "fallback" % (ids,))
+            return
         if device is None:
             device = int(os.environ.get("LSX_DEVICE", os.environ.get("LOCAL_RANK", "0")))
-        self.device = device
-        self._ctx = ctypes.c_void_p()
+        self.device, self.devices = device, [device]
         rc = lib.lsx_create(device, ctypes.byref(self._ctx))
         if rc != _lib.OK:
             self._ctx = None
@@ -528,6 +546,29 @@ class Engine:
         res = self._alloc(like, (prime_count,), np.uint32)
         self._check(lib.lsx_det_large_residues(self._ctx, pA, n, prime_begin, prime_count, mem, self._ptr(res), None))
         return res
+
+    def det_large(self, A):
+        """Exact determinant of ONE large integer matrix (host array) as a Python int, through ``lsx_det_large``:
+        primes sharded over this context's GPUs, residues all-gathered (NCCL), CRT on the first GPU."""
+        A = np.ascontiguousarray(A)
+        if A.dtype != np.int32:
+            if A.size and (A.max() > 2**31 - 1 or A.min() < -(2**31) + 1):
+                raise OverflowError("A has entries outside int32")
+            A = A.astype(np.int32)
+        if A.ndim != 2 or A.shape[0] != A.shape[1]:
+            raise ValueError("Determinant requires a square matrix")
+        n = A.shape[0]
+        k, bits = ctypes.c_int(), ctypes.c_double()
+        amax = int(np.abs(A.astype(np.int64)).max()) if A.size else 0
+        self._check_plan(lib.lsx_det_large_prime_count(n, amax, ctypes.byref(k), ctypes.byref(bits)), "det_large(n=%d)" % n)
+        cap = int(bits.value + 2) // 32 + 2
+        words = np.zeros(cap, dtype=np.uint32)
+        limbs, primes = ctypes.c_int(), ctypes.c_int()
+        self.set_stream(None)
+        self._check(lib.lsx_det_large(self._ctx, A.ctypes.data, n, cap, words.ctypes.data, ctypes.byref(limbs),
+                                      ctypes.byref(primes)))
+        from .convert import limbs_to_ints
+        return limbs_to_ints(words[: limbs.value].reshape(1, -1))[0], primes.value
 
     def rank_large(self, A):
         """Rank of ONE integer matrix of any size that fits device memory (``lsx_rank_large``: the batched rank keeps

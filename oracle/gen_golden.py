@@ -9,7 +9,7 @@ come from the reference's own ``RandomMatrixBuilder`` under fixed seeds and are
 rationalised with ``sympy.Rational`` exactly as reference main.py:20-31 does,
 because raw ints make ``row_reduce`` fall into floats (linalg.py:574).
 
-Usage:  python oracle/gen_golden.py [c1 c2 c3 c4 edge c5 trace eig traceq]   (default: all)
+Usage:  python oracle/gen_golden.py [c1 c2 c3 c4 edge c5 trace eig traceq ranklarge]   (default: all)
 """
 import os
 import random
@@ -479,8 +479,30 @@ def gen_c5():
         "cases": out})
 
 
+# ----------------------------------------------------------------------------- large-n rank stand-ins
+def gen_ranklarge():
+    """Not from the reference (its rank() is sympy.Matrix.rank, minutes to hours at these sizes):
+    sympy DomainMatrix(ZZ).rank() of products B (m x r) C (r x n) of numpy PCG64 matrices, as an exact cross-check of
+    the sizes beyond the batched kernels (m > 254)."""
+    import numpy as np
+    from sympy.polys.matrices import DomainMatrix
+    from sympy import ZZ
+    out = []
+    for m, n, r, seed in [(260, 270, 200, 2026000701), (300, 280, 280, 2026000702), (512, 512, 100, 2026000703)]:
+        rng = np.random.Generator(np.random.PCG64(seed))
+        B = rng.integers(-3, 4, size=(m, r), dtype=np.int64)
+        C = rng.integers(-3, 4, size=(r, n), dtype=np.int64)
+        A = B @ C
+        dm = DomainMatrix([[ZZ(int(x)) for x in row] for row in A.tolist()], (m, n), ZZ)
+        out.append({"m": m, "n": n, "r": r, "seed": seed, "rank": int(dm.rank())})
+    golden_io.save("rank_large", {
+        "about": "NOT from the reference: sympy DomainMatrix(ZZ).rank() of (PCG64(seed).integers(-3,4,(m,r)) @ "
+                 "PCG64-continued .integers(-3,4,(r,n))) as an independent exact cross-check",
+        "cases": out})
+
+
 ALL = {"c1": gen_c1, "c2": gen_c2, "c3": gen_c3, "c4": gen_c4, "edge": gen_edge, "c5": gen_c5, "trace": gen_trace,
-       "eig": gen_eig, "traceq": gen_trace_q}
+       "eig": gen_eig, "traceq": gen_trace_q, "ranklarge": gen_ranklarge}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(ALL)

@@ -314,3 +314,37 @@ def test_trace_votes_out_a_bad_prime():
         eng.debug_set_primes([])
     assert got[1] == want[1] and got[3] == want[3]
     assert [[pq(x) for row in f for x in row] for f in got[2]] == [[pq(x) for row in f for x in row] for f in want[2]]
+
+
+def test_rank_beyond_the_batched_kernels():
+    """rank() past the shared-memory tile (m > 254) through lsx_rank_large: DomainMatrix stand-ins (tests/golden/
+    rank_large) and constructions whose rank is certain ([I; X] [I | Y] has rank exactly r), rows and columns
+    shuffled; 1024 x 1024 included.  Also a small matrix with entries that need more than 32 primes."""
+    import numpy as np
+    from linalg_solver_b200 import Matrix, default_engine
+    eng = default_engine()
+    for c in golden_io.load("rank_large")["cases"]:
+        rng = np.random.Generator(np.random.PCG64(c["seed"]))
+        B = rng.integers(-3, 4, size=(c["m"], c["r"]), dtype=np.int64)
+        C = rng.integers(-3, 4, size=(c["r"], c["n"]), dtype=np.int64)
+        A = (B @ C).astype(np.int32)
+        got, used = eng.rank_large(A)
+        assert got == c["rank"], (c, got)
+        assert used >= 1
+    rng = np.random.Generator(np.random.PCG64(99))
+    for m, n, r in [(300, 300, 300), (400, 333, 57), (1024, 1024, 1000), (1024, 1024, 1024), (255, 600, 1)]:
+        B = np.vstack([np.eye(r, dtype=np.int64), rng.integers(-2, 3, size=(m - r, r))]) if m > r else np.eye(r, dtype=np.int64)[:m]
+        C = np.hstack([np.eye(r, dtype=np.int64), rng.integers(-2, 3, size=(r, n - r))]) if n > r else np.eye(r, dtype=np.int64)[:, :n]
+        A = (B @ C)[rng.permutation(m)][:, rng.permutation(n)].astype(np.int32)
+        import torch
+        got_h, _ = eng.rank_large(A)
+        got_d, _ = eng.rank_large(torch.from_numpy(A).cuda())
+        assert got_h == got_d == min(r, m, n), (m, n, r, got_h, got_d)
+    assert eng.rank_large(np.zeros((300, 10), dtype=np.int32)) == (0, 0)
+    # through the Matrix API: 260 x 260 (rows > 254) and a 6 x 6 whose entries need more primes than the batched limit
+    A = rng.integers(-5, 6, size=(260, 260), dtype=np.int64)
+    A[100] = A[3] - 2 * A[7]
+    assert Matrix(A.tolist()).rank() == 259
+    big = rng.integers(-2**30, 2**30, size=(40, 40), dtype=np.int64)
+    big[5] = big[6]
+    assert Matrix(big.tolist()).rank() == 39
