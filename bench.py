@@ -445,6 +445,28 @@ class Job:
         for c in range(self.e2e_calls):
             self.run({k: v[c * eb:(c + 1) * eb] for k, v in self.host_np.items()}, self.host_out)
 
+    def step_copy_only(self):
+        """The bytes of step_e2e as bare pinned-host <-> device copies on two streams (no kernels, no library): what
+        the box's PCIe / host memory lets this rank move while the other ranks do the same."""
+        torch = self.torch
+        if not hasattr(self, "_cp"):
+            dev = next(iter(self.dev.values())).device
+            h_in = [torch.from_numpy(v) for v in self.host_np.values()]           # pinned (views of pinned tensors)
+            d_in = [torch.empty(tuple(t.shape), dtype=t.dtype, device=dev) for t in h_in]
+            pairs = [(torch.from_numpy(vh), vd) for rh, rd in zip(self.host_out, self.res)
+                     for (_, vh), (_, vd) in zip(self._fields(rh), self._fields(rd))]
+            self._cp = (torch.cuda.Stream(dev), torch.cuda.Stream(dev), h_in, d_in, pairs)
+        s_in, s_out, h_in, d_in, pairs = self._cp
+        with torch.cuda.stream(s_in):
+            for h, d in zip(h_in, d_in):
+                d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for _ in range(self.e2e_calls):
+                for h, d in pairs:
+                    h.copy_(d[: h.shape[0]], non_blocking=True)
+        s_in.synchronize()
+        s_out.synchronize()
+
     def h2d_bytes(self):
         return int(sum(v.nbytes for v in self.host_np.values()))
 
@@ -542,9 +564,16 @@ def measure_batch(ctx, workload, steps, warmup, cpu):
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - e0) * 1e3 / e2e_steps
     job.check_e2e_equals_device()
+    # ---- the same bytes as bare copies, all ranks at once: the transfer ceiling of the box at this N ----
+    job.step_copy_only()
+    ctx.barrier()
+    c0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        job.step_copy_only()
+    copy_ms = (time.perf_counter() - c0) * 1e3 / e2e_steps
 
     # ---- reduce over ranks: the slowest rank defines the step ----
-    ms_total, e2e_ms, launches = ctx.max_over_ranks([ms_total, e2e_ms, float(launches)])
+    ms_total, e2e_ms, launches, copy_ms = ctx.max_over_ranks([ms_total, e2e_ms, float(launches), copy_ms])
     ms_step = ms_total / steps
     value = world * batch / (ms_step * 1e-3)
     h2d, d2h = job.h2d_bytes(), job.d2h_bytes()
@@ -596,6 +625,9 @@ def measure_batch(ctx, workload, steps, warmup, cpu):
         "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "matrices/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_calls_per_step": E2E_CALLS.get(workload, 1),
                 "gb_per_s_per_gpu": (h2d + d2h) / (e2e_ms * 1e-3) / 1e9,
+                "copy_only_ms": copy_ms, "frac_of_copy_ceiling": copy_ms / e2e_ms,
+                "copy_only": "the step's H2D and D2H bytes as bare pinned copies on two streams, all ranks at once, "
+                             "max over ranks: the PCIe / host-memory ceiling of this box at this N",
                 "path": "lsx_*_batch(mem=LSX_MEM_HOST) via ctypes, pinned host buffers"
                         + (" (int8 input container: lsx_inverse_batch_i8)" if workload == "c2" else "")},
         "gpu_launches": int(launches),

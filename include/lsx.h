@@ -101,6 +101,9 @@ void lsx_destroy(lsx_ctx* ctx);
  */
 int  lsx_create_multi(const int* device_ids, int n_dev, lsx_ctx** out);
 int  lsx_device_count(const lsx_ctx* ctx);
+/* 1 once the context's NCCL communicators exist (created by the first multi-GPU lsx_det_large), 0 before that or when
+ * libnccl could not be loaded and the residues are gathered by peer copies instead. */
+int  lsx_multi_uses_nccl(const lsx_ctx* ctx);
 const char* lsx_last_error(const lsx_ctx* ctx);
 /* Run on the caller's CUDA stream (a cudaStream_t passed as void*; NULL = the ctx's own). */
 int  lsx_set_stream(lsx_ctx* ctx, void* cuda_stream);

@@ -50,6 +50,7 @@ SIGNATURES = {
     "lsx_create": (_i, [_i, ctypes.POINTER(_vp)]),
     "lsx_create_multi": (_i, [ctypes.POINTER(_i), _i, ctypes.POINTER(_vp)]),
     "lsx_device_count": (_i, [_vp]),
+    "lsx_multi_uses_nccl": (_i, [_vp]),
     "lsx_destroy": (None, [_vp]),
     "lsx_last_error": (ctypes.c_char_p, [_vp]),
     "lsx_set_stream": (_i, [_vp, _vp]),

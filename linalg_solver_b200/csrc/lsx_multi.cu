@@ -119,6 +119,11 @@ int lsx_create_multi(const int* device_ids, int n_dev, lsx_ctx** out) {
 
 int lsx_device_count(const lsx_ctx* ctx) { return ctx ? 1 + (int)ctx->peers.size() : 0; }
 
+int lsx_multi_uses_nccl(const lsx_ctx* ctx) {
+    const MultiState* st = ctx ? (const MultiState*)ctx->nccl : nullptr;
+    return st && st->api.ok && !st->comms.empty() ? 1 : 0;
+}
+
 int lsx_det_large(lsx_ctx* ctx, const int32_t* A, int n, int limbs_cap, uint32_t* det_words, int* limbs_out,
                   int* n_primes_out) {
     if (!ctx) return LSX_ERR_NULL;

@@ -130,64 +130,94 @@ struct SwState {
     bool neg;
 };
 
-// One pivot column J (compile-time, so that every register index is static).
-template <int G, int NC, int J>
-__device__ __forceinline__ void sw_step(uint32_t (&row)[NC], SwState& st, const PrimeRec& P, int r, int gbase, unsigned gmask,
-                                        int m, int bar, bool live) {
+// One pivot column J (compile-time, so that every register index is static) for PP primes at once.  The primes of
+// a pass are independent dependency chains (ballot -> shuffle of the pivot -> multipliers -> row update -> next
+// ballot); a warp that runs them one after the other waits out every link of that chain (ncu, round 1: 12 cycles
+// per issued instruction per warp, "wait" and the shuffles' scoreboard on top), interleaved they fill each
+// other's latencies.  Every phase of the step is therefore written prime-major.
+template <int G, int NC, int PP, int J>
+__device__ __forceinline__ void sw_step(uint32_t (&row)[PP][NC], SwState (&st)[PP], const PrimeRec (&P)[PP], int r, int gbase,
+                                        unsigned gmask, int m, int bar, bool live) {
     constexpr unsigned FULL = 0xffffffffu;
     if (J >= bar) return;                 // uniform over the grid
-    const uint32_t p = P.p, pinv = P.pinv;
-    const int pi = st.pi;
-    const bool nz = r >= pi && r < m && row[J] != 0u;
-    const unsigned bal = (__ballot_sync(FULL, nz) >> gbase) & gmask;
-    const bool has = bal != 0u && pi < m;
-    const int src = has ? __ffs(bal) - 1 : pi;
-    if (__any_sync(FULL, has && src != pi)) {
-        // physical swap of rows pi and src (lanes of groups without a swap read themselves)
-        const int partner = (has && src != pi) ? (r == pi ? src : (r == src ? pi : r)) : r;
+    bool has[PP];
+    int src[PP], pi[PP];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) row[c] = __shfl_sync(FULL, row[c], gbase + partner);
+    for (int q = 0; q < PP; ++q) {
+        pi[q] = st[q].pi;
+        const bool nz = r >= pi[q] && r < m && row[q][J] != 0u;
+        const unsigned bal = (__ballot_sync(FULL, nz) >> gbase) & gmask;
+        has[q] = bal != 0u && pi[q] < m;
+        src[q] = has[q] ? __ffs(bal) - 1 : pi[q];
     }
-    st.neg ^= has && src != pi;
-    if (r == J % G) st.prof |= (uint64_t)(has ? src : SW_SKIP) << (6 * (J / G));
-    if (!__any_sync(FULL, has)) return;   // no group of this warp has a pivot in column J
-    const int pl = gbase + (has ? pi : 0);
-    const uint32_t piv = __shfl_sync(FULL, row[J], pl);
-    const uint32_t f = row[J];
-    const bool isp = r == pi;
-    const uint32_t x = has ? (isp ? st.S : piv) : P.one;
-    const uint32_t y = (has && !isp && f) ? p - f : 0u;
-    // While no column has been skipped (pi == J in every group of the warp) the columns left of J are
-    // finished pivot columns: they are not maintained any more (their final values are known: d on
-    // the pivot row, 0 elsewhere) and only columns > J are updated.
-    if (__all_sync(FULL, !live || (has && pi == J))) {
 #pragma unroll
-        for (int c = J + 1; c < NC; ++c) {
-            const uint32_t pc = __shfl_sync(FULL, row[c], pl);
-            row[c] = mont_fma2(x, row[c], y, pc, p, pinv);
+    for (int q = 0; q < PP; ++q) {
+        if (__any_sync(FULL, has[q] && src[q] != pi[q])) {
+            // physical swap of rows pi and src (lanes of groups without a swap read themselves)
+            const int partner = (has[q] && src[q] != pi[q]) ? (r == pi[q] ? src[q] : (r == src[q] ? pi[q] : r)) : r;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) row[q][c] = __shfl_sync(FULL, row[q][c], gbase + partner);
         }
-    } else {
+        st[q].neg ^= has[q] && src[q] != pi[q];
+        if (r == J % G) st[q].prof |= (uint64_t)(has[q] ? src[q] : SW_SKIP) << (6 * (J / G));
+    }
+    bool any_has[PP], fast[PP];
+    int pl[PP];
+    uint32_t piv[PP], x[PP], y[PP];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const uint32_t pc = __shfl_sync(FULL, row[c], pl);
-            row[c] = mont_fma2(x, row[c], y, pc, p, pinv);
+    for (int q = 0; q < PP; ++q) {
+        any_has[q] = __any_sync(FULL, has[q]);            // no group of this warp has a pivot in column J: nothing to do
+        pl[q] = gbase + (has[q] ? pi[q] : 0);
+        piv[q] = __shfl_sync(FULL, row[q][J], pl[q]);
+        const uint32_t f = row[q][J];
+        const bool isp = r == pi[q];
+        x[q] = has[q] ? (isp ? st[q].S : piv[q]) : P[q].one;
+        y[q] = (has[q] && !isp && f) ? P[q].p - f : 0u;
+        // While no column has been skipped (pi == J in every group of the warp) the columns left of J are
+        // finished pivot columns: they are not maintained any more (their final values are known: d on
+        // the pivot row, 0 elsewhere) and only columns > J are updated.
+        fast[q] = __all_sync(FULL, !live || (has[q] && pi[q] == J));
+    }
+    // columns right of J: always live
+#pragma unroll
+    for (int c = J + 1; c < NC; ++c) {
+#pragma unroll
+        for (int q = 0; q < PP; ++q) {
+            if (any_has[q]) {
+                const uint32_t pc = __shfl_sync(FULL, row[q][c], pl[q]);
+                row[q][c] = mont_fma2(x[q], row[q][c], y[q], pc, P[q].p, P[q].pinv);
+            }
         }
     }
-    if (has) {
-        st.Q = mont_mul(st.Q, st.S, p, pinv);
-        st.S = mont_mul(st.S, piv, p, pinv);
-        st.X = mont_mul(st.X, P.r2, p, pinv);
-        ++st.pi;
+    // columns up to J: only once a column has been skipped somewhere in the warp (rank-deficient input)
+#pragma unroll
+    for (int q = 0; q < PP; ++q) {
+        if (any_has[q] && !fast[q]) {
+#pragma unroll
+            for (int c = 0; c <= J; ++c) {
+                const uint32_t pc = __shfl_sync(FULL, row[q][c], pl[q]);
+                row[q][c] = mont_fma2(x[q], row[q][c], y[q], pc, P[q].p, P[q].pinv);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PP; ++q) {
+        if (has[q]) {
+            st[q].Q = mont_mul(st[q].Q, st[q].S, P[q].p, P[q].pinv);
+            st[q].S = mont_mul(st[q].S, piv[q], P[q].p, P[q].pinv);
+            st[q].X = mont_mul(st[q].X, P[q].r2, P[q].p, P[q].pinv);
+            ++st[q].pi;
+        }
     }
 }
 
-template <int G, int NC, int... Js>
-__device__ __forceinline__ void sw_steps(uint32_t (&row)[NC], SwState& st, const PrimeRec& P, int r, int gbase, unsigned gmask,
-                                         int m, int bar, bool live, std::integer_sequence<int, Js...>) {
-    (sw_step<G, NC, Js>(row, st, P, r, gbase, gmask, m, bar, live), ...);
+template <int G, int NC, int PP, int... Js>
+__device__ __forceinline__ void sw_steps(uint32_t (&row)[PP][NC], SwState (&st)[PP], const PrimeRec (&P)[PP], int r, int gbase,
+                                         unsigned gmask, int m, int bar, bool live, std::integer_sequence<int, Js...>) {
+    (sw_step<G, NC, PP, Js>(row, st, P, r, gbase, gmask, m, bar, live), ...);
 }
 
-template <int G, int NC>
+template <int G, int NC, int PP>
 __global__ void __launch_bounds__(SW_THREADS) k_subwarp(const SwArgs a) {
     extern __shared__ uint32_t sm[];          // res[K][NC][SW_THREADS] then dres[K][SW_THREADS]
     const int tid = threadIdx.x, lane = tid & 31;
@@ -236,39 +266,39 @@ __global__ void __launch_bounds__(SW_THREADS) k_subwarp(const SwArgs a) {
     int rank0 = 0;
     bool mismatch = false;
 
-    for (int k = 0; k < K; ++k) {
-        const PrimeRec P = s_primes[k];
-        const uint32_t p = P.p;
-        uint32_t row[NC];
+    for (int k0 = 0; k0 < K; k0 += PP) {
+        // PP primes per pass; an odd tail repeats the last prime (its second copy is not stored)
+        PrimeRec P[PP];
+        uint32_t row[PP][NC];
+        SwState st[PP];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) row[c] = word_of_int(in[c], p);
-        uint32_t S = P.one, Q = P.one, X = 1u;
-        int pi = 0;
-        bool neg = false;
-        uint64_t prof = 0;
-        SwState st{S, Q, X, prof, pi, neg};
-        sw_steps<G, NC>(row, st, P, r, gbase, gmask, m, bar, live, std::make_integer_sequence<int, NC>{});
-        S = st.S;
-        Q = st.Q;
-        X = st.X;
-        prof = st.prof;
-        pi = st.pi;
-        neg = st.neg;
-        // ---- raw words to shared memory; the scaling factors follow after the prime loop ----
+        for (int q = 0; q < PP; ++q) {
+            P[q] = s_primes[k0 + q < K ? k0 + q : K - 1];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) sm[((size_t)k * NC + c) * SW_THREADS + tid] = row[c];
-        if (r == 0) {
-            uint32_t* sc = scal + (size_t)k * 4 * SW_THREADS + tid;
-            sc[0] = Q;
-            sc[SW_THREADS] = X;
-            sc[2 * SW_THREADS] = S;
-            sc[3 * SW_THREADS] = (uint32_t)pi | (neg ? 256u : 0u);
+            for (int c = 0; c < NC; ++c) row[q][c] = word_of_int(in[c], P[q].p);
+            st[q] = SwState{P[q].one, P[q].one, 1u, 0ull, 0, false};
         }
-        if (k == 0) {
-            prof0 = prof;
-            rank0 = pi;
-        } else {
-            mismatch |= prof != prof0 || pi != rank0;
+        sw_steps<G, NC, PP>(row, st, P, r, gbase, gmask, m, bar, live, std::make_integer_sequence<int, NC>{});
+#pragma unroll
+        for (int q = 0; q < PP; ++q) {
+            const int k = k0 + q;
+            if (k >= K) break;
+            // ---- raw words to shared memory; the scaling factors follow after the prime loop ----
+#pragma unroll
+            for (int c = 0; c < NC; ++c) sm[((size_t)k * NC + c) * SW_THREADS + tid] = row[q][c];
+            if (r == 0) {
+                uint32_t* sc = scal + (size_t)k * 4 * SW_THREADS + tid;
+                sc[0] = st[q].Q;
+                sc[SW_THREADS] = st[q].X;
+                sc[2 * SW_THREADS] = st[q].S;
+                sc[3 * SW_THREADS] = (uint32_t)st[q].pi | (st[q].neg ? 256u : 0u);
+            }
+            if (k == 0) {
+                prof0 = st[q].prof;
+                rank0 = st[q].pi;
+            } else {
+                mismatch |= st[q].prof != prof0 || st[q].pi != rank0;
+            }
         }
     }
     mismatch = ((__ballot_sync(FULL, mismatch) >> gbase) & gmask) != 0u;
@@ -376,26 +406,44 @@ __global__ void __launch_bounds__(SW_THREADS) k_subwarp(const SwArgs a) {
         const unsigned freemask = ~pivmask & (nvars >= 32 ? 0xffffffffu : ((1u << nvars) - 1u));
         const int nfree = nvars - rank;
         const int per = nfree + 1, E = rank * per + nfree;
-        for (int e = r; e < E; e += G) {
-            if (e < rank * per) {
-                const int i = e / per, q = e - i * per;
-                const int pcol = (int)__fns(pivmask, 0, i + 1);
+        // lane t of the group keeps the column of pivot t and the t-th free column (one bit scan each instead of one
+        // per entry), G covers both lists twice over when m > G / 2 only for G = 32, where two slots per lane are used
+        const int my_pcol0 = r < rank ? (int)__fns(pivmask, 0, r + 1) : 0;
+        const int my_fcol0 = r < nfree ? (int)__fns(freemask, 0, r + 1) : 0;
+        const int my_fcol1 = r + G < nfree ? (int)__fns(freemask, 0, r + G + 1) : 0;     // nfree can reach 32 > G
+        // (i, q) = divmod(e, per) carried along instead of divided out per entry
+        const int di = G / per, dq = G - di * per;
+        int i = r / per, q = r - i * per;
+        const unsigned grp = gmask << gbase;                       // the other group of the warp may have left already
+        for (int e0 = 0; e0 < E; e0 += G) {                        // whole groups iterate together (shuffles inside)
+            const int e = e0 + r;
+            const bool on = e < E;
+            const bool in_rows = on && e < rank * per;
+            const int ii = in_rows ? i : 0, qq = on ? (in_rows ? q : e - rank * per) : 0;
+            const int pcol = __shfl_sync(grp, my_pcol0, gbase + (ii < G ? ii : 0));
+            const int fsel = qq < nfree ? qq : 0;
+            const int fc_lo = __shfl_sync(grp, my_fcol0, gbase + (fsel % G));
+            const int fc_hi = __shfl_sync(grp, my_fcol1, gbase + (fsel % G));
+            const int fc = fsel < G ? fc_lo : fc_hi;
+            if (in_rows) {
                 if (q == nfree) {
                     crt_entry_any(res_of(i, nvars), rstr, sc_piv, sstr, K, L, T, a.particular + (mat * nvars + pcol) * L,
                                   false, false);
                 } else if (q < a.gen_cap) {
-                    const int fc = (int)__fns(freemask, 0, q + 1);
                     crt_entry_any(res_of(i, fc), rstr, sc_piv, sstr, K, L, T,
                                   a.generators + ((mat * nvars + pcol) * (int64_t)a.gen_cap + q) * L, true, false);
                 }
-            } else {
+            } else if (on) {
                 // generator entries equal to d at the free columns (gen[f] = 1, linalg.py:976)
-                const int q = e - rank * per;
-                if (q < a.gen_cap) {
-                    const int fc = (int)__fns(freemask, 0, q + 1);
+                if (qq < a.gen_cap)
                     crt_entry_any(nullptr, 0, sc_d, sstr, K, L, T,
-                                  a.generators + ((mat * nvars + fc) * (int64_t)a.gen_cap + q) * L, false, false);
-                }
+                                  a.generators + ((mat * nvars + fc) * (int64_t)a.gen_cap + qq) * L, false, false);
+            }
+            i += di;
+            q += dq;
+            if (q >= per) {
+                q -= per;
+                ++i;
             }
         }
         if (r == 0 && nfree > a.gen_cap) atomicOr(&a.status[mat], LSX_ST_GEN_TRUNC);
@@ -406,19 +454,32 @@ size_t sw_smem_bytes(int K, int NC) {
     return ((size_t)K * NC + (size_t)K * 4) * SW_THREADS * 4 + (size_t)K * sizeof(PrimeRec) + (size_t)K * K * 4;
 }
 
-template <int G, int NC>
-int launch_sw(lsx_ctx* ctx, const SwArgs& a) {
+template <int G, int NC, int PP>
+int launch_sw_pp(lsx_ctx* ctx, const SwArgs& a) {
     const size_t smem = sw_smem_bytes(a.K, NC);
     if (smem > 48 * 1024)
-        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_subwarp<G, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_subwarp<G, NC, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t threads = a.batch * G;
     const unsigned grid = (unsigned)((threads + SW_THREADS - 1) / SW_THREADS);
     lsx_timing_begin(ctx);
-    k_subwarp<G, NC><<<grid, SW_THREADS, smem, ctx->stream>>>(a);
+    k_subwarp<G, NC, PP><<<grid, SW_THREADS, smem, ctx->stream>>>(a);
     lsx_timing_end(ctx);
     ctx->launches++;
     LSX_CUDA_TRY(ctx, cudaGetLastError());
     return LSX_OK;
+}
+
+// two primes per pass when the plan has at least two and the row fits the register budget twice
+template <int G, int NC>
+int launch_sw(lsx_ctx* ctx, const SwArgs& a) {
+    static const int pp_env = []() {
+        const char* e = getenv("LSX_SW_PP");
+        return e ? atoi(e) : 1;   // measured on B200 (profiles/r02e): two interleaved primes are SLOWER (3.37 vs 2.88 ms per 2^18 16x17 systems: 128 registers, fewer resident warps, twice the code per pass)
+    }();
+    if constexpr (NC <= 24) {
+        if (a.K >= 2 && pp_env >= 2) return launch_sw_pp<G, NC, 2>(ctx, a);
+    }
+    return launch_sw_pp<G, NC, 1>(ctx, a);
 }
 
 // Instantiated shapes: G lanes per matrix, NC register columns (n is padded up to NC with zero columns).

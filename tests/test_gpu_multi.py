@@ -70,6 +70,8 @@ def test_multi_context_matches_single_device():
             det, primes = two.det_large(A)
             assert det == int(c["det"]), c["n"]
         assert two.launch_count > 0
+        from linalg_solver_b200._lib import lib
+        assert lib.lsx_device_count(two._ctx) == 2 and lib.lsx_multi_uses_nccl(two._ctx) == 1   # NCCL all-gather ran
     finally:
         one.close()
         two.close()
