@@ -42,6 +42,9 @@ namespace lsx_inv_small {
 #ifndef LSX_TPM_WINDOW
 #define LSX_TPM_WINDOW 1          // rows below the pivot position tested before the full search
 #endif
+#ifndef LSX_TPM_X
+#define LSX_TPM_X 0               // experiment switch of the lab harness (1: inversion in the last step, as before)
+#endif
 constexpr int TPM_THREADS = LSX_TPM_THREADS;
 
 // Shared-memory tile: one matrix = ST 32-bit words.  With E = N*N a multiple of 4 the matrix is E/4 chunks of
@@ -95,7 +98,21 @@ __device__ __forceinline__ void cswap_rows(bool sw, uint32_t (&x)[N], uint32_t (
     py = sw ? a : b;
 }
 
-template <int N, int HEAD, bool I8>
+// exact integer (as double) -> residue in [0, p): q = rint(t / p) by a fused multiply-add against 1.5 * 2^52, r = t - q p
+// exactly (|t| < 2^53, q < 2^22), integer conversion by the same constant, sign fix by one add-min
+__device__ __forceinline__ uint32_t residue_of_double(double t, double pd, double pinvd, uint32_t p) {
+    const double MAGIC = 6755399441055744.0;
+    const double q = __fma_rn(t, pinvd, MAGIC) - MAGIC;
+    const double r = __fma_rn(-q, pd, t);                   // |r| <= p / 2 (+ p when q is off by one): below p
+    const uint32_t ri = (uint32_t)__double2loint(r + MAGIC);
+    return min(ri, ri + p);
+}
+// small signed integer held in a 32-bit register -> double, without the conversion pipe
+__device__ __forceinline__ double double_of_int(uint32_t w) {
+    return __hiloint2double(0x43300000, (int)(w ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
+}
+
+template <int N, int HEAD, bool I8, bool F64 = false>
 __global__ void __launch_bounds__(TPM_THREADS, LSX_TPM_MINB)
 k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max, int vec_ok,
           int32_t* __restrict__ adj, int32_t* __restrict__ det, int32_t* __restrict__ status) {
@@ -195,25 +212,38 @@ k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max
     uint32_t cw[N];                         // per-row multiplier words (what pivot row k still lacks)
     uint32_t sig = 1u;                      // head: product of the pivots so far (exact integer)
     uint32_t S = 1u, Q = P.one;
+    // F64: pivot step HEAD is still exact integer arithmetic, done on the otherwise idle FP64 pipe (the launcher
+    // guarantees 2 B^2 < 2^53 for the bound B of the entries after HEAD integer steps); its results are reduced to
+    // residue words on the way out, so the Montgomery steps start one step later: HEADX steps carry no factor R^-1.
+    constexpr int HEADX = HEAD + (F64 ? 1 : 0);
+    static_assert(!F64 || (HEAD >= 1 && HEADX <= N - 1), "the FP64 step needs an integer head before and a last step after it");
+    constexpr bool EARLY_INV = LSX_TPM_X != 1 && N >= 2 && N - 2 >= HEADX;   // step N-2 runs on residue words
+    uint32_t qinv_pre = 0u;
 
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         const bool head = j < HEAD;
         const bool last = j == N - 1;
-        if (j == HEAD) {
+        if (j == HEADX) {
             // ---- switch to residue words: S = sigma_h, Q = word(prod sigma_k), cw[k] = word(sigma_k) ----
             // cw[k] was stored as the plain integer sigma_k: to Montgomery form, and Q = their product
             uint32_t qh = P.one;
 #pragma unroll
-            for (int k = 0; k < HEAD; ++k) {
+            for (int k = 0; k < HEADX; ++k) {
                 cw[k] = mont_mul(word_of_small(cw[k], p), P.r2, p, pinv);
                 qh = k == 0 ? cw[0] : mont_mul(qh, cw[k], p, pinv);
             }
+            if (F64) {
+                // every row but the pivot row of the FP64 step already holds residue words; S was set there
 #pragma unroll
-            for (int r = 0; r < N; ++r)
+                for (int c = 0; c < N; ++c) W[HEAD][c] = word_of_small(W[HEAD][c], p);
+            } else {
 #pragma unroll
-                for (int c = 0; c < N; ++c) W[r][c] = word_of_small(W[r][c], p);
-            S = word_of_small(sig, p);
+                for (int r = 0; r < N; ++r)
+#pragma unroll
+                    for (int c = 0; c < N; ++c) W[r][c] = word_of_small(W[r][c], p);
+                S = word_of_small(sig, p);
+            }
             Q = qh;
         }
         // ---- pivot: position j, else a row of the window below it, else (rare, warp vote) any lower row ----
@@ -249,7 +279,27 @@ k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max
         uint32_t prow[N];
 #pragma unroll
         for (int c = 0; c < N; ++c) prow[c] = W[j][c];
-        if (head) {
+        if (F64 && j == HEAD) {
+            // exact integers through the FP64 pipe: t = piv * W[r][c] - f * prow[c] (|t| < 2^53), then t mod p
+            const double pd = (double)p, pinvd = 1.0 / pd;
+            const double pivd = double_of_int(piv), sigd = double_of_int(sig);
+            double prd[N];
+#pragma unroll
+            for (int c = 0; c < N; ++c) prd[c] = double_of_int(prow[c]);
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                if (r == j) continue;
+                const double nf = -double_of_int(W[r][j]);
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    const double t = (c == j) ? nf * sigd : __fma_rn(nf, prd[c], pivd * double_of_int(W[r][c]));
+                    W[r][c] = residue_of_double(t, pd, pinvd, p);
+                }
+            }
+            W[j][j] = sig;                                       // the pivot row stays integer until the switch
+            cw[j] = sig;
+            S = residue_of_double(sigd * pivd, pd, pinvd, p);    // sigma_{HEAD+1} as a residue word
+        } else if (head) {
             // plain two's-complement integers: W[r][c] = piv * W[r][c] - f * prow[c]
             const uint32_t nsig = 0u - sig;
 #pragma unroll
@@ -265,10 +315,19 @@ k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max
         } else {
             cw[j] = S;
             Q = mont_mul(Q, S, p, pinv);
+            // The one modular inversion is a chain of 38 dependent products.  Its argument, the product of all
+            // sigma_k, only needs the pivots up to step N-2, and the sign cannot change any more either (the last
+            // step has no row below it to exchange with): started HERE, in the second-to-last step, the chain
+            // interleaves with that step's 56 independent row updates instead of stalling the warp on its own.
+            if (EARLY_INV && j == N - 2) {
+                const uint32_t s_next = mont_mul(S, piv, p, pinv);            // sigma_{N-1}
+                qinv_pre = mont_inverse(mont_mul(Q, s_next, p, pinv), P);
+                if (neg) qinv_pre = p - qinv_pre;
+            }
             uint32_t qinv = 0u;
             if (last) {
-                qinv = mont_inverse(Q, P);
-                if (neg) qinv = p - qinv;               // Q is a unit unless the matrix is singular (discarded)
+                qinv = EARLY_INV ? qinv_pre : mont_inverse(Q, P);
+                if (!EARLY_INV && neg) qinv = p - qinv;   // Q is a unit unless the matrix is singular (discarded)
             }
 #pragma unroll
             for (int r = 0; r < N; ++r) {

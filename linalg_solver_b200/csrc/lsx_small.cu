@@ -21,17 +21,25 @@ int head_steps_for(int n, int64_t a_abs_max) {
     return h;
 }
 
-template <int N, int HEAD, bool I8>
+// The FP64 step (lsx_inv_small.cuh) computes piv * w - f * prow exactly in a double: the entries after h integer
+// steps are bounded by B_h (B -> 2 B^2 per step), so it needs 2 B_h^2 < 2^53.
+bool f64_step_ok(int64_t a_abs_max, int h) {
+    double B = (double)(a_abs_max < 1 ? 1 : a_abs_max);
+    for (int i = 0; i < h; ++i) B = 2.0 * B * B;
+    return 2.0 * B * B < 9007199254740992.0;
+}
+
+template <int N, int HEAD, bool I8, bool F64 = false>
 int launch_inv_tpm_h(lsx_ctx* ctx, const ElimJob& job) {
     const size_t smem = TpmTile<N>::BYTES;
     if (smem > 48 * 1024)
-        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_inv_tpm<N, HEAD, I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_inv_tpm<N, HEAD, I8, F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((job.batch + TPM_THREADS - 1) / TPM_THREADS);
     const PrimeRec P = lsx_make_prime_rec(ctx->primes[0]);
     // 16-byte accesses need 16-byte aligned caller pointers (a device view with an odd element offset is legal)
     const int vec_ok = (((uintptr_t)job.A | (uintptr_t)job.num) & 15u) == 0;
     lsx_timing_begin(ctx);
-    k_inv_tpm<N, HEAD, I8><<<grid, TPM_THREADS, smem, ctx->stream>>>(job.A, job.batch, P, (int)job.a_abs_max, vec_ok,
+    k_inv_tpm<N, HEAD, I8, F64><<<grid, TPM_THREADS, smem, ctx->stream>>>(job.A, job.batch, P, (int)job.a_abs_max, vec_ok,
                                                                  (int32_t*)job.num, (int32_t*)job.den, job.status);
     lsx_timing_end(ctx);
     ctx->launches++;
@@ -46,6 +54,16 @@ int launch_inv_tpm(lsx_ctx* ctx, const ElimJob& job) {
     const char* e = getenv("LSX_TPM_HEAD");
     const int want = e ? atoi(e) : HMAX;
     const bool head = HMAX > 0 && want >= HMAX && head_steps_for(N, job.a_abs_max) >= HMAX;
+    if constexpr (N == 8) {
+        // the benchmark shape: one more exact step on the FP64 pipe when the magnitudes allow it.  OFF by default:
+        // measured on B200 (profiles/r02f_inv8_lab_fp64_step.jsonl) it is bit-exact but SLOWER, 211 vs 199 us per 2^20
+        // matrices -- the 420 double-precision instructions it adds cost more issue/dispatch than the 105 IMAD.WIDE +
+        // 56 IMAD.HI it takes off the fmaheavy pipe (DFMA and IMAD have the same 64 lanes per clock per SM here).
+        const char* f64_env = getenv("LSX_TPM_F64");
+        const bool f64_on = f64_env && atoi(f64_env) != 0;
+        if (head && f64_on && f64_step_ok(job.a_abs_max, HMAX))
+            return job.in_i8 ? launch_inv_tpm_h<N, HMAX, true, true>(ctx, job) : launch_inv_tpm_h<N, HMAX, false, true>(ctx, job);
+    }
     if (job.in_i8) return head ? launch_inv_tpm_h<N, HMAX, true>(ctx, job) : launch_inv_tpm_h<N, 0, true>(ctx, job);
     return head ? launch_inv_tpm_h<N, HMAX, false>(ctx, job) : launch_inv_tpm_h<N, 0, false>(ctx, job);
 }
