@@ -188,9 +188,7 @@ def reference_line(workload, steps, warmup, gpus):
             times.append(cb["value"])
     val = statistics.mean(times)
     cb["value"] = val
-    ref = reference_unmodified(workload)
-    if ref is not None:
-        cb["reference_unmodified"] = ref
+    with_reference(cb, workload)
     return {
         "impl": "reference", "metric": METRIC[workload], "value": val, "unit": "matrices/s",
         "n_gpus": gpus, "steps": steps, "warmup": warmup,
@@ -760,9 +758,18 @@ def cpu_leg(workload, scale=8):
     if workload == "c5":
         return c5_cpu_baseline(c5_prime_count_numpy())
     cb, _ = cpu_baseline(workload, scale * CPU_PER_CORE[workload], SEED)
+    return with_reference(cb, workload)
+
+
+def with_reference(cb, workload):
+    """Adds the unmodified reference's own timing and says which CPU route is the faster one: the port restates
+    row_reduce on Fractions (linalg.py:534-630), the reference's DEFAULT routes go through sympy (inverse():
+    linalg.py:696-701), which is slower for small matrices and faster for 64x64."""
     ref = reference_unmodified(workload)
     if ref is not None:
         cb["reference_unmodified"] = ref
+        if "value" in ref:
+            cb["fastest_cpu_route"] = "reference_unmodified" if ref["value"] > cb["value"] else "port"
     return cb
 
 
