@@ -235,17 +235,16 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
             }
             // 1. publish column j (indexed by physical row)
             if (tx == (j & 15)) {
-                switch (j >> 4) {              // uniform: no select chain over the register tile
-#define LSX_PUB_COL(B)                                                        \
-    case B:                                                                    \
-        if (B < CB) {                                                          \
-            _Pragma("unroll") for (int ia = 0; ia < RA; ++ia) colbuf[ty + 16 * ia] = W[ia][B < CB ? B : 0]; \
-        }                                                                      \
-        break;
-                    LSX_PUB_COL(0) LSX_PUB_COL(1) LSX_PUB_COL(2) LSX_PUB_COL(3)
-                    LSX_PUB_COL(4) LSX_PUB_COL(5) LSX_PUB_COL(6) LSX_PUB_COL(7)
-#undef LSX_PUB_COL
-                    default: break;
+                // The block index j >> 4 is uniform, but a switch over it is turned into a dynamically indexed access
+                // by the compiler (common-code sinking), which put the whole tile into LOCAL memory (ncu, round 2: one
+                // LDL + one STL per cell update).  A select chain keeps every index static.
+                const int jb = j >> 4;
+#pragma unroll
+                for (int ia = 0; ia < RA; ++ia) {
+                    uint32_t v = W[ia][0];
+#pragma unroll
+                    for (int ib = 1; ib < CB; ++ib) v = (jb == ib) ? W[ia][ib] : v;
+                    colbuf[ty + 16 * ia] = v;
                 }
             }
             __syncthreads();
@@ -272,29 +271,29 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
             if (lazy_id) {
                 // the pivot row's own identity column (n_in + prp) becomes active now, with every block before it
                 while (rb_on <= (prp >> 4)) {
-                    if (tx == ty) {            // the diagonal cell (r, n_in + r) of row r = ty + 16 * rb_on
+                    // the diagonal cell (r, n_in + r) of row r = ty + 16 * rb_on.  Written as selects over the whole
+                    // tile: a conditional store at a run-time (ia, ib) is a dynamically indexed store to the compiler,
+                    // and that alone moved the tile from registers to local memory (128 bytes of stack per thread).
+                    const uint32_t sv = mont_redc((uint64_t)S, p, pinv);
 #pragma unroll
-                        for (int ia = 0; ia < RA; ++ia)
+                    for (int ia = 0; ia < RA; ++ia)
 #pragma unroll
-                            for (int ib = 0; ib < CB; ++ib)
-                                if (ia == rb_on && ib == nleft + rb_on && ty + 16 * ia < m) W[ia][ib] = mont_redc((uint64_t)S, p, pinv);
-                    }
+                        for (int ib = 0; ib < CB; ++ib) {
+                            const bool hit = tx == ty && ia == rb_on && ib == nleft + rb_on && ty + 16 * ia < m;
+                            W[ia][ib] = hit ? sv : W[ia][ib];
+                        }
                     ++rb_on;
                 }
             }
             // 3. publish the pivot row
             if (ty == (prp & 15)) {
-                switch (prp >> 4) {
-#define LSX_PUB_ROW(Aidx)                                                     \
-    case Aidx:                                                                 \
-        if (Aidx < RA) {                                                       \
-            _Pragma("unroll") for (int ib = 0; ib < CB; ++ib) prow[tx + 16 * ib] = W[Aidx < RA ? Aidx : 0][ib]; \
-        }                                                                      \
-        break;
-                    LSX_PUB_ROW(0) LSX_PUB_ROW(1) LSX_PUB_ROW(2) LSX_PUB_ROW(3)
-                    LSX_PUB_ROW(4) LSX_PUB_ROW(5) LSX_PUB_ROW(6) LSX_PUB_ROW(7)
-#undef LSX_PUB_ROW
-                    default: break;
+                const int pb = prp >> 4;       // same: selects, not a switch
+#pragma unroll
+                for (int ib = 0; ib < CB; ++ib) {
+                    uint32_t v = W[0][ib];
+#pragma unroll
+                    for (int ia = 1; ia < RA; ++ia) v = (pb == ia) ? W[ia][ib] : v;
+                    prow[tx + 16 * ib] = v;
                 }
             }
             const uint32_t piv = colbuf[prp];
@@ -333,13 +332,14 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
         if (lazy_id) {
             // rank-deficient input: blocks never switched on still hold the initial ones; give them the final scale
             while (rb_on < ((m + 15) >> 4)) {
-                if (tx == ty) {
+                const uint32_t sv = mont_redc((uint64_t)S, p, pinv);
 #pragma unroll
-                    for (int ia = 0; ia < RA; ++ia)
+                for (int ia = 0; ia < RA; ++ia)
 #pragma unroll
-                        for (int ib = 0; ib < CB; ++ib)
-                            if (ia == rb_on && ib == nleft + rb_on && ty + 16 * ia < m) W[ia][ib] = mont_redc((uint64_t)S, p, pinv);
-                }
+                    for (int ib = 0; ib < CB; ++ib) {
+                        const bool hit = tx == ty && ia == rb_on && ib == nleft + rb_on && ty + 16 * ia < m;
+                        W[ia][ib] = hit ? sv : W[ia][ib];
+                    }
                 ++rb_on;
             }
         }
