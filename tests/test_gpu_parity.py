@@ -219,6 +219,35 @@ def _limbs_mod(t, q):
     return acc.to(torch.float64)
 
 
+def _assert_canonical_solution_form(res, nvars, ok=None):
+    """Canonical form of the reference's solution sets (linalg.py:961-983), on the EXACT device words and for every
+    system of the batch: the particular solution is zero on the free columns; generator t is `den` at the t-th free
+    column (ascending order), zero at the other free columns, and unused generator columns are zero."""
+    import torch
+    B = res.rank.shape[0]
+    piv = res.pivot_col.to(torch.int64)                          # [B, slots], -1 padded
+    is_piv = torch.zeros((B, nvars + 1), dtype=torch.bool, device=piv.device)
+    is_piv.scatter_(1, torch.where(piv >= 0, piv, torch.full_like(piv, nvars)), True)
+    free = ~is_piv[:, :nvars]                                    # [B, nvars]
+    if ok is None:
+        ok = torch.ones(B, dtype=torch.bool, device=piv.device)
+    part_zero = (res.particular == 0).all(dim=-1)                # [B, nvars]
+    assert bool((part_zero | ~free)[ok].all())
+    G = res.generators.shape[2]
+    order = torch.cumsum(free.to(torch.int64), dim=1) - 1        # index of a free column among the free columns
+    gens = res.generators                                        # [B, nvars, G, L]
+    den = res.den[:, None, None, :].expand(-1, nvars, G, -1)
+    t_idx = torch.arange(G, device=piv.device)[None, None, :]
+    on_diag = free[:, :, None] & (order[:, :, None] == t_idx)    # (free column f, generator t = its order)
+    off_diag = free[:, :, None] & (order[:, :, None] != t_idx)
+    eq_den = (gens == den).all(dim=-1)
+    is_zero = (gens == 0).all(dim=-1)
+    assert bool((eq_den | ~on_diag)[ok].all()) and bool((is_zero | ~off_diag)[ok].all())
+    nfree = free.sum(dim=1)
+    unused = t_idx[0] >= nfree[:, None, None].clamp(max=G)       # [B, 1, G] broadcast over rows
+    assert bool((is_zero | ~unused.expand(-1, nvars, -1))[ok].all())
+
+
 def test_c3_full_size_properties(eng):
     """BASELINE.json configs[2] at its full size (2^18 systems): A * particular == den * b for the consistent
     half, A * generators == 0 everywhere, every odd (random right-hand side) system of rank-10 A is inconsistent or
@@ -245,6 +274,7 @@ def test_c3_full_size_properties(eng):
     assert bool((lhs[ok] == rhs[ok]).all())
     assert bool(((torch.einsum("bij,bjk->bik", Aq, gens) % q)[ok] == 0).all())
     assert bool((res.den != 0).any(dim=-1)[ok].all())            # exact words: a non-zero integer may vanish modulo q
+    _assert_canonical_solution_form(res, 16, ok)                 # free variables zero, gen[f] = den, unused columns zero
 
 
 def test_c4_full_size_properties(eng):
@@ -290,6 +320,7 @@ def test_c4_kernel_basis_full_size_properties(eng):
         # a non-zero integer may vanish modulo q)
         assert bool((res.den != 0).any(dim=-1).all())
         assert bool((res.generators != 0).any(dim=-1).any(dim=1).all())
+        _assert_canonical_solution_form(res, 64)
         del A, res, gens, den
 
 
