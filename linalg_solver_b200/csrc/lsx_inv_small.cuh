@@ -170,9 +170,18 @@ k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max
         if (T::VEC && vec_ok) {
             constexpr int CC = T::C > 0 ? T::C : 1;
             const int4* src4 = reinterpret_cast<const int4*>(src);
+            if (nmat == TPM_THREADS && TPM_THREADS % CC == 0) {
+                // full tile: chunk g = tid + k * THREADS lies THREADS / CC matrices further per k, so every address is
+                // one base plus a compile-time offset (C loads and stores, no index arithmetic in the loop)
+                const int4* s0 = src4 + tid;
+                int4* d0 = reinterpret_cast<int4*>(sm + (tid / CC) * ST + (tid % CC) * 4);
+#pragma unroll
+                for (int k = 0; k < T::C; ++k) d0[k * (TPM_THREADS / CC) * (ST / 4)] = __ldg(s0 + k * TPM_THREADS);
+            } else {
 #pragma unroll 4
-            for (int g = tid; g < nmat * T::C; g += TPM_THREADS)
-                *reinterpret_cast<int4*>(sm + (g / CC) * ST + (g % CC) * 4) = __ldg(src4 + g);
+                for (int g = tid; g < nmat * T::C; g += TPM_THREADS)
+                    *reinterpret_cast<int4*>(sm + (g / CC) * ST + (g % CC) * 4) = __ldg(src4 + g);
+            }
         } else {
             for (int w = tid; w < nmat * E; w += TPM_THREADS) sm[(w / E) * ST + (w % E)] = (uint32_t)__ldg(src + w);
         }
@@ -422,9 +431,16 @@ k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max
         if (T::VEC && vec_ok) {
             constexpr int CC = T::C > 0 ? T::C : 1;
             int4* dst4 = reinterpret_cast<int4*>(dst);
+            if (nmat == TPM_THREADS && TPM_THREADS % CC == 0) {
+                int4* o0 = dst4 + tid;
+                const int4* s0 = reinterpret_cast<const int4*>(sm + (tid / CC) * ST + (tid % CC) * 4);
+#pragma unroll
+                for (int k = 0; k < T::C; ++k) o0[k * TPM_THREADS] = s0[k * (TPM_THREADS / CC) * (ST / 4)];
+            } else {
 #pragma unroll 4
-            for (int g = tid; g < nmat * T::C; g += TPM_THREADS)
-                dst4[g] = *reinterpret_cast<const int4*>(sm + (g / CC) * ST + (g % CC) * 4);
+                for (int g = tid; g < nmat * T::C; g += TPM_THREADS)
+                    dst4[g] = *reinterpret_cast<const int4*>(sm + (g / CC) * ST + (g % CC) * 4);
+            }
         } else {
             for (int w = tid; w < nmat * E; w += TPM_THREADS) dst[w] = (int32_t)sm[(w / E) * ST + (w % E)];
         }
