@@ -112,7 +112,18 @@ __device__ __forceinline__ double double_of_int(uint32_t w) {
     return __hiloint2double(0x43300000, (int)(w ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
 }
 
-template <int N, int HEAD, bool I8, bool F64 = false>
+// exact 64-bit integer (made non-negative by a multiple of p) -> residue in [0, p) for p = 2^31 - 1: 2^31 = 1 mod p, so
+// t = hi * 2^31 + lo folds to hi + lo; with t < 2^55 the sum is below 2 p and one add-min finishes.  No multiply.
+__device__ __forceinline__ uint32_t mersenne31_of_u64(uint64_t t) {
+    const uint32_t lo = (uint32_t)t & 0x7fffffffu;
+    const uint32_t hi = (uint32_t)(t >> 31);
+    const uint32_t s = lo + hi;
+    return min(s, s - 0x7fffffffu);
+}
+
+// XS: how pivot step HEAD is done when it is still exact integer arithmetic (0: it is an ordinary Montgomery step),
+//   1 = on the FP64 pipe, 2 = 64-bit integers folded modulo the Mersenne prime 2^31 - 1 (needs p == 2^31 - 1)
+template <int N, int HEAD, bool I8, int XS = 0>
 __global__ void __launch_bounds__(TPM_THREADS, LSX_TPM_MINB)
 k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max, int vec_ok,
           int32_t* __restrict__ adj, int32_t* __restrict__ det, int32_t* __restrict__ status) {
@@ -224,6 +235,7 @@ k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max
     // F64: pivot step HEAD is still exact integer arithmetic, done on the otherwise idle FP64 pipe (the launcher
     // guarantees 2 B^2 < 2^53 for the bound B of the entries after HEAD integer steps); its results are reduced to
     // residue words on the way out, so the Montgomery steps start one step later: HEADX steps carry no factor R^-1.
+    constexpr bool F64 = XS != 0;                       // one more exact step before the Montgomery words start
     constexpr int HEADX = HEAD + (F64 ? 1 : 0);
     static_assert(!F64 || (HEAD >= 1 && HEADX <= N - 1), "the FP64 step needs an integer head before and a last step after it");
     constexpr bool EARLY_INV = LSX_TPM_X != 1 && N >= 2 && N - 2 >= HEADX;   // step N-2 runs on residue words
@@ -288,7 +300,27 @@ k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max
         uint32_t prow[N];
 #pragma unroll
         for (int c = 0; c < N; ++c) prow[c] = W[j][c];
-        if (F64 && j == HEAD) {
+        if (XS == 2 && j == HEAD) {
+            // exact 64-bit integers: t = piv * W[r][c] - f * prow[c] (|t| < 2^53 by the launcher's bound) plus 2^23 p to
+            // make it non-negative, folded modulo p = 2^31 - 1 without a multiply: the step costs two IMAD.WIDE per
+            // entry on the fmaheavy pipe instead of two IMAD.WIDE + IMAD + IMAD.HI, and carries no factor R^-1
+            const int64_t off = (int64_t)0x7fffffff << 23;
+            const int32_t pivs = (int32_t)piv, sigs = (int32_t)sig;
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                if (r == j) continue;
+                const int32_t nf = -(int32_t)W[r][j];
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    const int64_t t = (c == j) ? (int64_t)nf * sigs + off
+                                               : (int64_t)nf * (int32_t)prow[c] + ((int64_t)pivs * (int32_t)W[r][c] + off);
+                    W[r][c] = mersenne31_of_u64((uint64_t)t);
+                }
+            }
+            W[j][j] = sig;                                       // the pivot row stays integer until the switch
+            cw[j] = sig;
+            S = mersenne31_of_u64((uint64_t)((int64_t)sigs * pivs + off));   // sigma_{HEAD+1} as a residue word
+        } else if (XS == 1 && j == HEAD) {
             // exact integers through the FP64 pipe: t = piv * W[r][c] - f * prow[c] (|t| < 2^53), then t mod p
             const double pd = (double)p, pinvd = 1.0 / pd;
             const double pivd = double_of_int(piv), sigd = double_of_int(sig);

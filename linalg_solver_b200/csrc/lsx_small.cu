@@ -29,17 +29,17 @@ bool f64_step_ok(int64_t a_abs_max, int h) {
     return 2.0 * B * B < 9007199254740992.0;
 }
 
-template <int N, int HEAD, bool I8, bool F64 = false>
+template <int N, int HEAD, bool I8, int XS = 0>
 int launch_inv_tpm_h(lsx_ctx* ctx, const ElimJob& job) {
     const size_t smem = TpmTile<N>::BYTES;
     if (smem > 48 * 1024)
-        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_inv_tpm<N, HEAD, I8, F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_inv_tpm<N, HEAD, I8, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((job.batch + TPM_THREADS - 1) / TPM_THREADS);
     const PrimeRec P = lsx_make_prime_rec(ctx->primes[0]);
     // 16-byte accesses need 16-byte aligned caller pointers (a device view with an odd element offset is legal)
     const int vec_ok = (((uintptr_t)job.A | (uintptr_t)job.num) & 15u) == 0;
     lsx_timing_begin(ctx);
-    k_inv_tpm<N, HEAD, I8, F64><<<grid, TPM_THREADS, smem, ctx->stream>>>(job.A, job.batch, P, (int)job.a_abs_max, vec_ok,
+    k_inv_tpm<N, HEAD, I8, XS><<<grid, TPM_THREADS, smem, ctx->stream>>>(job.A, job.batch, P, (int)job.a_abs_max, vec_ok,
                                                                  (int32_t*)job.num, (int32_t*)job.den, job.status);
     lsx_timing_end(ctx);
     ctx->launches++;
@@ -55,14 +55,21 @@ int launch_inv_tpm(lsx_ctx* ctx, const ElimJob& job) {
     const int want = e ? atoi(e) : HMAX;
     const bool head = HMAX > 0 && want >= HMAX && head_steps_for(N, job.a_abs_max) >= HMAX;
     if constexpr (N == 8) {
-        // the benchmark shape: one more exact step on the FP64 pipe when the magnitudes allow it.  OFF by default:
-        // measured on B200 (profiles/r02f_inv8_lab_fp64_step.jsonl) it is bit-exact but SLOWER, 211 vs 199 us per 2^20
-        // matrices -- the 420 double-precision instructions it adds cost more issue/dispatch than the 105 IMAD.WIDE +
-        // 56 IMAD.HI it takes off the fmaheavy pipe (DFMA and IMAD have the same 64 lanes per clock per SM here).
-        const char* f64_env = getenv("LSX_TPM_F64");
-        const bool f64_on = f64_env && atoi(f64_env) != 0;
-        if (head && f64_on && f64_step_ok(job.a_abs_max, HMAX))
-            return job.in_i8 ? launch_inv_tpm_h<N, HMAX, true, true>(ctx, job) : launch_inv_tpm_h<N, HMAX, false, true>(ctx, job);
+        // the benchmark shape: pivot step 3 is still exact integer arithmetic when 2 B^2 < 2^53 for the bound B after
+        // the integer head, and can be done without a Montgomery reduction.  LSX_TPM_XS = 2: 64-bit integers folded
+        // modulo the Mersenne prime 2^31 - 1 (56 IMAD + 56 IMAD.HI less on the fmaheavy pipe); 1: the same step on the
+        // FP64 pipe.  Both are bit-exact (tests) and both measured NEUTRAL on B200 (198.4 / 199.4 vs 198.1 us per 2^20
+        // matrices, profiles/r02k_inv8_lab_mersenne_step.jsonl): with 4 warps per scheduler the kernel is bound by
+        // its dependency chains and the exposed tile load (ncu: 19 % of the stall samples sit on the first STS.128
+        // after the global loads), not by the count of fmaheavy instructions.  Default 0: the plain kernel.
+        const char* xs_env = getenv("LSX_TPM_XS");
+        const int xs = xs_env ? atoi(xs_env) : 0;
+        if (head && xs != 0 && f64_step_ok(job.a_abs_max, HMAX)) {
+            if (xs == 2 && ctx->primes[0] == 0x7fffffffu)
+                return job.in_i8 ? launch_inv_tpm_h<N, HMAX, true, 2>(ctx, job) : launch_inv_tpm_h<N, HMAX, false, 2>(ctx, job);
+            if (xs == 1)
+                return job.in_i8 ? launch_inv_tpm_h<N, HMAX, true, 1>(ctx, job) : launch_inv_tpm_h<N, HMAX, false, 1>(ctx, job);
+        }
     }
     if (job.in_i8) return head ? launch_inv_tpm_h<N, HMAX, true>(ctx, job) : launch_inv_tpm_h<N, 0, true>(ctx, job);
     return head ? launch_inv_tpm_h<N, HMAX, false>(ctx, job) : launch_inv_tpm_h<N, 0, false>(ctx, job);

@@ -466,11 +466,12 @@ def test_fused_small_inverse_equals_tile_path(eng, monkeypatch):
             assert np.array_equal(fused.adj, nohead.adj) and np.array_equal(fused.det, nohead.det)
             assert np.array_equal(fused.status, nohead.status)
             if n == 8:
-                monkeypatch.setenv("LSX_TPM_F64", "1")          # pivot step 3 as exact integers on the FP64 pipe
-                f64 = eng.inverse_batch(A, a_abs_max=5)
-                monkeypatch.delenv("LSX_TPM_F64")
-                assert np.array_equal(fused.adj, f64.adj) and np.array_equal(fused.det, f64.det)
-                assert np.array_equal(fused.status, f64.status)
+                for xs in ("0", "1", "2"):                      # pivot step 3: Montgomery / FP64 pipe / 64-bit + Mersenne fold
+                    monkeypatch.setenv("LSX_TPM_XS", xs)
+                    alt = eng.inverse_batch(A, a_abs_max=5)
+                    monkeypatch.delenv("LSX_TPM_XS")
+                    assert np.array_equal(fused.adj, alt.adj) and np.array_equal(fused.det, alt.det), xs
+                    assert np.array_equal(fused.status, alt.status), xs
             monkeypatch.setenv("LSX_DISABLE_SMALL", "1")
             tile = eng.inverse_batch(A, a_abs_max=5)
             monkeypatch.delenv("LSX_DISABLE_SMALL")

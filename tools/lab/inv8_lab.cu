@@ -39,20 +39,20 @@ typedef int (*inv_t)(void*, const lsx_plan*, const int32_t*, int64_t, int, uint3
 typedef int (*inv8_t)(void*, const lsx_plan*, const int8_t*, int64_t, int, uint32_t*, uint32_t*, int32_t*);
 typedef int (*setstream_t)(void*, void*);
 
-template <int N, int HEAD, bool I8, bool F64 = false>
+template <int N, int HEAD, bool I8, int XS = 0>
 float time_new(const void* dA, int64_t batch, PrimeRec P, int amax, int32_t* adj, int32_t* det, int32_t* st, int reps,
                cudaStream_t s) {
     using namespace lsx_inv_small;
     const size_t smem = TpmTile<N>::BYTES;
-    CK(cudaFuncSetAttribute(k_inv_tpm<N, HEAD, I8, F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_inv_tpm<N, HEAD, I8, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((batch + TPM_THREADS - 1) / TPM_THREADS);
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) k_inv_tpm<N, HEAD, I8, F64><<<grid, TPM_THREADS, smem, s>>>(dA, batch, P, amax, 1, adj, det, st);
+    for (int i = 0; i < 3; ++i) k_inv_tpm<N, HEAD, I8, XS><<<grid, TPM_THREADS, smem, s>>>(dA, batch, P, amax, 1, adj, det, st);
     CK(cudaStreamSynchronize(s));
     CK(cudaEventRecord(e0, s));
-    for (int i = 0; i < reps; ++i) k_inv_tpm<N, HEAD, I8, F64><<<grid, TPM_THREADS, smem, s>>>(dA, batch, P, amax, 1, adj, det, st);
+    for (int i = 0; i < reps; ++i) k_inv_tpm<N, HEAD, I8, XS><<<grid, TPM_THREADS, smem, s>>>(dA, batch, P, amax, 1, adj, det, st);
     CK(cudaEventRecord(e1, s));
     CK(cudaEventSynchronize(e1));
     float ms;
@@ -165,11 +165,17 @@ int main(int argc, char** argv) {
     const float ms32h0 = time_new<8, 0, false>(dA, batch, P, 5, adj1, det1, st1, reps, s);
     bad += compare("int32 head0");
     CK(cudaMemset(adj1, 0xff, A.size() * 4));
-    const float ms32f = time_new<8, 3, false, true>(dA, batch, P, 5, adj1, det1, st1, reps, s);
+    const float ms32f = time_new<8, 3, false, 1>(dA, batch, P, 5, adj1, det1, st1, reps, s);
     bad += compare("int32 head3 + fp64 step");
     CK(cudaMemset(adj1, 0xff, A.size() * 4));
-    const float ms8f = time_new<8, 3, true, true>(dA8, batch, P, 5, adj1, det1, st1, reps, s);
+    const float ms8f = time_new<8, 3, true, 1>(dA8, batch, P, 5, adj1, det1, st1, reps, s);
     bad += compare("int8 head3 + fp64 step");
+    CK(cudaMemset(adj1, 0xff, A.size() * 4));
+    const float ms32m = time_new<8, 3, false, 2>(dA, batch, P, 5, adj1, det1, st1, reps, s);
+    bad += compare("int32 head3 + mersenne step");
+    CK(cudaMemset(adj1, 0xff, A.size() * 4));
+    const float ms8m = time_new<8, 3, true, 2>(dA8, batch, P, 5, adj1, det1, st1, reps, s);
+    bad += compare("int8 head3 + mersenne step");
     // short batch (last block partly filled)
     CK(cudaMemset(adj1, 0xff, A.size() * 4));
     time_new<8, 3, false>(dA, 1000, P, 5, adj1, det1, st1, 1, s);
@@ -181,7 +187,7 @@ int main(int argc, char** argv) {
         }
     }
     printf("{\"tag\": \"%s\", \"threads\": %d, \"minb\": %d, \"window\": %d, \"ref_r1_ms\": %.4f, \"new_i32_ms\": %.4f, "
-           "\"new_i8_ms\": %.4f, \"new_i32_head0_ms\": %.4f, \"new_i32_f64_ms\": %.4f, \"new_i8_f64_ms\": %.4f, \"mismatches\": %ld}\n",
-           tag, LSX_TPM_THREADS, LSX_TPM_MINB, LSX_TPM_WINDOW, ref_ms, ms32, ms8, ms32h0, ms32f, ms8f, bad);
+           "\"new_i8_ms\": %.4f, \"new_i32_head0_ms\": %.4f, \"new_i32_f64_ms\": %.4f, \"new_i8_f64_ms\": %.4f, \"new_i32_mers_ms\": %.4f, \"new_i8_mers_ms\": %.4f, \"mismatches\": %ld}\n",
+           tag, LSX_TPM_THREADS, LSX_TPM_MINB, LSX_TPM_WINDOW, ref_ms, ms32, ms8, ms32h0, ms32f, ms8f, ms32m, ms8m, bad);
     return bad ? 5 : 0;
 }
