@@ -121,6 +121,192 @@ __device__ __forceinline__ uint32_t mersenne31_of_u64(uint64_t t) {
     return min(s, s - 0x7fffffffu);
 }
 
+// The elimination proper, on a matrix (its TRANSPOSE) that sits in registers: in-place division-free Gauss-Jordan as
+// described at the top of this file.  On return W holds the residues of the transposed adjugate with its columns in
+// pivot order (slot j = row perm[j] of the adjugate of A), `singular` says whether a pivot was missing, and with
+// KEEP_A0 (needs HEAD > 0) a0 is the first pivot row as loaded, i.e. column perm[0] of A.
+template <int N, int HEAD, int XS, bool KEEP_A0>
+__device__ __forceinline__ void tpm_eliminate(uint32_t (&W)[N][N], uint32_t (&perm)[N], uint32_t (&a0)[N], bool& singular,
+                                              const PrimeRec& P) {
+    static_assert(!KEEP_A0 || HEAD > 0, "the first pivot row is only an integer row when the head has a step");
+    const uint32_t p = P.p, pinv = P.pinv;
+#pragma unroll
+    for (int r = 0; r < N; ++r) perm[r] = (uint32_t)r;
+    bool neg = false;
+    singular = false;
+    uint32_t cw[N];                         // per-row multiplier words (what pivot row k still lacks)
+    uint32_t sig = 1u;                      // head: product of the pivots so far (exact integer)
+    uint32_t S = 1u, Q = P.one;
+    // F64: pivot step HEAD is still exact integer arithmetic, done on the otherwise idle FP64 pipe (the launcher
+    // guarantees 2 B^2 < 2^53 for the bound B of the entries after HEAD integer steps); its results are reduced to
+    // residue words on the way out, so the Montgomery steps start one step later: HEADX steps carry no factor R^-1.
+    constexpr bool F64 = XS != 0;                       // one more exact step before the Montgomery words start
+    constexpr int HEADX = HEAD + (F64 ? 1 : 0);
+    static_assert(!F64 || (HEAD >= 1 && HEADX <= N - 1), "the FP64 step needs an integer head before and a last step after it");
+    constexpr bool EARLY_INV = LSX_TPM_X != 1 && N >= 2 && N - 2 >= HEADX;   // step N-2 runs on residue words
+    uint32_t qinv_pre = 0u;
+
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const bool head = j < HEAD;
+        const bool last = j == N - 1;
+        if (j == HEADX) {
+            // ---- switch to residue words: S = sigma_h, Q = word(prod sigma_k), cw[k] = word(sigma_k) ----
+            // cw[k] was stored as the plain integer sigma_k: to Montgomery form, and Q = their product
+            uint32_t qh = P.one;
+#pragma unroll
+            for (int k = 0; k < HEADX; ++k) {
+                cw[k] = mont_mul(word_of_small(cw[k], p), P.r2, p, pinv);
+                qh = k == 0 ? cw[0] : mont_mul(qh, cw[k], p, pinv);
+            }
+            if (F64) {
+                // every row but the pivot row of the FP64 step already holds residue words; S was set there
+#pragma unroll
+                for (int c = 0; c < N; ++c) W[HEAD][c] = word_of_small(W[HEAD][c], p);
+            } else {
+#pragma unroll
+                for (int r = 0; r < N; ++r)
+#pragma unroll
+                    for (int c = 0; c < N; ++c) W[r][c] = word_of_small(W[r][c], p);
+                S = word_of_small(sig, p);
+            }
+            Q = qh;
+        }
+        // ---- pivot: position j, else a row of the window below it, else (rare, warp vote) any lower row ----
+        if (j + 1 < N) {
+            bool found = W[j][j] != 0u;
+            const int WEND = j + LSX_TPM_WINDOW < N - 1 ? j + LSX_TPM_WINDOW : N - 1;       // last row of the window
+            bool swn[LSX_TPM_WINDOW > 0 ? LSX_TPM_WINDOW : 1];
+#pragma unroll
+            for (int r = j + 1; r <= WEND; ++r) {
+                swn[r - j - 1] = !found && W[r][j] != 0u;
+                found = found || swn[r - j - 1];
+            }
+            if (WEND < N - 1) {
+                if (__any_sync(0xffffffffu, !found)) {
+                    int src = -1;
+#pragma unroll
+                    for (int r = N - 1; r > WEND; --r)
+                        if (W[r][j] != 0u) src = r;
+                    const bool far = !found && src >= 0;
+#pragma unroll
+                    for (int r = WEND + 1; r < N; ++r) cswap_rows<N>(far && r == src, W[j], W[r], perm[j], perm[r]);
+                    neg = neg != far;
+                }
+            }
+#pragma unroll
+            for (int r = j + 1; r <= WEND; ++r) {
+                cswap_rows<N>(swn[r - j - 1], W[j], W[r], perm[j], perm[r]);
+                neg = neg != swn[r - j - 1];
+            }
+        }
+        const uint32_t piv = W[j][j];
+        singular = singular || piv == 0u;   // keep going on garbage: every operation below is total
+        uint32_t prow[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) prow[c] = W[j][c];
+        if (KEEP_A0 && j == 0) {               // the first pivot row as loaded = column perm[0] of A (HEAD > 0: integers)
+#pragma unroll
+            for (int c = 0; c < N; ++c) a0[c] = prow[c];
+        }
+        if (XS == 2 && j == HEAD) {
+            // exact 64-bit integers: t = piv * W[r][c] - f * prow[c] (|t| < 2^53 by the launcher's bound) plus 2^23 p to
+            // make it non-negative, folded modulo p = 2^31 - 1 without a multiply: the step costs two IMAD.WIDE per
+            // entry on the fmaheavy pipe instead of two IMAD.WIDE + IMAD + IMAD.HI, and carries no factor R^-1
+            const int64_t off = (int64_t)0x7fffffff << 23;
+            const int32_t pivs = (int32_t)piv, sigs = (int32_t)sig;
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                if (r == j) continue;
+                const int32_t nf = -(int32_t)W[r][j];
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    const int64_t t = (c == j) ? (int64_t)nf * sigs + off
+                                               : (int64_t)nf * (int32_t)prow[c] + ((int64_t)pivs * (int32_t)W[r][c] + off);
+                    W[r][c] = mersenne31_of_u64((uint64_t)t);
+                }
+            }
+            W[j][j] = sig;                                       // the pivot row stays integer until the switch
+            cw[j] = sig;
+            S = mersenne31_of_u64((uint64_t)((int64_t)sigs * pivs + off));   // sigma_{HEAD+1} as a residue word
+        } else if (XS == 1 && j == HEAD) {
+            // exact integers through the FP64 pipe: t = piv * W[r][c] - f * prow[c] (|t| < 2^53), then t mod p
+            const double pd = (double)p, pinvd = 1.0 / pd;
+            const double pivd = double_of_int(piv), sigd = double_of_int(sig);
+            double prd[N];
+#pragma unroll
+            for (int c = 0; c < N; ++c) prd[c] = double_of_int(prow[c]);
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                if (r == j) continue;
+                const double nf = -double_of_int(W[r][j]);
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    const double t = (c == j) ? nf * sigd : __fma_rn(nf, prd[c], pivd * double_of_int(W[r][c]));
+                    W[r][c] = residue_of_double(t, pd, pinvd, p);
+                }
+            }
+            W[j][j] = sig;                                       // the pivot row stays integer until the switch
+            cw[j] = sig;
+            S = residue_of_double(sigd * pivd, pd, pinvd, p);    // sigma_{HEAD+1} as a residue word
+        } else if (head) {
+            // plain two's-complement integers: W[r][c] = piv * W[r][c] - f * prow[c]
+            const uint32_t nsig = 0u - sig;
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                if (r == j) continue;
+                const uint32_t f = W[r][j];
+#pragma unroll
+                for (int c = 0; c < N; ++c) W[r][c] = (c == j) ? f * nsig : (piv * W[r][c] - f * prow[c]);
+            }
+            W[j][j] = sig;
+            cw[j] = sig;
+            sig *= piv;
+        } else {
+            cw[j] = S;
+            Q = mont_mul(Q, S, p, pinv);
+            // The one modular inversion is a chain of 38 dependent products.  Its argument, the product of all
+            // sigma_k, only needs the pivots up to step N-2, and the sign cannot change any more either (the last
+            // step has no row below it to exchange with): started HERE, in the second-to-last step, the chain
+            // interleaves with that step's 56 independent row updates instead of stalling the warp on its own.
+            if (EARLY_INV && j == N - 2) {
+                const uint32_t s_next = mont_mul(S, piv, p, pinv);            // sigma_{N-1}
+                qinv_pre = mont_inverse(mont_mul(Q, s_next, p, pinv), P);
+                if (neg) qinv_pre = p - qinv_pre;
+            }
+            uint32_t qinv = 0u;
+            if (last) {
+                qinv = EARLY_INV ? qinv_pre : mont_inverse(Q, P);
+                if (!EARLY_INV && neg) qinv = p - qinv;   // Q is a unit unless the matrix is singular (discarded)
+            }
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                if (r == j) {
+                    if (last) {
+                        const uint32_t g = mont_mul(qinv, cw[r], p, pinv);
+#pragma unroll
+                        for (int c = 0; c < N; ++c) W[r][c] = mont_mul(g, c == j ? S : prow[c], p, pinv);
+                    } else {
+                        W[r][j] = S;
+                    }
+                } else {
+                    uint32_t y = p - W[r][j];           // in [1, p]: a valid operand of the two-product reduction
+                    uint32_t x = piv;
+                    if (last) {
+                        const uint32_t g = mont_mul(qinv, cw[r], p, pinv);
+                        x = mont_mul(g, x, p, pinv);
+                        y = mont_mul(g, y, p, pinv);
+                    }
+#pragma unroll
+                    for (int c = 0; c < N; ++c)
+                        W[r][c] = (c == j) ? mont_mul(y, S, p, pinv) : mont_fma2(x, W[r][c], y, prow[c], p, pinv);
+                }
+            }
+            S = mont_mul(S, piv, p, pinv);
+        }
+    }
+}
+
 // XS: how pivot step HEAD is done when it is still exact integer arithmetic (0: it is an ordinary Montgomery step),
 //   1 = on the FP64 pipe, 2 = 64-bit integers folded modulo the Mersenne prime 2^31 - 1 (needs p == 2^31 - 1)
 template <int N, int HEAD, bool I8, int XS = 0>
@@ -226,179 +412,11 @@ k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max
     const bool bound_bad = vmax > a_abs_max || vmin < -a_abs_max;
 
     uint32_t perm[N];                       // perm[r]: original index of the transpose row now at position r
-#pragma unroll
-    for (int r = 0; r < N; ++r) perm[r] = (uint32_t)r;
-    bool neg = false, singular = false;
-    uint32_t cw[N];                         // per-row multiplier words (what pivot row k still lacks)
-    uint32_t sig = 1u;                      // head: product of the pivots so far (exact integer)
-    uint32_t S = 1u, Q = P.one;
-    // F64: pivot step HEAD is still exact integer arithmetic, done on the otherwise idle FP64 pipe (the launcher
-    // guarantees 2 B^2 < 2^53 for the bound B of the entries after HEAD integer steps); its results are reduced to
-    // residue words on the way out, so the Montgomery steps start one step later: HEADX steps carry no factor R^-1.
-    constexpr bool F64 = XS != 0;                       // one more exact step before the Montgomery words start
-    constexpr int HEADX = HEAD + (F64 ? 1 : 0);
-    static_assert(!F64 || (HEAD >= 1 && HEADX <= N - 1), "the FP64 step needs an integer head before and a last step after it");
-    constexpr bool EARLY_INV = LSX_TPM_X != 1 && N >= 2 && N - 2 >= HEADX;   // step N-2 runs on residue words
-    uint32_t qinv_pre = 0u;
-
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        const bool head = j < HEAD;
-        const bool last = j == N - 1;
-        if (j == HEADX) {
-            // ---- switch to residue words: S = sigma_h, Q = word(prod sigma_k), cw[k] = word(sigma_k) ----
-            // cw[k] was stored as the plain integer sigma_k: to Montgomery form, and Q = their product
-            uint32_t qh = P.one;
-#pragma unroll
-            for (int k = 0; k < HEADX; ++k) {
-                cw[k] = mont_mul(word_of_small(cw[k], p), P.r2, p, pinv);
-                qh = k == 0 ? cw[0] : mont_mul(qh, cw[k], p, pinv);
-            }
-            if (F64) {
-                // every row but the pivot row of the FP64 step already holds residue words; S was set there
-#pragma unroll
-                for (int c = 0; c < N; ++c) W[HEAD][c] = word_of_small(W[HEAD][c], p);
-            } else {
-#pragma unroll
-                for (int r = 0; r < N; ++r)
-#pragma unroll
-                    for (int c = 0; c < N; ++c) W[r][c] = word_of_small(W[r][c], p);
-                S = word_of_small(sig, p);
-            }
-            Q = qh;
-        }
-        // ---- pivot: position j, else a row of the window below it, else (rare, warp vote) any lower row ----
-        if (j + 1 < N) {
-            bool found = W[j][j] != 0u;
-            const int WEND = j + LSX_TPM_WINDOW < N - 1 ? j + LSX_TPM_WINDOW : N - 1;       // last row of the window
-            bool swn[LSX_TPM_WINDOW > 0 ? LSX_TPM_WINDOW : 1];
-#pragma unroll
-            for (int r = j + 1; r <= WEND; ++r) {
-                swn[r - j - 1] = !found && W[r][j] != 0u;
-                found = found || swn[r - j - 1];
-            }
-            if (WEND < N - 1) {
-                if (__any_sync(0xffffffffu, !found)) {
-                    int src = -1;
-#pragma unroll
-                    for (int r = N - 1; r > WEND; --r)
-                        if (W[r][j] != 0u) src = r;
-                    const bool far = !found && src >= 0;
-#pragma unroll
-                    for (int r = WEND + 1; r < N; ++r) cswap_rows<N>(far && r == src, W[j], W[r], perm[j], perm[r]);
-                    neg = neg != far;
-                }
-            }
-#pragma unroll
-            for (int r = j + 1; r <= WEND; ++r) {
-                cswap_rows<N>(swn[r - j - 1], W[j], W[r], perm[j], perm[r]);
-                neg = neg != swn[r - j - 1];
-            }
-        }
-        const uint32_t piv = W[j][j];
-        singular = singular || piv == 0u;   // keep going on garbage: every operation below is total
-        uint32_t prow[N];
-#pragma unroll
-        for (int c = 0; c < N; ++c) prow[c] = W[j][c];
-        if (XS == 2 && j == HEAD) {
-            // exact 64-bit integers: t = piv * W[r][c] - f * prow[c] (|t| < 2^53 by the launcher's bound) plus 2^23 p to
-            // make it non-negative, folded modulo p = 2^31 - 1 without a multiply: the step costs two IMAD.WIDE per
-            // entry on the fmaheavy pipe instead of two IMAD.WIDE + IMAD + IMAD.HI, and carries no factor R^-1
-            const int64_t off = (int64_t)0x7fffffff << 23;
-            const int32_t pivs = (int32_t)piv, sigs = (int32_t)sig;
-#pragma unroll
-            for (int r = 0; r < N; ++r) {
-                if (r == j) continue;
-                const int32_t nf = -(int32_t)W[r][j];
-#pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    const int64_t t = (c == j) ? (int64_t)nf * sigs + off
-                                               : (int64_t)nf * (int32_t)prow[c] + ((int64_t)pivs * (int32_t)W[r][c] + off);
-                    W[r][c] = mersenne31_of_u64((uint64_t)t);
-                }
-            }
-            W[j][j] = sig;                                       // the pivot row stays integer until the switch
-            cw[j] = sig;
-            S = mersenne31_of_u64((uint64_t)((int64_t)sigs * pivs + off));   // sigma_{HEAD+1} as a residue word
-        } else if (XS == 1 && j == HEAD) {
-            // exact integers through the FP64 pipe: t = piv * W[r][c] - f * prow[c] (|t| < 2^53), then t mod p
-            const double pd = (double)p, pinvd = 1.0 / pd;
-            const double pivd = double_of_int(piv), sigd = double_of_int(sig);
-            double prd[N];
-#pragma unroll
-            for (int c = 0; c < N; ++c) prd[c] = double_of_int(prow[c]);
-#pragma unroll
-            for (int r = 0; r < N; ++r) {
-                if (r == j) continue;
-                const double nf = -double_of_int(W[r][j]);
-#pragma unroll
-                for (int c = 0; c < N; ++c) {
-                    const double t = (c == j) ? nf * sigd : __fma_rn(nf, prd[c], pivd * double_of_int(W[r][c]));
-                    W[r][c] = residue_of_double(t, pd, pinvd, p);
-                }
-            }
-            W[j][j] = sig;                                       // the pivot row stays integer until the switch
-            cw[j] = sig;
-            S = residue_of_double(sigd * pivd, pd, pinvd, p);    // sigma_{HEAD+1} as a residue word
-        } else if (head) {
-            // plain two's-complement integers: W[r][c] = piv * W[r][c] - f * prow[c]
-            const uint32_t nsig = 0u - sig;
-#pragma unroll
-            for (int r = 0; r < N; ++r) {
-                if (r == j) continue;
-                const uint32_t f = W[r][j];
-#pragma unroll
-                for (int c = 0; c < N; ++c) W[r][c] = (c == j) ? f * nsig : (piv * W[r][c] - f * prow[c]);
-            }
-            W[j][j] = sig;
-            cw[j] = sig;
-            sig *= piv;
-        } else {
-            cw[j] = S;
-            Q = mont_mul(Q, S, p, pinv);
-            // The one modular inversion is a chain of 38 dependent products.  Its argument, the product of all
-            // sigma_k, only needs the pivots up to step N-2, and the sign cannot change any more either (the last
-            // step has no row below it to exchange with): started HERE, in the second-to-last step, the chain
-            // interleaves with that step's 56 independent row updates instead of stalling the warp on its own.
-            if (EARLY_INV && j == N - 2) {
-                const uint32_t s_next = mont_mul(S, piv, p, pinv);            // sigma_{N-1}
-                qinv_pre = mont_inverse(mont_mul(Q, s_next, p, pinv), P);
-                if (neg) qinv_pre = p - qinv_pre;
-            }
-            uint32_t qinv = 0u;
-            if (last) {
-                qinv = EARLY_INV ? qinv_pre : mont_inverse(Q, P);
-                if (!EARLY_INV && neg) qinv = p - qinv;   // Q is a unit unless the matrix is singular (discarded)
-            }
-#pragma unroll
-            for (int r = 0; r < N; ++r) {
-                if (r == j) {
-                    if (last) {
-                        const uint32_t g = mont_mul(qinv, cw[r], p, pinv);
-#pragma unroll
-                        for (int c = 0; c < N; ++c) W[r][c] = mont_mul(g, c == j ? S : prow[c], p, pinv);
-                    } else {
-                        W[r][j] = S;
-                    }
-                } else {
-                    uint32_t y = p - W[r][j];           // in [1, p]: a valid operand of the two-product reduction
-                    uint32_t x = piv;
-                    if (last) {
-                        const uint32_t g = mont_mul(qinv, cw[r], p, pinv);
-                        x = mont_mul(g, x, p, pinv);
-                        y = mont_mul(g, y, p, pinv);
-                    }
-#pragma unroll
-                    for (int c = 0; c < N; ++c)
-                        W[r][c] = (c == j) ? mont_mul(y, S, p, pinv) : mont_fma2(x, W[r][c], y, prow[c], p, pinv);
-                }
-            }
-            S = mont_mul(S, piv, p, pinv);
-        }
-    }
+    uint32_t a0[N];
+    bool singular;
+    tpm_eliminate<N, HEAD, XS, false>(W, perm, a0, singular, P);
     // Column perm[0] of A (= the first pivot row of the transpose as loaded) for the determinant identity below:
     // read back from the input tile, which is intact until the barrier, instead of living in 8 registers.
-    uint32_t a0[N];
     if (I8) {
         const int8_t* mine = reinterpret_cast<const int8_t*>(sm) + me * T::STB;
 #pragma unroll
@@ -475,6 +493,129 @@ k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max
             }
         } else {
             for (int w = tid; w < nmat * E; w += TPM_THREADS) dst[w] = (int32_t)sm[(w / E) * ST + (w % E)];
+        }
+    }
+}
+
+
+// ---- streaming form of the same kernel (N * N a multiple of 16 bytes, aligned pointers, HEAD > 0) -------------------
+// ncu on k_inv_tpm: a fifth of the stall samples sit on the first shared-memory store behind the tile's global
+// loads, i.e. every block waits out the DRAM latency of its own tile with its four warps parked.  Here a block is
+// persistent and loops over tiles; the input tile is only needed until every thread holds its matrix in registers, so
+// right after that barrier the SAME buffer is refilled with the block's next tile by `cp.async` (LDGSTS: no registers,
+// no waiting) while the elimination of the current tile runs -- the load latency disappears behind ~14 us of
+// arithmetic without a second buffer.  The price is that the tile buffer cannot double as the result staging area,
+// so result rows go straight to global memory as 16-byte stores (two per adjugate row, at the permuted row address;
+// the two halves of every 32-byte sector are written by the same warp back to back and merge in L2), and the column
+// of A that the determinant identity needs is kept in registers from pivot step 0.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+
+template <int N, int HEAD, bool I8, int XS = 0>
+__global__ void __launch_bounds__(TPM_THREADS, LSX_TPM_MINB)
+k_inv_tpm_stream(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max,
+                 int32_t* __restrict__ adj, int32_t* __restrict__ det, int32_t* __restrict__ status) {
+    using T = TpmTile<N>;
+    constexpr int E = T::E, ST = T::ST;
+    static_assert(T::VEC && (!I8 || T::VEC8) && HEAD > 0, "streaming form: vector tiles and an integer head");
+    constexpr int CH = I8 ? T::C8 : T::C;                 // 16-byte chunks per matrix in the input container
+    extern __shared__ __align__(16) uint32_t sm[];
+    const int tid = threadIdx.x;
+    const uint32_t p = P.p;
+    const int64_t ntiles = (batch + TPM_THREADS - 1) / TPM_THREADS;
+
+    auto issue = [&](int64_t tile) {                      // this thread's share of the tile's chunks, asynchronously
+        const int64_t t0 = tile * TPM_THREADS;
+        const int nm = (int)min((int64_t)TPM_THREADS, batch - t0);
+        const char* src = reinterpret_cast<const char*>(Ain) + t0 * E * (I8 ? 1 : 4);
+        char* dst = reinterpret_cast<char*>(sm);
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const int g = tid + k * TPM_THREADS;          // chunk g = matrix g / CH, chunk g % CH of it
+            if (g < nm * CH) cp_async16(dst + (g / CH) * (I8 ? T::STB : ST * 4) + (g % CH) * 16, src + (size_t)g * 16);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int64_t tile = blockIdx.x;
+    if (tile < ntiles) issue(tile);
+    for (; tile < ntiles; tile += gridDim.x) {
+        const int64_t tile0 = tile * TPM_THREADS;
+        const int nmat = (int)min((int64_t)TPM_THREADS, batch - tile0);
+        const int me = tid < nmat ? tid : 0;              // idle lanes of the last tile redo matrix 0
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                  // the tile is in shared memory
+
+        uint32_t W[N][N];                                 // TRANSPOSE of the matrix
+        int vmax = INT32_MIN, vmin = INT32_MAX;
+        if (I8) {
+            const uint8_t* mine = reinterpret_cast<const uint8_t*>(sm) + me * T::STB;
+#pragma unroll
+            for (int q = 0; q < T::C8; ++q) {
+                const int4 v4 = *reinterpret_cast<const int4*>(mine + 16 * q);
+                const int w4[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int e = 16 * q + i;
+                    const int v = (int)(int8_t)(w4[i >> 2] >> (8 * (i & 3)));
+                    vmax = max(vmax, v);
+                    vmin = min(vmin, v);
+                    W[e % N][e / N] = (uint32_t)v;
+                }
+            }
+        } else {
+            const uint32_t* mine = sm + me * ST;
+#pragma unroll
+            for (int q = 0; q < T::C; ++q) {
+                const int4 v4 = *reinterpret_cast<const int4*>(mine + 4 * q);
+                const int w4[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int e = 4 * q + i;
+                    vmax = max(vmax, w4[i]);
+                    vmin = min(vmin, w4[i]);
+                    W[e % N][e / N] = (uint32_t)w4[i];
+                }
+            }
+        }
+        const bool bound_bad = vmax > a_abs_max || vmin < -a_abs_max;
+        __syncthreads();                                  // every thread holds its matrix: the buffer is free again
+        if (tile + gridDim.x < ntiles) issue(tile + gridDim.x);
+
+        uint32_t perm[N], a0[N];
+        bool singular;
+        tpm_eliminate<N, HEAD, XS, true>(W, perm, a0, singular, P);
+
+        if (singular || bound_bad) {                      // rare: zeros (the reference returns NoSolution())
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < N; ++c) W[r][c] = 0u;
+        }
+        const uint32_t half = p >> 1;
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                const uint32_t v = W[r][c];
+                W[r][c] = v > half ? v - p : v;
+            }
+        uint32_t dsum = 0u;                               // det = sum_c adj[i][c] * A[c][i], i = perm[0] (wrapping: exact)
+#pragma unroll
+        for (int c = 0; c < N; ++c) dsum += a0[c] * W[c][0];
+        if (tid < nmat) {
+            uint32_t* mine = reinterpret_cast<uint32_t*>(adj) + (tile0 + tid) * E;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                uint32_t* orow = mine + perm[j] * N;      // slot j = row perm[j] of the adjugate of A
+#pragma unroll
+                for (int q = 0; q < N / 4; ++q)
+                    *reinterpret_cast<uint4*>(orow + 4 * q) =
+                        make_uint4(W[4 * q][j], W[4 * q + 1][j], W[4 * q + 2][j], W[4 * q + 3][j]);
+            }
+            det[tile0 + tid] = (int32_t)dsum;
+            status[tile0 + tid] = (singular && !bound_bad ? LSX_ST_SINGULAR : 0) | (bound_bad ? LSX_ST_BOUND : 0);
         }
     }
 }

@@ -7,6 +7,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <random>
 #include <vector>
@@ -53,6 +54,28 @@ float time_new(const void* dA, int64_t batch, PrimeRec P, int amax, int32_t* adj
     CK(cudaStreamSynchronize(s));
     CK(cudaEventRecord(e0, s));
     for (int i = 0; i < reps; ++i) k_inv_tpm<N, HEAD, I8, XS><<<grid, TPM_THREADS, smem, s>>>(dA, batch, P, amax, 1, adj, det, st);
+    CK(cudaEventRecord(e1, s));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    return ms / reps;
+}
+
+template <int N, int HEAD, bool I8, int XS = 0>
+float time_stream(const void* dA, int64_t batch, PrimeRec P, int amax, int32_t* adj, int32_t* det, int32_t* st, int reps,
+                  cudaStream_t s, int ctas_per_sm) {
+    using namespace lsx_inv_small;
+    const size_t smem = I8 ? (size_t)TPM_THREADS * TpmTile<N>::STB : TpmTile<N>::BYTES;
+    CK(cudaFuncSetAttribute(k_inv_tpm_stream<N, HEAD, I8, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (batch + TPM_THREADS - 1) / TPM_THREADS;
+    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)148 * ctas_per_sm);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) k_inv_tpm_stream<N, HEAD, I8, XS><<<grid, TPM_THREADS, smem, s>>>(dA, batch, P, amax, adj, det, st);
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventRecord(e0, s));
+    for (int i = 0; i < reps; ++i) k_inv_tpm_stream<N, HEAD, I8, XS><<<grid, TPM_THREADS, smem, s>>>(dA, batch, P, amax, adj, det, st);
     CK(cudaEventRecord(e1, s));
     CK(cudaEventSynchronize(e1));
     float ms;
@@ -176,6 +199,22 @@ int main(int argc, char** argv) {
     CK(cudaMemset(adj1, 0xff, A.size() * 4));
     const float ms8m = time_new<8, 3, true, 2>(dA8, batch, P, 5, adj1, det1, st1, reps, s);
     bad += compare("int8 head3 + mersenne step");
+    CK(cudaMemset(adj1, 0xff, A.size() * 4));
+    const float ms32s = time_stream<8, 3, false>(dA, batch, P, 5, adj1, det1, st1, reps, s, LSX_TPM_MINB);
+    bad += compare("int32 stream");
+    CK(cudaMemset(adj1, 0xff, A.size() * 4));
+    const float ms8s = time_stream<8, 3, true>(dA8, batch, P, 5, adj1, det1, st1, reps, s, LSX_TPM_MINB);
+    bad += compare("int8 stream");
+    CK(cudaMemset(adj1, 0xff, A.size() * 4));
+    time_stream<8, 3, false>(dA, 1000, P, 5, adj1, det1, st1, 1, s, LSX_TPM_MINB);
+    {
+        CK(cudaMemcpy(h_adj1.data(), adj1, (size_t)1001 * E * 4, cudaMemcpyDeviceToHost));
+        if (memcmp(h_adj0.data(), h_adj1.data(), (size_t)1000 * E * 4) != 0 || h_adj1[(size_t)1000 * E] != -1) {
+            fprintf(stderr, "stream: short batch differs or wrote past the end\n");
+            ++bad;
+        }
+    }
+    printf("{\"tag\": \"%s\", \"stream_i32_ms\": %.4f, \"stream_i8_ms\": %.4f}\n", tag, ms32s, ms8s);
     // short batch (last block partly filled)
     CK(cudaMemset(adj1, 0xff, A.size() * 4));
     time_new<8, 3, false>(dA, 1000, P, 5, adj1, det1, st1, 1, s);
