@@ -154,6 +154,11 @@ void lsx_destroy(lsx_ctx* ctx) {
         if (e) cudaEventDestroy(e);
     for (auto& e : ctx->pev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->side_events)
+        if (e) cudaEventDestroy(e);
+    if (ctx->side_fork) cudaEventDestroy(ctx->side_fork);
+    for (auto& s : ctx->side_streams)
+        if (s) cudaStreamDestroy(s);
     for (auto& s : ctx->copy_streams)
         if (s) cudaStreamDestroy(s);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

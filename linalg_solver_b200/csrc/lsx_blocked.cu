@@ -21,6 +21,8 @@
 //               (64-bit accumulators, lazy high-word reduction, one REDC at the end)
 //   k_finish    sign, zero flag, Montgomery -> plain residue
 #include <algorithm>
+#include <atomic>
+#include <thread>
 
 #include "lsx_internal.h"
 #include "lsx_tc.cuh"
@@ -557,6 +559,10 @@ __global__ void k_finish(LargeArgs a, uint32_t* residues) {
 // ---- host-side recursion over one group of primes -----------------------------------------------------
 struct Driver {
     lsx_ctx* ctx;
+    cudaStream_t stream;  // the stream this group of primes runs on (ctx->stream or one of its side streams)
+    int64_t launches;     // counted here (several drivers run from their own host threads), added to ctx at the end
+    bool timing;          // event-time the depth-256 updates (single-stream runs only)
+    int max_tiles;        // cap on the tiles one tensor-kernel CTA loops over (0: none); short CTAs free their SM soon
     LargeArgs a;
     uint8_t* AP;          // byte planes for the tensor-core update (lsx_tc.cuh)
     uint8_t* BP;
@@ -570,7 +576,7 @@ struct Driver {
     }
     void gemm(int r0, int r1, int c0, int c1, int k0, int K) {
         if (r1 <= r0 || c1 <= c0) return;
-        cudaStream_t st = ctx->stream;
+        cudaStream_t st = stream;
         if (use_tc && lsx_tc::depth_ok(K)) {
             lsx_tc::Region g{};
             g.n = n, g.r0 = r0, g.r1 = r1, g.c0 = c0, g.c1 = c1, g.k0 = k0, g.K = K;
@@ -583,20 +589,21 @@ struct Driver {
             const int units = fixed * a.G;
             int groups = std::min(looped, std::max(1, (2 * ctx->sm_count + units - 1) / units));
             g.tiles_per_cta = (looped + groups - 1) / groups;
+            if (max_tiles > 0) g.tiles_per_cta = std::min(g.tiles_per_cta, max_tiles);
             groups = (looped + g.tiles_per_cta - 1) / g.tiles_per_cta;
             lsx_tc::launch_split(a.W, AP, BP, g, a.G, st);
             lsx_tc::GemmArgs ga{};
             ga.W = a.W, ga.AP = AP, ga.BP = BP, ga.primes = a.primes, ga.g = g;
-            const bool big = K == NB_OUT;
+            const bool big = timing && K == NB_OUT;
             if (big) lsx_timing_begin(ctx);
             lsx_tc::k_gemm_tc<<<dim3(fixed, groups, a.G), lsx_tc::THREADS, lsx_tc::smem_bytes(K, g.b_stationary), st>>>(ga);
             if (big) lsx_timing_end(ctx);
-            ctx->launches += 3;
+            launches += 3;
             return;
         }
         if (K <= NARROW && c1 - c0 <= NARROW) {   // tall and narrow: one thread per row
             k_gemm_narrow<<<dim3((r1 - r0 + 127) / 128, a.G), 128, 0, st>>>(a, r0, r1, c0, c1, k0, K);
-            ctx->launches++;
+            launches++;
             return;
         }
         for (int kk = 0; kk < K; kk += KI) {      // integer pipe, at most 64 deep per launch
@@ -604,26 +611,26 @@ struct Driver {
             const size_t smem = (size_t)(KI * (GM + 4) + KI * GN) * 4;
             k_gemm_int<<<dim3((c1 - c0 + GN - 1) / GN, (r1 - r0 + GM - 1) / GM, a.G), 256, smem, st>>>(a, r0, r1, c0, c1,
                                                                                                         k0 + kk, kd);
-            ctx->launches++;
+            launches++;
         }
     }
     void swap(int ja, int jb, int ca, int cb) {
         if (jb <= ja || cb <= ca) return;
-        k_swap<<<dim3((cb - ca + 127) / 128, a.G), 128, 0, ctx->stream>>>(a, ja, jb, ca, cb);
-        ctx->launches++;
+        k_swap<<<dim3((cb - ca + 127) / 128, a.G), 128, 0, stream>>>(a, ja, jb, ca, cb);
+        launches++;
     }
     // columns [ca, cb): U = L11^-1 * A for the diagonal block [k0, k0 + w)
     void trsm(int k0, int w, int ca, int cb) {
         if (cb <= ca || w <= 0) return;
         if (w <= TS) {
-            k_trsm32<<<dim3((cb - ca + 127) / 128, a.G), 128, 0, ctx->stream>>>(a, k0, w, ca, cb);
-            ctx->launches++;
+            k_trsm32<<<dim3((cb - ca + 127) / 128, a.G), 128, 0, stream>>>(a, k0, w, ca, cb);
+            launches++;
             return;
         }
         if (!use_tc && w <= KI) {
             const size_t smem = (size_t)(KI * KI + KI * 128) * 4;
-            k_trsm<<<dim3((cb - ca + 127) / 128, a.G), 128, smem, ctx->stream>>>(a, k0, w, ca, cb);
-            ctx->launches++;
+            k_trsm<<<dim3((cb - ca + 127) / 128, a.G), 128, smem, stream>>>(a, k0, w, ca, cb);
+            launches++;
             return;
         }
         const int w1 = left_width(w);
@@ -635,9 +642,9 @@ struct Driver {
     // (cl = first column of the enclosing outer block: the L columns to its left are never read again).
     void lu(int k0, int w, int cl) {
         if (w <= NB_BASE) {
-            if (n - k0 <= LU8_T * LU8_RPT) k_lu8<<<a.G, LU8_T, 0, ctx->stream>>>(a, k0, w);
-            else k_panel_gmem<<<a.G, PANEL_T, 0, ctx->stream>>>(a, k0, w);
-            ctx->launches++;
+            if (n - k0 <= LU8_T * LU8_RPT) k_lu8<<<a.G, LU8_T, 0, stream>>>(a, k0, w);
+            else k_panel_gmem<<<a.G, PANEL_T, 0, stream>>>(a, k0, w);
+            launches++;
             swap(k0, k0 + w, cl, k0);                       // multipliers of earlier panels in the same block
             return;
         }
@@ -664,21 +671,51 @@ struct Driver {
 
 }  // namespace
 
+// Independent groups of primes run CONCURRENTLY on S streams (default 2, LSX_LARGE_STREAMS), each fed by its own host
+// thread: the base panels, the narrow solves and the in-panel updates are latency-bound launches of one CTA per prime
+// (or a few CTAs per prime) that leave most of the GPU idle, and a group's chain of ~3500 launches is strictly
+// ordered -- but nothing orders one group against another, so the tensor-core updates of one group fill the SMs that
+// the panel phase of the other leaves free.  The streams fork from and join into ctx->stream through events, so the
+// call stays asynchronous for the caller.  With event timing of the depth-256 updates switched on
+// (lsx_timing_enable) everything runs on ctx->stream alone, because a kernel's duration means nothing while it
+// shares the GPU.
 int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_begin, int count, uint32_t* d_res) {
     static const size_t budget = []() {
         const char* e = getenv("LSX_LARGE_WS_MB");
         size_t mb = e ? (size_t)strtoull(e, nullptr, 10) : 24576;
         return (mb < 64 ? 64 : mb) << 20;
     }();
+    static const int env_streams = []() {
+        const char* e = getenv("LSX_LARGE_STREAMS");
+        const int s = e ? atoi(e) : 2;
+        return s < 1 ? 1 : (s > 8 ? 8 : s);
+    }();
+    static const int env_prio = []() {
+        const char* e = getenv("LSX_LARGE_PRIO");
+        return e ? atoi(e) : 0;
+    }();
+    static const int env_max_tiles = []() {
+        const char* e = getenv("LSX_TC_MAX_TILES");
+        return e ? std::max(0, atoi(e)) : 0;
+    }();
+    static const int env_group = []() {
+        const char* e = getenv("LSX_LARGE_GROUP");
+        return e ? std::max(1, atoi(e)) : 0;
+    }();
+    if (count <= 0) return LSX_OK;
     const bool use_tc = !getenv("LSX_NO_TC");
+    const int S = ctx->timing ? 1 : std::min(env_streams, count);
     const size_t rt = (size_t)(n + lsx_tc::TM - 1) / lsx_tc::TM, ct = (size_t)(n + lsx_tc::TN - 1) / lsx_tc::TN;
     const size_t ap_per = rt * lsx_tc::TM * 4 * NB_OUT, bp_per = ct * lsx_tc::TN * 4 * NB_OUT;   // byte planes per prime
     const size_t per = (size_t)n * n * 4 + (size_t)n * 4 + 64 + (use_tc ? ap_per + bp_per : 0);
-    // groups of about one prime per SM, evenly sized, within the workspace budget
-    int G = (int)std::min<size_t>((size_t)count, std::max<size_t>(1, budget / per));
-    if (G > ctx->sm_count) {
-        const int ngroups = (count + ctx->sm_count - 1) / ctx->sm_count;
-        G = std::min(G, (count + ngroups - 1) / ngroups);
+    // groups of at most one prime per SM (the base-panel kernel is one CTA per prime), evenly sized, within the
+    // workspace budget
+    const int share = (count + S - 1) / S;                   // primes per stream
+    const int cap = env_group ? env_group : ctx->sm_count;   // measured: 2 x 127 beats 2 x 74 and 1 x 145 (profiles/r02m)
+    int G = (int)std::min<size_t>((size_t)share, std::max<size_t>(1, budget / S / per));
+    if (G > cap) {
+        const int ngroups = (share + cap - 1) / cap;
+        G = std::min(G, (share + ngroups - 1) / ngroups);
     }
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -688,9 +725,8 @@ int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_b
     };
     const size_t o_w = take((size_t)G * n * n * 4), o_piv = take((size_t)G * n * 4), o_det = take((size_t)G * 4),
                  o_flag = take((size_t)G * 4), o_ap = take(use_tc ? G * ap_per : 0), o_bp = take(use_tc ? G * bp_per : 0);
-    int rc = lsx_ws_reserve(ctx, off);
+    int rc = lsx_ws_reserve(ctx, off * S);
     if (rc != LSX_OK) return rc;
-    char* base = (char*)ctx->d_ws;
     const size_t smem_trsm = (size_t)(KI * KI + KI * 128) * 4;
     const size_t smem_gemm = (size_t)(KI * (GM + 4) + KI * GN) * 4;
     LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_trsm));
@@ -700,27 +736,80 @@ int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_b
         const int smax = (int)std::max(lsx_tc::smem_bytes(lsx_tc::MAX_K, 0), lsx_tc::smem_bytes(lsx_tc::MAX_K, 1));
         LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(lsx_tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
     }
-    for (int g0 = 0; g0 < count; g0 += G) {
-        const int Gc = std::min(G, count - g0);
-        Driver d{};
-        d.ctx = ctx;
-        d.a.W = (uint32_t*)(base + o_w);
-        d.a.primes = ctx->d_primes + prime_begin + g0;
-        d.a.piv_row = (int32_t*)(base + o_piv);
-        d.a.detM = (uint32_t*)(base + o_det);
-        d.a.flags = (int32_t*)(base + o_flag);
-        d.a.n = n;
-        d.a.G = Gc;
-        d.AP = (uint8_t*)(base + o_ap);
-        d.BP = (uint8_t*)(base + o_bp);
-        d.use_tc = use_tc;
-        d.n = n;
-        k_load<<<dim3(ctx->sm_count * 2, Gc), 256, 0, ctx->stream>>>(dA, d.a);
-        ctx->launches++;
-        d.run();
-        k_finish<<<(Gc + 127) / 128, 128, 0, ctx->stream>>>(d.a, d_res + g0);
-        ctx->launches++;
-        LSX_CUDA_TRY(ctx, cudaGetLastError());
+    // side streams (created once per ctx) start behind everything already enqueued on ctx->stream
+    if (S > 1) {
+        while ((int)ctx->side_streams.size() < S) {
+            cudaStream_t st = nullptr;
+            cudaEvent_t ev = nullptr;
+            int lo = 0, hi = 0;                              // numerically lower = higher priority
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            const int idx = (int)ctx->side_streams.size();
+            const int prio = env_prio == 1 ? (idx & 1 ? lo : hi) : 0;
+            LSX_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio));
+            ctx->side_streams.push_back(st);
+            LSX_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ctx->side_events.push_back(ev);
+        }
+        if (!ctx->side_fork) LSX_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->side_fork, cudaEventDisableTiming));
+        LSX_CUDA_TRY(ctx, cudaEventRecord(ctx->side_fork, ctx->stream));
+        for (int s = 0; s < S; ++s) LSX_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side_streams[s], ctx->side_fork, 0));
     }
+    const int ngroups = (count + G - 1) / G;
+    std::atomic<int> next_group{0};
+    std::vector<cudaError_t> errs(S, cudaSuccess);
+    std::vector<int64_t> launched(S, 0);
+    auto worker = [&](int s) {
+        if (cudaSetDevice(ctx->device) != cudaSuccess) {
+            errs[s] = cudaGetLastError();
+            return;
+        }
+        char* base = (char*)ctx->d_ws + (size_t)s * off;
+        cudaStream_t st = S > 1 ? ctx->side_streams[s] : ctx->stream;
+        for (;;) {
+            const int gi = next_group.fetch_add(1);
+            if (gi >= ngroups) break;
+            const int g0 = gi * G, Gc = std::min(G, count - g0);
+            Driver d{};
+            d.ctx = ctx;
+            d.stream = st;
+            d.timing = S == 1 && ctx->timing;
+            d.max_tiles = S > 1 ? env_max_tiles : 0;
+            d.a.W = (uint32_t*)(base + o_w);
+            d.a.primes = ctx->d_primes + prime_begin + g0;
+            d.a.piv_row = (int32_t*)(base + o_piv);
+            d.a.detM = (uint32_t*)(base + o_det);
+            d.a.flags = (int32_t*)(base + o_flag);
+            d.a.n = n;
+            d.a.G = Gc;
+            d.AP = (uint8_t*)(base + o_ap);
+            d.BP = (uint8_t*)(base + o_bp);
+            d.use_tc = use_tc;
+            d.n = n;
+            k_load<<<dim3(ctx->sm_count * 2, Gc), 256, 0, st>>>(dA, d.a);
+            d.run();
+            k_finish<<<(Gc + 127) / 128, 128, 0, st>>>(d.a, d_res + g0);
+            launched[s] += d.launches + 2;
+            const cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) {
+                errs[s] = e;
+                break;
+            }
+        }
+    };
+    if (S == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> threads;
+        for (int s = 0; s < S; ++s) threads.emplace_back(worker, s);
+        for (auto& t : threads) t.join();
+        for (int s = 0; s < S; ++s) {                         // join, also after an error: ctx->stream must not run ahead
+            cudaEventRecord(ctx->side_events[s], ctx->side_streams[s]);
+            cudaStreamWaitEvent(ctx->stream, ctx->side_events[s], 0);
+        }
+    }
+    for (int s = 0; s < S; ++s) ctx->launches += launched[s];
+    for (int s = 0; s < S; ++s)
+        if (errs[s] != cudaSuccess)
+            return lsx_fail(ctx, LSX_ERR_CUDA, "blocked LU launch failed on stream %d: %s", s, cudaGetErrorString(errs[s]));
     return LSX_OK;
 }

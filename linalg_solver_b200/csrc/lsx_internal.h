@@ -47,6 +47,11 @@ struct lsx_ctx {
     int tev_used = 0;
     std::vector<cudaEvent_t> tev;        // pairs: [2*i] before, [2*i+1] after
     std::vector<cudaEvent_t> pev;        // events of the host-call pipeline
+    // side streams of the blocked LU (independent prime groups run concurrently, lsx_blocked.cu) with one join
+    // event each; side_fork orders them behind the work already on `stream`
+    std::vector<cudaStream_t> side_streams;
+    std::vector<cudaEvent_t> side_events;
+    cudaEvent_t side_fork = nullptr;
     // lsx_create_multi: the other GPUs of this context (each a full single-device ctx, driven by its own host
     // thread inside a call); empty for a single-device ctx.  nccl: communicators of all devices (lsx_multi.cpp)
     std::vector<lsx_ctx*> peers;

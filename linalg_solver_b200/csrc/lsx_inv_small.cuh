@@ -307,8 +307,126 @@ __device__ __forceinline__ void tpm_eliminate(uint32_t (&W)[N][N], uint32_t (&pe
     }
 }
 
+// ---- the same elimination over the INTEGERS: one-step fraction-free (Bareiss) Gauss-Jordan, in place ---------------
+// Every entry the fraction-free Gauss-Jordan of [M | I] ever holds is a minor of M (Bareiss), and the launcher takes
+// the fused path only when every minor of A is below 2^31 -- so the whole elimination fits two's-complement 32-bit
+// registers and needs no prime at all.  Step j with pivot piv and previous pivot d (d = 1 before step 0):
+//     rows r != j:   W[r][c] <- (piv * W[r][c] - W[r][j] * W[j][c]) / d   (c != j),   W[r][j] <- -W[r][j]
+//     pivot row j:   W[j][j] <- d, the rest stays
+// and after the last step W is the adjugate (of the row-permuted matrix) and the last pivot its determinant: no
+// Montgomery form, no symmetric lift, no modular inversion (the 38 dependent products of the residue kernel), and
+// the determinant is free.  The division is EXACT, so it is a multiplication modulo 2^32: with d = 2^s * o, o odd,
+//     q = ((t >> s) * o^-1) mod 2^32        (|q| < 2^31: the low word IS the quotient)
+// where o^-1 mod 2^32 comes from three Newton steps (6 dependent IMADs per pivot step, computed one step ahead of
+// its use).  t = piv * w - f * prow fits 32 bits in the first H32 steps (launcher: 2 M^2 < 2^31 for the Hadamard
+// bound M of the minors that step combines): IMAD, IMAD, SHF, IMAD per entry.  Later steps form t in 64 bits and
+// take bits [s, s + 32) with one funnel shift: IMAD.WIDE, IMAD.WIDE, SHF, IMAD -- 5.6 issue slots of the fmaheavy
+// pipe per entry where the two-product Montgomery update needs 7.9 (2 IMAD.WIDE + IMAD + IMAD.HI), and 3 in the
+// 32-bit steps.  Pivoting (window + rare warp-voted search), the row permutation and the output convention are the
+// residue kernel's: slot j = row perm[j] of the adjugate of A, the sign of the exchanges folded into the last step.
+__device__ __forceinline__ int64_t mul_wide_s32(uint32_t a, uint32_t b) {
+    int64_t r;
+    asm("mul.wide.s32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ int64_t mad_wide_s32(uint32_t a, uint32_t b, int64_t c) {
+    int64_t r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+}
+// o^-1 modulo 2^32 for odd o: (3 o) xor 2 is right to 5 bits, every Newton step doubles that
+__device__ __forceinline__ uint32_t inv_odd_u32(uint32_t o) {
+    uint32_t x = (o * 3u) ^ 2u;
+    x *= 2u - o * x;
+    x *= 2u - o * x;
+    x *= 2u - o * x;
+    return x;
+}
+
+template <int N, int H32>
+__device__ __forceinline__ void tpm_eliminate_bareiss(uint32_t (&W)[N][N], uint32_t (&perm)[N], bool& singular, uint32_t& det) {
+#pragma unroll
+    for (int r = 0; r < N; ++r) perm[r] = (uint32_t)r;
+    bool neg = false;
+    singular = false;
+    uint32_t dprev = 1u, dinv = 1u;         // previous pivot d = 2^dsh * o and o^-1 mod 2^32
+    int dsh = 0;
+    uint32_t piv = 0u;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const bool last = j == N - 1;
+        // ---- pivot: position j, else a row of the window below it, else (rare, warp vote) any lower row ----
+        if (j + 1 < N) {
+            bool found = W[j][j] != 0u;
+            const int WEND = j + LSX_TPM_WINDOW < N - 1 ? j + LSX_TPM_WINDOW : N - 1;       // last row of the window
+            bool swn[LSX_TPM_WINDOW > 0 ? LSX_TPM_WINDOW : 1];
+#pragma unroll
+            for (int r = j + 1; r <= WEND; ++r) {
+                swn[r - j - 1] = !found && W[r][j] != 0u;
+                found = found || swn[r - j - 1];
+            }
+            if (WEND < N - 1) {
+                if (__any_sync(0xffffffffu, !found)) {
+                    int src = -1;
+#pragma unroll
+                    for (int r = N - 1; r > WEND; --r)
+                        if (W[r][j] != 0u) src = r;
+                    const bool far = !found && src >= 0;
+#pragma unroll
+                    for (int r = WEND + 1; r < N; ++r) cswap_rows<N>(far && r == src, W[j], W[r], perm[j], perm[r]);
+                    neg = neg != far;
+                }
+            }
+#pragma unroll
+            for (int r = j + 1; r <= WEND; ++r) {
+                cswap_rows<N>(swn[r - j - 1], W[j], W[r], perm[j], perm[r]);
+                neg = neg != swn[r - j - 1];
+            }
+        }
+        piv = W[j][j];
+        singular = singular || piv == 0u;   // keep going on garbage: every operation below is total
+        uint32_t prow[N];
+#pragma unroll
+        for (int c = 0; c < N; ++c) prow[c] = W[j][c];
+        const bool flip = last && neg;                          // the sign of the row exchanges, folded into the last step
+        const uint32_t minv = flip ? 0u - dinv : dinv;
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            if (r == j) continue;
+            const uint32_t f = W[r][j], nf = 0u - f;
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                if (c == j) {
+                    W[r][c] = flip ? f : nf;
+                } else if (j == 0) {                            // d = 1: the wrapping 32-bit result is the minor itself
+                    const uint32_t t = piv * W[r][c] + nf * prow[c];
+                    W[r][c] = flip ? 0u - t : t;
+                } else if (j < H32) {                           // t fits 32 bits: exact arithmetic shift, then o^-1
+                    const uint32_t t = piv * W[r][c] + nf * prow[c];
+                    W[r][c] = (uint32_t)((int32_t)t >> dsh) * minv;
+                } else {                                        // t in 64 bits, bits [dsh, dsh + 32) of it, then o^-1
+                    const int64_t t = mad_wide_s32(nf, prow[c], mul_wide_s32(piv, W[r][c]));
+                    W[r][c] = __funnelshift_r((uint32_t)t, (uint32_t)((uint64_t)t >> 32), dsh) * minv;
+                }
+            }
+        }
+        W[j][j] = dprev;
+        if (flip) {
+#pragma unroll
+            for (int c = 0; c < N; ++c) W[j][c] = 0u - W[j][c];
+        }
+        if (!last) {                                            // the next step divides by this pivot
+            dprev = piv;
+            dsh = (__ffs((int)piv) - 1) & 31;                   // piv == 0: singular, results are discarded
+            dinv = inv_odd_u32((uint32_t)((int32_t)piv >> dsh));
+        }
+    }
+    det = neg ? 0u - piv : piv;
+}
+
 // XS: how pivot step HEAD is done when it is still exact integer arithmetic (0: it is an ordinary Montgomery step),
-//   1 = on the FP64 pipe, 2 = 64-bit integers folded modulo the Mersenne prime 2^31 - 1 (needs p == 2^31 - 1)
+//   1 = on the FP64 pipe, 2 = 64-bit integers folded modulo the Mersenne prime 2^31 - 1 (needs p == 2^31 - 1);
+//   3 = the whole elimination over the integers (tpm_eliminate_bareiss, HEAD = its count of 32-bit steps, P unused)
 template <int N, int HEAD, bool I8, int XS = 0>
 __global__ void __launch_bounds__(TPM_THREADS, LSX_TPM_MINB)
 k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max, int vec_ok,
@@ -414,6 +532,17 @@ k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max
     uint32_t perm[N];                       // perm[r]: original index of the transpose row now at position r
     uint32_t a0[N];
     bool singular;
+    uint32_t dsum = 0u;
+    if constexpr (XS == 3) {
+        tpm_eliminate_bareiss<N, HEAD>(W, perm, singular, dsum);
+        if (singular || bound_bad) {            // rare: zeros (the reference returns NoSolution(), linalg.py:725-737)
+            dsum = 0u;
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < N; ++c) W[r][c] = 0u;
+        }
+    } else {
     tpm_eliminate<N, HEAD, XS, false>(W, perm, a0, singular, P);
     // Column perm[0] of A (= the first pivot row of the transpose as loaded) for the determinant identity below:
     // read back from the input tile, which is intact until the barrier, instead of living in 8 registers.
@@ -444,9 +573,9 @@ k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max
         }
     // det = sum_c adj[i][c] * A[c][i] with i = perm[0]: adj[i][c] = W[c][0], A[c][i] = a0[c].  The launcher's bound
     // (|det| < 2^31) makes the wrapping 32-bit sum exact.
-    uint32_t dsum = 0u;
 #pragma unroll
     for (int c = 0; c < N; ++c) dsum += a0[c] * W[c][0];
+    }
 
     __syncthreads();                        // everybody has read its input tile: reuse it for the output
     {

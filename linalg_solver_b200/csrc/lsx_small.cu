@@ -2,6 +2,8 @@
 // lsx_inv_small.cuh (k_inv_tpm<N, HEAD, I8>: inverse + determinant of n x n matrices, n <= 8, one launch per
 // batch, one thread per matrix; see the header for the algorithm).  Singular matrices get LSX_ST_SINGULAR and
 // zeros, which is where the reference returns NoSolution() (linalg.py:725-737).
+#include <string.h>
+
 #include "lsx_inv_small.cuh"
 
 namespace {
@@ -19,14 +21,6 @@ int head_steps_for(int n, int64_t a_abs_max) {
         ++h;
     }
     return h;
-}
-
-// The FP64 step (lsx_inv_small.cuh) computes piv * w - f * prow exactly in a double: the entries after h integer
-// steps are bounded by B_h (B -> 2 B^2 per step), so it needs 2 B_h^2 < 2^53.
-bool f64_step_ok(int64_t a_abs_max, int h) {
-    double B = (double)(a_abs_max < 1 ? 1 : a_abs_max);
-    for (int i = 0; i < h; ++i) B = 2.0 * B * B;
-    return 2.0 * B * B < 9007199254740992.0;
 }
 
 template <int N, int HEAD, bool I8, int XS = 0>
@@ -47,30 +41,37 @@ int launch_inv_tpm_h(lsx_ctx* ctx, const ElimJob& job) {
     return LSX_OK;
 }
 
-// Two instantiations per size: the full integer head when the declared magnitudes allow it, none otherwise.
+// Leading pivot steps of the integer (Bareiss) kernel whose t = piv * w - f * prow fits 32 bits: step j combines minors
+// of order j + 1, so it needs 2 M^2 < 2^31 for their Hadamard bound M.
+int h32_steps_for(int n, int64_t a_abs_max) {
+    int h = 0;
+    for (int j = 0; j < n; ++j) {
+        const double bits = lsx_log2_minor_bound(j + 1, j + 1, false, a_abs_max, 0, false, j + 1);
+        if (1.0 + 2.0 * bits >= 31.0 - 1e-6) break;
+        h = j + 1;
+    }
+    return h;
+}
+
+// Default: the elimination over the integers (tpm_eliminate_bareiss; 126 us per 2^20 8 x 8 matrices on B200 against
+// 198 us for the residue kernel, profiles/r02n_inv8_lab_bareiss.jsonl), with 32-bit arithmetic in the first min(N, 4)
+// pivot steps when the declared magnitudes allow it and 64-bit products from the start otherwise.
+// LSX_TPM_ALGO=mont selects the single-prime residue kernel (round-2 v3; kept for A/B measurements and as a second
+// implementation the tests compare word for word): the full integer head when the magnitudes allow it, none otherwise.
 template <int N>
 int launch_inv_tpm(lsx_ctx* ctx, const ElimJob& job) {
+    const char* algo = getenv("LSX_TPM_ALGO");
+    const bool mont = algo && strcmp(algo, "mont") == 0;
+    if (!mont) {
+        constexpr int HB = N < 4 ? N : 4;
+        const bool h32 = h32_steps_for(N, job.a_abs_max) >= HB;
+        if (job.in_i8) return h32 ? launch_inv_tpm_h<N, HB, true, 3>(ctx, job) : launch_inv_tpm_h<N, 0, true, 3>(ctx, job);
+        return h32 ? launch_inv_tpm_h<N, HB, false, 3>(ctx, job) : launch_inv_tpm_h<N, 0, false, 3>(ctx, job);
+    }
     constexpr int HMAX = N - 1 < 3 ? N - 1 : 3;
     const char* e = getenv("LSX_TPM_HEAD");
     const int want = e ? atoi(e) : HMAX;
     const bool head = HMAX > 0 && want >= HMAX && head_steps_for(N, job.a_abs_max) >= HMAX;
-    if constexpr (N == 8) {
-        // the benchmark shape: pivot step 3 is still exact integer arithmetic when 2 B^2 < 2^53 for the bound B after
-        // the integer head, and can be done without a Montgomery reduction.  LSX_TPM_XS = 2: 64-bit integers folded
-        // modulo the Mersenne prime 2^31 - 1 (56 IMAD + 56 IMAD.HI less on the fmaheavy pipe); 1: the same step on the
-        // FP64 pipe.  Both are bit-exact (tests) and both measured NEUTRAL on B200 (198.4 / 199.4 vs 198.1 us per 2^20
-        // matrices, profiles/r02k_inv8_lab_mersenne_step.jsonl): with 4 warps per scheduler the kernel is bound by
-        // its dependency chains and the exposed tile load (ncu: 19 % of the stall samples sit on the first STS.128
-        // after the global loads), not by the count of fmaheavy instructions.  Default 0: the plain kernel.
-        const char* xs_env = getenv("LSX_TPM_XS");
-        const int xs = xs_env ? atoi(xs_env) : 0;
-        if (head && xs != 0 && f64_step_ok(job.a_abs_max, HMAX)) {
-            if (xs == 2 && ctx->primes[0] == 0x7fffffffu)
-                return job.in_i8 ? launch_inv_tpm_h<N, HMAX, true, 2>(ctx, job) : launch_inv_tpm_h<N, HMAX, false, 2>(ctx, job);
-            if (xs == 1)
-                return job.in_i8 ? launch_inv_tpm_h<N, HMAX, true, 1>(ctx, job) : launch_inv_tpm_h<N, HMAX, false, 1>(ctx, job);
-        }
-    }
     if (job.in_i8) return head ? launch_inv_tpm_h<N, HMAX, true>(ctx, job) : launch_inv_tpm_h<N, 0, true>(ctx, job);
     return head ? launch_inv_tpm_h<N, HMAX, false>(ctx, job) : launch_inv_tpm_h<N, 0, false>(ctx, job);
 }

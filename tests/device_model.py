@@ -354,3 +354,97 @@ def inverse_inplace_v2(A, P, head):
             adj[r][outcol[j]] = v - p if v > half else v
     det = sum(A[0][c] * adj[c][0] for c in range(n))
     return adj, det
+
+
+# ---- mirror of tpm_eliminate_bareiss (lsx_inv_small.cuh): the fused small inverse over the integers ----------------
+_M32 = 0xFFFFFFFF
+
+
+def _s32(x):
+    x &= _M32
+    return x - (1 << 32) if x & 0x80000000 else x
+
+
+def inv_odd_u32(o):
+    """o^-1 modulo 2^32 for odd o: (3 o) xor 2 is right to 5 bits, three Newton steps."""
+    o &= _M32
+    x = ((o * 3) ^ 2) & _M32
+    for _ in range(3):
+        x = (x * ((2 - o * x) & _M32)) & _M32
+    return x
+
+
+def h32_steps_for(n, a_abs_max):
+    """Leading pivot steps whose t = piv * w - f * prow fits 32 bits: 2 M^2 < 2^31 for the Hadamard bound M of the
+    minors of order j + 1 (lsx_small.cu::h32_steps_for)."""
+    import math
+    h = 0
+    for j in range(n):
+        k = j + 1
+        bits = log2_minor_bound(k, k, False, a_abs_max, 0, False, k)
+        if 1.0 + 2.0 * bits >= 31.0 - 1e-6:
+            break
+        h = j + 1
+    return h
+
+
+def inverse_inplace_bareiss(A, h32):
+    """One-step fraction-free (Bareiss) Gauss-Jordan in place, on 32-bit two's-complement words exactly as the kernel
+    does it: the exact division by the previous pivot d = 2^s * o is ((t >> s) * o^-1) mod 2^32, with t formed in 32
+    bits for the first h32 steps and in 64 bits afterwards.  Returns (adj, det) or None (singular)."""
+    n = len(A)
+    W = [[int(a) & _M32 for a in row] for row in A]
+    unit = list(range(n))
+    outcol = [0] * n
+    neg = False
+    dprev, dinv, dsh = 1, 1, 0
+    piv = 0
+    for j in range(n):
+        last = j == n - 1
+        src = next((r for r in range(j, n) if W[r][j] != 0), None)
+        if src is None:
+            return None
+        if src != j:
+            W[j], W[src] = W[src], W[j]
+            unit[j], unit[src] = unit[src], unit[j]
+            neg = not neg
+        outcol[j] = unit[j]
+        piv = W[j][j]
+        prow = list(W[j])
+        flip = last and neg
+        minv = (-dinv) & _M32 if flip else dinv
+        for r in range(n):
+            if r == j:
+                continue
+            f = W[r][j]
+            nf = (-f) & _M32
+            for c in range(n):
+                if c == j:
+                    W[r][c] = f if flip else nf
+                elif j == 0:
+                    t = (piv * W[r][c] + nf * prow[c]) & _M32
+                    W[r][c] = (-t) & _M32 if flip else t
+                elif j < h32:
+                    t = (piv * W[r][c] + nf * prow[c]) & _M32
+                    exact = _s32(piv) * _s32(W[r][c]) - _s32(f) * _s32(prow[c])
+                    assert _s32(t) == exact, "32-bit step overflowed"
+                    W[r][c] = ((_s32(t) >> dsh) * minv) & _M32
+                else:
+                    t = _s32(piv) * _s32(W[r][c]) + _s32(nf) * _s32(prow[c])
+                    assert -(1 << 63) <= t < (1 << 63)
+                    assert t % _s32(dprev) == 0, "Bareiss division must be exact"
+                    W[r][c] = (((t >> dsh) & _M32) * minv) & _M32
+        W[j][j] = dprev
+        if flip:
+            W[j] = [(-x) & _M32 for x in W[j]]
+        if not last:
+            dprev = piv
+            sp = _s32(piv)
+            dsh = ((sp & -sp).bit_length() - 1) & 31
+            dinv = inv_odd_u32(sp >> dsh)
+    det = _s32((-piv) & _M32 if neg else piv)
+    adj = [[0] * n for _ in range(n)]
+    for r in range(n):
+        for j in range(n):
+            adj[r][outcol[j]] = _s32(W[r][j])
+    return adj, det

@@ -157,3 +157,46 @@ def test_inplace_v2_head_steps_and_folding():
                     assert det == ref_port.bareiss_det(A), (n, head, A)
                     assert [[Fraction(x, det) for x in row] for row in adj] == want, (n, head, A)
     assert n_sing > 10
+
+
+def test_inplace_bareiss_integer_kernel_mirror():
+    """tpm_eliminate_bareiss (the default fused 8x8 kernel): exact 32-bit integer Gauss-Jordan with division by the
+    previous pivot as a multiplication modulo 2^32; both the 32-bit-step and the all-64-bit instantiation."""
+    assert dm.h32_steps_for(8, 5) == 4 and dm.h32_steps_for(8, 9) == 3 and dm.h32_steps_for(4, 5) == 4
+    assert dm.h32_steps_for(8, 40000) == 0 and dm.h32_steps_for(1, 5) == 1
+    for o in (1, 3, 5, -7, 0x7fffffff, -0x7fffffff, 123456789):
+        assert (dm.inv_odd_u32(o) * (o & 0xFFFFFFFF)) & 0xFFFFFFFF == 1
+    rnd = random.Random(23)
+    n_sing = 0
+    for n in (1, 2, 3, 4, 5, 6, 7, 8):
+        for h32 in sorted({0, min(n, 4)}):
+            for t in range(16):
+                A = [[rnd.randint(-5, 5) for _ in range(n)] for _ in range(n)]
+                if t % 4 == 0 and n > 1:
+                    A[rnd.randrange(n)][0] = 0
+                    A[0][0] = 0
+                if t % 5 == 0 and n > 1:
+                    A[-1] = list(A[0])
+                if t % 6 == 1 and n > 2:
+                    A[n - 1][n - 1] = 0
+                    A[n - 2][n - 2] = 0
+                if t % 7 == 2:
+                    A = [[2 * x for x in row] for row in A]          # even pivots: shifts in every division
+                    A = [[max(-5, min(5, x)) for x in row] for row in A]
+                got = dm.inverse_inplace_bareiss(A, h32)
+                want = ref_port.inverse(A)
+                if want is None:
+                    assert got is None
+                    n_sing += 1
+                    continue
+                adj, det = got
+                assert det == ref_port.bareiss_det(A), (n, h32, A)
+                assert [[Fraction(x, det) for x in row] for row in adj] == want, (n, h32, A)
+    assert n_sing > 10
+    # entries near the limit of the fused path for n = 4: |a| <= 180 keeps every minor below 2^31
+    for t in range(20):
+        A = [[rnd.randint(-180, 180) for _ in range(4)] for _ in range(4)]
+        got = dm.inverse_inplace_bareiss(A, dm.h32_steps_for(4, 180) if dm.h32_steps_for(4, 180) >= 4 else 0)
+        want = ref_port.inverse(A)
+        if want is not None:
+            assert [[Fraction(x, got[1]) for x in row] for row in got[0]] == want

@@ -450,8 +450,10 @@ def test_device_memory_path_matches_host_path(eng):
 
 
 def test_fused_small_inverse_equals_tile_path(eng, monkeypatch):
-    """The single-prime register-resident kernel and the multi-prime shared-memory path must agree
-    word for word, for every n <= 8, including singular inputs, row swaps and ragged batch sizes."""
+    """The fused register-resident kernel in its two arithmetics -- exact 32-bit integers (Bareiss, the default) and
+    residues modulo one prime (LSX_TPM_ALGO=mont, with and without the plain-integer head) -- and the multi-prime
+    shared-memory path must agree word for word, for every n <= 8, including singular inputs, row swaps and ragged
+    batch sizes."""
     rng = np.random.Generator(np.random.PCG64(99))
     for n in range(1, 9):
         for B in (1, 127, 128, 129, 1000):
@@ -460,24 +462,46 @@ def test_fused_small_inverse_equals_tile_path(eng, monkeypatch):
             if n > 1:
                 A[::11, n - 1] = A[::11, 0]                    # singular
             fused = eng.inverse_batch(A, a_abs_max=5)
-            monkeypatch.setenv("LSX_TPM_HEAD", "0")             # same kernel without the plain-integer head steps
+            monkeypatch.setenv("LSX_TPM_ALGO", "mont")          # the residue kernel
+            mont = eng.inverse_batch(A, a_abs_max=5)
+            monkeypatch.setenv("LSX_TPM_HEAD", "0")             # ... and without its plain-integer head steps
             nohead = eng.inverse_batch(A, a_abs_max=5)
             monkeypatch.delenv("LSX_TPM_HEAD")
-            assert np.array_equal(fused.adj, nohead.adj) and np.array_equal(fused.det, nohead.det)
-            assert np.array_equal(fused.status, nohead.status)
-            if n == 8:
-                for xs in ("0", "1", "2"):                      # pivot step 3: Montgomery / FP64 pipe / 64-bit + Mersenne fold
-                    monkeypatch.setenv("LSX_TPM_XS", xs)
-                    alt = eng.inverse_batch(A, a_abs_max=5)
-                    monkeypatch.delenv("LSX_TPM_XS")
-                    assert np.array_equal(fused.adj, alt.adj) and np.array_equal(fused.det, alt.det), xs
-                    assert np.array_equal(fused.status, alt.status), xs
+            monkeypatch.delenv("LSX_TPM_ALGO")
+            for alt in (mont, nohead):
+                assert np.array_equal(fused.adj, alt.adj) and np.array_equal(fused.det, alt.det)
+                assert np.array_equal(fused.status, alt.status)
             monkeypatch.setenv("LSX_DISABLE_SMALL", "1")
             tile = eng.inverse_batch(A, a_abs_max=5)
             monkeypatch.delenv("LSX_DISABLE_SMALL")
             assert np.array_equal(fused.status, tile.status & ~32)
             assert np.array_equal(fused.det, tile.det)
             assert np.array_equal(fused.adj, tile.adj)
+    # magnitudes where the 32-bit steps of the integer kernel do not apply (its all-64-bit instantiation) and minors
+    # close to 2^31: still the fused path (one limb), still equal to the other two
+    for n, amax in ((2, 30000), (3, 600), (4, 100), (5, 30), (6, 14), (7, 8)):
+        A = rng.integers(-amax, amax + 1, size=(777, n, n), dtype=np.int32)
+        A[::13, 0] = 0
+        A[::13, 0, n - 1] = amax
+        A[::17, n - 1] = A[::17, 0]
+        fused = eng.inverse_batch(A, a_abs_max=amax)
+        assert fused.plan.limbs == 1
+        monkeypatch.setenv("LSX_TPM_ALGO", "mont")
+        mont = eng.inverse_batch(A, a_abs_max=amax)
+        monkeypatch.delenv("LSX_TPM_ALGO")
+        monkeypatch.setenv("LSX_DISABLE_SMALL", "1")
+        tile = eng.inverse_batch(A, a_abs_max=amax)
+        monkeypatch.delenv("LSX_DISABLE_SMALL")
+        for alt in (mont, tile):
+            assert np.array_equal(fused.adj, alt.adj) and np.array_equal(fused.det, alt.det), (n, amax)
+            assert np.array_equal(fused.status, alt.status & ~32), (n, amax)
+        for i in range(0, 777, 97):
+            inv = ref_port.inverse(A[i].tolist())
+            d = int(fused.det.view(np.int32).reshape(-1)[i])
+            assert d == ref_port.bareiss_det(A[i].tolist())
+            if inv is not None:
+                adj = fused.adj.view(np.int32).reshape(777, n, n)[i]
+                assert [[Fraction(int(x), d) for x in row] for row in adj] == inv
     # entries above the declared bound are flagged, not mis-computed
     A = rng.integers(-5, 6, size=(300, 8, 8), dtype=np.int32)
     A[5, 3, 3] = 77

@@ -200,6 +200,16 @@ int main(int argc, char** argv) {
     const float ms8m = time_new<8, 3, true, 2>(dA8, batch, P, 5, adj1, det1, st1, reps, s);
     bad += compare("int8 head3 + mersenne step");
     CK(cudaMemset(adj1, 0xff, A.size() * 4));
+    const float ms32b = time_new<8, 4, false, 3>(dA, batch, P, 5, adj1, det1, st1, reps, s);
+    bad += compare("int32 bareiss h32=4");
+    CK(cudaMemset(adj1, 0xff, A.size() * 4));
+    const float ms8b = time_new<8, 4, true, 3>(dA8, batch, P, 5, adj1, det1, st1, reps, s);
+    bad += compare("int8 bareiss h32=4");
+    CK(cudaMemset(adj1, 0xff, A.size() * 4));
+    const float ms32b0 = time_new<8, 0, false, 3>(dA, batch, P, 5, adj1, det1, st1, reps, s);
+    bad += compare("int32 bareiss h32=0");
+    printf("{\"tag\": \"%s\", \"bareiss_i32_ms\": %.4f, \"bareiss_i8_ms\": %.4f, \"bareiss_i32_h0_ms\": %.4f}\n", tag, ms32b, ms8b, ms32b0);
+    CK(cudaMemset(adj1, 0xff, A.size() * 4));
     const float ms32s = time_stream<8, 3, false>(dA, batch, P, 5, adj1, det1, st1, reps, s, LSX_TPM_MINB);
     bad += compare("int32 stream");
     CK(cudaMemset(adj1, 0xff, A.size() * 4));
