@@ -602,10 +602,15 @@ def measure_batch(ctx, workload, steps, warmup, cpu):
         roof["issue_slots"] = {"warp_instructions_per_step": cnt["warp_inst_per_step"], "slots": slots,
                                "frac": cnt["warp_inst_per_step"] / slots, "sm_mhz": sm_run,
                                "source": cnt.get("source")}
-    if workload in ALG_OPS:
-        # ALGORITHMIC count, not executed instructions: the fused 8x8 kernel runs ONE prime and
-        # part of its steps on plain int32, so it executes fewer and cheaper operations than this count
-        n_pr = 1 if workload == "c2" else int(plan.n_primes)
+    if workload == "c2":
+        # the fused 8x8 kernel computes over the integers (Bareiss): no modular multiply-subtracts to count.  Its limiting
+        # unit is the fmaheavy pipe (IMAD / IMAD.WIDE), whose busy fraction is an ncu figure of the same kernel source
+        roof["int_pipe"] = {"fmaheavy_busy_ncu": 0.754, "issue_slots_busy_ncu": 0.52, "warp_instructions_per_32_matrices": 2183,
+                            "source": "profiles/r02o_ncu_full_k_inv_tpm8_bareiss.txt (sm__pipe_fmaheavy_cycles_active, one launch "
+                                      "under ncu at 128 us); static mix: profiles/r02o_sass_hist_k_inv_tpm8_bareiss.txt"}
+    elif workload in ALG_OPS:
+        # ALGORITHMIC count, not executed instructions
+        n_pr = int(plan.n_primes)
         ip_peak = MONT_MUL_PER_SM_CLK * 148 * sm_max * 1e6
         ip_ach = ALG_OPS[workload] * n_pr * batch / (k_ms * 1e-3)
         roof["algorithmic_int"] = {"ops_per_matrix": ALG_OPS[workload] * n_pr, "achieved": ip_ach, "peak": ip_peak,
@@ -615,7 +620,8 @@ def measure_batch(ctx, workload, steps, warmup, cpu):
     return {
         "metric": METRIC[workload], "value": value, "unit": "matrices/s", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32 (Montgomery words modulo 31-bit primes)",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "i32 (exact integers, fraction-free elimination)" if workload == "c2" else "u32 (Montgomery words modulo 31-bit primes)",
         "data": "synthetic",
         "config": config_for(workload, world),
         "roofline": roof,

@@ -2,6 +2,11 @@
 // thread per matrix, the matrix resident in N*N registers (reference semantics: linalg.py:682-743 through
 // [A|I] row_reduce(bar_col = n), results as adjugate + determinant).
 //
+// TWO arithmetics share the kernel frame (tile staging, transpose, pivot window, output convention):
+//   XS == 3 (the default dispatch): exact integers, one-step fraction-free (Bareiss) Gauss-Jordan -- see
+//            tpm_eliminate_bareiss below; 126 us per 2^20 8 x 8 matrices on B200, 0.70 of the measured HBM peak.
+//   XS <= 2 (LSX_TPM_ALGO=mont): residues modulo one prime, described next; 198 us.
+//
 // Arithmetic (mirror: tests/device_model.py::inverse_inplace_v2): in-place division-free Gauss-Jordan modulo ONE
 // 31-bit prime.  The launcher takes this path only when the Hadamard bound of every minor of A is below the
 // prime, so zero tests modulo p are exact and the adjugate entries come back exactly by the symmetric lift.

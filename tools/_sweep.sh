@@ -1,11 +1,5 @@
-run() { env "$@" python tools/sweep_c5.py >> gpurun_out/r02m_c5_streams2.jsonl 2>> gpurun_out/r02m_c5_streams2.err; }
-run LSX_LARGE_STREAMS=2 LSX_LARGE_GROUP=127 LSX_TAG=base
-run LSX_LARGE_STREAMS=2 LSX_LARGE_GROUP=127 LSX_TC_MAX_TILES=8 LSX_TAG=t8
-run LSX_LARGE_STREAMS=2 LSX_LARGE_GROUP=127 LSX_TC_MAX_TILES=16 LSX_TAG=t16
-run LSX_LARGE_STREAMS=2 LSX_LARGE_GROUP=127 LSX_LARGE_PRIO=1 LSX_TAG=prio
-run LSX_LARGE_STREAMS=2 LSX_LARGE_GROUP=127 LSX_LARGE_PRIO=1 LSX_TC_MAX_TILES=8 LSX_TAG=prio_t8
-run LSX_LARGE_STREAMS=2 LSX_LARGE_GROUP=127 LSX_LARGE_PRIO=1 LSX_TC_MAX_TILES=16 LSX_TAG=prio_t16
-run LSX_LARGE_STREAMS=2 LSX_LARGE_GROUP=74 LSX_LARGE_PRIO=1 LSX_TC_MAX_TILES=8 LSX_TAG=g74_prio_t8
-run LSX_LARGE_STREAMS=3 LSX_LARGE_GROUP=127 LSX_LARGE_PRIO=1 LSX_TC_MAX_TILES=8 LSX_TAG=s3_prio_t8
-run LSX_LARGE_STREAMS=4 LSX_LARGE_GROUP=127 LSX_TC_MAX_TILES=8 LSX_TAG=s4_t8
-cat gpurun_out/r02m_c5_streams2.jsonl; tail -3 gpurun_out/r02m_c5_streams2.err
+VARIANTS="128:4:1:0 128:5:1:0 128:6:1:0 64:8:1:0 64:10:1:0 64:12:1:0 96:6:1:0 96:7:1:0 256:2:1:0 128:4:0:0 128:4:2:0" bash tools/lab/run_inv8_lab.sh run gpurun_out/r02o_lab_variants.jsonl
+grep bareiss gpurun_out/r02o_lab_variants.jsonl
+tail -3 gpurun_out/r02o_lab_variants.jsonl.err
+timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:k_inv_tpmILi8ELi4ELb0ELi3 -s 3 -c 1 -f -o gpurun_out/r02o_inv8_bareiss tools/lab/bin/inv8_bareiss 5 ncu > gpurun_out/r02o_ncu.log 2>&1
+tail -3 gpurun_out/r02o_ncu.log
