@@ -22,7 +22,13 @@
 
 namespace {
 
-constexpr int SW_THREADS = 128;
+#ifndef LSX_SW_THREADS
+#define LSX_SW_THREADS 128
+#endif
+#ifndef LSX_SW_SYNC
+#define LSX_SW_SYNC 0            // experiment: a CTA barrier every LSX_SW_SYNC pivot steps keeps the warps of a CTA on the same
+#endif                           // stretch of the unrolled instruction stream (instruction-cache sharing)
+constexpr int SW_THREADS = LSX_SW_THREADS;
 constexpr int SW_SKIP = 63;          // profile code of a column without pivot
 
 struct SwArgs {
@@ -214,7 +220,11 @@ __device__ __forceinline__ void sw_step(uint32_t (&row)[PP][NC], SwState (&st)[P
 template <int G, int NC, int PP, int... Js>
 __device__ __forceinline__ void sw_steps(uint32_t (&row)[PP][NC], SwState (&st)[PP], const PrimeRec (&P)[PP], int r, int gbase,
                                          unsigned gmask, int m, int bar, bool live, std::integer_sequence<int, Js...>) {
+#if LSX_SW_SYNC > 0
+    ((sw_step<G, NC, PP, Js>(row, st, P, r, gbase, gmask, m, bar, live), (Js % LSX_SW_SYNC == 0 ? __syncthreads() : (void)0)), ...);
+#else
     (sw_step<G, NC, PP, Js>(row, st, P, r, gbase, gmask, m, bar, live), ...);
+#endif
 }
 
 template <int G, int NC, int PP>
