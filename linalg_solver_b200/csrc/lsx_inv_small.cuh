@@ -348,7 +348,7 @@ __device__ __forceinline__ uint32_t inv_odd_u32(uint32_t o) {
     return x;
 }
 
-template <int N, int H32>
+template <int N, int H32, int H53 = H32>
 __device__ __forceinline__ void tpm_eliminate_bareiss(uint32_t (&W)[N][N], uint32_t (&perm)[N], bool& singular, uint32_t& det) {
 #pragma unroll
     for (int r = 0; r < N; ++r) perm[r] = (uint32_t)r;
@@ -357,6 +357,13 @@ __device__ __forceinline__ void tpm_eliminate_bareiss(uint32_t (&W)[N][N], uint3
     uint32_t dprev = 1u, dinv = 1u;         // previous pivot d = 2^dsh * o and o^-1 mod 2^32
     int dsh = 0;
     uint32_t piv = 0u;
+    // Steps H32 <= j < H53 run on the FP64 pipe, which is idle otherwise: there |piv * w| and |f * prow| stay below 2^53
+    // (launcher), so t is exact in a double, and q = t / d comes from ONE fused multiply-add against 1.5 * 2^52 with
+    // the reciprocal of d: t * fl(1/d) is within 2^-21 of the integer q (|q| < 2^31), the magic constant rounds it
+    // there and leaves q in two's complement in the low word of the sum.  DADD (word -> double), DMUL, DFMA, DFMA per
+    // entry instead of IMAD.WIDE, IMAD.WIDE, SHF, IMAD.
+    constexpr double MAGIC = 6755399441055744.0;
+    double rd = 1.0;                        // fl(1 / d)
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         const bool last = j == N - 1;
@@ -395,14 +402,25 @@ __device__ __forceinline__ void tpm_eliminate_bareiss(uint32_t (&W)[N][N], uint3
         for (int c = 0; c < N; ++c) prow[c] = W[j][c];
         const bool flip = last && neg;                          // the sign of the row exchanges, folded into the last step
         const uint32_t minv = flip ? 0u - dinv : dinv;
+        const bool f64 = j >= H32 && j < H53 && j > 0 && !last;
+        double pivd = 0.0, prd[N];
+        if (f64) {
+            pivd = double_of_int(piv);
+#pragma unroll
+            for (int c = 0; c < N; ++c) prd[c] = double_of_int(prow[c]);
+        }
 #pragma unroll
         for (int r = 0; r < N; ++r) {
             if (r == j) continue;
             const uint32_t f = W[r][j], nf = 0u - f;
+            const double nfd = f64 ? double_of_int(nf) : 0.0;
 #pragma unroll
             for (int c = 0; c < N; ++c) {
                 if (c == j) {
                     W[r][c] = flip ? f : nf;
+                } else if (f64) {
+                    const double td = __fma_rn(nfd, prd[c], pivd * double_of_int(W[r][c]));
+                    W[r][c] = (uint32_t)__double2loint(__fma_rn(td, rd, MAGIC));
                 } else if (j == 0) {                            // d = 1: the wrapping 32-bit result is the minor itself
                     const uint32_t t = piv * W[r][c] + nf * prow[c];
                     W[r][c] = flip ? 0u - t : t;
@@ -424,6 +442,7 @@ __device__ __forceinline__ void tpm_eliminate_bareiss(uint32_t (&W)[N][N], uint3
             dprev = piv;
             dsh = (__ffs((int)piv) - 1) & 31;                   // piv == 0: singular, results are discarded
             dinv = inv_odd_u32((uint32_t)((int32_t)piv >> dsh));
+            if (j + 1 >= H32 && j + 1 < H53) rd = 1.0 / (double)(int32_t)piv;
         }
     }
     det = neg ? 0u - piv : piv;
@@ -538,8 +557,9 @@ k_inv_tpm(const void* __restrict__ Ain, int64_t batch, PrimeRec P, int a_abs_max
     uint32_t a0[N];
     bool singular;
     uint32_t dsum = 0u;
-    if constexpr (XS == 3) {
-        tpm_eliminate_bareiss<N, HEAD>(W, perm, singular, dsum);
+    if constexpr (XS == 3 || XS == 4) {
+        if constexpr (XS == 4) tpm_eliminate_bareiss<N, HEAD, (HEAD + 2 < N - 1 ? HEAD + 2 : N - 1)>(W, perm, singular, dsum);
+        else tpm_eliminate_bareiss<N, HEAD>(W, perm, singular, dsum);
         if (singular || bound_bad) {            // rare: zeros (the reference returns NoSolution(), linalg.py:725-737)
             dsum = 0u;
 #pragma unroll

@@ -208,6 +208,13 @@ int main(int argc, char** argv) {
     CK(cudaMemset(adj1, 0xff, A.size() * 4));
     const float ms32b0 = time_new<8, 0, false, 3>(dA, batch, P, 5, adj1, det1, st1, reps, s);
     bad += compare("int32 bareiss h32=0");
+    CK(cudaMemset(adj1, 0xff, A.size() * 4));
+    const float ms32bf = time_new<8, 4, false, 4>(dA, batch, P, 5, adj1, det1, st1, reps, s);
+    bad += compare("int32 bareiss h32=4 + 2 fp64 steps");
+    CK(cudaMemset(adj1, 0xff, A.size() * 4));
+    const float ms8bf = time_new<8, 4, true, 4>(dA8, batch, P, 5, adj1, det1, st1, reps, s);
+    bad += compare("int8 bareiss h32=4 + 2 fp64 steps");
+    printf("{\"tag\": \"%s\", \"bareiss_f64_i32_ms\": %.4f, \"bareiss_f64_i8_ms\": %.4f}\n", tag, ms32bf, ms8bf);
     printf("{\"tag\": \"%s\", \"bareiss_i32_ms\": %.4f, \"bareiss_i8_ms\": %.4f, \"bareiss_i32_h0_ms\": %.4f}\n", tag, ms32b, ms8b, ms32b0);
     CK(cudaMemset(adj1, 0xff, A.size() * 4));
     const float ms32s = time_stream<8, 3, false>(dA, batch, P, 5, adj1, det1, st1, reps, s, LSX_TPM_MINB);
