@@ -17,6 +17,9 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <type_traits>
+#include <utility>
+
 #include "lsx_internal.h"
 #include "lsx_crt.cuh"
 
@@ -169,12 +172,28 @@ __global__ void __launch_bounds__(T) k_tile_elim(const TileArgs a) {
 // words and RA pivot-column words from shared memory -- the smem traffic of k_tile_elim (3 accesses
 // per cell and step) is gone.  While no column has been skipped, 16-column blocks that lie completely
 // left of the pivot column are finished pivot columns and are not updated any more.
-template <int RA, int CB>
-__global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const TileArgs a) {
+// TYN = thread rows (16: 256 threads; 8: 128 threads, every thread owns twice the rows -- the per-step bookkeeping
+// (column publish, multiplier set-up, block tests) is per thread, so it is spread over twice the cell updates).
+// any int32 into [0, p) for p > 2^30 (|v| <= 2^31 < 2 p): conditional corrections, no division
+__device__ __forceinline__ uint32_t residue_fast(int32_t v, uint32_t p) {
+    int64_t t = v;
+    if (t < 0) t += p;
+    if (t < 0) t += p;
+    if (t >= (int64_t)p) t -= p;
+    return (uint32_t)t;
+}
+
+template <class F, int... Is>
+__device__ __forceinline__ void for_each_block(F& f, std::integer_sequence<int, Is...>) {
+    (f(std::integral_constant<int, Is>{}), ...);
+}
+
+template <int RA, int CB, int TYN>
+__global__ void __launch_bounds__(16 * TYN, TYN == 16 ? ((RA * CB <= 32) ? 3 : 2) : ((RA * CB <= 64) ? 4 : 2)) k_tile_reg(const TileArgs a) {
     __shared__ uint32_t prow[16 * CB];
-    __shared__ uint32_t colbuf[16 * RA];
-    __shared__ uint8_t perm[16 * RA];
-    __shared__ uint8_t inv[16 * RA];
+    __shared__ uint32_t colbuf[TYN * RA];
+    __shared__ uint8_t perm[TYN * RA];
+    __shared__ uint8_t inv[TYN * RA];
     const int m = a.m, n = a.n, bar = a.bar;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
     const int kslot = blockIdx.y;
@@ -189,7 +208,7 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
         bool bad = false;
 #pragma unroll
         for (int ia = 0; ia < RA; ++ia) {
-            const int r = ty + 16 * ia;
+            const int r = ty + TYN * ia;
 #pragma unroll
             for (int ib = 0; ib < CB; ++ib) {
                 const int c = tx + 16 * ib;
@@ -209,11 +228,11 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
                     const int64_t av = v < 0 ? -(int64_t)v : (int64_t)v;
                     bad |= av > lim;
                 }
-                W[ia][ib] = word_of_int_any(v, p);
+                W[ia][ib] = p > (1u << 30) ? residue_fast(v, p) : word_of_int_any(v, p);   // tiny test primes divide
             }
         }
         if (bad) atomicOr(&a.status[mat], LSX_ST_BOUND);
-        if (tid < 16 * RA) perm[tid] = (uint8_t)tid;
+        for (int q = tid; q < TYN * RA; q += 16 * TYN) perm[q] = (uint8_t)q;
         __syncthreads();
 
         uint32_t S = P.one, Q = P.one, X = 1u;
@@ -228,24 +247,24 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
         const int nleft = a.n_in >> 4;         // 16-column blocks of the left part
         int rb_on = 0;
         uint8_t* prof = a.prof + ((int64_t)kslot * a.cap + slot) * bar;
-        for (int j = 0; j < bar; ++j) {
+        // The pivot columns are walked block by block with the 16-column block index JB a COMPILE-TIME constant (the
+        // loop body is instantiated once per block): the column publish then reads W[ia][JB] with a static register
+        // index.  With a run-time block index it took a select chain over all CB blocks per row and step (a switch is
+        // turned into a dynamically indexed access by the compiler, which put the whole tile into LOCAL memory: ncu,
+        // round 2, one LDL + one STL per cell update).
+        auto block_steps = [&](auto jb_c) {
+          constexpr int JB = decltype(jb_c)::value;
+          for (int jj = 0; jj < 16; ++jj) {
+            const int j = 16 * JB + jj;
+            if (j >= bar) break;
             if (pi >= m) {
                 if (tid == 0) prof[j] = LSX_PROF_SKIP;
                 continue;
             }
             // 1. publish column j (indexed by physical row)
-            if (tx == (j & 15)) {
-                // The block index j >> 4 is uniform, but a switch over it is turned into a dynamically indexed access
-                // by the compiler (common-code sinking), which put the whole tile into LOCAL memory (ncu, round 2: one
-                // LDL + one STL per cell update).  A select chain keeps every index static.
-                const int jb = j >> 4;
+            if (tx == jj) {
 #pragma unroll
-                for (int ia = 0; ia < RA; ++ia) {
-                    uint32_t v = W[ia][0];
-#pragma unroll
-                    for (int ib = 1; ib < CB; ++ib) v = (jb == ib) ? W[ia][ib] : v;
-                    colbuf[ty + 16 * ia] = v;
-                }
+                for (int ia = 0; ia < RA; ++ia) colbuf[ty + TYN * ia] = W[ia][JB];
             }
             __syncthreads();
             // 2. pivot search over logical positions pi .. m-1: the first non-zero.  Every warp does it
@@ -279,15 +298,15 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
                     for (int ia = 0; ia < RA; ++ia)
 #pragma unroll
                         for (int ib = 0; ib < CB; ++ib) {
-                            const bool hit = tx == ty && ia == rb_on && ib == nleft + rb_on && ty + 16 * ia < m;
+                            const bool hit = ib == nleft + rb_on && ty + TYN * ia == tx + 16 * rb_on && ty + TYN * ia < m;
                             W[ia][ib] = hit ? sv : W[ia][ib];
                         }
                     ++rb_on;
                 }
             }
             // 3. publish the pivot row
-            if (ty == (prp & 15)) {
-                const int pb = prp >> 4;       // same: selects, not a switch
+            if (ty == prp % TYN) {
+                const int pb = prp / TYN;      // same: selects, not a switch
 #pragma unroll
                 for (int ib = 0; ib < CB; ++ib) {
                     uint32_t v = W[0][ib];
@@ -300,7 +319,7 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
             uint32_t xs[RA], ys[RA];
 #pragma unroll
             for (int ia = 0; ia < RA; ++ia) {
-                const int r = ty + 16 * ia;
+                const int r = ty + TYN * ia;
                 const uint32_t f = colbuf[r];
                 const bool isp = r == prp;
                 xs[ia] = isp ? S : piv;
@@ -328,7 +347,9 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
             }
             ++pi;
             __syncthreads();                   // prow / colbuf / perm are rewritten by the next column
-        }
+          }
+        };
+        for_each_block(block_steps, std::make_integer_sequence<int, CB>{});
         if (lazy_id) {
             // rank-deficient input: blocks never switched on still hold the initial ones; give them the final scale
             while (rb_on < ((m + 15) >> 4)) {
@@ -337,14 +358,14 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
                 for (int ia = 0; ia < RA; ++ia)
 #pragma unroll
                     for (int ib = 0; ib < CB; ++ib) {
-                        const bool hit = tx == ty && ia == rb_on && ib == nleft + rb_on && ty + 16 * ia < m;
+                        const bool hit = ib == nleft + rb_on && ty + TYN * ia == tx + 16 * rb_on && ty + TYN * ia < m;
                         W[ia][ib] = hit ? sv : W[ia][ib];
                     }
                 ++rb_on;
             }
         }
         // ---- one inversion, scale to N = d * RREF (plain residues), rows in logical order ----
-        if (tid < m) inv[perm[tid]] = (uint8_t)tid;
+        for (int q = tid; q < m; q += 16 * TYN) inv[perm[q]] = (uint8_t)q;
         __syncthreads();
         const uint32_t qinv = mont_pow(Q, p - 2u, P.one, p, pinv);
         uint32_t Gw = mont_mul(qinv, X, p, pinv);
@@ -354,7 +375,7 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
             uint32_t* out = a.res + ((int64_t)kslot * a.cap + slot) * ((int64_t)m * ncs);
 #pragma unroll
             for (int ia = 0; ia < RA; ++ia) {
-                const int r = ty + 16 * ia;
+                const int r = ty + TYN * ia;
                 if (r < m) {
                     const int q = inv[r];
                     const uint32_t g = q < pi ? Gw : G2w;
@@ -374,11 +395,11 @@ __global__ void __launch_bounds__(256, (RA * CB <= 32) ? 3 : 2) k_tile_reg(const
     }
 }
 
-template <int RA, int CB>
+template <int RA, int CB, int TYN = 16>
 int launch_tile_reg(lsx_ctx* ctx, const TileArgs& ta, int Ktot, int64_t grid_x) {
     dim3 grid((unsigned)grid_x, (unsigned)Ktot);
     lsx_timing_begin(ctx);
-    k_tile_reg<RA, CB><<<grid, 256, 0, ctx->stream>>>(ta);
+    k_tile_reg<RA, CB, TYN><<<grid, 16 * TYN, 0, ctx->stream>>>(ta);
     lsx_timing_end(ctx);
     ctx->launches++;
     return LSX_OK;
@@ -389,9 +410,17 @@ bool launch_tile_reg_any(lsx_ctx* ctx, const TileArgs& ta, int Ktot, int64_t gri
     if (getenv("LSX_DISABLE_TILE_REG")) return false;
     const int m = ta.m, n = ta.n;
     if (m > 128 || n > 128 || m * n < 256) return false;
+    // 64-row tiles, measured on B200 with the block-static step loop (profiles/r02t_tile.txt, per 4096 matrices):
+    //   64 x 65 (kernel basis, 21 primes): 128 threads x 8 rows <8,5,8> 13.3 ms, 256 threads <4,5> 15.5 ms (was 18.5)
+    //   64 x 128 (inverse, 12 primes):     256 threads <4,8> 13.5 ms, 128 threads <8,8,8> 16.3 ms (was 16.0; the eight
+    //                                      instantiated step bodies of the 64-cell shape no longer share the instruction cache
+    //                                      between the CTAs of an SM)
+    // LSX_TILE_TY8 = 0 / 1 forces the 256- / 128-thread shapes for both.
+    const char* ty8 = getenv("LSX_TILE_TY8");
+    const int t8 = ty8 ? (atoi(ty8) != 0 ? 1 : 0) : -1;
     if (m <= 32 && n <= 48) *rc = launch_tile_reg<2, 3>(ctx, ta, Ktot, grid_x);
-    else if (m <= 64 && n <= 80) *rc = launch_tile_reg<4, 5>(ctx, ta, Ktot, grid_x);
-    else if (m <= 64 && n <= 128) *rc = launch_tile_reg<4, 8>(ctx, ta, Ktot, grid_x);
+    else if (m <= 64 && n <= 80) *rc = t8 != 0 ? launch_tile_reg<8, 5, 8>(ctx, ta, Ktot, grid_x) : launch_tile_reg<4, 5>(ctx, ta, Ktot, grid_x);
+    else if (m <= 64 && n <= 128) *rc = t8 == 1 ? launch_tile_reg<8, 8, 8>(ctx, ta, Ktot, grid_x) : launch_tile_reg<4, 8>(ctx, ta, Ktot, grid_x);
     else *rc = launch_tile_reg<8, 8>(ctx, ta, Ktot, grid_x);
     return true;
 }

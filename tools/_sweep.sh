@@ -1,6 +1,7 @@
-for v in base 128_1 256_0 256_1 512_1 512_2; do
-  if [ $v = base ]; then L=linalg_solver_b200/liblsx.so; else L=tools/lab/so/liblsx_sw_$v.so; fi
-  echo "== $v" >> gpurun_out/r02p_sw_variants.txt
-  LSX_LIB_PATH=$PWD/$L python tools/time_configs.py c3 c1 >> gpurun_out/r02p_sw_variants.txt 2>&1
-done
-cat gpurun_out/r02p_sw_variants.txt
+echo "== ty8 default + static blocks" > gpurun_out/r02t_tile.txt
+python tools/time_configs.py c4inv c4ker >> gpurun_out/r02t_tile.txt 2>&1
+echo "== 256-thread shapes + static blocks" >> gpurun_out/r02t_tile.txt
+LSX_TILE_TY8=0 python tools/time_configs.py c4inv c4ker >> gpurun_out/r02t_tile.txt 2>&1
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3 >> gpurun_out/r02t_tile.txt
+LSX_TILE_TY8=0 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -3 >> gpurun_out/r02t_tile.txt
+cat gpurun_out/r02t_tile.txt
