@@ -535,17 +535,64 @@ template <int KT>
 __global__ void __launch_bounds__(128) k_assemble(const AsmArgs a) {
     const int64_t nslots = a.list ? min((int64_t)*a.list_count, a.cap) : a.batch;
     const int64_t E = (int64_t)a.m * a.ncs;       // stored entries per matrix
-    const int64_t per = E + 1;                    // + the denominator
+    // threads per matrix: one per stored entry + the denominator; a solve keeps at most gen_cap + 1 entries of a row
+    // (free columns and the right-hand side), so its threads are dealt over (row, kept slot) instead
+    const bool compact = a.op == LSX_OP_SOLVE;
+    const int kept = a.gen_cap + 1;
+    const int64_t per = (compact ? (int64_t)a.m * kept : E) + 1;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nslots * per) return;
     const int64_t slot = t / per;
-    const int64_t e = t - slot * per;
+    int64_t e = t - slot * per;
     const int64_t mat = a.list ? (int64_t)a.list[slot] : slot;
     const int st = a.status[mat];
     if (st & (LSX_ST_INTERNAL_RETRY | LSX_ST_NO_GOOD_PRIME | LSX_ST_BOUND)) return;
     const uint8_t* sel = a.sel + slot * LSX_MAX_BATCH_PRIMES;
     const int K = a.K, L = a.L;
     const int rank = a.rank_ws[slot];
+
+    // A solve keeps only part of the tile: the right-hand-side column and the FREE columns of the pivot rows (and a
+    // zero test of the right-hand side below them).  Decide that before the residues are loaded and reconstructed:
+    // for the rank-48 kernel bases of config 4 four fifths of the entries are pivot columns or zero rows.
+    int solve_tfree = 0;
+    if (compact) {
+        if (e == per - 1) {
+            e = E;                                // the denominator
+        } else {
+            const int nvars = a.n - 1;
+            const int i = (int)(e / kept), q = (int)(e - (int64_t)i * kept);     // q < gen_cap: q-th free column, else rhs
+            int j = nvars;
+            if (i >= rank) {
+                // zero left row: inconsistent iff the rhs is non-zero (linalg.py:913-934)
+                if (q != a.gen_cap) return;
+                const int64_t er = (int64_t)i * a.ncs + (nvars - a.c0);
+                bool zero = true;
+                for (int k = 0; k < K; ++k) zero &= a.res[((int64_t)sel[k] * a.cap + slot) * E + er] == 0u;
+                if (!zero) atomicOr(&a.status[mat], LSX_ST_INCONSISTENT);
+                return;
+            }
+            if (q != a.gen_cap) {
+                // column of the q-th free variable (none: fewer than q + 1 free columns)
+                const int32_t* piv = a.piv_ws + slot * a.pivot_slots;
+                int k = 0, tfree = 0;
+                j = -1;
+                for (int c = 0; c < nvars; ++c) {
+                    if (k < rank && piv[k] == c) {
+                        ++k;
+                    } else {
+                        if (tfree == q) {
+                            j = c;
+                            break;
+                        }
+                        ++tfree;
+                    }
+                }
+                if (j < 0) return;
+                solve_tfree = q;
+            }
+            e = (int64_t)i * a.ncs + (j - a.c0);
+        }
+    }
 
     uint32_t r[KT];
 #pragma unroll
@@ -625,32 +672,14 @@ __global__ void __launch_bounds__(128) k_assemble(const AsmArgs a) {
             store_limbs<KT>(a.num + (mat * E + e) * L, acc, L, false, rank < m);
             break;
         case LSX_OP_SOLVE: {
+            // only the kept entries get here (see the early exit above): pivot rows, rhs or free column
             const int nvars = a.n - 1;
             const int32_t* piv = a.piv_ws + slot * a.pivot_slots;
-            if (i >= rank) {
-                // zero left row: inconsistent iff the rhs is non-zero (linalg.py:913-934)
-                if (j == nvars && !is_zero) atomicOr(&a.status[mat], LSX_ST_INCONSISTENT);
-                break;
-            }
             const int ci = piv[i];
-            if (j == nvars) {
+            if (j == nvars)
                 store_limbs<KT>(a.particular + (mat * nvars + ci) * L, acc, L, false, false);
-            } else {
-                // free column? its index among the free columns
-                int k = 0, tfree = 0;
-                bool is_pivot = false;
-                for (int c = 0; c <= j; ++c) {
-                    if (k < rank && piv[k] == c) {
-                        ++k;
-                        is_pivot = (c == j);
-                    } else if (c < j) {
-                        ++tfree;
-                    }
-                }
-                if (!is_pivot && tfree < a.gen_cap)
-                    store_limbs<KT>(a.generators + ((mat * nvars + ci) * a.gen_cap + tfree) * L, acc, L, true,
-                                    false);
-            }
+            else
+                store_limbs<KT>(a.generators + ((mat * nvars + ci) * a.gen_cap + solve_tfree) * L, acc, L, true, false);
             break;
         }
         default:
@@ -865,7 +894,7 @@ int lsx_run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const
         aa.den = job.den;
         aa.particular = job.particular;
         aa.generators = job.generators;
-        const int64_t nthreads = cap * ((int64_t)m * ncs + 1);
+        const int64_t nthreads = cap * ((job.op == LSX_OP_SOLVE ? (int64_t)m * (job.gen_cap + 1) : (int64_t)m * ncs) + 1);
         const int bs = 128;
         const unsigned gridn = (unsigned)((nthreads + bs - 1) / bs);
         if (K <= 4)
