@@ -190,7 +190,7 @@ __device__ __forceinline__ void for_each_block(F& f, std::integer_sequence<int, 
 
 template <int RA, int CB, int TYN>
 __global__ void __launch_bounds__(16 * TYN, TYN == 16 ? ((RA * CB <= 32) ? 3 : 2) : ((RA * CB <= 64) ? 4 : 2)) k_tile_reg(const TileArgs a) {
-    __shared__ uint32_t prow[16 * CB];
+    __shared__ uint32_t prow2[2][16 * CB];   // double buffered by the parity of the column: no barrier at the end of a step
     __shared__ uint32_t colbuf[TYN * RA];
     __shared__ uint8_t perm[TYN * RA];
     __shared__ uint8_t inv[TYN * RA];
@@ -206,29 +206,37 @@ __global__ void __launch_bounds__(16 * TYN, TYN == 16 ? ((RA * CB <= 32) ? 3 : 2
         const int64_t mat = a.list ? (int64_t)a.list[slot] : slot;
         uint32_t W[RA][CB];
         bool bad = false;
+        {
+            // declared magnitudes as 32-bit limits (an int32 entry cannot exceed a larger one anyway), one row pointer
+            // per register row, and the division only for the tiny primes of the tests
+            const int lim_a = (int)(a.a_abs_max < 0x7fffffff ? a.a_abs_max : 0x7fffffff);
+            const int lim_b = (int)(a.b_abs_max < 0x7fffffff ? a.b_abs_max : 0x7fffffff);
+            const bool big_p = p > (1u << 30);
 #pragma unroll
-        for (int ia = 0; ia < RA; ++ia) {
-            const int r = ty + TYN * ia;
+            for (int ia = 0; ia < RA; ++ia) {
+                const int r = ty + TYN * ia;
+                const bool rowlive = r < m;
+                const int32_t* arow = a.A + (mat * m + (rowlive ? r : 0)) * (int64_t)a.n_in;
+                const int32_t bv = (rowlive && !a.right_identity && a.bvec && n > a.n_in) ? a.bvec[mat * m + r] : 0;
 #pragma unroll
-            for (int ib = 0; ib < CB; ++ib) {
-                const int c = tx + 16 * ib;
-                int32_t v = 0;
-                if (r < m && c < n) {
-                    int64_t lim;
-                    if (c < a.n_in) {
-                        v = a.A[(mat * m + r) * a.n_in + c];
-                        lim = c < bar ? a.a_abs_max : a.b_abs_max;
-                    } else if (a.right_identity) {
-                        v = (c - a.n_in == r) ? 1 : 0;
-                        lim = 1;
-                    } else {
-                        v = a.bvec[mat * m + r];
-                        lim = a.b_abs_max;
+                for (int ib = 0; ib < CB; ++ib) {
+                    const int c = tx + 16 * ib;
+                    int32_t v = 0;
+                    int lim = 0x7fffffff;
+                    if (rowlive && c < n) {
+                        if (c < a.n_in) {
+                            v = arow[c];
+                            lim = c < bar ? lim_a : lim_b;
+                        } else if (a.right_identity) {
+                            v = (c - a.n_in == r) ? 1 : 0;
+                        } else {
+                            v = bv;
+                            lim = lim_b;
+                        }
                     }
-                    const int64_t av = v < 0 ? -(int64_t)v : (int64_t)v;
-                    bad |= av > lim;
+                    bad |= v > lim || v < -lim;
+                    W[ia][ib] = big_p ? residue_fast(v, p) : word_of_int_any(v, p);
                 }
-                W[ia][ib] = p > (1u << 30) ? residue_fast(v, p) : word_of_int_any(v, p);   // tiny test primes divide
             }
         }
         if (bad) atomicOr(&a.status[mat], LSX_ST_BOUND);
@@ -305,6 +313,7 @@ __global__ void __launch_bounds__(16 * TYN, TYN == 16 ? ((RA * CB <= 32) ? 3 : 2
                 }
             }
             // 3. publish the pivot row
+            uint32_t* prow = prow2[j & 1];
             if (ty == prp % TYN) {
                 const int pb = prp / TYN;      // same: selects, not a switch
 #pragma unroll
@@ -346,7 +355,9 @@ __global__ void __launch_bounds__(16 * TYN, TYN == 16 ? ((RA * CB <= 32) ? 3 : 2
                 perm[src] = t0;
             }
             ++pi;
-            __syncthreads();                   // prow / colbuf / perm are rewritten by the next column
+            // No barrier here.  colbuf and perm were last read before barrier 2 of this step; the pivot row is still being
+            // read by slower warps, but the next column writes the OTHER pivot-row buffer, and this one is not written again
+            // before every warp has passed a barrier of the column in between.
           }
         };
         for_each_block(block_steps, std::make_integer_sequence<int, CB>{});
