@@ -379,7 +379,10 @@ __global__ void __launch_bounds__(SW_THREADS) k_subwarp(const SwArgs a) {
     const int sstr = 4 * SW_THREADS, rstr = NC * SW_THREADS;
     auto res_of = [&](int i, int c) { return sm + (size_t)c * SW_THREADS + gt0 + i; };
     const bool singular = rank < m;
-    if (r == 0) {
+    // Every branch below first picks its operands per lane and then makes ONE convergent call of the Garner routine
+    // per round: called from inside the branches, lanes with different kinds of entries (particular solution /
+    // generator / denominator copies) ran the 200-instruction routine one kind after the other.
+    if (r == 0 && a.op != LSX_OP_SOLVE) {       // a solve folds the denominator into its entry list
         const bool zero_det = (a.op == LSX_OP_INVERSE || a.op == LSX_OP_DET) && singular;
         crt_entry_any(nullptr, 0, sc_d, sstr, K, L, T, a.den + mat * L, false, zero_det);
         if (a.op == LSX_OP_INVERSE && singular) atomicOr(&a.status[mat], LSX_ST_SINGULAR);
@@ -390,13 +393,11 @@ __global__ void __launch_bounds__(SW_THREADS) k_subwarp(const SwArgs a) {
         for (int e = r; e < E; e += G) {
             const int i = e / n, c = e - i * n;
             uint32_t* dst = a.num + ((mat * m + i) * (int64_t)n + c) * L;
-            if (c < bar && (pivmask >> c & 1u)) {
-                // finished pivot column: d on its pivot row, 0 elsewhere
-                const bool mine = i < rank && c == (int)__fns(pivmask, 0, i + 1);
-                crt_entry_any(nullptr, 0, sc_d, sstr, K, L, T, dst, false, !mine);
-            } else {
-                crt_entry_any(res_of(i, c), rstr, i < rank ? sc_piv : sc_non, sstr, K, L, T, dst, false, false);
-            }
+            // finished pivot column: d on its pivot row, 0 elsewhere
+            const bool pcol = c < bar && (pivmask >> c & 1u);
+            const bool mine = pcol && i < rank && c == (int)__fns(pivmask, 0, i + 1);
+            crt_entry_any(pcol ? nullptr : res_of(i, c), rstr, pcol ? sc_d : (i < rank ? sc_piv : sc_non), sstr, K, L, T, dst,
+                          false, pcol && !mine);
         }
     } else if (a.op == LSX_OP_INVERSE) {
         const int nn = a.n_in, E = m * nn;
@@ -425,8 +426,8 @@ __global__ void __launch_bounds__(SW_THREADS) k_subwarp(const SwArgs a) {
         const int di = G / per, dq = G - di * per;
         int i = r / per, q = r - i * per;
         const unsigned grp = gmask << gbase;                       // the other group of the warp may have left already
-        for (int e0 = 0; e0 < E; e0 += G) {                        // whole groups iterate together (shuffles inside)
-            const int e = e0 + r;
+        for (int e0 = 0; e0 <= E; e0 += G) {                       // whole groups iterate together (shuffles inside);
+            const int e = e0 + r;                                  // entry E is the common denominator
             const bool on = e < E;
             const bool in_rows = on && e < rank * per;
             const int ii = in_rows ? i : 0, qq = on ? (in_rows ? q : e - rank * per) : 0;
@@ -435,20 +436,28 @@ __global__ void __launch_bounds__(SW_THREADS) k_subwarp(const SwArgs a) {
             const int fc_lo = __shfl_sync(grp, my_fcol0, gbase + (fsel % G));
             const int fc_hi = __shfl_sync(grp, my_fcol1, gbase + (fsel % G));
             const int fc = fsel < G ? fc_lo : fc_hi;
+            const uint32_t* res = nullptr;
+            const uint32_t* scl = sc_d;
+            uint32_t* dst = nullptr;
+            bool negate = false;
             if (in_rows) {
                 if (q == nfree) {
-                    crt_entry_any(res_of(i, nvars), rstr, sc_piv, sstr, K, L, T, a.particular + (mat * nvars + pcol) * L,
-                                  false, false);
+                    res = res_of(i, nvars);
+                    scl = sc_piv;
+                    dst = a.particular + (mat * nvars + pcol) * L;
                 } else if (q < a.gen_cap) {
-                    crt_entry_any(res_of(i, fc), rstr, sc_piv, sstr, K, L, T,
-                                  a.generators + ((mat * nvars + pcol) * (int64_t)a.gen_cap + q) * L, true, false);
+                    res = res_of(i, fc);
+                    scl = sc_piv;
+                    dst = a.generators + ((mat * nvars + pcol) * (int64_t)a.gen_cap + q) * L;
+                    negate = true;
                 }
             } else if (on) {
                 // generator entries equal to d at the free columns (gen[f] = 1, linalg.py:976)
-                if (qq < a.gen_cap)
-                    crt_entry_any(nullptr, 0, sc_d, sstr, K, L, T,
-                                  a.generators + ((mat * nvars + fc) * (int64_t)a.gen_cap + qq) * L, false, false);
+                if (qq < a.gen_cap) dst = a.generators + ((mat * nvars + fc) * (int64_t)a.gen_cap + qq) * L;
+            } else if (e == E) {
+                dst = a.den + mat * L;
             }
+            if (dst) crt_entry_any(res, rstr, scl, sstr, K, L, T, dst, negate, false);
             i += di;
             q += dq;
             if (q >= per) {
