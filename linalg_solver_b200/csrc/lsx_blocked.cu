@@ -107,8 +107,17 @@ __device__ __forceinline__ uint32_t pivot_scale(uint32_t piv, const PrimeRec& P,
 // multiplier is l = f / piv'_j (same step, same factor), the true pivot row is row'_j / S_j and the true pivot is
 // piv'_j / S_j.  One inversion of the product of all piv' gives every 1 / piv'_j and 1 / S_j (Montgomery's trick);
 // a final pass rescales each register once.
-__global__ void __launch_bounds__(LU8_T) k_lu8(LargeArgs a, int k0, int nb) {
-    __shared__ uint32_t rowbuf[2][NB_BASE];      // [0]: old row j, [1]: pivot row (old row src)
+// Pivot search, the common case first: the diagonal entry itself is the first non-zero at or below the diagonal
+// unless it is zero (probability 1 / p once the entries are residues of an eliminated matrix), so the owner of row j
+// publishes its row together with a "diagonal is non-zero" flag and the block-wide search (two shuffle reductions, two
+// more barriers, the exchange through shared memory) only runs when the flag says it must.  The published row is
+// double-buffered by the parity of the column, which also removes the barrier at the end of a column: ONE barrier per
+// column on the common path instead of three.
+// After the panel the same CTA applies its (rare) row swaps to the columns [col_left, k0) left of the panel -- the multipliers
+// of the earlier panels of the outer block -- which used to be a k_swap launch of its own after every base panel.
+__global__ void __launch_bounds__(LU8_T) k_lu8(LargeArgs a, int k0, int nb, int col_left) {
+    __shared__ uint32_t rowbuf[2][2][NB_BASE];   // [column parity][0: old row j, 1: pivot row (old row src)]
+    __shared__ int s_nz[2];                      // [column parity] the diagonal entry is non-zero
     __shared__ int red[LU8_T / 32];
     const int n = a.n, g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const PrimeRec P = a.primes[g];
@@ -136,57 +145,71 @@ __global__ void __launch_bounds__(LU8_T) k_lu8(LargeArgs a, int k0, int nb) {
     }
     int flags = a.flags[g];
     uint32_t pivw[NB_BASE];                      // piv'_j as Montgomery words (R for a column without pivot)
+    int srcs[NB_BASE];                           // pivot rows of the panel (uniform over the CTA)
 #pragma unroll
     for (int jj = 0; jj < NB_BASE; ++jj) {
         pivw[jj] = P.one;
+        srcs[jj] = k0 + jj;
         if (jj < nb) {                                            // uniform
-            const int j = k0 + jj;
-            // ---- pivot search: first row >= j with a non-zero entry in column jj ----
-            int best = INT32_MAX;
+            const int j = k0 + jj, par = jj & 1;
+            // ---- common case: row j (thread jj, slot 0) is the pivot row ----
+            if (tid == jj) {
 #pragma unroll
-            for (int i = LU8_RPT - 1; i >= 0; --i) {
-                const int r = k0 + tid + i * LU8_T;
-                if (r >= j && r < n && v[i][jj] != 0u) best = r;
-            }
-            for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-            if (lane == 0) red[warp] = best;
-            __syncthreads();
-            best = lane < LU8_T / 32 ? red[lane] : INT32_MAX;
-            for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-            int src = best;
-            const bool zero_col = src == INT32_MAX;
-            if (zero_col) src = j;                                // column is zero below the diagonal: det = 0
-            // ---- exchange rows j and src through shared memory; everyone then reads the pivot row ----
-#pragma unroll
-            for (int i = 0; i < LU8_RPT; ++i) {
-                const int r = k0 + tid + i * LU8_T;
-                if (r == j) {
-#pragma unroll
-                    for (int c = 0; c < NB_BASE; ++c) rowbuf[0][c] = v[i][c];
-                }
-                if (r == src) {
-#pragma unroll
-                    for (int c = 0; c < NB_BASE; ++c) rowbuf[1][c] = v[i][c];
-                }
+                for (int c = 0; c < NB_BASE; ++c) rowbuf[par][1][c] = v[0][c];
+                s_nz[par] = v[0][jj] != 0u;
             }
             __syncthreads();
-            if (src != j) {
+            int src = j;
+            bool zero_col = false;
+            if (!s_nz[par]) {                                     // uniform; rare
+                // ---- pivot search: first row >= j with a non-zero entry in column jj ----
+                int best = INT32_MAX;
+#pragma unroll
+                for (int i = LU8_RPT - 1; i >= 0; --i) {
+                    const int r = k0 + tid + i * LU8_T;
+                    if (r >= j && r < n && v[i][jj] != 0u) best = r;
+                }
+                for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+                if (lane == 0) red[warp] = best;
+                __syncthreads();
+                best = lane < LU8_T / 32 ? red[lane] : INT32_MAX;
+                for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+                src = best;
+                zero_col = src == INT32_MAX;
+                if (zero_col) src = j;                            // column is zero below the diagonal: det = 0
+                // ---- exchange rows j and src through shared memory; everyone then reads the pivot row ----
 #pragma unroll
                 for (int i = 0; i < LU8_RPT; ++i) {
                     const int r = k0 + tid + i * LU8_T;
                     if (r == j) {
 #pragma unroll
-                        for (int c = 0; c < NB_BASE; ++c) v[i][c] = rowbuf[1][c];
+                        for (int c = 0; c < NB_BASE; ++c) rowbuf[par][0][c] = v[i][c];
                     }
                     if (r == src) {
 #pragma unroll
-                        for (int c = 0; c < NB_BASE; ++c) v[i][c] = rowbuf[0][c];
+                        for (int c = 0; c < NB_BASE; ++c) rowbuf[par][1][c] = v[i][c];
+                    }
+                }
+                __syncthreads();
+                if (src != j) {
+#pragma unroll
+                    for (int i = 0; i < LU8_RPT; ++i) {
+                        const int r = k0 + tid + i * LU8_T;
+                        if (r == j) {
+#pragma unroll
+                            for (int c = 0; c < NB_BASE; ++c) v[i][c] = rowbuf[par][1][c];
+                        }
+                        if (r == src) {
+#pragma unroll
+                            for (int c = 0; c < NB_BASE; ++c) v[i][c] = rowbuf[par][0][c];
+                        }
                     }
                 }
             }
+            srcs[jj] = src;
             uint32_t prow[NB_BASE];
 #pragma unroll
-            for (int c = 0; c < NB_BASE; ++c) prow[c] = rowbuf[1][c];
+            for (int c = 0; c < NB_BASE; ++c) prow[c] = rowbuf[par][1][c];
             if (tid == 0) {
                 a.piv_row[(int64_t)g * n + j] = src;
                 if (zero_col) flags |= 2;
@@ -205,7 +228,8 @@ __global__ void __launch_bounds__(LU8_T) k_lu8(LargeArgs a, int k0, int nb) {
                     for (int c = jj + 1; c < NB_BASE; ++c) v[i][c] = mont_fma2(pm, v[i][c], nf, prow[c], p, pinv);
                 }
             }
-            __syncthreads();                                      // rowbuf / red are reused by the next column
+            // no barrier here: the next column publishes into the other half of rowbuf / s_nz, and red is only written
+            // behind that column's publish barrier
         }
     }
     // ---- one inversion for the whole panel: ip[j] = word of 1 / (piv'_0 ... piv'_j) ----
@@ -274,6 +298,23 @@ __global__ void __launch_bounds__(LU8_T) k_lu8(LargeArgs a, int k0, int nb) {
     if (tid == 0) {
         a.detM[g] = detM;
         a.flags[g] = flags;
+    }
+    // ---- the panel's row swaps on the columns [col_left, k0) (at most NB_OUT - NB_BASE of them: one per thread) ----
+    bool any_swap = false;
+#pragma unroll
+    for (int jj = 0; jj < NB_BASE; ++jj) any_swap |= srcs[jj] != k0 + jj;
+    if (any_swap) {                                               // uniform; rare
+        for (int c = col_left + tid; c < k0; c += LU8_T) {
+#pragma unroll
+            for (int jj = 0; jj < NB_BASE; ++jj) {
+                const int j = k0 + jj, src = srcs[jj];
+                if (jj < nb && src != j) {
+                    const uint32_t t0 = Wg[(int64_t)j * n + c];
+                    Wg[(int64_t)j * n + c] = Wg[(int64_t)src * n + c];
+                    Wg[(int64_t)src * n + c] = t0;
+                }
+            }
+        }
     }
 }
 
@@ -394,8 +435,11 @@ __global__ void __launch_bounds__(128) k_trsm(LargeArgs a, int k0, int nb, int c
 // Same solve for nb <= 32 with the column in REGISTERS: all 32 loads are issued up front, the multipliers
 // come from shared memory as broadcast 16-byte loads (4 multiply-adds per load), fully unrolled.
 constexpr int TS = 32;
-__global__ void __launch_bounds__(128) k_trsm32(LargeArgs a, int k0, int nb, int ca, int cb) {
+// with_swap: the row swaps of the pivots [k0, k0 + nb) are applied to the columns first (every thread on its own
+// column; a swap is rare, so this replaces a k_swap launch that did nothing most of the time).
+__global__ void __launch_bounds__(128) k_trsm32(LargeArgs a, int k0, int nb, int ca, int cb, int with_swap) {
     __shared__ __align__(16) uint32_t Ln[TS][TS];
+    __shared__ int s_piv[TS];
     const int n = a.n, g = blockIdx.y, tid = threadIdx.x;
     const uint32_t p = a.primes[g].p, pinv = a.primes[g].pinv;
     uint32_t* Wg = a.W + (int64_t)g * n * n;
@@ -403,14 +447,30 @@ __global__ void __launch_bounds__(128) k_trsm32(LargeArgs a, int k0, int nb, int
         const int i = e / TS, t = e % TS;
         Ln[i][t] = (i < nb && t < i) ? Wg[(int64_t)(k0 + i) * n + k0 + t] : 0u;
     }
+    if (tid < TS) s_piv[tid] = (with_swap && tid < nb) ? a.piv_row[(int64_t)g * n + k0 + tid] : k0 + tid;
     __syncthreads();
     const int c = ca + blockIdx.x * 128 + tid;
     if (c >= cb) return;
+    if (with_swap) {
+        bool any_swap = false;
+        for (int i = 0; i < nb; ++i) any_swap |= s_piv[i] != k0 + i;
+        if (any_swap) {                                           // uniform over the CTA; rare
+            for (int i = 0; i < nb; ++i) {
+                const int j = k0 + i, src = s_piv[i];
+                if (src != j) {
+                    const uint32_t t0 = Wg[(int64_t)j * n + c];
+                    Wg[(int64_t)j * n + c] = Wg[(int64_t)src * n + c];
+                    Wg[(int64_t)src * n + c] = t0;
+                }
+            }
+        }
+    }
     uint32_t u[TS];
 #pragma unroll
     for (int i = 0; i < TS; ++i) u[i] = i < nb ? Wg[(int64_t)(k0 + i) * n + c] : 0u;
 #pragma unroll
     for (int i = 1; i < TS; ++i) {
+        if (i >= nb) break;                       // uniform: most calls solve an 8- or 16-wide block
         uint64_t acc = (uint64_t)u[i] << 32;
 #pragma unroll
         for (int t4 = 0; t4 < i; t4 += 4) {
@@ -596,9 +656,20 @@ struct Driver {
             ga.W = a.W, ga.AP = AP, ga.BP = BP, ga.primes = a.primes, ga.g = g;
             const bool big = timing && K == NB_OUT;
             if (big) lsx_timing_begin(ctx);
-            lsx_tc::k_gemm_tc<<<dim3(fixed, groups, a.G), lsx_tc::THREADS, lsx_tc::smem_bytes(K, g.b_stationary), st>>>(ga);
+            // epilogue mapping, measured on B200 (profiles/r02aa_tc_epilogue_coalesced_vs_rowmap.jsonl): staging the update
+            // through shared memory for coalesced C accesses pays at depth 128 (5.80 -> 5.25 ms per 127 primes x 3968^2),
+            // where the MMAs of a tile take about as long as its epilogue and both want the L1 data pipe; at depth 256
+            // the kernel is MMA bound either way (8.08 vs 8.17 ms) and at depth 32 / 64 the extra hop through shared
+            // memory lengthens a latency-bound tile (69 -> 75 us).  LSX_TC_COAL = 0 / 1 forces one mapping.
+            static const int env_coal = []() {
+                const char* e = getenv("LSX_TC_COAL");
+                return e ? atoi(e) : -1;
+            }();
+            const bool coal = env_coal >= 0 ? env_coal != 0 : K == 128;
+            auto kern = coal ? lsx_tc::k_gemm_tc : lsx_tc::k_gemm_tc_rowmap;
+            kern<<<dim3(fixed, groups, a.G), lsx_tc::THREADS, lsx_tc::smem_bytes(K, g.b_stationary), st>>>(ga);
             if (big) lsx_timing_end(ctx);
-            launches += 3;
+            launches += 2;
             return;
         }
         if (K <= NARROW && c1 - c0 <= NARROW) {   // tall and narrow: one thread per row
@@ -620,10 +691,11 @@ struct Driver {
         launches++;
     }
     // columns [ca, cb): U = L11^-1 * A for the diagonal block [k0, k0 + w)
-    void trsm(int k0, int w, int ca, int cb) {
+    // with_swap (w <= TS only): the row swaps of the pivots [k0, k0 + w) are applied to the columns by the same launch
+    void trsm(int k0, int w, int ca, int cb, bool with_swap = false) {
         if (cb <= ca || w <= 0) return;
         if (w <= TS) {
-            k_trsm32<<<dim3((cb - ca + 127) / 128, a.G), 128, 0, stream>>>(a, k0, w, ca, cb);
+            k_trsm32<<<dim3((cb - ca + 127) / 128, a.G), 128, 0, stream>>>(a, k0, w, ca, cb, with_swap ? 1 : 0);
             launches++;
             return;
         }
@@ -642,16 +714,25 @@ struct Driver {
     // (cl = first column of the enclosing outer block: the L columns to its left are never read again).
     void lu(int k0, int w, int cl) {
         if (w <= NB_BASE) {
-            if (n - k0 <= LU8_T * LU8_RPT) k_lu8<<<a.G, LU8_T, 0, stream>>>(a, k0, w);
-            else k_panel_gmem<<<a.G, PANEL_T, 0, stream>>>(a, k0, w);
-            launches++;
-            swap(k0, k0 + w, cl, k0);                       // multipliers of earlier panels in the same block
+            if (n - k0 <= LU8_T * LU8_RPT) {
+                k_lu8<<<a.G, LU8_T, 0, stream>>>(a, k0, w, cl);   // swaps the multipliers of earlier panels of the block itself
+                launches++;
+            } else {
+                k_panel_gmem<<<a.G, PANEL_T, 0, stream>>>(a, k0, w);
+                launches++;
+                swap(k0, k0 + w, cl, k0);                   // multipliers of earlier panels in the same block
+            }
             return;
         }
         const int w1 = left_width(w);
         lu(k0, w1, cl);
-        swap(k0, k0 + w1, k0 + w1, k0 + w);                 // right half of this panel
-        trsm(k0, w1, k0 + w1, k0 + w);
+        // right half of this panel: row swaps, then the solve (one launch when the diagonal block fits k_trsm32)
+        if (w1 <= TS) {
+            trsm(k0, w1, k0 + w1, k0 + w, true);
+        } else {
+            swap(k0, k0 + w1, k0 + w1, k0 + w);
+            trsm(k0, w1, k0 + w1, k0 + w);
+        }
         gemm(k0 + w1, n, k0 + w1, k0 + w, k0, w1);
         lu(k0 + w1, w - w1, cl);
     }
@@ -735,6 +816,7 @@ int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_b
     {
         const int smax = (int)std::max(lsx_tc::smem_bytes(lsx_tc::MAX_K, 0), lsx_tc::smem_bytes(lsx_tc::MAX_K, 1));
         LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(lsx_tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
+        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(lsx_tc::k_gemm_tc_rowmap, cudaFuncAttributeMaxDynamicSharedMemorySize, smax));
     }
     // side streams (created once per ctx) start behind everything already enqueued on ctx->stream
     if (S > 1) {

@@ -66,9 +66,11 @@ struct Region {
 
 inline size_t a_plane_bytes(const Region& g) { return (size_t)g.m_tiles * g.K * 4 * TM; }   // per prime
 inline size_t b_plane_bytes(const Region& g) { return (size_t)g.n_tiles * g.K * 4 * TN; }   // per prime
+constexpr int EPI_ROW_BYTES = 80;  // row pitch of the epilogue's staging blocks (64 data bytes + 16: conflict-free)
+constexpr int EPI_STAGE = 8 * 32 * EPI_ROW_BYTES;   // eight epilogue warps x 32 rows
 inline size_t smem_bytes(int K, int b_stationary) {
-    return b_stationary ? (size_t)K * 4 * TN + (size_t)STAGES_B * A_CHUNK + 256
-                        : (size_t)K * 4 * TM + (size_t)STAGES_A * B_CHUNK + 256;
+    return (b_stationary ? (size_t)K * 4 * TN + (size_t)STAGES_B * A_CHUNK : (size_t)K * 4 * TM + (size_t)STAGES_A * B_CHUNK) +
+           256 + EPI_STAGE;
 }
 inline bool depth_ok(int K) { return K == 32 || (K % KC == 0 && K >= KC && K <= MAX_K); }
 
@@ -89,12 +91,12 @@ __device__ __forceinline__ void split_store(uint8_t* dst, int plane_stride, cons
         *reinterpret_cast<uint4*>(dst + a * plane_stride) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
-__global__ void __launch_bounds__(256) k_tc_split_a(const uint32_t* __restrict__ W, uint8_t* __restrict__ AP, Region g) {
+__device__ __forceinline__ void split_a_body(const uint32_t* __restrict__ W, uint8_t* __restrict__ AP, const Region& g,
+                                             int64_t block, int prime) {
     const int q_per = g.K / 16;                       // 16-byte k groups
     const int64_t per_prime = (int64_t)g.m_tiles * TM * q_per;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = block * blockDim.x + threadIdx.x;
     if (t >= per_prime) return;
-    const int prime = blockIdx.y;
     const int r = (int)(t % TM);
     const int q = (int)((t / TM) % q_per);
     const int ti = (int)(t / ((int64_t)TM * q_per));
@@ -121,12 +123,12 @@ __global__ void __launch_bounds__(256) k_tc_split_a(const uint32_t* __restrict__
                    (q % qc) * (TM * 16) + r * 16;
     split_store(dst, TM * g.kc, w);
 }
-__global__ void __launch_bounds__(256) k_tc_split_b(const uint32_t* __restrict__ W, uint8_t* __restrict__ BP, Region g) {
+__device__ __forceinline__ void split_b_body(const uint32_t* __restrict__ W, uint8_t* __restrict__ BP, const Region& g,
+                                             int64_t block, int prime) {
     const int q_per = g.K / 16;
     const int64_t per_prime = (int64_t)g.n_tiles * TN * q_per;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = block * blockDim.x + threadIdx.x;
     if (t >= per_prime) return;
-    const int prime = blockIdx.y;
     const int c = (int)(t % TN);
     const int q = (int)((t / TN) % q_per);
     const int tj = (int)(t / ((int64_t)TN * q_per));
@@ -145,10 +147,17 @@ __global__ void __launch_bounds__(256) k_tc_split_b(const uint32_t* __restrict__
                    (q % qc) * (4 * TN * 16) + c * 16;
     split_store(dst, TN * 16, w);
 }
+// ONE launch splits both operands (the first blocks_a blocks of a prime do the A planes, the rest the B planes): the two
+// are independent, and inside a panel each of them is a few blocks per prime that did not fill the GPU on its own.
+__global__ void __launch_bounds__(256) k_tc_split(const uint32_t* __restrict__ W, uint8_t* __restrict__ AP,
+                                                  uint8_t* __restrict__ BP, Region g, int blocks_a) {
+    if ((int)blockIdx.x < blocks_a) split_a_body(W, AP, g, blockIdx.x, blockIdx.y);
+    else split_b_body(W, BP, g, (int64_t)blockIdx.x - blocks_a, blockIdx.y);
+}
 inline void launch_split(const uint32_t* W, uint8_t* AP, uint8_t* BP, const Region& g, int G, cudaStream_t st) {
     const int64_t ta = (int64_t)g.m_tiles * TM * (g.K / 16), tb = (int64_t)g.n_tiles * TN * (g.K / 16);
-    k_tc_split_a<<<dim3((unsigned)((ta + 255) / 256), G), 256, 0, st>>>(W, AP, g);
-    k_tc_split_b<<<dim3((unsigned)((tb + 255) / 256), G), 256, 0, st>>>(W, BP, g);
+    const int blocks_a = (int)((ta + 255) / 256), blocks_b = (int)((tb + 255) / 256);
+    k_tc_split<<<dim3((unsigned)(blocks_a + blocks_b), G), 256, 0, st>>>(W, AP, BP, g, blocks_a);
 }
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -226,15 +235,15 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
 
 struct GemmArgs {
     uint32_t* W;                // [G][n][n]
-    const uint8_t* AP;          // byte planes of L, see k_tc_split_a
-    const uint8_t* BP;          // byte planes of U, see k_tc_split_b
+    const uint8_t* AP;          // byte planes of L, see split_a_body
+    const uint8_t* BP;          // byte planes of U, see split_b_body
     const PrimeRec* primes;     // [G]
     Region g;
 };
 
 // DBG (timing experiments of tools/tc_gemm_test only; the library instantiates DBG = 0):
 //   bit 1 skip the epilogue arithmetic, bit 2 skip the TMEM loads
-template <int DBG>
+template <int DBG, int COAL>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const Region& g = a.g;
@@ -369,6 +378,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
         }
     } else {
         // ===== epilogue: 8 warps; warp w reads TMEM lanes 32 * (w % 4) .. + 31, 16 of the 32 columns =====
+        // Two thread-to-cell mappings.  TMEM hands lane l the 16 columns of ROW l, and in that mapping a 16-byte access to
+        // C touches 32 different rows per warp instruction (32 cache lines for 512 bytes): ncu showed the L1 data pipe
+        // busy with exactly these accesses.  So the accumulators are reduced in the row mapping to T = S / 2^32 mod p
+        // (which does not need C:  redc(C * 2^32 + S) = C + redc(S) mod p, both canonical), T goes through a per-warp
+        // staging block in shared memory, and C is loaded, corrected and stored in a COALESCED mapping: lane l owns the
+        // 16-byte chunk l / 8 of the rows 8 i + l % 8, i = 0..3 -- 8 rows x 64 contiguous bytes per instruction.
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const PrimeRec P = a.primes[prime];
         const uint32_t p = P.p, pinv = P.pinv;
@@ -377,93 +392,207 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
         uint32_t* Wg = a.W + (int64_t)prime * g.n * g.n;
         const bool vec_ok = (g.n & 3) == 0 && (g.c0 & 3) == 0;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 16);
-        // Tile t of this thread: 16 consecutive words of one row of C.
-        auto tile_ptr = [&](int t, bool& live, bool& full) -> uint32_t* {
-            const int ti = bst ? t0 + t : fixed_tile, tj = bst ? fixed_tile : t0 + t;
-            const int row = g.r0 + ti * TM + quad * 32 + lane;
-            const int colb = g.c0 + tj * TN + half * 16;
-            live = t < ntiles && row < g.r1 && colb < g.c1;
-            full = live && vec_ok && colb + 16 <= g.c1;
-            return Wg + (int64_t)row * g.n + colb;
-        };
-        // C does not depend on the MMAs, and a warp handles its tiles one after the other: the loads of a tile are
-        // issued TWO tiles ahead (three register buffers), so their HBM/L2 latency (about as long as a whole tile
-        // takes) is hidden instead of being paid once per tile.
-        auto load_c = [&](int t, uint32_t (&cv)[16]) {
-            bool live, full;
-            const uint32_t* cp = tile_ptr(t, live, full);
-            if (full) {
+        if constexpr (COAL) {
+            uint8_t* stage = reinterpret_cast<uint8_t*>(bars) + 256 + (size_t)(warp - 2) * (32 * EPI_ROW_BYTES);
+            const int crow = lane & 7, cchunk = lane >> 3;
+            // rows 8 i + crow (i = 0..3) of this warp's 32 x 16 piece of tile t, words 4 cchunk .. + 3
+            auto piece_ptr = [&](int t, int i, bool& live, bool& full, int& colb) -> uint32_t* {
+                const int ti = bst ? t0 + t : fixed_tile, tj = bst ? fixed_tile : t0 + t;
+                const int row = g.r0 + ti * TM + quad * 32 + 8 * i + crow;
+                colb = g.c0 + tj * TN + half * 16 + 4 * cchunk;
+                live = t < ntiles && row < g.r1 && colb < g.c1;
+                full = live && vec_ok && colb + 4 <= g.c1;
+                return Wg + (int64_t)row * g.n + colb;
+            };
+            // C does not depend on the MMAs, and a warp handles its tiles one after the other: the loads of a tile are
+            // issued TWO tiles ahead (three register buffers), so their HBM/L2 latency (about as long as a whole tile
+            // takes) is hidden instead of being paid once per tile.
+            auto load_c = [&](int t, uint32_t (&cv)[16]) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(cp + 4 * i);
-                    cv[4 * i] = v.x, cv[4 * i + 1] = v.y, cv[4 * i + 2] = v.z, cv[4 * i + 3] = v.w;
+                    bool live, full;
+                    int colb;
+                    const uint32_t* cp = piece_ptr(t, i, live, full, colb);
+                    if (full) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(cp);
+                        cv[4 * i] = v.x, cv[4 * i + 1] = v.y, cv[4 * i + 2] = v.z, cv[4 * i + 3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) cv[4 * i + e] = (live && colb + e < g.c1) ? cp[e] : 0u;
+                    }
                 }
-            } else {
-                const int colb = g.c0 + (bst ? fixed_tile : t0 + t) * TN + half * 16;
+            };
+            auto process = [&](int t, uint32_t (&cv)[16]) {
+                const uint32_t buf = (uint32_t)t & 1u, use = (uint32_t)t >> 1;
+                mbar_wait(bar_acc_full + 8 * buf, use & 1u);
+                tc_fence_after();
+                uint32_t q[7][16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) cv[i] = (live && colb + i < g.c1) ? cp[i] : 0u;
+                for (int s = 0; s < 7; ++s) {
+                    if (DBG & 4) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) q[s][i] = 0u;
+                    } else {
+                        tmem_ld16(lane_base + buf * ACC_STRIDE + (uint32_t)(s * TN), q[s]);
+                    }
+                }
+                tmem_wait_ld();
+                tc_fence_before();                                   // all accumulator words of this warp are in registers:
+                __syncwarp();                                        // hand the buffer back (the MMAs of tile t + 2 reuse it);
+                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf); // also: every lane is done reading the previous tile's stage
+                uint32_t tv[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (DBG & 2) {
+                        tv[i] = q[0][i] + q[6][i];
+                    } else {
+                        // S < 2^60; one conditional subtraction of p * 2^32 (as in mac_lazy) covers primes below 2^28 too,
+                        // then REDC gives S / 2^32 mod p in [0, p)
+                        uint64_t acc = (uint64_t)q[0][i] + ((uint64_t)q[1][i] << 8) + ((uint64_t)q[2][i] << 16) +
+                                       ((uint64_t)q[3][i] << 24) + (uint64_t)q[4][i] * c4 + (uint64_t)q[5][i] * c5 +
+                                       (uint64_t)q[6][i] * c6;
+                        uint32_t hi = (uint32_t)(acc >> 32);
+                        hi = min(hi, hi - p);
+                        acc = ((uint64_t)hi << 32) | (uint32_t)acc;
+                        tv[i] = mont_redc(acc, p, pinv);
+                    }
+                }
+                // row mapping -> coalesced mapping (rows are EPI_ROW_BYTES apart: both the 16-byte row writes of a quarter
+                // warp and the reads of 8 consecutive rows at one chunk hit 8 different bank groups)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    *reinterpret_cast<uint4*>(stage + lane * EPI_ROW_BYTES + 16 * k) =
+                        make_uint4(tv[4 * k], tv[4 * k + 1], tv[4 * k + 2], tv[4 * k + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(stage + (8 * i + crow) * EPI_ROW_BYTES + 16 * cchunk);
+                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (DBG & 2) {
+                            cv[4 * i + e] += w4[e];
+                        } else {
+                            const uint32_t sum = cv[4 * i + e] + w4[e];              // both below p < 2^31
+                            cv[4 * i + e] = min(sum, sum - p);
+                        }
+                    }
+                    bool live, full;
+                    int colb;
+                    uint32_t* cp = piece_ptr(t, i, live, full, colb);
+                    if (full) {
+                        *reinterpret_cast<uint4*>(cp) = make_uint4(cv[4 * i], cv[4 * i + 1], cv[4 * i + 2], cv[4 * i + 3]);
+                    } else if (live) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (colb + e < g.c1) cp[e] = cv[4 * i + e];
+                    }
+                }
+            };
+            uint32_t cva[16], cvb[16], cvc[16];
+            load_c(0, cva);
+            load_c(1, cvb);
+            for (int t = 0; t < ntiles; t += 3) {
+                load_c(t + 2, cvc);
+                process(t, cva);
+                if (t + 1 < ntiles) {
+                    load_c(t + 3, cva);
+                    process(t + 1, cvb);
+                }
+                if (t + 2 < ntiles) {
+                    load_c(t + 4, cvb);
+                    process(t + 2, cvc);
+                }
             }
-        };
-        auto process = [&](int t, uint32_t (&cv)[16]) {
-            const uint32_t buf = (uint32_t)t & 1u, use = (uint32_t)t >> 1;
-            mbar_wait(bar_acc_full + 8 * buf, use & 1u);
-            tc_fence_after();
-            uint32_t q[7][16];
+        } else {
+            // Tile t of this thread: 16 consecutive words of one row of C.
+            auto tile_ptr = [&](int t, bool& live, bool& full) -> uint32_t* {
+                const int ti = bst ? t0 + t : fixed_tile, tj = bst ? fixed_tile : t0 + t;
+                const int row = g.r0 + ti * TM + quad * 32 + lane;
+                const int colb = g.c0 + tj * TN + half * 16;
+                live = t < ntiles && row < g.r1 && colb < g.c1;
+                full = live && vec_ok && colb + 16 <= g.c1;
+                return Wg + (int64_t)row * g.n + colb;
+            };
+            // C does not depend on the MMAs, and a warp handles its tiles one after the other: the loads of a tile are
+            // issued TWO tiles ahead (three register buffers), so their HBM/L2 latency (about as long as a whole tile
+            // takes) is hidden instead of being paid once per tile.
+            auto load_c = [&](int t, uint32_t (&cv)[16]) {
+                bool live, full;
+                const uint32_t* cp = tile_ptr(t, live, full);
+                if (full) {
 #pragma unroll
-            for (int s = 0; s < 7; ++s) {
-                if (DBG & 4) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) q[s][i] = 0u;
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(cp + 4 * i);
+                        cv[4 * i] = v.x, cv[4 * i + 1] = v.y, cv[4 * i + 2] = v.z, cv[4 * i + 3] = v.w;
+                    }
                 } else {
-                    tmem_ld16(lane_base + buf * ACC_STRIDE + (uint32_t)(s * TN), q[s]);
+                    const int colb = g.c0 + (bst ? fixed_tile : t0 + t) * TN + half * 16;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) cv[i] = (live && colb + i < g.c1) ? cp[i] : 0u;
                 }
-            }
-            tmem_wait_ld();
-            tc_fence_before();                                   // all accumulator words of this warp are in registers:
-            __syncwarp();                                        // hand the buffer back (the MMAs of tile t + 2 reuse it)
-            if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+            };
+            auto process = [&](int t, uint32_t (&cv)[16]) {
+                const uint32_t buf = (uint32_t)t & 1u, use = (uint32_t)t >> 1;
+                mbar_wait(bar_acc_full + 8 * buf, use & 1u);
+                tc_fence_after();
+                uint32_t q[7][16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if (DBG & 2) {
-                    cv[i] += q[0][i] + q[6][i];
-                } else {
-                    // C * 2^32 + S  with S < 2^60: bring the sum below p * 2^32 (one conditional subtraction of
-                    // p * 2^32, as in mac_lazy), then REDC gives (C + S / 2^32) mod p in [0, p)
-                    uint64_t acc = ((uint64_t)cv[i] << 32) + (uint64_t)q[0][i] + ((uint64_t)q[1][i] << 8) +
-                                   ((uint64_t)q[2][i] << 16) + ((uint64_t)q[3][i] << 24) + (uint64_t)q[4][i] * c4 +
-                                   (uint64_t)q[5][i] * c5 + (uint64_t)q[6][i] * c6;
-                    uint32_t hi = (uint32_t)(acc >> 32);
-                    hi = min(hi, hi - p);
-                    acc = ((uint64_t)hi << 32) | (uint32_t)acc;
-                    cv[i] = mont_redc(acc, p, pinv);
+                for (int s = 0; s < 7; ++s) {
+                    if (DBG & 4) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) q[s][i] = 0u;
+                    } else {
+                        tmem_ld16(lane_base + buf * ACC_STRIDE + (uint32_t)(s * TN), q[s]);
+                    }
                 }
-            }
-            bool live, full;
-            uint32_t* cp = tile_ptr(t, live, full);
-            if (full) {
+                tmem_wait_ld();
+                tc_fence_before();                                   // all accumulator words of this warp are in registers:
+                __syncwarp();                                        // hand the buffer back (the MMAs of tile t + 2 reuse it)
+                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    *reinterpret_cast<uint4*>(cp + 4 * i) = make_uint4(cv[4 * i], cv[4 * i + 1], cv[4 * i + 2], cv[4 * i + 3]);
-            } else if (live) {
-                const int colb = g.c0 + (bst ? fixed_tile : t0 + t) * TN + half * 16;
+                for (int i = 0; i < 16; ++i) {
+                    if (DBG & 2) {
+                        cv[i] += q[0][i] + q[6][i];
+                    } else {
+                        // C * 2^32 + S  with S < 2^60: bring the sum below p * 2^32 (one conditional subtraction of
+                        // p * 2^32, as in mac_lazy), then REDC gives (C + S / 2^32) mod p in [0, p)
+                        uint64_t acc = ((uint64_t)cv[i] << 32) + (uint64_t)q[0][i] + ((uint64_t)q[1][i] << 8) +
+                                       ((uint64_t)q[2][i] << 16) + ((uint64_t)q[3][i] << 24) + (uint64_t)q[4][i] * c4 +
+                                       (uint64_t)q[5][i] * c5 + (uint64_t)q[6][i] * c6;
+                        uint32_t hi = (uint32_t)(acc >> 32);
+                        hi = min(hi, hi - p);
+                        acc = ((uint64_t)hi << 32) | (uint32_t)acc;
+                        cv[i] = mont_redc(acc, p, pinv);
+                    }
+                }
+                bool live, full;
+                uint32_t* cp = tile_ptr(t, live, full);
+                if (full) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (colb + i < g.c1) cp[i] = cv[i];
-            }
-        };
-        uint32_t cva[16], cvb[16], cvc[16];
-        load_c(0, cva);
-        load_c(1, cvb);
-        for (int t = 0; t < ntiles; t += 3) {
-            load_c(t + 2, cvc);
-            process(t, cva);
-            if (t + 1 < ntiles) {
-                load_c(t + 3, cva);
-                process(t + 1, cvb);
-            }
-            if (t + 2 < ntiles) {
-                load_c(t + 4, cvb);
-                process(t + 2, cvc);
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<uint4*>(cp + 4 * i) = make_uint4(cv[4 * i], cv[4 * i + 1], cv[4 * i + 2], cv[4 * i + 3]);
+                } else if (live) {
+                    const int colb = g.c0 + (bst ? fixed_tile : t0 + t) * TN + half * 16;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (colb + i < g.c1) cp[i] = cv[i];
+                }
+            };
+            uint32_t cva[16], cvb[16], cvc[16];
+            load_c(0, cva);
+            load_c(1, cvb);
+            for (int t = 0; t < ntiles; t += 3) {
+                load_c(t + 2, cvc);
+                process(t, cva);
+                if (t + 1 < ntiles) {
+                    load_c(t + 3, cva);
+                    process(t + 1, cvb);
+                }
+                if (t + 2 < ntiles) {
+                    load_c(t + 4, cvb);
+                    process(t + 2, cvc);
+                }
             }
         }
     }
@@ -475,8 +604,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc_t(GemmArgs a) {
     }
 }
 
-// the library's instantiation
-constexpr auto k_gemm_tc = k_gemm_tc_t<0>;
+// the library's instantiations: epilogue with C in the coalesced mapping / in the TMEM row mapping
+constexpr auto k_gemm_tc = k_gemm_tc_t<0, 1>;
+constexpr auto k_gemm_tc_rowmap = k_gemm_tc_t<0, 0>;
 
 #endif  // __CUDACC__
 

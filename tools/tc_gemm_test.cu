@@ -91,9 +91,10 @@ int main(int argc, char** argv) {
     CK(cudaDeviceSynchronize());
     CK(cudaEventElapsedTime(&ms_ref, e0, e1));
     const size_t smem = smem_bytes(K, bst);
-    void (*kern)(GemmArgs) = k_gemm_tc_t<0>;
-    if (swap == 2) kern = k_gemm_tc_t<2>;       // no epilogue arithmetic
-    if (swap == 6) kern = k_gemm_tc_t<6>;       // no TMEM loads, no arithmetic: the MMA pipeline alone
+    void (*kern)(GemmArgs) = k_gemm_tc_t<0, 1>;  // epilogue with coalesced C accesses
+    if (swap == 1) kern = k_gemm_tc_t<0, 0>;     // epilogue in the TMEM row mapping
+    if (swap == 2) kern = k_gemm_tc_t<2, 0>;     // no epilogue arithmetic
+    if (swap == 6) kern = k_gemm_tc_t<6, 0>;     // no TMEM loads, no arithmetic: the MMA pipeline alone
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GemmArgs a{};
     a.W = dW;
