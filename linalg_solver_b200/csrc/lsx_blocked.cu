@@ -115,15 +115,65 @@ __device__ __forceinline__ uint32_t pivot_scale(uint32_t piv, const PrimeRec& P,
 // column on the common path instead of three.
 // After the panel the same CTA applies its (rare) row swaps to the columns [col_left, k0) left of the panel -- the multipliers
 // of the earlier panels of the outer block -- which used to be a k_swap launch of its own after every base panel.
-__global__ void __launch_bounds__(LU8_T) k_lu8(LargeArgs a, int k0, int nb, int col_left) {
+// fuse_prev: the previous launch factored the full 8-column panel [k0 - 8, k0) of the same 16-column pair.  This launch
+// then brings its own columns up to date first -- the row swaps of that panel, U12 = L11^-1 A12 for the rows k0 - 8 ..
+// k0 - 1 (an 8 x 8 unit-lower solve in shared memory), and A22 -= L21 U12 on the register-resident rows (64 multiply-adds
+// per row, U12 as broadcast shared loads) -- which used to be a k_trsm32 and a k_gemm_narrow launch between the two base
+// panels (8 + 18 us of mostly launch and load latency per pair).
+__global__ void __launch_bounds__(LU8_T) k_lu8(LargeArgs a, int k0, int nb, int col_left, int fuse_prev) {
     __shared__ uint32_t rowbuf[2][2][NB_BASE];   // [column parity][0: old row j, 1: pivot row (old row src)]
     __shared__ int s_nz[2];                      // [column parity] the diagonal entry is non-zero
     __shared__ int red[LU8_T / 32];
+    __shared__ __align__(16) uint32_t s_u[NB_BASE][NB_BASE];     // fuse_prev: A12, then U12 ([k][c])
+    __shared__ uint32_t s_l11[NB_BASE][NB_BASE];                 // fuse_prev: multipliers of the previous diagonal block
+    __shared__ int s_prev_piv[NB_BASE];
     const int n = a.n, g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const PrimeRec P = a.primes[g];
     const uint32_t p = P.p, pinv = P.pinv;
     uint32_t* Wg = a.W + (int64_t)g * n * n;
     const bool vec = nb == NB_BASE && (n & 3) == 0 && (k0 & 3) == 0;
+    if (fuse_prev) {
+        const int kp = k0 - NB_BASE;
+        if (tid < NB_BASE) s_prev_piv[tid] = a.piv_row[(int64_t)g * n + kp + tid];
+        __syncthreads();
+        bool any_swap = false;
+#pragma unroll
+        for (int i = 0; i < NB_BASE; ++i) any_swap |= s_prev_piv[i] != kp + i;
+        if (any_swap) {                                           // uniform; rare
+            if (tid < nb) {
+                const int c = k0 + tid;
+                for (int i = 0; i < NB_BASE; ++i) {
+                    const int j = kp + i, src = s_prev_piv[i];
+                    if (src != j) {
+                        const uint32_t t0 = Wg[(int64_t)j * n + c];
+                        Wg[(int64_t)j * n + c] = Wg[(int64_t)src * n + c];
+                        Wg[(int64_t)src * n + c] = t0;
+                    }
+                }
+            }
+            __syncthreads();                                      // the swapped words are read below by other threads
+        }
+        if (tid < NB_BASE * NB_BASE) {
+            const int i = tid / NB_BASE, t = tid % NB_BASE;
+            s_l11[i][t] = t < i ? Wg[(int64_t)(kp + i) * n + kp + t] : 0u;
+            s_u[i][t] = t < nb ? Wg[(int64_t)(kp + i) * n + k0 + t] : 0u;
+        }
+        __syncthreads();
+        if (tid < nb) {                                           // column tid of U12 (same arithmetic as k_trsm32)
+            uint32_t u[NB_BASE];
+            u[0] = s_u[0][tid];
+#pragma unroll
+            for (int i = 1; i < NB_BASE; ++i) {
+                uint64_t acc = (uint64_t)s_u[i][tid] << 32;
+#pragma unroll
+                for (int t = 0; t < i; ++t) acc = mac_lazy(acc, s_l11[i][t], u[t], p);
+                u[i] = mont_redc(acc, p, pinv);
+                s_u[i][tid] = u[i];
+                Wg[(int64_t)(kp + i) * n + k0 + tid] = u[i];
+            }
+        }
+        __syncthreads();
+    }
     uint32_t v[LU8_RPT][NB_BASE];
 #pragma unroll
     for (int i = 0; i < LU8_RPT; ++i) {
@@ -141,6 +191,37 @@ __global__ void __launch_bounds__(LU8_T) k_lu8(LargeArgs a, int k0, int nb, int 
         } else {
 #pragma unroll
             for (int c = 0; c < NB_BASE; ++c) v[i][c] = 0u;
+        }
+    }
+    if (fuse_prev) {
+        // A22 -= L21 U12: the row's eight multipliers of the previous panel come from global memory (just written: L2)
+        const int kp = k0 - NB_BASE;
+#pragma unroll
+        for (int i = 0; i < LU8_RPT; ++i) {
+            const int r = k0 + tid + i * LU8_T;
+            if (r < n) {
+                const uint32_t* lsrc = Wg + (int64_t)r * n + kp;
+                uint32_t l[NB_BASE];
+                if ((n & 3) == 0 && (kp & 3) == 0) {
+                    const uint4 x = *reinterpret_cast<const uint4*>(lsrc), y = *reinterpret_cast<const uint4*>(lsrc + 4);
+                    l[0] = x.x, l[1] = x.y, l[2] = x.z, l[3] = x.w, l[4] = y.x, l[5] = y.y, l[6] = y.z, l[7] = y.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NB_BASE; ++k) l[k] = lsrc[k];
+                }
+                uint64_t acc[NB_BASE];
+#pragma unroll
+                for (int c = 0; c < NB_BASE; ++c) acc[c] = (uint64_t)v[i][c] << 32;
+#pragma unroll
+                for (int k = 0; k < NB_BASE; ++k) {
+                    const uint4 ua = *reinterpret_cast<const uint4*>(&s_u[k][0]), ub = *reinterpret_cast<const uint4*>(&s_u[k][4]);
+                    const uint32_t uk[NB_BASE] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+                    for (int c = 0; c < NB_BASE; ++c) acc[c] = mac_lazy(acc[c], l[k], uk[c], p);
+                }
+#pragma unroll
+                for (int c = 0; c < NB_BASE; ++c) v[i][c] = mont_redc(acc[c], p, pinv);
+            }
         }
     }
     int flags = a.flags[g];
@@ -627,6 +708,7 @@ struct Driver {
     uint8_t* AP;          // byte planes for the tensor-core update (lsx_tc.cuh)
     uint8_t* BP;
     bool use_tc;
+    bool fuse_pair;       // pairs of base panels without the k_trsm32 / k_gemm_narrow launches in between (LSX_LU_PAIR=0: off)
     int n;
 
     static int left_width(int w) {               // largest power of two below w (w > NB_BASE)
@@ -715,7 +797,7 @@ struct Driver {
     void lu(int k0, int w, int cl) {
         if (w <= NB_BASE) {
             if (n - k0 <= LU8_T * LU8_RPT) {
-                k_lu8<<<a.G, LU8_T, 0, stream>>>(a, k0, w, cl);   // swaps the multipliers of earlier panels of the block itself
+                k_lu8<<<a.G, LU8_T, 0, stream>>>(a, k0, w, cl, 0);   // swaps the multipliers of earlier panels of the block itself
                 launches++;
             } else {
                 k_panel_gmem<<<a.G, PANEL_T, 0, stream>>>(a, k0, w);
@@ -725,6 +807,13 @@ struct Driver {
             return;
         }
         const int w1 = left_width(w);
+        if (w1 == NB_BASE && fuse_pair && n - k0 <= LU8_T * LU8_RPT) {
+            // a pair of base panels: the second launch does the solve and the update of its own columns itself
+            k_lu8<<<a.G, LU8_T, 0, stream>>>(a, k0, w1, cl, 0);
+            k_lu8<<<a.G, LU8_T, 0, stream>>>(a, k0 + w1, w - w1, cl, 1);
+            launches += 2;
+            return;
+        }
         lu(k0, w1, cl);
         // right half of this panel: row swaps, then the solve (one launch when the diagonal block fits k_trsm32)
         if (w1 <= TS) {
@@ -866,6 +955,7 @@ int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_b
             d.AP = (uint8_t*)(base + o_ap);
             d.BP = (uint8_t*)(base + o_bp);
             d.use_tc = use_tc;
+            d.fuse_pair = !getenv("LSX_LU_PAIR") || atoi(getenv("LSX_LU_PAIR")) != 0;
             d.n = n;
             k_load<<<dim3(ctx->sm_count * 2, Gc), 256, 0, st>>>(dA, d.a);
             d.run();
