@@ -513,22 +513,29 @@ __global__ void __launch_bounds__(128) k_trsm(LargeArgs a, int k0, int nb, int c
     }
 }
 
-// Same solve for nb <= 32 with the column in REGISTERS: all 32 loads are issued up front, the multipliers
-// come from shared memory as broadcast 16-byte loads (4 multiply-adds per load), fully unrolled.
-constexpr int TS = 32;
+// Same solve for nb <= TSZ (32 or 64) with the column in REGISTERS: all loads are issued up front, the multipliers
+// come from shared memory as broadcast 16-byte loads (4 multiply-adds per load), fully unrolled.  Every row's sum runs
+// on TWO accumulators (alternate groups of four terms) that are merged before the reduction: one accumulator is a
+// dependent chain of up to TSZ multiply-adds, and with 128 registers per thread there are not enough resident warps
+// to hide it (ncu: the 32-wide solve of 3840 columns x 127 primes took 75 us for 28 us of issue slots).
+// The 64-wide form replaces the recursion  solve 32 / tensor update of 32 rows / solve 32:  a tensor-core update with 32
+// live rows of a 128-row tile costs as much as a full tile (170 us per 3840 columns x 127 primes, plus its plane split).
 // with_swap: the row swaps of the pivots [k0, k0 + nb) are applied to the columns first (every thread on its own
 // column; a swap is rare, so this replaces a k_swap launch that did nothing most of the time).
-__global__ void __launch_bounds__(128) k_trsm32(LargeArgs a, int k0, int nb, int ca, int cb, int with_swap) {
-    __shared__ __align__(16) uint32_t Ln[TS][TS];
-    __shared__ int s_piv[TS];
+constexpr int TS = 32;
+constexpr int TS2 = 64;
+template <int TSZ>
+__global__ void __launch_bounds__(128, TSZ > 32 ? 2 : 4) k_trsm_reg(LargeArgs a, int k0, int nb, int ca, int cb, int with_swap) {
+    __shared__ __align__(16) uint32_t Ln[TSZ][TSZ];
+    __shared__ int s_piv[TSZ];
     const int n = a.n, g = blockIdx.y, tid = threadIdx.x;
     const uint32_t p = a.primes[g].p, pinv = a.primes[g].pinv;
     uint32_t* Wg = a.W + (int64_t)g * n * n;
-    for (int e = tid; e < TS * TS; e += 128) {
-        const int i = e / TS, t = e % TS;
+    for (int e = tid; e < TSZ * TSZ; e += 128) {
+        const int i = e / TSZ, t = e % TSZ;
         Ln[i][t] = (i < nb && t < i) ? Wg[(int64_t)(k0 + i) * n + k0 + t] : 0u;
     }
-    if (tid < TS) s_piv[tid] = (with_swap && tid < nb) ? a.piv_row[(int64_t)g * n + k0 + tid] : k0 + tid;
+    if (tid < TSZ) s_piv[tid] = (with_swap && tid < nb) ? a.piv_row[(int64_t)g * n + k0 + tid] : k0 + tid;
     __syncthreads();
     const int c = ca + blockIdx.x * 128 + tid;
     if (c >= cb) return;
@@ -546,25 +553,32 @@ __global__ void __launch_bounds__(128) k_trsm32(LargeArgs a, int k0, int nb, int
             }
         }
     }
-    uint32_t u[TS];
+    uint32_t u[TSZ];
 #pragma unroll
-    for (int i = 0; i < TS; ++i) u[i] = i < nb ? Wg[(int64_t)(k0 + i) * n + c] : 0u;
+    for (int i = 0; i < TSZ; ++i) u[i] = i < nb ? Wg[(int64_t)(k0 + i) * n + c] : 0u;
 #pragma unroll
-    for (int i = 1; i < TS; ++i) {
+    for (int i = 1; i < TSZ; ++i) {
         if (i >= nb) break;                       // uniform: most calls solve an 8- or 16-wide block
-        uint64_t acc = (uint64_t)u[i] << 32;
+        uint64_t acc0 = (uint64_t)u[i] << 32, acc1 = 0ull;
 #pragma unroll
         for (int t4 = 0; t4 < i; t4 += 4) {
             const uint4 l = *reinterpret_cast<const uint4*>(&Ln[i][t4]);     // entries at t >= i are zero
+            uint64_t& acc = (t4 & 4) ? acc1 : acc0;
             acc = mac_lazy(acc, l.x, u[t4], p);
             if (t4 + 1 < i) acc = mac_lazy(acc, l.y, u[t4 + 1], p);
             if (t4 + 2 < i) acc = mac_lazy(acc, l.z, u[t4 + 2], p);
             if (t4 + 3 < i) acc = mac_lazy(acc, l.w, u[t4 + 3], p);
         }
-        u[i] = mont_redc(acc, p, pinv);
+        if (i > 4) {                              // merge: both below p * 2^32 < 2^63, one conditional subtraction
+            acc0 += acc1;
+            uint32_t hi = (uint32_t)(acc0 >> 32);
+            hi = min(hi, hi - p);
+            acc0 = ((uint64_t)hi << 32) | (uint32_t)acc0;
+        }
+        u[i] = mont_redc(acc0, p, pinv);
     }
 #pragma unroll
-    for (int i = 1; i < TS; ++i)
+    for (int i = 1; i < TSZ; ++i)
         if (i < nb) Wg[(int64_t)(k0 + i) * n + c] = u[i];
 }
 
@@ -708,6 +722,7 @@ struct Driver {
     uint8_t* AP;          // byte planes for the tensor-core update (lsx_tc.cuh)
     uint8_t* BP;
     bool use_tc;
+    bool trsm64;          // 64-wide register solve instead of solve 32 / tensor update / solve 32 (LSX_TRSM64=0: off)
     bool fuse_pair;       // pairs of base panels without the k_trsm32 / k_gemm_narrow launches in between (LSX_LU_PAIR=0: off)
     int n;
 
@@ -773,11 +788,16 @@ struct Driver {
         launches++;
     }
     // columns [ca, cb): U = L11^-1 * A for the diagonal block [k0, k0 + w)
-    // with_swap (w <= TS only): the row swaps of the pivots [k0, k0 + w) are applied to the columns by the same launch
+    // with_swap (register solves only, w <= 64): the row swaps of the pivots [k0, k0 + w) are applied to the columns by the same launch
     void trsm(int k0, int w, int ca, int cb, bool with_swap = false) {
         if (cb <= ca || w <= 0) return;
         if (w <= TS) {
-            k_trsm32<<<dim3((cb - ca + 127) / 128, a.G), 128, 0, stream>>>(a, k0, w, ca, cb, with_swap ? 1 : 0);
+            k_trsm_reg<TS><<<dim3((cb - ca + 127) / 128, a.G), 128, 0, stream>>>(a, k0, w, ca, cb, with_swap ? 1 : 0);
+            launches++;
+            return;
+        }
+        if (w <= TS2 && trsm64) {
+            k_trsm_reg<TS2><<<dim3((cb - ca + 127) / 128, a.G), 128, 0, stream>>>(a, k0, w, ca, cb, with_swap ? 1 : 0);
             launches++;
             return;
         }
@@ -816,7 +836,7 @@ struct Driver {
         }
         lu(k0, w1, cl);
         // right half of this panel: row swaps, then the solve (one launch when the diagonal block fits k_trsm32)
-        if (w1 <= TS) {
+        if (w1 <= (trsm64 ? TS2 : TS)) {
             trsm(k0, w1, k0 + w1, k0 + w, true);
         } else {
             swap(k0, k0 + w1, k0 + w1, k0 + w);
@@ -956,6 +976,7 @@ int lsx_blocked_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_b
             d.BP = (uint8_t*)(base + o_bp);
             d.use_tc = use_tc;
             d.fuse_pair = !getenv("LSX_LU_PAIR") || atoi(getenv("LSX_LU_PAIR")) != 0;
+            d.trsm64 = !getenv("LSX_TRSM64") || atoi(getenv("LSX_TRSM64")) != 0;
             d.n = n;
             k_load<<<dim3(ctx->sm_count * 2, Gc), 256, 0, st>>>(dA, d.a);
             d.run();

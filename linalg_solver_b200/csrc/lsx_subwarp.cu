@@ -227,10 +227,11 @@ __device__ __forceinline__ void sw_steps(uint32_t (&row)[PP][NC], SwState (&st)[
 #endif
 }
 
-// MINB = CTAs per SM the register allocation must allow (1: no limit; ptxas then takes ~126 registers for the 16 x 17
-// shape, 4 CTAs per SM; shared memory allows 5 at four primes)
-template <int G, int NC, int PP, int MINB>
-__global__ void __launch_bounds__(SW_THREADS, MINB) k_subwarp(const SwArgs a) {
+// No minimum-CTAs bound on purpose: ptxas takes ~126 registers for the 16 x 17 shape (4 CTAs per SM); forcing 5 CTAs
+// (96 registers, 8 bytes of spills) or 6 (80 registers, 40 bytes) measured SLOWER on B200: 2.53 / 2.76 against 2.41 ms
+// per 2^18 systems (profiles/r02af_c3_minblocks.txt).
+template <int G, int NC, int PP>
+__global__ void __launch_bounds__(SW_THREADS) k_subwarp(const SwArgs a) {
     extern __shared__ uint32_t sm[];          // res[K][NC][SW_THREADS] then dres[K][SW_THREADS]
     const int tid = threadIdx.x, lane = tid & 31;
     const int r = lane % G;                   // my row
@@ -475,31 +476,19 @@ size_t sw_smem_bytes(int K, int NC) {
     return ((size_t)K * NC + (size_t)K * 4) * SW_THREADS * 4 + (size_t)K * sizeof(PrimeRec) + (size_t)K * K * 4;
 }
 
-template <int G, int NC, int PP, int MINB>
-int launch_sw_mb(lsx_ctx* ctx, const SwArgs& a) {
+template <int G, int NC, int PP>
+int launch_sw_pp(lsx_ctx* ctx, const SwArgs& a) {
     const size_t smem = sw_smem_bytes(a.K, NC);
     if (smem > 48 * 1024)
-        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_subwarp<G, NC, PP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSX_CUDA_TRY(ctx, cudaFuncSetAttribute(k_subwarp<G, NC, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t threads = a.batch * G;
     const unsigned grid = (unsigned)((threads + SW_THREADS - 1) / SW_THREADS);
     lsx_timing_begin(ctx);
-    k_subwarp<G, NC, PP, MINB><<<grid, SW_THREADS, smem, ctx->stream>>>(a);
+    k_subwarp<G, NC, PP><<<grid, SW_THREADS, smem, ctx->stream>>>(a);
     lsx_timing_end(ctx);
     ctx->launches++;
     LSX_CUDA_TRY(ctx, cudaGetLastError());
     return LSX_OK;
-}
-template <int G, int NC, int PP>
-int launch_sw_pp(lsx_ctx* ctx, const SwArgs& a) {
-    static const int minb_env = []() {
-        const char* e = getenv("LSX_SW_MINB");
-        return e ? atoi(e) : 1;
-    }();
-    if constexpr (PP == 1 && NC >= 17 && NC <= 24) {          // the wide-row shapes are the register-bound ones
-        if (minb_env >= 6) return launch_sw_mb<G, NC, PP, 6>(ctx, a);
-        if (minb_env == 5) return launch_sw_mb<G, NC, PP, 5>(ctx, a);
-    }
-    return launch_sw_mb<G, NC, PP, 1>(ctx, a);
 }
 
 // two primes per pass when the plan has at least two and the row fits the register budget twice
