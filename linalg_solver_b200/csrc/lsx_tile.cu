@@ -376,6 +376,7 @@ __global__ void __launch_bounds__(16 * TYN, TYN == 16 ? ((RA * CB <= 32) ? 3 : 2
             }
         }
         // ---- one inversion, scale to N = d * RREF (plain residues), rows in logical order ----
+        __syncthreads();                       // thread 0 may have swapped perm in the last step
         for (int q = tid; q < m; q += 16 * TYN) inv[perm[q]] = (uint8_t)q;
         __syncthreads();
         const uint32_t qinv = mont_pow(Q, p - 2u, P.one, p, pinv);
@@ -404,6 +405,208 @@ __global__ void __launch_bounds__(16 * TYN, TYN == 16 ? ((RA * CB <= 32) ? 3 : 2
         }
         __syncthreads();
     }
+}
+
+// ---- in-place inverse: [A|I] with square A in an m x m register tile ------------------------------------------------
+// Gauss-Jordan on [A|I] keeps exactly m "live" columns while no column has been skipped: the left columns right of the
+// pivot column, and the identity columns of the rows that have been pivot rows already.  The left column that step j
+// eliminates dies in the same step in which the identity column of its pivot row comes alive, so the new column takes
+// its slot: the owner of slot j replaces its (published) column by the unit column of the pivot row under the common
+// scale (S / R on the pivot row, 0 elsewhere) before the pivot row is published, and the ordinary two-product update of
+// ALL slots then yields the same words as the update of the 2m-wide tile in k_tile_reg.  Half the registers of the
+// 64 x 128 tile, every update a useful one (k_tile_reg<4,8> carries 5 live blocks of 8 on average), and shapes that are
+// no multiple of 16 need no special case.  At the end slot j holds the right column of the row at logical position j
+// (perm[j]), which is undone in the store.  After a skipped column (singular input, or a prime that divides a pivot
+// candidate) the right part is abandoned -- k_assemble stores zeros for rank < m and k_verify drops a deviating
+// prime -- and the elimination goes on over the left columns alone, so rank and pivot profile stay those of k_tile_reg.
+// Only LSX_OP_INVERSE takes this kernel (columns [n_in, n_in + m) stored, bar == n_in == m).
+template <int RA, int CB, int TYN, int MINB>
+__global__ void __launch_bounds__(16 * TYN, MINB) k_tile_inv(const TileArgs a) {
+    __shared__ uint32_t prow2[2][16 * CB];   // double buffered by the parity of the column (see k_tile_reg)
+    __shared__ uint32_t colbuf[TYN * RA];
+    __shared__ uint8_t perm[TYN * RA];
+    __shared__ uint8_t inv[TYN * RA];
+    const int m = a.m;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
+    const int kslot = blockIdx.y;
+    const PrimeRec P = a.primes[kslot];
+    const uint32_t p = P.p, pinv = P.pinv;
+    const int64_t nslots = a.list ? min((int64_t)*a.list_count, a.cap) : a.batch;
+
+    for (int64_t slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+        const int64_t mat = a.list ? (int64_t)a.list[slot] : slot;
+        uint32_t W[RA][CB];
+        bool bad = false;
+        {
+            const int lim_a = (int)(a.a_abs_max < 0x7fffffff ? a.a_abs_max : 0x7fffffff);
+            const bool big_p = p > (1u << 30);
+#pragma unroll
+            for (int ia = 0; ia < RA; ++ia) {
+                const int r = ty + TYN * ia;
+                const bool rowlive = r < m;
+                const int32_t* arow = a.A + (mat * m + (rowlive ? r : 0)) * (int64_t)m;
+#pragma unroll
+                for (int ib = 0; ib < CB; ++ib) {
+                    const int c = tx + 16 * ib;
+                    const int32_t v = (rowlive && c < m) ? arow[c] : 0;
+                    bad |= v > lim_a || v < -lim_a;
+                    W[ia][ib] = big_p ? residue_fast(v, p) : word_of_int_any(v, p);
+                }
+            }
+        }
+        if (bad) atomicOr(&a.status[mat], LSX_ST_BOUND);
+        for (int q = tid; q < TYN * RA; q += 16 * TYN) perm[q] = (uint8_t)q;
+        __syncthreads();
+
+        uint32_t S = P.one, Q = P.one, X = 1u;
+        int pi = 0;
+        bool neg = false, tri = true;          // tri: no column skipped so far (pi == j), the slots hold the live columns
+        uint8_t* prof = a.prof + ((int64_t)kslot * a.cap + slot) * a.bar;
+        auto block_steps = [&](auto jb_c) {
+          constexpr int JB = decltype(jb_c)::value;
+          for (int jj = 0; jj < 16; ++jj) {
+            const int j = 16 * JB + jj;
+            if (j >= m) break;
+            if (pi >= m) {
+                if (tid == 0) prof[j] = LSX_PROF_SKIP;
+                continue;
+            }
+            // 1. publish column j (indexed by physical row)
+            if (tx == jj) {
+#pragma unroll
+                for (int ia = 0; ia < RA; ++ia) colbuf[ty + TYN * ia] = W[ia][JB];
+            }
+            __syncthreads();
+            // 2. pivot search over logical positions pi .. m-1: the first non-zero (every warp for itself)
+            int src = -1;
+            for (int base = pi; base < m; base += 32) {
+                const int q = base + lane;
+                const bool nz = q < m && colbuf[perm[q]] != 0u;
+                const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                if (bal) {
+                    src = base + __ffs(bal) - 1;
+                    break;
+                }
+            }
+            if (tid == 0) prof[j] = src >= 0 ? (uint8_t)src : (uint8_t)LSX_PROF_SKIP;
+            if (src < 0) {
+                tri = false;
+                __syncthreads();               // colbuf is rewritten by the next column
+                continue;
+            }
+            neg ^= src != pi;
+            const int prp = perm[src];         // physical row of the pivot (perm is swapped after the barrier)
+            // 3. slot j dies as a left column and comes alive as the identity column of the pivot row
+            if (tri && tx == jj) {
+                const uint32_t sv = mont_redc((uint64_t)S, p, pinv);
+#pragma unroll
+                for (int ia = 0; ia < RA; ++ia) W[ia][JB] = (ty + TYN * ia == prp) ? sv : 0u;
+            }
+            // 4. publish the pivot row (selects, not a switch: see k_tile_reg)
+            uint32_t* prow = prow2[j & 1];
+            if (ty == prp % TYN) {
+                const int pb = prp / TYN;
+#pragma unroll
+                for (int ib = 0; ib < CB; ++ib) {
+                    uint32_t v = W[0][ib];
+#pragma unroll
+                    for (int ia = 1; ia < RA; ++ia) v = (pb == ia) ? W[ia][ib] : v;
+                    prow[tx + 16 * ib] = v;
+                }
+            }
+            const uint32_t piv = colbuf[prp];
+            uint32_t xs[RA], ys[RA];
+#pragma unroll
+            for (int ia = 0; ia < RA; ++ia) {
+                const int r = ty + TYN * ia;
+                const uint32_t f = colbuf[r];
+                const bool isp = r == prp;
+                xs[ia] = isp ? S : piv;
+                ys[ia] = (isp || f == 0u) ? 0u : p - f;
+            }
+            __syncthreads();
+            // 5. update every slot
+#pragma unroll
+            for (int ib = 0; ib < CB; ++ib) {
+                const uint32_t pc = prow[tx + 16 * ib];
+#pragma unroll
+                for (int ia = 0; ia < RA; ++ia) W[ia][ib] = mont_fma2(xs[ia], W[ia][ib], ys[ia], pc, p, pinv);
+            }
+            Q = mont_mul(Q, S, p, pinv);
+            S = mont_mul(S, piv, p, pinv);
+            X = mont_mul(X, P.r2, p, pinv);
+            if (tid == 0 && src != pi) {       // every warp has read perm[src] before the barrier above
+                const uint8_t t0 = perm[pi];
+                perm[pi] = perm[src];
+                perm[src] = t0;
+            }
+            ++pi;
+            // no barrier here: see k_tile_reg
+          }
+        };
+        for_each_block(block_steps, std::make_integer_sequence<int, CB>{});
+        // ---- one inversion, scale to N = d * RREF (plain residues), rows in logical order, columns by pivot row ----
+        __syncthreads();                       // the last swap of perm
+        for (int q = tid; q < m; q += 16 * TYN) inv[perm[q]] = (uint8_t)q;
+        __syncthreads();
+        const uint32_t qinv = mont_pow(Q, p - 2u, P.one, p, pinv);
+        uint32_t Gw = mont_mul(qinv, X, p, pinv);
+        if (neg && Gw) Gw = p - Gw;
+        const uint32_t G2w = mont_mul(Gw, P.r2, p, pinv);
+        {
+            uint32_t* out = a.res + ((int64_t)kslot * a.cap + slot) * ((int64_t)m * m);
+            int colof[CB];                     // slot c holds the identity column of the row at logical position c
+#pragma unroll
+            for (int ib = 0; ib < CB; ++ib) {
+                const int c = tx + 16 * ib;
+                colof[ib] = c < m ? perm[c] : -1;
+            }
+#pragma unroll
+            for (int ia = 0; ia < RA; ++ia) {
+                const int r = ty + TYN * ia;
+                if (r < m) {
+                    const int q = inv[r];
+                    const uint32_t g = q < pi ? Gw : G2w;
+#pragma unroll
+                    for (int ib = 0; ib < CB; ++ib)
+                        if (colof[ib] >= 0) out[q * m + colof[ib]] = mont_mul(g, W[ia][ib], p, pinv);
+                }
+            }
+        }
+        if (tid == 0) {
+            a.dres[(int64_t)kslot * a.cap + slot] = mont_mul(Gw, S, p, pinv);
+            a.rankk[(int64_t)kslot * a.cap + slot] = pi;
+        }
+        __syncthreads();
+    }
+}
+
+template <int RA, int CB, int TYN, int MINB>
+int launch_tile_inv(lsx_ctx* ctx, const TileArgs& ta, int Ktot, int64_t grid_x) {
+    dim3 grid((unsigned)grid_x, (unsigned)Ktot);
+    lsx_timing_begin(ctx);
+    k_tile_inv<RA, CB, TYN, MINB><<<grid, 16 * TYN, 0, ctx->stream>>>(ta);
+    lsx_timing_end(ctx);
+    ctx->launches++;
+    return LSX_OK;
+}
+
+// In-place inverse kernel for a square [A|I] job whose right part alone is stored, or false.
+bool launch_tile_inv_any(lsx_ctx* ctx, const TileArgs& ta, int Ktot, int64_t grid_x, int* rc) {
+    if (getenv("LSX_DISABLE_TILE_REG") || getenv("LSX_DISABLE_TILE_INV")) return false;
+    const int m = ta.m;
+    if (!ta.right_identity || ta.n_in != m || ta.bar != m || ta.n != 2 * m || ta.c0 != m || ta.c1 != 2 * m) return false;
+    if (m > 128 || m < 9) return false;
+    const char* shp = getenv("LSX_TILE_INV_SHAPE");      // measurement switch for the 64-row tile
+    const int s = shp ? atoi(shp) : 0;
+    if (m <= 32) *rc = launch_tile_inv<2, 2, 16, 4>(ctx, ta, Ktot, grid_x);
+    else if (m <= 64) {
+        if (s == 1) *rc = launch_tile_inv<4, 4, 16, 3>(ctx, ta, Ktot, grid_x);
+        else if (s == 2) *rc = launch_tile_inv<8, 4, 8, 4>(ctx, ta, Ktot, grid_x);
+        else if (s == 3) *rc = launch_tile_inv<8, 4, 8, 6>(ctx, ta, Ktot, grid_x);
+        else *rc = launch_tile_inv<8, 4, 8, 5>(ctx, ta, Ktot, grid_x);
+    } else *rc = launch_tile_inv<8, 8, 16, 2>(ctx, ta, Ktot, grid_x);
+    return true;
 }
 
 template <int RA, int CB, int TYN = 16>
@@ -826,7 +1029,8 @@ int lsx_run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const
     if (gx > max_gx) gx = max_gx;
     const int cells = m * n;
     int rc;
-    if (launch_tile_reg_any(ctx, ta, Ktot, gx, &rc)) {
+    if (job.op == LSX_OP_INVERSE && launch_tile_inv_any(ctx, ta, Ktot, gx, &rc)) {
+    } else if (launch_tile_reg_any(ctx, ta, Ktot, gx, &rc)) {
     } else if (cells <= 128)
         rc = launch_tile<32>(ctx, ta, Ktot, gx, smem);
     else if (cells <= 1024)

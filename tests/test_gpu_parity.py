@@ -867,3 +867,53 @@ def test_register_tiled_kernel_equals_smem_kernel(eng, monkeypatch):
     # an exact check against the oracle on one rank-deficient mid-size input
     A = (rng.integers(-2, 3, size=(36, 30)) @ rng.integers(-2, 3, size=(30, 40))).astype(np.int32)
     check_rref_against_oracle(eng, [A.tolist()], 38)
+
+
+def test_in_place_inverse_kernel_equals_wide_tile_kernels(eng, monkeypatch):
+    """k_tile_inv (square [A|I] in an m x m register tile: the identity column of a pivot row takes the slot of the left
+    column its step eliminates) against the 2m-wide k_tile_reg and the shared-memory k_tile_elim, word for word: every
+    size class incl. sizes that are no multiple of 16, forced row swaps in the first, a middle and the LAST column,
+    singular inputs of several ranks (linalg.py:682-743 returns NoSolution: status bit, zero words), and the thread
+    shapes behind LSX_TILE_INV_SHAPE."""
+    rng = np.random.Generator(np.random.PCG64(43))
+    monkeypatch.setenv("LSX_DISABLE_SUBWARP", "1")           # sizes up to 16 would take the fused sub-warp kernel
+    for n in (9, 16, 17, 31, 32, 33, 47, 50, 64, 65, 96, 100, 128):
+        B = 10
+        lo = 5 if n <= 100 else 2                            # 128 x 128 with |a| <= 5 would need more than 32 primes
+        mats = rng.integers(-lo, lo + 1, size=(B, n, n)).astype(np.int32)
+        mats[1, 0, 0] = 0
+        mats[1, 1, :2] = 0                                   # swaps in the first columns
+        h = n // 2
+        mats[2, h:, :h] = 0
+        mats[2, h, h] = 0                                    # middle column: the diagonal candidate is zero
+        mats[3] = np.eye(n, dtype=np.int32)[rng.permutation(n)] * rng.integers(1, lo + 1, size=(n, 1))   # swaps everywhere
+        mats[4] = np.eye(n, dtype=np.int32)
+        mats[4, [n - 2, n - 1]] = mats[4, [n - 1, n - 2]]    # one swap, in the second-to-last column
+        mats[5, n - 1] = mats[5, 0] + mats[5, n // 3]        # rank n - 1 (entries stay within 2 lo: the plan's 32 primes)
+        mats[6, h:] = 0                                      # rank n // 2
+        mats[7] = np.outer(rng.choice([-1, 1], size=n), rng.choice([-1, 1], size=n))   # rank 1
+        mats[8, :, n - 1] = mats[8, :, 0]                    # singular, found in the last column
+        mats[9, :, 1] = 2 * mats[9, :, 0]                    # singular, found in the second column
+        x = eng.inverse_batch(mats)
+        monkeypatch.setenv("LSX_DISABLE_TILE_INV", "1")
+        y = eng.inverse_batch(mats)
+        monkeypatch.delenv("LSX_DISABLE_TILE_INV")
+        monkeypatch.setenv("LSX_DISABLE_TILE_REG", "1")
+        z = eng.inverse_batch(mats)
+        monkeypatch.delenv("LSX_DISABLE_TILE_REG")
+        for other in (y, z):
+            assert np.array_equal(x.status, other.status), n
+            assert np.array_equal(x.adj, other.adj) and np.array_equal(x.det, other.det), n
+        assert [int(v) & 1 for v in x.status] == [0, 0, 0, 0, 0, 1, 1, 1, 1, 1], (n, x.status)
+        if 32 < n <= 64:
+            for shape in ("1", "2", "3"):
+                monkeypatch.setenv("LSX_TILE_INV_SHAPE", shape)
+                w = eng.inverse_batch(mats)
+                monkeypatch.delenv("LSX_TILE_INV_SHAPE")
+                assert np.array_equal(x.status, w.status) and np.array_equal(x.adj, w.adj) and np.array_equal(x.det, w.det)
+    # exact values against the oracle (reference inverse = adj / det in lowest terms)
+    A = rng.integers(-3, 4, size=(1, 20, 20)).astype(np.int32)
+    r = eng.inverse_batch(A)
+    adj, det = limbs_to_ints(r.adj), limbs_to_ints(r.det)
+    want = ref_port.inverse(A[0].tolist())
+    assert want is not None and [[Fraction(v, det[0]) for v in row] for row in adj[0]] == want
