@@ -111,6 +111,11 @@ int  lsx_set_stream(lsx_ctx* ctx, void* cuda_stream);
 int  lsx_synchronize(lsx_ctx* ctx);
 /* Number of kernels this ctx has launched so far (for launch accounting in benchmarks). */
 int64_t lsx_launch_count(const lsx_ctx* ctx);
+/* Primes per matrix the most recent tile-path pass of this ctx really used.  The plan's n_primes covers the DECLARED
+ * magnitudes; the tile path bounds the minors of the matrices it is given by the product of their largest row norms
+ * (Hadamard) and runs only the primes that bound needs -- never more than the plan's.  *out = 0 when the last call
+ * did not take the tile path (fused small kernels) or computes a rank.  Waits for the ctx's stream. */
+int  lsx_last_prime_count(lsx_ctx* ctx, int* out);
 /* Device timing of the DOMINANT kernel of each following call (the elimination kernel): enable
  * records a CUDA event pair around it on the ctx stream; lsx_timing_read waits for the recorded
  * pairs, writes up to `cap` durations in milliseconds (oldest first), returns how many were

@@ -56,6 +56,7 @@ SIGNATURES = {
     "lsx_set_stream": (_i, [_vp, _vp]),
     "lsx_synchronize": (_i, [_vp]),
     "lsx_launch_count": (_i64, [_vp]),
+    "lsx_last_prime_count": (_i, [_vp, ctypes.POINTER(_i)]),
     "lsx_timing_enable": (_i, [_vp, _i]),
     "lsx_timing_read": (_i, [_vp, _vp, _i, ctypes.POINTER(_i)]),
     "lsx_debug_set_primes": (_i, [_vp, _vp, _i]),

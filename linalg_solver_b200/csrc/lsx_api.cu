@@ -182,6 +182,18 @@ int lsx_synchronize(lsx_ctx* ctx) {
 
 int64_t lsx_launch_count(const lsx_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int lsx_last_prime_count(lsx_ctx* ctx, int* out) {
+    if (!ctx || !out) return LSX_ERR_NULL;
+    *out = 0;
+    if (!ctx->last_kword) return LSX_OK;
+    LSX_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int32_t kw[2] = {0, 0};
+    LSX_CUDA_TRY(ctx, cudaMemcpyAsync(kw, ctx->last_kword, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    LSX_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = kw[1];
+    return LSX_OK;
+}
+
 int lsx_timing_enable(lsx_ctx* ctx, int enable) {
     if (!ctx) return LSX_ERR_NULL;
     ctx->timing = enable != 0;

@@ -56,6 +56,8 @@ struct lsx_ctx {
     // thread inside a call); empty for a single-device ctx.  nccl: communicators of all devices (lsx_multi.cpp)
     std::vector<lsx_ctx*> peers;
     void* nccl = nullptr;
+    // device word pair of the last generic pass: [1] = primes its data needed (lsx_last_prime_count), or NULL
+    const int32_t* last_kword = nullptr;
 };
 // Record CUDA events around the dominant kernel of an operation when timing is enabled.
 void lsx_timing_begin(lsx_ctx* ctx);

@@ -41,7 +41,71 @@ struct TileArgs {
     int32_t* rankk;             // [Ktot][cap]
     uint8_t* prof;              // [Ktot][cap][bar]
     int32_t* status;            // [batch] (indexed by matrix)
+    const int32_t* kword;       // NULL, or kword[1] = primes the data of this pass needs (k_row_bound)
+    int k_extra;                // replacement primes on top of that (list mode)
 };
+
+// ---- prime count from the data -------------------------------------------------------------------------------------
+// The plan sizes K for the declared magnitudes (every entry at a_abs_max).  Every integer an elimination returns is a
+// minor of [A | right part] of order <= r_top, so by Hadamard's inequality over ROWS its magnitude is at most the
+// product of the r_top largest row norms of the batch's own matrices -- rows of a minor are sub-rows.  k_row_bound
+// takes the maximum of that product over the matrices of a pass, k_bound_to_primes turns it into a prime count
+// (never above the plan's K; same rounding as lsx_bits_to_plan), and the CTAs of the primes beyond it leave at once;
+// k_verify and k_assemble read the same word.  Random entries in [-5, 5] have row norms of sqrt(640) where the plan
+// assumes 40: 10 primes instead of 12 for the 64 x 64 inverse, 15 instead of 21 for the rank-48 kernel bases.
+struct BoundArgs {
+    const int32_t* A;
+    const int32_t* bvec;
+    int64_t batch;
+    int m, n_in, r_top, right_identity;
+    int32_t* kword;             // [0] = max over matrices of ceil(256 log2 bound), [1] = prime count
+};
+
+__global__ void __launch_bounds__(128) k_row_bound(const BoundArgs a) {
+    __shared__ double lg_all[4][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t mat = (int64_t)blockIdx.x * 4 + w;
+    if (mat >= a.batch) return;
+    double* lg = lg_all[w];
+    const int m = a.m, n = a.n_in;
+    for (int r = 0; r < m; ++r) {
+        const int32_t* row = a.A + (mat * m + r) * (int64_t)n;
+        double s = 0.0;
+        for (int c = lane; c < n; c += 32) {
+            const double v = (double)row[c];
+            s += v * v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (a.right_identity) s += 1.0;
+        if (a.bvec) {
+            const double b = (double)a.bvec[mat * m + r];
+            s += b * b;
+        }
+        if (lane == 0) lg[r] = s > 1.0 ? 0.5 * log2(s) * (1.0 + 1e-12) : 0.0;
+    }
+    __syncwarp();
+    double tot = 0.0;
+    for (int r = lane; r < m; r += 32) {
+        const double v = lg[r];
+        bool take = true;
+        if (a.r_top < m) {                      // the r_top largest: position of row r in the descending order
+            int above = 0;
+            for (int q = 0; q < m; ++q) above += (lg[q] > v || (lg[q] == v && q < r)) ? 1 : 0;
+            take = above < a.r_top;
+        }
+        if (take) tot += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) atomicMax(a.kword, (int)ceil(tot * 256.0) + 1);
+}
+
+__global__ void k_bound_to_primes(int32_t* kword, int K) {
+    const double need = (double)kword[0] / 256.0 + 1.0 + 1e-6;      // sign bit + slack, as lsx_bits_to_plan
+    int k = (int)ceil(need / 30.999);
+    kword[1] = k < 1 ? 1 : (k > K ? K : k);
+}
 
 template <int T>
 __global__ void __launch_bounds__(T) k_tile_elim(const TileArgs a) {
@@ -55,6 +119,7 @@ __global__ void __launch_bounds__(T) k_tile_elim(const TileArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = T / 32;
     const int kslot = blockIdx.y;
+    if (a.kword && kslot >= a.kword[1] + a.k_extra) return;   // more primes than the data of this pass needs
     const PrimeRec P = a.primes[kslot];
     const uint32_t p = P.p, pinv = P.pinv;
     const int64_t nslots = a.list ? min((int64_t)*a.list_count, a.cap) : a.batch;
@@ -197,6 +262,7 @@ __global__ void __launch_bounds__(16 * TYN, TYN == 16 ? ((RA * CB <= 32) ? 3 : 2
     const int m = a.m, n = a.n, bar = a.bar;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
     const int kslot = blockIdx.y;
+    if (a.kword && kslot >= a.kword[1] + a.k_extra) return;   // more primes than the data of this pass needs
     const PrimeRec P = a.primes[kslot];
     const uint32_t p = P.p, pinv = P.pinv;
     const int64_t nslots = a.list ? min((int64_t)*a.list_count, a.cap) : a.batch;
@@ -429,6 +495,7 @@ __global__ void __launch_bounds__(16 * TYN, MINB) k_tile_inv(const TileArgs a) {
     const int m = a.m;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
     const int kslot = blockIdx.y;
+    if (a.kword && kslot >= a.kword[1] + a.k_extra) return;   // more primes than the data of this pass needs
     const PrimeRec P = a.primes[kslot];
     const uint32_t p = P.p, pinv = P.pinv;
     const int64_t nslots = a.list ? min((int64_t)*a.list_count, a.cap) : a.batch;
@@ -645,6 +712,7 @@ struct VerifyArgs {
     const int32_t* list_count;
     int64_t batch, cap;
     int bar, K, Ktot, max_rank, pivot_slots, allow_retry;
+    const int32_t* kword;
     const uint8_t* prof;
     const int32_t* rankk;
     uint8_t* sel;        // [cap][LSX_MAX_BATCH_PRIMES]
@@ -664,13 +732,15 @@ __global__ void k_verify(const VerifyArgs a) {
     if (slot >= nslots) return;
     const int64_t mat = a.list ? (int64_t)a.list[slot] : slot;
     const int bar = a.bar;
+    const int K = a.kword ? min(a.K, a.kword[1]) : a.K;       // primes the data needs (k_row_bound)
+    const int Ktot = K + (a.Ktot - a.K);
     // A prime whose profile deviates from the rational one picks a LATER row or skips a column
     // at the first deviation (a non-zero candidate looked like zero), so the rational profile is
     // the lexicographic minimum as soon as one prime is good; if the primes agreeing with the
     // minimum have a product above the Hadamard bound the minimum is provably the rational
     // profile.
     int best = 0;
-    for (int k = 1; k < a.Ktot; ++k) {
+    for (int k = 1; k < Ktot; ++k) {
         const uint8_t* pk = a.prof + ((int64_t)k * a.cap + slot) * bar;
         const uint8_t* pb = a.prof + ((int64_t)best * a.cap + slot) * bar;
         for (int j = 0; j < bar; ++j) {
@@ -683,14 +753,14 @@ __global__ void k_verify(const VerifyArgs a) {
     const uint8_t* pb = a.prof + ((int64_t)best * a.cap + slot) * bar;
     int cnt = 0;
     uint8_t* sel = a.sel + slot * LSX_MAX_BATCH_PRIMES;
-    for (int k = 0; k < a.Ktot && cnt < a.K; ++k) {
+    for (int k = 0; k < Ktot && cnt < K; ++k) {
         const uint8_t* pk = a.prof + ((int64_t)k * a.cap + slot) * bar;
         bool same = true;
         for (int j = 0; j < bar; ++j) same &= pk[j] == pb[j];
         if (same) sel[cnt++] = (uint8_t)k;
     }
     int st = 0;
-    if (cnt < a.K) {
+    if (cnt < K) {
         if (a.allow_retry) {
             int pos = atomicAdd(a.retry_count, 1);
             if (pos < a.retry_cap) {
@@ -733,6 +803,7 @@ struct AsmArgs {
     int op, m, n, n_in, bar, K, L, ncs, c0, pivot_slots, gen_cap;
     const PrimeRec* primes;
     const uint32_t* garner;   // [GD][GD]
+    const int32_t* kword;
     const uint32_t* res;
     const uint32_t* dres;
     const uint8_t* sel;
@@ -762,7 +833,7 @@ __global__ void __launch_bounds__(128) k_assemble(const AsmArgs a) {
     const int st = a.status[mat];
     if (st & (LSX_ST_INTERNAL_RETRY | LSX_ST_NO_GOOD_PRIME | LSX_ST_BOUND)) return;
     const uint8_t* sel = a.sel + slot * LSX_MAX_BATCH_PRIMES;
-    const int K = a.K, L = a.L;
+    const int K = a.kword ? min(a.K, a.kword[1]) : a.K, L = a.L;
     const int rank = a.rank_ws[slot];
 
     // A solve keeps only part of the tile: the right-hand-side column and the FREE columns of the pivot rows (and a
@@ -922,7 +993,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 namespace {
 // Scratch layout of one generic pass (Ktot primes, `cap` slots).
 struct GenericWs {
-    size_t o_res, o_dres, o_rankk, o_prof, o_sel, o_rank, o_piv, o_rlist, o_rcount, total;
+    size_t o_res, o_dres, o_rankk, o_prof, o_sel, o_rank, o_piv, o_rlist, o_rcount, o_kword, total;
 };
 GenericWs generic_ws(int Ktot, int64_t cap, int m, int ncs, int bar, int pivot_slots) {
     GenericWs w{};
@@ -941,6 +1012,7 @@ GenericWs generic_ws(int Ktot, int64_t cap, int m, int ncs, int bar, int pivot_s
     w.o_piv = take((size_t)cap * pivot_slots * 4);
     w.o_rlist = take((size_t)LSX_RETRY_CAP * 4);
     w.o_rcount = take(256);
+    w.o_kword = take(256);
     w.total = off;
     return w;
 }
@@ -962,8 +1034,16 @@ size_t lsx_generic_ws_bytes(const ElimJob& job, int64_t batch) {
 // the K plan primes are used and matrices whose primes disagree are appended to an internal
 // retry list and recomputed with K + LSX_RETRY_EXTRA primes.  Scratch is taken from the ctx
 // workspace starting at byte ws_offset (the caller has reserved lsx_generic_ws_bytes).
+static int run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const int32_t* list_count,
+                       int list_cap, size_t ws_offset, const int32_t* kword_parent);
+
 int lsx_run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const int32_t* list_count,
                     int list_cap, size_t ws_offset) {
+    return run_generic(ctx, job, list, list_count, list_cap, ws_offset, nullptr);
+}
+
+static int run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const int32_t* list_count,
+                       int list_cap, size_t ws_offset, const int32_t* kword_parent) {
     const bool list_mode = list != nullptr;
     const int K = job.K;
     const int Ktot = list_mode ? K + LSX_RETRY_EXTRA : K;
@@ -1001,6 +1081,32 @@ int lsx_run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const
 
     if (!list_mode) LSX_CUDA_TRY(ctx, cudaMemsetAsync(rcount, 0, 4, ctx->stream));
 
+    // prime count from the row norms of this pass's matrices (a retry pass behind it keeps the parent's count; a
+    // retry list handed in by the fused kernels has none and runs with the plan's K)
+    const int32_t* kword = kword_parent;
+    if (!list_mode && K > 1 && job.op != LSX_OP_RANK && !getenv("LSX_NO_DATA_BOUND")) {
+        int32_t* kw = (int32_t*)(base + w.o_kword);
+        LSX_CUDA_TRY(ctx, cudaMemsetAsync(kw, 0, 8, ctx->stream));
+        BoundArgs ba{};
+        ba.A = job.A;
+        ba.bvec = (!job.right_identity && n > job.n_in) ? job.bvec : nullptr;
+        ba.batch = job.batch;
+        ba.m = m;
+        ba.n_in = job.n_in;
+        ba.right_identity = job.right_identity;
+        int r = m < bar ? m : bar;
+        if (job.max_rank > 0 && job.max_rank < r) r = job.max_rank;
+        ba.r_top = (n > bar && r < m) ? r + 1 : r;          // zero-left rows hold minors of order r + 1
+        ba.kword = kw;
+        k_row_bound<<<(unsigned)((job.batch + 3) / 4), 128, 0, ctx->stream>>>(ba);
+        k_bound_to_primes<<<1, 1, 0, ctx->stream>>>(kw, K);
+        ctx->launches += 2;
+        kword = kw;
+        ctx->last_kword = kw;
+    } else if (!list_mode) {
+        ctx->last_kword = nullptr;
+    }
+
     TileArgs ta{};
     ta.A = job.A;
     ta.bvec = job.bvec;
@@ -1023,6 +1129,8 @@ int lsx_run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const
     ta.rankk = rankk;
     ta.prof = prof;
     ta.status = job.status;
+    ta.kword = kword;
+    ta.k_extra = Ktot - K;
 
     int64_t gx = list_mode ? 256 : job.batch;
     const int64_t max_gx = (int64_t)ctx->sm_count * 64;
@@ -1052,6 +1160,7 @@ int lsx_run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const
     va.max_rank = job.max_rank;
     va.pivot_slots = pivot_slots;
     va.allow_retry = list_mode ? 0 : 1;
+    va.kword = kword;
     va.prof = prof;
     va.rankk = rankk;
     va.sel = sel;
@@ -1099,6 +1208,7 @@ int lsx_run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const
         aa.gen_cap = job.gen_cap;
         aa.primes = ctx->d_primes;
         aa.garner = ctx->d_garner;
+        aa.kword = kword;
         aa.res = res;
         aa.dres = dres;
         aa.sel = sel;
@@ -1130,7 +1240,7 @@ int lsx_run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const
 
     if (!list_mode) {
         // recompute flagged matrices with replacement primes (a no-op grid when none was flagged)
-        rc = lsx_run_generic(ctx, job, rlist, rcount, LSX_RETRY_CAP, ws_offset + w.total);
+        rc = run_generic(ctx, job, rlist, rcount, LSX_RETRY_CAP, ws_offset + w.total, kword);
         if (rc != LSX_OK) return rc;
     }
     return LSX_OK;

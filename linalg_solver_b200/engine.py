@@ -130,6 +130,12 @@ class Engine:
     def launch_count(self) -> int:
         return int(lib.lsx_launch_count(self._ctx))
 
+    def last_prime_count(self) -> int:
+        """Primes per matrix the last tile-path call used (its row-norm Hadamard bound; 0: not the tile path)."""
+        k = ctypes.c_int(0)
+        self._check(lib.lsx_last_prime_count(self._ctx, ctypes.byref(k)))
+        return int(k.value)
+
     def timing_enable(self, on: bool = True):
         """Record CUDA events around the dominant kernel of each following call."""
         self._check(lib.lsx_timing_enable(self._ctx, 1 if on else 0))

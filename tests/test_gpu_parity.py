@@ -869,6 +869,66 @@ def test_register_tiled_kernel_equals_smem_kernel(eng, monkeypatch):
     check_rref_against_oracle(eng, [A.tolist()], 38)
 
 
+def test_prime_count_from_row_norms(eng, monkeypatch):
+    """The tile path runs only the primes the Hadamard bound of the batch's own row norms needs (k_row_bound), never more
+    than the plan: identical words with the data bound switched off, fewer primes on random data, the plan's count on
+    worst-case data, and exact answers where the determinant EQUALS the row-norm bound (diagonal matrices)."""
+    rng = np.random.Generator(np.random.PCG64(47))
+    def both(f):
+        x = f()
+        kx = eng.last_prime_count()
+        monkeypatch.setenv("LSX_NO_DATA_BOUND", "1")
+        y = f()
+        ky = eng.last_prime_count()
+        monkeypatch.delenv("LSX_NO_DATA_BOUND")
+        return x, y, kx, ky
+    A = rng.integers(-5, 6, size=(12, 64, 64)).astype(np.int32)
+    A[3, 7] = A[3, 9]                                                        # one singular matrix
+    plan = eng.plan_inverse(64, 5)
+    x, y, kx, ky = both(lambda: eng.inverse_batch(A, plan=plan))
+    assert ky == 0 and 1 <= kx < plan.n_primes, (kx, ky, plan.n_primes)
+    assert np.array_equal(x.status, y.status) and np.array_equal(x.adj, y.adj) and np.array_equal(x.det, y.det)
+    W = A.copy()
+    W[0] = 5                                                                 # every entry at the declared magnitude
+    x, y, kx, ky = both(lambda: eng.inverse_batch(W, plan=plan))
+    assert kx == plan.n_primes
+    assert np.array_equal(x.status, y.status) and np.array_equal(x.adj, y.adj) and np.array_equal(x.det, y.det)
+    # rank-deficient products, solve and rref: top-(r + 1) rows
+    Bm = rng.integers(-5, 6, size=(10, 40, 25)); Cm = rng.integers(-5, 6, size=(10, 25, 44))
+    M = np.einsum("bik,bkj->bij", Bm, Cm).astype(np.int32)
+    x, y, kx, ky = both(lambda: eng.rref_batch(M, 40))
+    assert 1 <= kx
+    for f in ("status", "num", "den", "pivot_col", "rank"):
+        assert np.array_equal(getattr(x, f), getattr(y, f)), f
+    S = M[:, :, :40].copy()
+    b = rng.integers(-9, 10, size=(10, 40)).astype(np.int32)
+    b[::2] = np.einsum("bij,bj->bi", S[::2], rng.integers(-2, 3, size=(5, 40)))
+    pl = eng.plan_solve(40, 40, int(np.abs(S).max()), int(np.abs(b).max()), 25, 15)
+    x, y, kx, ky = both(lambda: eng.solve_batch(S, b, plan=pl))
+    assert 1 <= kx < pl.n_primes
+    assert np.array_equal(x.status, y.status)
+    ok = (x.status & 2) == 0
+    assert ok.any() and not ok.all()
+    for f in ("den", "particular", "generators", "pivot_col", "rank"):
+        assert np.array_equal(getattr(x, f)[ok], getattr(y, f)[ok]), f
+    # the bound is attained: det(diag) = product of the row norms; declared magnitude far above the data
+    for n, v, amax in ((40, 1000, 50000), (33, 46340, 50000), (64, 3, 100)):
+        D = np.zeros((3, n, n), dtype=np.int32)
+        D[0] = np.diag(np.full(n, v))
+        D[1] = np.diag(np.full(n, -v))
+        D[2] = np.diag(rng.integers(1, v + 1, size=n))[rng.permutation(n)]
+        d = eng.det_batch(D, a_abs_max=amax)
+        k = eng.last_prime_count()
+        got = limbs_to_ints(d.det)
+        want = [v ** n, (-v) ** n, ref_port.bareiss_det(D[2].tolist())]
+        assert got == want, (n, v)
+        assert k == -(-(n * np.log2(v) + 1) // 30.999) or k == -(-(n * np.log2(v) + 1) // 30.999) + 1, (n, v, k)
+        r = eng.inverse_batch(D, a_abs_max=amax)
+        adj, det = limbs_to_ints(r.adj), limbs_to_ints(r.det)
+        assert det == want
+        assert [adj[0][i][i] for i in range(n)] == [v ** (n - 1)] * n
+
+
 def test_in_place_inverse_kernel_equals_wide_tile_kernels(eng, monkeypatch):
     """k_tile_inv (square [A|I] in an m x m register tile: the identity column of a pivot row takes the slot of the left
     column its step eliminates) against the 2m-wide k_tile_reg and the shared-memory k_tile_elim, word for word: every

@@ -1,4 +1,7 @@
 set -x
-python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "in_place" > gpurun_out/r02ai_pytest_inv.txt 2>&1; tail -5 gpurun_out/r02ai_pytest_inv.txt
-ncu --set full --clock-control none --import-source on -k regex:k_tile_inv -s 2 -c 1 -o gpurun_out/r02ai_tile_inv python tools/time_configs.py c4inv > gpurun_out/r02ai_ncu.log 2>&1
-tail -3 gpurun_out/r02ai_ncu.log
+python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/r02aj_pytest_parity.txt 2>&1; tail -5 gpurun_out/r02aj_pytest_parity.txt
+{
+echo "== row-norm prime count (default)"; python tools/time_configs.py c4inv c4ker
+echo "== LSX_NO_DATA_BOUND=1"; LSX_NO_DATA_BOUND=1 python tools/time_configs.py c4inv c4ker
+} > gpurun_out/r02aj_c4_data_bound.txt 2>&1
+cat gpurun_out/r02aj_c4_data_bound.txt
