@@ -55,7 +55,7 @@ __device__ __forceinline__ void crt_limbs(const uint32_t (&r)[KT], const uint8_t
         if (i < K) {
             uint64_t carry = v[i];
 #pragma unroll
-            for (int l = 0; l < KT; ++l) {
+            for (int l = 0; l < KT - i; ++l) {     // acc < 2^(32 (KT - 1 - i)) before this digit: the limbs above are zero
                 uint64_t t = (uint64_t)acc[l] * pp[i] + carry;
                 acc[l] = (uint32_t)t;
                 carry = t >> 32;

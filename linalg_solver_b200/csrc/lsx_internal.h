@@ -167,6 +167,8 @@ struct ElimJob {
 int lsx_run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const int32_t* list_count,
                     int list_cap, size_t ws_offset);
 size_t lsx_generic_ws_bytes(const ElimJob& job, int64_t batch);
+// kword[0..1] (device) <- primes per matrix the row norms of the job's own matrices need, at most job.K (lsx_tile.cu)
+int lsx_row_bound_primes(lsx_ctx* ctx, const ElimJob& job, int32_t* kword);
 // Fused register-resident kernels for small shapes; *handled = 1 if the job was covered.
 int lsx_run_small(lsx_ctx* ctx, const ElimJob& job, int* handled);
 // Fused sub-warp kernel (row per lane, all primes + CRT in one launch) for m <= 32, n <= 33.

@@ -37,6 +37,7 @@ struct SwArgs {
     int64_t batch;
     int m, n_in, n, bar, right_identity, op;
     int K, L, gen_cap, pivot_slots, max_rank;
+    const int32_t* kword;       // NULL, or kword[1] = primes the batch's own row norms need (lsx_row_bound_primes)
     int a_abs_max, b_abs_max;
     const PrimeRec* primes;
     const uint32_t* garner;
@@ -105,7 +106,7 @@ __device__ __noinline__ void crt_entry(const uint32_t* res, int res_stride, cons
         if (i < K) {
             uint64_t carry = v[i];
 #pragma unroll
-            for (int l = 0; l < KT; ++l) {
+            for (int l = 0; l < KT - i; ++l) {     // acc < 2^(32 (KT - 1 - i)) before this digit: the limbs above are zero
                 const uint64_t t = (uint64_t)acc[l] * pp[i] + carry;
                 acc[l] = (uint32_t)t;
                 carry = t >> 32;
@@ -124,8 +125,9 @@ __device__ __noinline__ void crt_entry(const uint32_t* res, int res_stride, cons
 // instruction fetch ("no_instruction").
 __device__ __noinline__ void crt_entry_any(const uint32_t* res, int res_stride, const uint32_t* scale, int scale_stride,
                                               int K, int L, SwTables T, uint32_t* dst, bool negate, bool zero_out) {
-    if (K <= 1) crt_entry<1>(res, res_stride, scale, scale_stride, K, L, T, dst, negate, zero_out);
-    else if (K <= 4) crt_entry<4>(res, res_stride, scale, scale_stride, K, L, T, dst, negate, zero_out);
+    // KT covers the limbs as well: with the prime count taken from the data K can be below L (sign extension)
+    if (K <= 1 && L <= 1) crt_entry<1>(res, res_stride, scale, scale_stride, K, L, T, dst, negate, zero_out);
+    else if (K <= 4 && L <= 4) crt_entry<4>(res, res_stride, scale, scale_stride, K, L, T, dst, negate, zero_out);
     else crt_entry<8>(res, res_stride, scale, scale_stride, K, L, T, dst, negate, zero_out);
 }
 
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_subwarp(const SwArgs a) {
     const int gbase = lane - r;               // first lane of my group
     const unsigned gmask = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
     constexpr unsigned FULL = 0xffffffffu;
-    const int m = a.m, n = a.n, bar = a.bar, K = a.K, L = a.L;
+    const int m = a.m, n = a.n, bar = a.bar, K = a.kword ? min(a.K, a.kword[1]) : a.K, L = a.L;
     const int64_t mat = ((int64_t)blockIdx.x * SW_THREADS + tid) / G;
     const bool live = mat < a.batch;          // whole groups are live or not
     const bool rowlive = live && r < m;
@@ -590,6 +592,15 @@ int lsx_run_subwarp(lsx_ctx* ctx, const ElimJob& job, int* handled) {
     a.retry_list = rlist;
     a.retry_count = rcount;
     a.retry_cap = LSX_RETRY_CAP;
+    if (job.K > 1 && job.op != LSX_OP_RANK && !getenv("LSX_NO_DATA_BOUND")) {
+        // prime count from the row norms of the batch (the plan's K covers the declared magnitudes)
+        int32_t* kw = (int32_t*)(base + o_count + 64);
+        rc = lsx_row_bound_primes(ctx, job, kw);
+        if (rc != LSX_OK) return rc;
+        a.kword = kw;
+    } else {
+        ctx->last_kword = nullptr;
+    }
     rc = launch_shape(ctx, a, shape);
     if (rc != LSX_OK) return rc;
     // bad-prime matrices (normally none): tile path in list mode, scratch behind the list

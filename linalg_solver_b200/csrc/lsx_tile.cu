@@ -55,11 +55,24 @@ struct TileArgs {
 // assumes 40: 10 primes instead of 12 for the 64 x 64 inverse, 15 instead of 21 for the rank-48 kernel bases.
 struct BoundArgs {
     const int32_t* A;
-    const int32_t* bvec;
+    const int32_t* bvec;        // right-hand side of a solve (kept out of the row norms, see below) or NULL
     int64_t batch;
-    int m, n_in, r_top, right_identity;
+    int m, n_in, r, r_top, right_identity;
     int32_t* kword;             // [0] = max over matrices of ceil(256 log2 bound), [1] = prime count
 };
+// With a right-hand side b the minors are of two kinds.  Those without the column b have order <= r and rows that are
+// sub-rows of A: at most T_r = the product of the r largest row norms of A.  Those with it (the particular solution,
+// and the entries of the zero-left rows that decide consistency, order r_top) expand along that column into
+// sum_i +- b_i M_i with minors M_i of A of order r_top - 1: at most |b|_1 T_(r_top - 1).  Folding b into the row norms
+// instead would cost every row the magnitude of b (b = A x makes |b_i| as large as a whole row norm of A).
+__device__ __forceinline__ int bound_word(double t_r, double t_s1, double b1, bool has_b) {
+    double tot = t_r;
+    if (has_b) {
+        const double lb = b1 > 1.0 ? log2(b1) * (1.0 + 1e-12) : 0.0;
+        tot = fmax(t_r, lb + t_s1);
+    }
+    return (int)ceil(tot * 256.0) + 1;
+}
 
 __global__ void __launch_bounds__(128) k_row_bound(const BoundArgs a) {
     __shared__ double lg_all[4][256];
@@ -78,27 +91,81 @@ __global__ void __launch_bounds__(128) k_row_bound(const BoundArgs a) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (a.right_identity) s += 1.0;
-        if (a.bvec) {
-            const double b = (double)a.bvec[mat * m + r];
-            s += b * b;
-        }
         if (lane == 0) lg[r] = s > 1.0 ? 0.5 * log2(s) * (1.0 + 1e-12) : 0.0;
     }
     __syncwarp();
-    double tot = 0.0;
+    double b1 = 0.0;
+    if (a.bvec)
+        for (int r = lane; r < m; r += 32) b1 += fabs((double)a.bvec[mat * m + r]);
+    double t_r = 0.0, t_s1 = 0.0;               // sums over the a.r / a.r_top - 1 largest
     for (int r = lane; r < m; r += 32) {
         const double v = lg[r];
-        bool take = true;
-        if (a.r_top < m) {                      // the r_top largest: position of row r in the descending order
-            int above = 0;
+        int above = 0;                          // position of row r in the descending order
+        if (a.r < m || a.bvec)
             for (int q = 0; q < m; ++q) above += (lg[q] > v || (lg[q] == v && q < r)) ? 1 : 0;
-            take = above < a.r_top;
-        }
-        if (take) tot += v;
+        if (above < (a.bvec ? a.r : a.r_top)) t_r += v;
+        if (above < a.r_top - 1) t_s1 += v;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0) atomicMax(a.kword, (int)ceil(tot * 256.0) + 1);
+    for (int o = 16; o > 0; o >>= 1) {
+        t_r += __shfl_xor_sync(0xffffffffu, t_r, o);
+        t_s1 += __shfl_xor_sync(0xffffffffu, t_s1, o);
+        b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+    }
+    if (lane == 0) atomicMax(a.kword, bound_word(t_r, t_s1, b1, a.bvec != nullptr));
+}
+
+// Small shapes (the sub-warp kernel's: m <= 32, n_in <= 33): one thread per ROW, the rows of a matrix next to each
+// other in the CTA, their logarithms exchanged through shared memory.
+__global__ void __launch_bounds__(256) k_row_bound_small(const BoundArgs a) {
+    __shared__ double lg[256];
+    __shared__ double part[3][256];
+    const int m = a.m, n = a.n_in;
+    const int per = 256 / m;                                    // matrices per CTA
+    const int q = threadIdx.x / m, r = threadIdx.x - q * m;
+    const int64_t mat = (int64_t)blockIdx.x * per + q;
+    const bool live = q < per && mat < a.batch;
+    double v = 0.0, babs = 0.0;
+    if (live) {
+        const int32_t* row = a.A + (mat * m + r) * (int64_t)n;
+        double s = a.right_identity ? 1.0 : 0.0;
+        if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(a.A) & 15) == 0) {
+            const int4* row4 = reinterpret_cast<const int4*>(row);
+            for (int c = 0; c < (n >> 2); ++c) {
+                const int4 x = row4[c];
+                s += (double)x.x * (double)x.x + (double)x.y * (double)x.y + (double)x.z * (double)x.z +
+                     (double)x.w * (double)x.w;
+            }
+        } else {
+            for (int c = 0; c < n; ++c) {
+                const double x = (double)row[c];
+                s += x * x;
+            }
+        }
+        if (a.bvec) babs = fabs((double)a.bvec[mat * m + r]);
+        v = s > 1.0 ? 0.5 * log2(s) * (1.0 + 1e-12) : 0.0;
+    }
+    lg[threadIdx.x] = v;
+    __syncthreads();
+    int above = 0;
+    if (live && (a.r < m || a.bvec))
+        for (int t = 0; t < m; ++t) {
+            const double o = lg[q * m + t];
+            above += (o > v || (o == v && t < r)) ? 1 : 0;
+        }
+    part[0][threadIdx.x] = (live && above < (a.bvec ? a.r : a.r_top)) ? v : 0.0;
+    part[1][threadIdx.x] = (live && above < a.r_top - 1) ? v : 0.0;
+    part[2][threadIdx.x] = babs;
+    __syncthreads();
+    if (live && r == 0) {
+        double t_r = 0.0, t_s1 = 0.0, b1 = 0.0;
+        for (int t = 0; t < m; ++t) {
+            t_r += part[0][q * m + t];
+            t_s1 += part[1][q * m + t];
+            b1 += part[2][q * m + t];
+        }
+        atomicMax(a.kword, bound_word(t_r, t_s1, b1, a.bvec != nullptr));
+    }
 }
 
 __global__ void k_bound_to_primes(int32_t* kword, int K) {
@@ -319,6 +386,11 @@ __global__ void __launch_bounds__(16 * TYN, TYN == 16 ? ((RA * CB <= 32) ? 3 : 2
         // that lose a factor R per step while S is a Montgomery word: the cell value is S / R).
         const bool lazy_id = a.right_identity && (a.n_in & 15) == 0 && n == a.n_in + m;
         const int nleft = a.n_in >> 4;         // 16-column blocks of the left part
+        // homogeneous system (kernel(), linalg.py:749-756): the right-hand side is declared zero (entries above the
+        // declared magnitude are flagged at the load) and row operations keep it zero; when it has its last 16-column
+        // block to itself that block is never updated (64 x 65: 4 live blocks of 5)
+        const int cb_live = (!a.right_identity && a.bvec && a.b_abs_max == 0 && n == a.n_in + 1 && (a.n_in & 15) == 0 &&
+                             n > 16 * (CB - 1)) ? CB - 1 : CB;
         int rb_on = 0;
         uint8_t* prof = a.prof + ((int64_t)kslot * a.cap + slot) * bar;
         // The pivot columns are walked block by block with the 16-column block index JB a COMPILE-TIME constant (the
@@ -403,7 +475,7 @@ __global__ void __launch_bounds__(16 * TYN, TYN == 16 ? ((RA * CB <= 32) ? 3 : 2
             __syncthreads();
             // 4. update (register resident)
             const int b0 = tri ? ((j + 1) >> 4) : 0;        // blocks left of the pivot column are finished
-            const int b1 = lazy_id ? nleft + rb_on : CB;    // right blocks that are still pure unit columns
+            const int b1 = lazy_id ? nleft + rb_on : cb_live;   // right blocks that are still pure unit columns
 #pragma unroll
             for (int ib = 0; ib < CB; ++ib) {
                 if (ib >= b0 && ib < b1) {
@@ -1034,6 +1106,35 @@ size_t lsx_generic_ws_bytes(const ElimJob& job, int64_t batch) {
 // the K plan primes are used and matrices whose primes disagree are appended to an internal
 // retry list and recomputed with K + LSX_RETRY_EXTRA primes.  Scratch is taken from the ctx
 // workspace starting at byte ws_offset (the caller has reserved lsx_generic_ws_bytes).
+// kword[0..1] <- the prime count the matrices of `job` need (see k_row_bound); enqueued on the ctx's stream.
+int lsx_row_bound_primes(lsx_ctx* ctx, const ElimJob& job, int32_t* kword) {
+    LSX_CUDA_TRY(ctx, cudaMemsetAsync(kword, 0, 8, ctx->stream));
+    const int m = job.m, n = job.n, bar = job.bar;
+    BoundArgs ba{};
+    ba.A = job.A;
+    ba.bvec = (!job.right_identity && n > job.n_in) ? job.bvec : nullptr;
+    ba.batch = job.batch;
+    ba.m = m;
+    ba.n_in = job.n_in;
+    ba.right_identity = job.right_identity;
+    int r = m < bar ? m : bar;
+    if (job.max_rank > 0 && job.max_rank < r) r = job.max_rank;
+    ba.r = r;
+    ba.r_top = (n > bar && r < m) ? r + 1 : r;              // zero-left rows hold minors of order r + 1
+    ba.kword = kword;
+    if (m <= 32 && job.n_in <= 33) {
+        const int per = 256 / m;
+        k_row_bound_small<<<(unsigned)((job.batch + per - 1) / per), 256, 0, ctx->stream>>>(ba);
+    } else {
+        k_row_bound<<<(unsigned)((job.batch + 3) / 4), 128, 0, ctx->stream>>>(ba);
+    }
+    k_bound_to_primes<<<1, 1, 0, ctx->stream>>>(kword, job.K);
+    ctx->launches += 2;
+    ctx->last_kword = kword;
+    LSX_CUDA_TRY(ctx, cudaGetLastError());
+    return LSX_OK;
+}
+
 static int run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, const int32_t* list_count,
                        int list_cap, size_t ws_offset, const int32_t* kword_parent);
 
@@ -1086,23 +1187,9 @@ static int run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, co
     const int32_t* kword = kword_parent;
     if (!list_mode && K > 1 && job.op != LSX_OP_RANK && !getenv("LSX_NO_DATA_BOUND")) {
         int32_t* kw = (int32_t*)(base + w.o_kword);
-        LSX_CUDA_TRY(ctx, cudaMemsetAsync(kw, 0, 8, ctx->stream));
-        BoundArgs ba{};
-        ba.A = job.A;
-        ba.bvec = (!job.right_identity && n > job.n_in) ? job.bvec : nullptr;
-        ba.batch = job.batch;
-        ba.m = m;
-        ba.n_in = job.n_in;
-        ba.right_identity = job.right_identity;
-        int r = m < bar ? m : bar;
-        if (job.max_rank > 0 && job.max_rank < r) r = job.max_rank;
-        ba.r_top = (n > bar && r < m) ? r + 1 : r;          // zero-left rows hold minors of order r + 1
-        ba.kword = kw;
-        k_row_bound<<<(unsigned)((job.batch + 3) / 4), 128, 0, ctx->stream>>>(ba);
-        k_bound_to_primes<<<1, 1, 0, ctx->stream>>>(kw, K);
-        ctx->launches += 2;
+        const int brc = lsx_row_bound_primes(ctx, job, kw);
+        if (brc != LSX_OK) return brc;
         kword = kw;
-        ctx->last_kword = kw;
     } else if (!list_mode) {
         ctx->last_kword = nullptr;
     }

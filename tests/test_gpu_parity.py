@@ -911,6 +911,25 @@ def test_prime_count_from_row_norms(eng, monkeypatch):
     assert ok.any() and not ok.all()
     for f in ("den", "particular", "generators", "pivot_col", "rank"):
         assert np.array_equal(getattr(x, f)[ok], getattr(y, f)[ok]), f
+    # the fused sub-warp kernel takes the same word (thread-per-row bound kernel): config 3 shape, 4 -> 3 primes
+    Bm = rng.integers(-5, 6, size=(300, 16, 10)); Cm = rng.integers(-5, 6, size=(300, 10, 16))
+    S = np.einsum("bik,bkj->bij", Bm, Cm).astype(np.int32)
+    b = rng.integers(-5, 6, size=(300, 16)).astype(np.int32)
+    b[::2] = np.einsum("bij,bj->bi", S[::2], rng.integers(-5, 6, size=(150, 16)))
+    pl = eng.plan_solve(16, 16, 250, int(np.abs(b).max()), 10, 6)
+    x, y, kx, ky = both(lambda: eng.solve_batch(S, b, plan=pl))
+    assert ky == 0 and 1 <= kx < pl.n_primes, (kx, pl.n_primes)
+    assert np.array_equal(x.status, y.status)
+    ok = (x.status & 2) == 0
+    assert ok.any() and not ok.all()
+    for f in ("den", "particular", "generators", "pivot_col", "rank"):
+        assert np.array_equal(getattr(x, f)[ok], getattr(y, f)[ok]), f
+    for mm, nn, bar in ((6, 7, 6), (12, 12, 12), (20, 24, 18), (32, 33, 32)):
+        M = rng.integers(-50, 51, size=(40, mm, nn)).astype(np.int32)
+        M[1] = 50                                                            # worst case for the declared magnitude
+        x, y, kx, ky = both(lambda: eng.rref_batch(M, bar, a_abs_max=50, b_abs_max=50))
+        for f in ("status", "num", "den", "pivot_col", "rank"):
+            assert np.array_equal(getattr(x, f), getattr(y, f)), (mm, nn, f)
     # the bound is attained: det(diag) = product of the row norms; declared magnitude far above the data
     for n, v, amax in ((40, 1000, 50000), (33, 46340, 50000), (64, 3, 100)):
         D = np.zeros((3, n, n), dtype=np.int32)
