@@ -549,6 +549,7 @@ def measure_batch(ctx, workload, steps, warmup, cpu):
     eng.timing_enable(False)
     launches = eng.launch_count - launches0
     clocks = sampler.stop(t0, t1)
+    primes_run = eng.last_prime_count()      # 0: fused small kernels (no modular primes) or a single prime
 
     # ---- end to end through the C-ABI with host buffers (pinned): H2D + kernels + D2H per step ----
     job.make_host_outputs()
@@ -593,15 +594,25 @@ def measure_batch(ctx, workload, steps, warmup, cpu):
             "traffic": None, "kernel_ms": k_ms, "kernel_launches_per_step": per_step,
             "algorithmic_bytes_per_matrix": alg_bytes,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"}
+    if primes_run:
+        roof["primes_run"] = primes_run
+        roof["primes_note"] = ("the plan's %d primes cover the declared magnitudes; the row-norm Hadamard bound of the batch's own "
+                               "matrices (k_row_bound, inside the timed step) needs %d" % (int(plan.n_primes), primes_run))
     cnt = ctx.counts.get(workload)
-    if cnt and cnt.get("batch") == batch:
+    if cnt and (cnt.get("batch") == batch or cnt.get("per_matrix")) \
+            and cnt.get("primes_run", primes_run) == primes_run:
         # executed figures: warp instructions of the dominant kernel(s) per step (ncu capture of this build) over
-        # the issue slots the live-timed kernel had: 4 schedulers x SMs x cycles at the SM clock sampled in this run
+        # the issue slots the live-timed kernel had: 4 schedulers x SMs x cycles at the SM clock sampled in this run.
+        # per_matrix: the step runs the captured launch batch / capture-batch times (chunks of the same kernel)
+        scale = batch / cnt["batch"]
         slots = 4.0 * 148 * (k_ms * 1e-3) * sm_run * 1e6
-        roof["traffic"] = cnt.get("dram_bytes_per_step")
-        roof["issue_slots"] = {"warp_instructions_per_step": cnt["warp_inst_per_step"], "slots": slots,
-                               "frac": cnt["warp_inst_per_step"] / slots, "sm_mhz": sm_run,
+        roof["traffic"] = cnt.get("dram_bytes_per_step") * scale if cnt.get("dram_bytes_per_step") else None
+        roof["issue_slots"] = {"warp_instructions_per_step": cnt["warp_inst_per_step"] * scale, "slots": slots,
+                               "frac": cnt["warp_inst_per_step"] * scale / slots, "sm_mhz": sm_run,
                                "source": cnt.get("source")}
+        if cnt.get("fmaheavy_busy_ncu") is not None:
+            roof["int_pipe"] = {"fmaheavy_busy_ncu": cnt["fmaheavy_busy_ncu"], "issue_slots_busy_ncu": cnt.get("issue_slots_busy_ncu"),
+                                "kernel": cnt.get("kernel"), "source": cnt.get("source")}
     if workload == "c2":
         # the fused 8x8 kernel computes over the integers (Bareiss): no modular multiply-subtracts to count.  Its limiting
         # unit is the fmaheavy pipe (IMAD / IMAD.WIDE), whose busy fraction is an ncu figure of the same kernel source
@@ -610,7 +621,7 @@ def measure_batch(ctx, workload, steps, warmup, cpu):
                                       "under ncu at 128 us); static mix: profiles/r02o_sass_hist_k_inv_tpm8_bareiss.txt"}
     elif workload in ALG_OPS:
         # ALGORITHMIC count, not executed instructions
-        n_pr = int(plan.n_primes)
+        n_pr = primes_run or int(plan.n_primes)
         ip_peak = MONT_MUL_PER_SM_CLK * 148 * sm_max * 1e6
         ip_ach = ALG_OPS[workload] * n_pr * batch / (k_ms * 1e-3)
         roof["algorithmic_int"] = {"ops_per_matrix": ALG_OPS[workload] * n_pr, "achieved": ip_ach, "peak": ip_peak,

@@ -57,7 +57,7 @@ struct BoundArgs {
     const int32_t* A;
     const int32_t* bvec;        // right-hand side of a solve (kept out of the row norms, see below) or NULL
     int64_t batch;
-    int m, n_in, r, r_top, right_identity;
+    int m, n_in, r, r_top, right_identity, exact_int;
     int32_t* kword;             // [0] = max over matrices of ceil(256 log2 bound), [1] = prime count
 };
 // With a right-hand side b the minors are of two kinds.  Those without the column b have order <= r and rows that are
@@ -74,50 +74,13 @@ __device__ __forceinline__ int bound_word(double t_r, double t_s1, double b1, bo
     return (int)ceil(tot * 256.0) + 1;
 }
 
-__global__ void __launch_bounds__(128) k_row_bound(const BoundArgs a) {
-    __shared__ double lg_all[4][256];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t mat = (int64_t)blockIdx.x * 4 + w;
-    if (mat >= a.batch) return;
-    double* lg = lg_all[w];
-    const int m = a.m, n = a.n_in;
-    for (int r = 0; r < m; ++r) {
-        const int32_t* row = a.A + (mat * m + r) * (int64_t)n;
-        double s = 0.0;
-        for (int c = lane; c < n; c += 32) {
-            const double v = (double)row[c];
-            s += v * v;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (a.right_identity) s += 1.0;
-        if (lane == 0) lg[r] = s > 1.0 ? 0.5 * log2(s) * (1.0 + 1e-12) : 0.0;
-    }
-    __syncwarp();
-    double b1 = 0.0;
-    if (a.bvec)
-        for (int r = lane; r < m; r += 32) b1 += fabs((double)a.bvec[mat * m + r]);
-    double t_r = 0.0, t_s1 = 0.0;               // sums over the a.r / a.r_top - 1 largest
-    for (int r = lane; r < m; r += 32) {
-        const double v = lg[r];
-        int above = 0;                          // position of row r in the descending order
-        if (a.r < m || a.bvec)
-            for (int q = 0; q < m; ++q) above += (lg[q] > v || (lg[q] == v && q < r)) ? 1 : 0;
-        if (above < (a.bvec ? a.r : a.r_top)) t_r += v;
-        if (above < a.r_top - 1) t_s1 += v;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        t_r += __shfl_xor_sync(0xffffffffu, t_r, o);
-        t_s1 += __shfl_xor_sync(0xffffffffu, t_s1, o);
-        b1 += __shfl_xor_sync(0xffffffffu, b1, o);
-    }
-    if (lane == 0) atomicMax(a.kword, bound_word(t_r, t_s1, b1, a.bvec != nullptr));
-}
-
-// Small shapes (the sub-warp kernel's: m <= 32, n_in <= 33): one thread per ROW, the rows of a matrix next to each
-// other in the CTA, their logarithms exchanged through shared memory.
-__global__ void __launch_bounds__(256) k_row_bound_small(const BoundArgs a) {
+// One thread per ROW, the rows of a matrix next to each other in the CTA (256 / m matrices per CTA), their logarithms
+// exchanged through shared memory.  Declared magnitudes up to 2^27 (every call of the benchmarks): the squares are summed
+// exactly in 64-bit integers and the logarithm is a float one taken of the sum rounded UP, plus 1e-4 (log2f is good to
+// a few ulp: < 1e-5 on values below 64); beyond that everything in double.  An entry above the declared magnitude can
+// wrap the integer sum -- that matrix is flagged LSX_ST_BOUND by the elimination kernel and returns nothing, and a
+// smaller contribution of ITS rows does not affect the bound of the others.
+__global__ void __launch_bounds__(256) k_row_bound(const BoundArgs a) {
     __shared__ double lg[256];
     __shared__ double part[3][256];
     const int m = a.m, n = a.n_in;
@@ -128,26 +91,33 @@ __global__ void __launch_bounds__(256) k_row_bound_small(const BoundArgs a) {
     double v = 0.0, babs = 0.0;
     if (live) {
         const int32_t* row = a.A + (mat * m + r) * (int64_t)n;
-        double s = a.right_identity ? 1.0 : 0.0;
-        if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(a.A) & 15) == 0) {
-            const int4* row4 = reinterpret_cast<const int4*>(row);
-            for (int c = 0; c < (n >> 2); ++c) {
-                const int4 x = row4[c];
-                s += (double)x.x * (double)x.x + (double)x.y * (double)x.y + (double)x.z * (double)x.z +
-                     (double)x.w * (double)x.w;
+        const bool vec = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(a.A) & 15) == 0;
+        if (a.exact_int) {
+            unsigned long long s = a.right_identity ? 1ull : 0ull;
+            if (vec) {
+                const int4* row4 = reinterpret_cast<const int4*>(row);
+                for (int c = 0; c < (n >> 2); ++c) {
+                    const int4 x = row4[c];
+                    s += (unsigned long long)((long long)x.x * x.x) + (unsigned long long)((long long)x.y * x.y) +
+                         (unsigned long long)((long long)x.z * x.z) + (unsigned long long)((long long)x.w * x.w);
+                }
+            } else {
+                for (int c = 0; c < n; ++c) s += (unsigned long long)((long long)row[c] * row[c]);
             }
+            v = s > 1ull ? (double)(0.5f * log2f(__ull2float_ru(s)) + 1e-4f) : 0.0;
         } else {
+            double s = a.right_identity ? 1.0 : 0.0;
             for (int c = 0; c < n; ++c) {
                 const double x = (double)row[c];
                 s += x * x;
             }
+            v = s > 1.0 ? 0.5 * log2(s) * (1.0 + 1e-12) : 0.0;
         }
         if (a.bvec) babs = fabs((double)a.bvec[mat * m + r]);
-        v = s > 1.0 ? 0.5 * log2(s) * (1.0 + 1e-12) : 0.0;
     }
     lg[threadIdx.x] = v;
     __syncthreads();
-    int above = 0;
+    int above = 0;                                              // position of my row in the descending order
     if (live && (a.r < m || a.bvec))
         for (int t = 0; t < m; ++t) {
             const double o = lg[q * m + t];
@@ -1122,12 +1092,9 @@ int lsx_row_bound_primes(lsx_ctx* ctx, const ElimJob& job, int32_t* kword) {
     ba.r = r;
     ba.r_top = (n > bar && r < m) ? r + 1 : r;              // zero-left rows hold minors of order r + 1
     ba.kword = kword;
-    if (m <= 32 && job.n_in <= 33) {
-        const int per = 256 / m;
-        k_row_bound_small<<<(unsigned)((job.batch + per - 1) / per), 256, 0, ctx->stream>>>(ba);
-    } else {
-        k_row_bound<<<(unsigned)((job.batch + 3) / 4), 128, 0, ctx->stream>>>(ba);
-    }
+    ba.exact_int = (job.a_abs_max <= (1 << 27) && job.b_abs_max <= (1 << 27)) ? 1 : 0;
+    const int per = 256 / m;                                // m <= 254 on every path that gets here
+    k_row_bound<<<(unsigned)((job.batch + per - 1) / per), 256, 0, ctx->stream>>>(ba);
     k_bound_to_primes<<<1, 1, 0, ctx->stream>>>(kword, job.K);
     ctx->launches += 2;
     ctx->last_kword = kword;

@@ -1,7 +1,5 @@
 set -x
-python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/r02ak_pytest_parity.txt 2>&1; tail -5 gpurun_out/r02ak_pytest_parity.txt
-{
-echo "== row-norm prime count (default)"; python tools/time_configs.py c3 c4inv c4ker
-echo "== LSX_NO_DATA_BOUND=1"; LSX_NO_DATA_BOUND=1 python tools/time_configs.py c3
-} > gpurun_out/r02ak_c3_c4.txt 2>&1
-cat gpurun_out/r02ak_c3_c4.txt
+python -m pytest tests -x -q -m gpu > gpurun_out/r02an_pytest_gpu.txt 2>&1; tail -5 gpurun_out/r02an_pytest_gpu.txt
+( time python bench.py ) > gpurun_out/r02an_bench_1gpu.json 2> gpurun_out/r02an_bench_1gpu.err
+tail -c 300 gpurun_out/r02an_bench_1gpu.json; tail -5 gpurun_out/r02an_bench_1gpu.err
+python tools/time_configs.py c1 c3 c4inv c4ker > gpurun_out/r02an_time_configs.txt 2>&1; cat gpurun_out/r02an_time_configs.txt
