@@ -603,9 +603,13 @@ int lsx_run_subwarp(lsx_ctx* ctx, const ElimJob& job, int* handled) {
     }
     rc = launch_shape(ctx, a, shape);
     if (rc != LSX_OK) return rc;
-    // bad-prime matrices (normally none): tile path in list mode, scratch behind the list
-    rc = lsx_run_generic(ctx, job, rlist, rcount, LSX_RETRY_CAP, o_child);
-    if (rc != LSX_OK) return rc;
+    // bad-prime matrices (normally none): tile path in list mode, scratch behind the list.  A plan of ONE prime has no
+    // such matrices: the prime exceeds twice the Hadamard bound, so no non-zero minor vanishes modulo it and there is
+    // no second profile to disagree with -- the three launches of the empty retry pass were half of a config 1 step.
+    if (job.K > 1) {
+        rc = lsx_run_generic(ctx, job, rlist, rcount, LSX_RETRY_CAP, o_child);
+        if (rc != LSX_OK) return rc;
+    }
     *handled = 1;
     return LSX_OK;
 }

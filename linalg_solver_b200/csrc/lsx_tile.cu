@@ -1323,8 +1323,9 @@ static int run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, co
     }
     LSX_CUDA_TRY(ctx, cudaGetLastError());
 
-    if (!list_mode) {
-        // recompute flagged matrices with replacement primes (a no-op grid when none was flagged)
+    if (!list_mode && K > 1) {
+        // recompute flagged matrices with replacement primes (a no-op grid when none was flagged; a single prime
+        // above twice the bound cannot be flagged)
         rc = run_generic(ctx, job, rlist, rcount, LSX_RETRY_CAP, ws_offset + w.total, kword);
         if (rc != LSX_OK) return rc;
     }
