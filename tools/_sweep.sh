@@ -1,4 +1,11 @@
 set -x
-timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/r02au_pytest_gpu.txt 2>&1; tail -4 gpurun_out/r02au_pytest_gpu.txt
-timeout 200 python tools/time_configs.py c1 > gpurun_out/r02au_c1.txt 2>&1; cat gpurun_out/r02au_c1.txt
-timeout 300 python bench.py --workload c1 --no-cpu > gpurun_out/r02au_bench_c1.json 2> gpurun_out/r02au_bench_c1.err; tail -c 600 gpurun_out/r02au_bench_c1.json
+for mb in 8192 2048; do
+  for w in c4inv c4ker; do
+    LSX_WS_MB=$mb timeout 300 python bench.py --workload $w --no-cpu --steps 5 > gpurun_out/r02av_ws${mb}_$w.json 2> gpurun_out/r02av_ws${mb}_$w.err
+    python -c "
+import json,sys
+d=json.loads(open('gpurun_out/r02av_ws${mb}_$w.json').read().strip().splitlines()[-1])
+print('ws_mb', $mb, '$w', d['value'], d['ms_per_step'], d['roofline']['kernel_ms'], 'e2e', d['e2e']['value'], 'launches', d['gpu_launches'])
+" | tee -a gpurun_out/r02av_ws_sweep.txt
+  done
+done
