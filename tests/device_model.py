@@ -181,6 +181,32 @@ def plan_bits(log2_bound):
     return K, L
 
 
+def row_norm_bits(A, b, bar, max_rank=0, right_identity=False):
+    """Mirror of k_row_bound / bound_word (lsx_tile.cu): log2 of the Hadamard bound over the row norms of the matrix at
+    hand for every integer an elimination of [A | right part] returns, in the kernel's 1/256-bit fixed point.  A holds
+    the n_in stored columns (a general right block included), b is the right-hand side of a solve or None, and
+    right_identity says that an identity block follows A.  plan_bits() of the result is the prime count the device runs
+    (never above the plan's)."""
+    m, n_in = len(A), len(A[0])
+    n = n_in + (1 if b is not None else 0) + (m if right_identity else 0)
+    lg = []
+    for row in A:
+        s = sum(x * x for x in row) + (1 if right_identity else 0)
+        lg.append(0.5 * math.log2(s) * (1.0 + 1e-12) + 1e-4 if s > 1 else 0.0)
+    r = min(m, bar)
+    if 0 < max_rank < r:
+        r = max_rank
+    r_top = r + 1 if (n > bar and r < m) else r
+    top = sorted(lg, reverse=True)
+    if b is None:
+        tot = sum(top[:r_top])
+    else:
+        b1 = sum(abs(x) for x in b)
+        lb = math.log2(b1) * (1.0 + 1e-12) if b1 > 1 else 0.0
+        tot = max(sum(top[:r]), lb + sum(top[:r_top - 1]))
+    return (math.ceil(tot * 256.0) + 1) / 256.0
+
+
 def inverse_inplace_words(A, P):
     """Mirror of the fused small-matrix kernel (lsx_small.cu, k_inv_tpm): in-place uniform-scale
     Gauss-Jordan inversion of one n x n matrix modulo ONE prime larger than every minor of A.

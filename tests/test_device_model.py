@@ -76,6 +76,72 @@ def test_random_shapes():
         check_against_oracle(A, rnd.randint(1, n))
 
 
+def test_row_norm_bound_is_rigorous_and_never_above_the_plan():
+    """The prime count the device takes from the row norms of the matrices at hand (k_row_bound, mirrored by
+    dm.row_norm_bits): every exact integer of the elimination stays below the bound, the count never exceeds the
+    plan's, and the reconstruction from that many primes is the one from the plan's count.  Shapes with a general
+    right block, an identity block ([A|I], incl. singular A), right-hand sides of solves (consistent and not),
+    rank-deficient products with a declared maximal rank, zero rows and worst-case rows."""
+    rng = random.Random(20260219)
+    def ints(m, n, lo):
+        return [[rng.randint(-lo, lo) for _ in range(n)] for _ in range(m)]
+    def product(m, n, rk, lo):
+        B, C = ints(m, rk, lo), ints(rk, n, lo)
+        return [[sum(B[i][k] * C[k][j] for k in range(rk)) for j in range(n)] for i in range(m)]
+    cases = []
+    for _ in range(40):
+        m, n = rng.randint(1, 7), rng.randint(1, 8)
+        bar = rng.randint(1, n)
+        A = ints(m, n, rng.choice([1, 5, 50, 3000]))
+        if rng.random() < 0.3:
+            A[rng.randrange(m)] = [0] * n
+        cases.append(("rref", A, None, bar, 0, False))
+    for _ in range(25):
+        m = rng.randint(2, 7)
+        n = rng.randint(2, 7)
+        rk = rng.randint(1, min(m, n))
+        A = product(m, n, rk, 5)
+        x = [rng.randint(-5, 5) for _ in range(n)]
+        b = [sum(A[i][j] * x[j] for j in range(n)) for i in range(m)] if rng.random() < 0.6 else [rng.randint(-9, 9) for _ in range(m)]
+        cases.append(("solve", A, b, n, rk, False))
+    for _ in range(20):
+        m = rng.randint(1, 6)
+        A = ints(m, m, rng.choice([1, 5, 100]))
+        if rng.random() < 0.3 and m > 1:
+            A[-1] = list(A[0])
+        cases.append(("inverse", A, None, m, 0, True))
+    for _ in range(8):                                     # one large entry sets the declared magnitude, the rest is small
+        m = rng.randint(7, 10)
+        A = ints(m, m + 1, 5)
+        A[rng.randrange(m)][rng.randrange(m)] = 30000
+        cases.append(("rref", A, None, m, 0, False))
+        B = ints(m, m, 3)
+        B[0][0] = 2000
+        cases.append(("inverse", B, None, m, 0, True))
+    cases.append(("rref", [[7, 7, 7], [7, 7, 7], [7, 7, 7]], None, 3, 0, False))           # every entry at the declared magnitude
+    cases.append(("inverse", [[1000, 0, 0], [0, -1000, 0], [0, 0, 1000]], None, 3, 0, True))  # the bound is attained
+    fewer = 0
+    for op, A, b, bar, max_rank, ident in cases:
+        m = len(A)
+        full = [list(row) + ([b[i]] if b is not None else []) + ([1 if i == j else 0 for j in range(m)] if ident else [])
+                for i, row in enumerate(A)]
+        n = len(full[0])
+        amax = max(1, max(abs(x) for r in A for x in r))
+        bmax = max(1, max(abs(x) for x in b)) if b is not None else (amax if not ident else 1)
+        Kp, _ = dm.plan_bits(dm.log2_minor_bound(m, bar, n > bar, amax, bmax, ident, max_rank))
+        bits = dm.row_norm_bits(A, b, bar, max_rank, ident)
+        Ke = min(Kp, dm.plan_bits(bits)[0])
+        Kbig = Kp + 2
+        N, d, prof, rank = modular_rref(full, bar, Kbig)
+        assert max_rank == 0 or rank <= max_rank
+        biggest = max([abs(d)] + [abs(x) for r in N for x in r])
+        assert biggest <= 2.0 ** bits * (1 + 1e-9), (op, A, b, bar, biggest, bits)
+        N2, d2, prof2, rank2 = modular_rref(full, bar, Ke)
+        assert (N2, d2, prof2, rank2) == (N, d, prof, rank), (op, A, b, bar, Ke, Kp)
+        fewer += Ke < Kp
+    assert fewer >= 5
+
+
 def test_garner_signed_range():
     ps = PRIMES[:3]
     M = ps[0] * ps[1] * ps[2]
