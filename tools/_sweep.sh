@@ -1,3 +1,4 @@
 set -x
-( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 ) > gpurun_out/r02aw_bench_8gpu.json 2> gpurun_out/r02aw_bench_8gpu.err
-tail -c 300 gpurun_out/r02aw_bench_8gpu.json; tail -5 gpurun_out/r02aw_bench_8gpu.err
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02ax_smoke.txt 2>&1; tail -2 gpurun_out/r02ax_smoke.txt
+timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/r02ax_pytest_gpu.txt 2>&1; tail -4 gpurun_out/r02ax_pytest_gpu.txt
+nvidia-smi --query-gpu=memory.used --format=csv
