@@ -528,11 +528,17 @@ def measure_batch(ctx, workload, steps, warmup, cpu):
     if ctx.rank == 0:
         job.check_against_oracle()
 
+    # config 1 is launch bound by construction (three calls on 10k 4x4 matrices: 38 us of kernels in a 79 us step):
+    # its device-resident step is captured once into a CUDA graph (Engine.capture) and replayed; the kernels are the
+    # same, the library's per-kernel event timing is off for it (kernel_ms = the step)
+    captured = eng.capture(job.step_device) if workload == "c1" else None
+    step_device = captured.replay if captured else job.step_device
     for _ in range(warmup):
-        job.step_device()
+        step_device()
     ctx.barrier()
     launches0 = eng.launch_count
-    eng.timing_enable(True)
+    if not captured:
+        eng.timing_enable(True)
     sampler = ClockSampler(ctx.local)
     sampler.start()
     time.sleep(0.25)
@@ -540,12 +546,12 @@ def measure_batch(ctx, workload, steps, warmup, cpu):
     t0 = time.perf_counter()
     ev0.record()
     for _ in range(steps):
-        job.step_device()
+        step_device()
     ev1.record()
     ctx.barrier()
     t1 = time.perf_counter()
     ms_total = ev0.elapsed_time(ev1)
-    kernel_ms = eng.timing_read()
+    kernel_ms = eng.timing_read() if not captured else []
     eng.timing_enable(False)
     launches = eng.launch_count - launches0
     clocks = sampler.stop(t0, t1)
@@ -594,6 +600,9 @@ def measure_batch(ctx, workload, steps, warmup, cpu):
             "traffic": None, "kernel_ms": k_ms, "kernel_launches_per_step": per_step,
             "algorithmic_bytes_per_matrix": alg_bytes,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650"}
+    if captured:
+        roof["kernel_launches_per_step"] = captured.kernels
+        roof["launch"] = "one CUDA graph per step, captured from the three device-memory calls (%d kernels)" % captured.kernels
     if primes_run:
         roof["primes_run"] = primes_run
         roof["primes_note"] = ("the plan's %d primes cover the declared magnitudes; the row-norm Hadamard bound of the batch's own "

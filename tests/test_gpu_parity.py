@@ -869,6 +869,49 @@ def test_register_tiled_kernel_equals_smem_kernel(eng, monkeypatch):
     check_rref_against_oracle(eng, [A.tolist()], 38)
 
 
+def test_device_calls_capture_into_a_cuda_graph(eng):
+    """Device-memory calls only enqueue on the caller's stream, so a sequence of them is capturable into one CUDA graph
+    (Engine.capture): the fused sub-warp kernel (config 1's three calls, a solve with its output memsets), the fused
+    8x8 kernel and the tile path with its row-bound pass and retry pass.  A replay into zeroed outputs gives the words
+    of the direct calls, and the launch count keeps counting."""
+    import dataclasses
+    import torch
+    rng = np.random.Generator(np.random.PCG64(53))
+    def tensors(r):
+        return [getattr(r, f.name) for f in dataclasses.fields(r) if torch.is_tensor(getattr(r, f.name))]
+    A4 = torch.from_numpy(rng.integers(-5, 6, size=(1000, 4, 4), dtype=np.int32)).cuda()
+    A8 = torch.from_numpy(rng.integers(-5, 6, size=(512, 8, 8), dtype=np.int32)).cuda()
+    A20 = torch.from_numpy(rng.integers(-5, 6, size=(40, 20, 20), dtype=np.int32)).cuda()
+    S = torch.from_numpy(rng.integers(-5, 6, size=(300, 6, 9), dtype=np.int32)).cuda()
+    b = torch.from_numpy(rng.integers(-5, 6, size=(300, 6), dtype=np.int32)).cuda()
+    plans = (eng.plan_det(4, 5), eng.plan_rank(4, 4, 5), eng.plan_rref(4, 4, 3, 5, 5), eng.plan_inverse(8, 5),
+             eng.plan_inverse(20, 5), eng.plan_solve(6, 9, 5, 5, 0, 4))
+    res = [eng.det_batch(A4, plan=plans[0]), eng.rank_batch(A4, plan=plans[1]), eng.rref_batch(A4, 3, plan=plans[2]),
+           eng.inverse_batch(A8, plan=plans[3]), eng.inverse_batch(A20, plan=plans[4]), eng.solve_batch(S, b, plan=plans[5])]
+    def step():
+        eng.det_batch(A4, plan=plans[0], out=res[0])
+        eng.rank_batch(A4, plan=plans[1], out=res[1])
+        eng.rref_batch(A4, 3, plan=plans[2], out=res[2])
+        eng.inverse_batch(A8, plan=plans[3], out=res[3])
+        eng.inverse_batch(A20, plan=plans[4], out=res[4])
+        eng.solve_batch(S, b, plan=plans[5], out=res[5])
+    step()
+    torch.cuda.synchronize()
+    want = [t.clone() for r in res for t in tensors(r)]
+    cap = eng.capture(step)
+    assert cap.kernels >= 6
+    for _ in range(2):
+        for r in res:
+            for t in tensors(r):
+                t.zero_()
+        n0 = eng.launch_count
+        cap.replay()
+        torch.cuda.synchronize()
+        assert eng.launch_count - n0 == cap.kernels
+        got = [t for r in res for t in tensors(r)]
+        assert len(got) == len(want) and all(torch.equal(x, y) for x, y in zip(want, got))
+
+
 def test_prime_count_from_row_norms(eng, monkeypatch):
     """The tile path runs only the primes the Hadamard bound of the batch's own row norms needs (k_row_bound), never more
     than the plan: identical words with the data bound switched off, fewer primes on random data, the plan's count on
