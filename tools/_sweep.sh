@@ -1,3 +1,3 @@
 set -x
-( time timeout 900 python bench.py ) > gpurun_out/r02ba_bench_1gpu.json 2> gpurun_out/r02ba_bench_1gpu.err
-tail -c 200 gpurun_out/r02ba_bench_1gpu.json; tail -4 gpurun_out/r02ba_bench_1gpu.err
+timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/r02bb_pytest_gpu.txt 2>&1; tail -6 gpurun_out/r02bb_pytest_gpu.txt
+timeout 200 python tools/time_configs.py c3 > gpurun_out/r02bb_c3.txt 2>&1; cat gpurun_out/r02bb_c3.txt
