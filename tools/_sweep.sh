@@ -1,1 +1,3 @@
-timeout 300 python tools/graph_probe2.py > gpurun_out/r02bc_graph_probe2.txt 2>&1; tail -12 gpurun_out/r02bc_graph_probe2.txt
+set -x
+timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/r02be_pytest_gpu.txt 2>&1; tail -4 gpurun_out/r02be_pytest_gpu.txt
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
