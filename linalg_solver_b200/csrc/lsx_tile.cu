@@ -6,6 +6,11 @@
 // pivot profile (a "bad prime" divided an intermediate pivot candidate) are recomputed here with
 // replacement primes.
 //
+// Kernels of this file: k_row_bound / k_bound_to_primes (prime count from the row norms of the pass's matrices),
+// k_tile_elim (tile in shared memory, any shape), k_tile_reg (tile in registers, up to 128 x 128 cells), k_tile_inv
+// (in-place inverse of a square [A|I] in an m x m register tile), k_verify (pivot profiles of the primes), k_assemble
+// (Garner CRT into the layout of the operation).
+//
 // Algorithm per (matrix, prime) -- mirrors tests/device_model.py::elim_words:
 //   uniform-scale division-free Gauss-Jordan on Montgomery words.  At a pivot step with pivot
 //   value piv (row pi, column j) and current common scale S every row r != pi becomes
