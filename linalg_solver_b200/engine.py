@@ -163,7 +163,9 @@ class Engine:
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         n0 = int(lib.lsx_launch_count(self._ctx))
-        with torch.cuda.graph(graph, stream=side):
+        # thread_local: CUDA calls of OTHER host threads (the NCCL watchdog of an initialised process group polls
+        # events) must not invalidate the capture
+        with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
             fn()
         return CapturedCalls(self, graph, int(lib.lsx_launch_count(self._ctx)) - n0)
 
