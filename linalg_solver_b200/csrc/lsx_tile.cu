@@ -49,6 +49,7 @@ struct TileArgs {
     const int32_t* kword;       // NULL, or kword[1] = primes the data of this pass needs (k_row_bound)
     int rhs_out_of_tile;        // k_tile_reg: the declared-zero right-hand side column n - 1 is not kept in the tile
     int k_extra;                // replacement primes on top of that (list mode)
+    int ktot;                   // primes of the launch: the grid is grid_x * ktot CTAs, prime index fastest
 };
 
 // ---- prime count from the data -------------------------------------------------------------------------------------
@@ -161,14 +162,16 @@ __global__ void __launch_bounds__(T) k_tile_elim(const TileArgs a) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = T / 32;
-    const int kslot = blockIdx.y;
+    // one-dimensional grid, the prime index fastest: the CTAs of one matrix are neighbours in launch order, so its
+    // input is read from DRAM once and served from L2 to the other primes
+    const int kslot = (int)(blockIdx.x % (unsigned)a.ktot), slot0 = (int)(blockIdx.x / (unsigned)a.ktot);
     if (a.kword && kslot >= a.kword[1] + a.k_extra) return;   // more primes than the data of this pass needs
     const PrimeRec P = a.primes[kslot];
     const uint32_t p = P.p, pinv = P.pinv;
     const int64_t nslots = a.list ? min((int64_t)*a.list_count, a.cap) : a.batch;
     const int ncs = a.c1 - a.c0;
 
-    for (int64_t slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+    for (int64_t slot = slot0; slot < nslots; slot += gridDim.x / (unsigned)a.ktot) {
         const int64_t mat = a.list ? (int64_t)a.list[slot] : slot;
         // ---- load the tile as raw words (value = a / R, see device_model.elim_words) ----
         bool bad = false;
@@ -304,14 +307,16 @@ __global__ void __launch_bounds__(16 * TYN, TYN == 16 ? ((RA * CB <= 32) ? 3 : 2
     __shared__ uint8_t inv[TYN * RA];
     const int m = a.m, n = a.n, bar = a.bar;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
-    const int kslot = blockIdx.y;
+    // one-dimensional grid, the prime index fastest: the CTAs of one matrix are neighbours in launch order, so its
+    // input is read from DRAM once and served from L2 to the other primes
+    const int kslot = (int)(blockIdx.x % (unsigned)a.ktot), slot0 = (int)(blockIdx.x / (unsigned)a.ktot);
     if (a.kword && kslot >= a.kword[1] + a.k_extra) return;   // more primes than the data of this pass needs
     const PrimeRec P = a.primes[kslot];
     const uint32_t p = P.p, pinv = P.pinv;
     const int64_t nslots = a.list ? min((int64_t)*a.list_count, a.cap) : a.batch;
     const int ncs = a.c1 - a.c0;
 
-    for (int64_t slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+    for (int64_t slot = slot0; slot < nslots; slot += gridDim.x / (unsigned)a.ktot) {
         const int64_t mat = a.list ? (int64_t)a.list[slot] : slot;
         uint32_t W[RA][CB];
         bool bad = false;
@@ -546,13 +551,15 @@ __global__ void __launch_bounds__(16 * TYN, MINB) k_tile_inv(const TileArgs a) {
     __shared__ uint8_t inv[TYN * RA];
     const int m = a.m;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
-    const int kslot = blockIdx.y;
+    // one-dimensional grid, the prime index fastest: the CTAs of one matrix are neighbours in launch order, so its
+    // input is read from DRAM once and served from L2 to the other primes
+    const int kslot = (int)(blockIdx.x % (unsigned)a.ktot), slot0 = (int)(blockIdx.x / (unsigned)a.ktot);
     if (a.kword && kslot >= a.kword[1] + a.k_extra) return;   // more primes than the data of this pass needs
     const PrimeRec P = a.primes[kslot];
     const uint32_t p = P.p, pinv = P.pinv;
     const int64_t nslots = a.list ? min((int64_t)*a.list_count, a.cap) : a.batch;
 
-    for (int64_t slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+    for (int64_t slot = slot0; slot < nslots; slot += gridDim.x / (unsigned)a.ktot) {
         const int64_t mat = a.list ? (int64_t)a.list[slot] : slot;
         uint32_t W[RA][CB];
         bool bad = false;
@@ -702,7 +709,7 @@ __global__ void __launch_bounds__(16 * TYN, MINB) k_tile_inv(const TileArgs a) {
 
 template <int RA, int CB, int TYN, int MINB>
 int launch_tile_inv(lsx_ctx* ctx, const TileArgs& ta, int Ktot, int64_t grid_x) {
-    dim3 grid((unsigned)grid_x, (unsigned)Ktot);
+    dim3 grid((unsigned)(grid_x * Ktot));      // prime index fastest (TileArgs.ktot == Ktot)
     lsx_timing_begin(ctx);
     k_tile_inv<RA, CB, TYN, MINB><<<grid, 16 * TYN, 0, ctx->stream>>>(ta);
     lsx_timing_end(ctx);
@@ -730,7 +737,7 @@ bool launch_tile_inv_any(lsx_ctx* ctx, const TileArgs& ta, int Ktot, int64_t gri
 
 template <int RA, int CB, int TYN = 16>
 int launch_tile_reg(lsx_ctx* ctx, const TileArgs& ta, int Ktot, int64_t grid_x) {
-    dim3 grid((unsigned)grid_x, (unsigned)Ktot);
+    dim3 grid((unsigned)(grid_x * Ktot));      // prime index fastest (TileArgs.ktot == Ktot)
     lsx_timing_begin(ctx);
     k_tile_reg<RA, CB, TYN><<<grid, 16 * TYN, 0, ctx->stream>>>(ta);
     lsx_timing_end(ctx);
@@ -1056,7 +1063,7 @@ int launch_tile(lsx_ctx* ctx, const TileArgs& ta, int Ktot, int64_t grid_x, size
         cudaError_t e = cudaFuncSetAttribute(k_tile_elim<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return lsx_fail(ctx, LSX_ERR_CUDA, "smem attribute: %s", cudaGetErrorString(e));
     }
-    dim3 grid((unsigned)grid_x, (unsigned)Ktot);
+    dim3 grid((unsigned)(grid_x * Ktot));      // prime index fastest (TileArgs.ktot == Ktot)
     lsx_timing_begin(ctx);
     k_tile_elim<T><<<grid, T, smem, ctx->stream>>>(ta);
     lsx_timing_end(ctx);
@@ -1221,6 +1228,7 @@ static int run_generic(lsx_ctx* ctx, const ElimJob& job, const int32_t* list, co
     ta.status = job.status;
     ta.kword = kword;
     ta.k_extra = Ktot - K;
+    ta.ktot = Ktot;
 
     int64_t gx = list_mode ? 256 : job.batch;
     const int64_t max_gx = (int64_t)ctx->sm_count * 64;
@@ -1369,6 +1377,7 @@ int lsx_tile_det_residues(lsx_ctx* ctx, const int32_t* dA, int n, int prime_begi
     ta.a_abs_max = 0x7fffffffLL;
     ta.b_abs_max = 0;
     ta.primes = ctx->d_primes + prime_begin;
+    ta.ktot = count;
     ta.dres = (uint32_t*)(base + o_dres);
     ta.rankk = (int32_t*)(base + o_rank);
     ta.prof = (uint8_t*)(base + o_prof);
