@@ -1,3 +1,2 @@
-set -x
-timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/r02bh_pytest_gpu.txt 2>&1; tail -4 gpurun_out/r02bh_pytest_gpu.txt
-timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+( time timeout 900 python bench.py ) > gpurun_out/r02bi_bench_1gpu.json 2> gpurun_out/r02bi_bench_1gpu.err
+tail -3 gpurun_out/r02bi_bench_1gpu.err
